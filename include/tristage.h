@@ -1,0 +1,200 @@
+/*
+ * tristage.h -- C ABI of libtristage.so: the B200 (sm_100a) candidate-scoring
+ * hot path of TriStage-RAG.
+ *
+ * The reference (pure Python) has no FFI of its own; the boundary it does have
+ * is two library calls inside two classes:
+ *
+ *   Stage 1  faiss.IndexFlatIP(d) / .add(x) / .search(q, k)
+ *            /root/reference/src/stage1_retriever.py:263,270,276-277,313,380
+ *            + numpy row normalisation                         :285-288
+ *   Stage 2  F.normalize / matmul / max / mean (softmax-sum)
+ *            /root/reference/src/stage2_rescorer.py:173-183, :188-199
+ *            + stable descending sort and truncate             :294-297
+ *
+ * Every entry point below names the reference line(s) it stands in for.  The
+ * ctypes binding a maintainer of the reference would add is in
+ * INTEGRATION.md; the shipped binding is tristage_rag_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch/C++ types.  `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every function returns TS_OK (0) or a negative ts_status; the message
+ *     for the calling thread's last failure is ts_last_error().
+ *   - "dev" pointers are CUDA device pointers on the handle's device; "host"
+ *     pointers are ordinary host memory (pinned or pageable).
+ *   - the caller owns every in/out buffer; the library owns the corpus /
+ *     token shards and its scratch space behind the opaque handles.
+ *   - a handle is not re-entrant: one call at a time per handle.
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute
+ *     entry point fails with TS_ERR_CUDA / TS_ERR_UNSUPPORTED.
+ */
+#ifndef TRISTAGE_H_
+#define TRISTAGE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TS_ABI_VERSION 1
+
+typedef enum ts_status {
+  TS_OK = 0,
+  TS_ERR_INVALID = -1,     /* bad argument                                   */
+  TS_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed              */
+  TS_ERR_NOMEM = -3,       /* device or host allocation failed               */
+  TS_ERR_UNSUPPORTED = -4, /* valid request this build cannot serve          */
+  TS_ERR_IO = -5,          /* save/load failure                              */
+  TS_ERR_EMPTY = -6        /* search on an empty index (reference raises
+                              ValueError, stage1_retriever.py:370-371)       */
+} ts_status;
+
+typedef enum ts_dtype { TS_F32 = 0, TS_BF16 = 1, TS_F16 = 2 } ts_dtype;
+
+/* TS_METRIC_IP: rows are scored as stored (the reference normalises BEFORE
+ * add, so IP == cosine).  TS_METRIC_COSINE: rows are stored un-normalised and
+ * the scan epilogue multiplies each score by 1/(|x|+1e-8) of the stored row
+ * (fp32, computed at add time) -- L2-norm scaling fused into the top-k.     */
+typedef enum ts_metric { TS_METRIC_IP = 0, TS_METRIC_COSINE = 1 } ts_metric;
+
+/* which Stage-1 scan kernel serves a search call */
+typedef enum ts_path {
+  TS_PATH_AUTO = 0,   /* B <= 4 -> stream, else umma                         */
+  TS_PATH_STREAM = 1, /* CUDA-core 128-bit streaming scan (bandwidth path)   */
+  TS_PATH_UMMA = 2    /* TMA -> smem -> tcgen05.mma -> TMEM (tensor path)    */
+} ts_path;
+
+/* search / maxsim flags */
+#define TS_FLAG_NORMALIZE_Q 1u /* normalise queries with the reference formula
+                                  x/(|x|+1e-8) (stage1_retriever.py:377) or, in
+                                  Stage 2, F.normalize (stage2_rescorer.py:173) */
+
+typedef enum ts_s2_mode {
+  TS_S2_MAXSIM = 0, /* mean_i max_j  (stage2_rescorer.py:180-183)            */
+  TS_S2_COLBERT = 1 /* sum_i softmax(m)_i m_i  (stage2_rescorer.py:195-199)  */
+} ts_s2_mode;
+
+#define TS_MAX_K 512        /* largest fused top-k (reference default k = 500) */
+#define TS_S2_MAX_LQ 128    /* query tokens per query (reference: <= 192 after
+                               truncation; BASELINE config: 32)               */
+#define TS_S2_MAX_LD 256    /* doc tokens per doc (reference max_seq_length 192) */
+
+typedef struct ts_index ts_index;       /* one Stage-1 corpus shard            */
+typedef struct ts_tokstore ts_tokstore; /* one Stage-2 token-embedding shard   */
+
+/* ------------------------------------------------------------------ misc -- */
+int ts_abi_version(void);
+const char* ts_last_error(void);
+/* number of visible CUDA devices with compute capability 10.x; <0 on error  */
+int ts_device_count(void);
+
+/* ---------------------------------------------------------------- Stage 1 -- */
+
+/* faiss.IndexFlatIP(d)   (stage1_retriever.py:263,276).
+ * storage: TS_BF16 / TS_F16 (both scan kernels) or TS_F32 (stream kernel only).
+ * reserve_rows: rows to pre-allocate (grows by doubling beyond that).        */
+int ts_index_create(ts_index** out, int device, int dim, int storage_dtype, int metric,
+                    int64_t reserve_rows);
+int ts_index_destroy(ts_index* h);
+
+/* index.add(x) preceded by _normalize_embeddings
+ * (stage1_retriever.py:307 + :270,277,313).
+ * rows: [n, dim] row-major, src_dtype TS_F32 or the storage dtype, on the host
+ * (src_on_device = 0) or the device.  normalize != 0 applies x/(|x|+1e-8) in
+ * fp32 before the cast to the storage dtype (METRIC_IP) or records the
+ * inverse norms (METRIC_COSINE).  Row ids are positional: ntotal .. ntotal+n. */
+int ts_index_add(ts_index* h, const void* rows, int64_t n, int src_dtype, int src_on_device,
+                 int normalize, void* stream);
+
+int64_t ts_index_ntotal(const ts_index* h);
+int ts_index_dim(const ts_index* h);
+/* mcp clear_index (src/mcp_retrieval_server.py:243-247): drop all rows       */
+int ts_index_reset(ts_index* h);
+/* global id of local row 0 (row-sharded corpus: rank r owns [base, base+n))  */
+int ts_index_set_id_base(ts_index* h, int64_t id_base);
+
+/* index.search(q, k)   (stage1_retriever.py:380), batched.
+ * q_dev:  [B, dim] row-major, q_dtype TS_F32 or the storage dtype (device).
+ * out:    scores [B, k] fp32 descending, ids [B, k] int64 (global ids);
+ *         unused slots hold id -1 and the lowest float, as FAISS does.
+ * Ties: score descending, then id ascending (deterministic).
+ * Everything is enqueued on `stream`; nothing synchronises.                  */
+int ts_index_search(ts_index* h, const void* q_dev, int q_dtype, int B, int k, unsigned flags,
+                    int path, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+
+/* Same call with HOST buffers (the reference's numpy in / numpy out): copies
+ * q host->device, searches, copies results back and synchronises `stream`.   */
+int ts_index_search_host(ts_index* h, const void* q_host, int q_dtype, int B, int k,
+                         unsigned flags, int path, float* out_scores_host,
+                         int64_t* out_ids_host, void* stream);
+
+/* Merge n_lists per-shard results (what an all-gather of ts_index_search
+ * outputs delivers) into one top-k per query: scores/ids [n_lists, B, k] ->
+ * [B, k].  Lists must be ordered by ascending id range for the id-ascending
+ * tie rule to hold across shards.  Device pointers.                          */
+int ts_topk_merge(int device, const float* scores_dev, const int64_t* ids_dev, int n_lists, int B,
+                  int k, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+
+/* faiss.write_index / read_index  (stage1_retriever.py:436,463).             */
+int ts_index_save(const ts_index* h, const char* path);
+int ts_index_load(ts_index** out, int device, const char* path);
+
+/* copy stored rows [start, start+n) back as fp32 [n, dim] to host (tests,
+ * migration); not on the hot path.                                           */
+int ts_index_get_rows(const ts_index* h, int64_t start, int64_t n, float* out_host);
+
+/* kernels launched by this handle since creation (bench.py gpu_launches)     */
+int64_t ts_index_launch_count(const ts_index* h);
+
+/* ---------------------------------------------------------------- Stage 2 -- */
+
+/* Token-embedding shard: the reference re-encodes every candidate per query
+ * (stage2_rescorer.py:255-259); the store keeps encode_documents_batch's
+ * outputs ([Ld_i, dim] per doc, :226-231) resident, L2-normalised at add.    */
+int ts_tokstore_create(ts_tokstore** out, int device, int dim, int storage_dtype,
+                       int64_t reserve_docs, int64_t reserve_tokens);
+int ts_tokstore_destroy(ts_tokstore* h);
+
+/* tok: concatenated [sum(lens), dim] rows, src_dtype TS_F32 or storage dtype,
+ * host or device; lens_host[n_docs] (1 <= len <= TS_S2_MAX_LD).
+ * normalize != 0 applies F.normalize (x / max(|x|, 1e-12), :174) per token
+ * in fp32 before the cast.  Doc ids are positional.                          */
+int ts_tokstore_add(ts_tokstore* h, const void* tok, int src_dtype, int src_on_device,
+                    const int32_t* lens_host, int n_docs, int normalize, void* stream);
+int64_t ts_tokstore_ndocs(const ts_tokstore* h);
+int64_t ts_tokstore_ntokens(const ts_tokstore* h);
+int ts_tokstore_reset(ts_tokstore* h);
+int ts_tokstore_set_id_base(ts_tokstore* h, int64_t id_base);
+int64_t ts_tokstore_launch_count(const ts_tokstore* h);
+
+/* _maxsim_score / _colbert_score for every (query, candidate) pair in one
+ * launch (replaces the loop at stage2_rescorer.py:268-273).
+ * q_tok_dev:  [B, lq_stride, dim], q_dtype TS_F32 or storage dtype
+ * q_len_dev:  [B] int32 real query-token counts (NULL -> lq_stride each)
+ * cand_dev:   [B, C] int64 global doc ids; entries outside this shard's
+ *             [id_base, id_base+ndocs) -- including -1 -- score 0.0, so
+ *             per-shard outputs can be summed (all-reduce) across ranks
+ * n_cand_dev: [B] int32 valid candidates per query (NULL -> C each)
+ * out:        [B, C] fp32 scores, 0.0 beyond n_cand                          */
+int ts_maxsim(ts_tokstore* h, const void* q_tok_dev, int q_dtype, const int32_t* q_len_dev, int B,
+              int lq_stride, const int64_t* cand_dev, const int32_t* n_cand_dev, int C, int mode,
+              unsigned flags, float* out_scores_dev, void* stream);
+
+/* host-buffer variant (copies in, scores, copies out, synchronises)          */
+int ts_maxsim_host(ts_tokstore* h, const void* q_tok_host, int q_dtype, const int32_t* q_len_host,
+                   int B, int lq_stride, const int64_t* cand_host, const int32_t* n_cand_host,
+                   int C, int mode, unsigned flags, float* out_scores_host, void* stream);
+
+/* scored_candidates.sort(reverse=True)[:top_k]  (stage2_rescorer.py:294-297):
+ * per query, the positions of the top_k scores in STABLE descending order
+ * (equal scores keep incoming order).  scores [B, C], n_cand [B] or NULL;
+ * out_pos [B, top_k] int32 (-1 padded), out_scores [B, top_k].               */
+int ts_rank_desc(int device, const float* scores_dev, const int32_t* n_cand_dev, int B, int C,
+                 int top_k, float* out_scores_dev, int32_t* out_pos_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRISTAGE_H_ */

@@ -1,0 +1,362 @@
+"""ctypes binding of ``lib/libtristage.so`` (the C ABI in ``include/tristage.h``).
+
+There is no CPU fallback anywhere in this package: if the shared library is
+missing, or no sm_100 device is usable, the calls below raise.  The library is
+built in-tree by ``tristage_rag_b200/csrc/Makefile`` (``build()`` here, or
+``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtristage.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+TS_F32, TS_BF16, TS_F16 = 0, 1, 2
+TS_METRIC_IP, TS_METRIC_COSINE = 0, 1
+TS_PATH_AUTO, TS_PATH_STREAM, TS_PATH_UMMA = 0, 1, 2
+TS_FLAG_NORMALIZE_Q = 1
+TS_S2_MAXSIM, TS_S2_COLBERT = 0, 1
+TS_S2_FORCE_SIMT = 0x100          # mode bit: take the CUDA-core Stage-2 kernel
+TS_MAX_K = 512
+TS_S2_MAX_LQ = 128
+TS_S2_MAX_LD = 256
+TS_ERR_EMPTY = -6
+
+DTYPES = {"f32": TS_F32, "fp32": TS_F32, "float32": TS_F32,
+          "bf16": TS_BF16, "bfloat16": TS_BF16,
+          "f16": TS_F16, "fp16": TS_F16, "float16": TS_F16}
+PATHS = {"auto": TS_PATH_AUTO, "stream": TS_PATH_STREAM, "umma": TS_PATH_UMMA}
+
+# every symbol include/tristage.h declares: name -> (restype, argtypes)
+_vp, _i, _i64, _u = C.c_void_p, C.c_int, C.c_int64, C.c_uint
+SYMBOLS = {
+    "ts_abi_version": (_i, []),
+    "ts_last_error": (C.c_char_p, []),
+    "ts_device_count": (_i, []),
+    "ts_index_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i64]),
+    "ts_index_destroy": (_i, [_vp]),
+    "ts_index_add": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
+    "ts_index_ntotal": (_i64, [_vp]),
+    "ts_index_dim": (_i, [_vp]),
+    "ts_index_reset": (_i, [_vp]),
+    "ts_index_set_id_base": (_i, [_vp, _i64]),
+    "ts_index_search": (_i, [_vp, _vp, _i, _i, _i, _u, _i, _vp, _vp, _vp]),
+    "ts_index_search_host": (_i, [_vp, _vp, _i, _i, _i, _u, _i, _vp, _vp, _vp]),
+    "ts_topk_merge": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "ts_index_save": (_i, [_vp, C.c_char_p]),
+    "ts_index_load": (_i, [C.POINTER(_vp), _i, C.c_char_p]),
+    "ts_index_get_rows": (_i, [_vp, _i64, _i64, _vp]),
+    "ts_index_launch_count": (_i64, [_vp]),
+    "ts_tokstore_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i64, _i64]),
+    "ts_tokstore_destroy": (_i, [_vp]),
+    "ts_tokstore_add": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp]),
+    "ts_tokstore_ndocs": (_i64, [_vp]),
+    "ts_tokstore_ntokens": (_i64, [_vp]),
+    "ts_tokstore_reset": (_i, [_vp]),
+    "ts_tokstore_set_id_base": (_i, [_vp, _i64]),
+    "ts_tokstore_launch_count": (_i64, [_vp]),
+    "ts_maxsim": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _u, _vp, _vp]),
+    "ts_maxsim_host": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _u, _vp, _vp]),
+    "ts_rank_desc": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class TristageError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libtristage error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libtristage.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    cmd = ["make", "-C", CSRC, "-j", str(min(8, os.cpu_count() or 1))]
+    out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout)
+    if out.returncode != 0:
+        raise RuntimeError("building libtristage.so failed")
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it is missing."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ImportError(
+                    f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(or `make -C tristage_rag_b200/csrc`). There is no CPU fallback.")
+            L = C.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(L, name)          # AttributeError if the ABI lost a symbol
+                fn.restype, fn.argtypes = res, args
+            if L.ts_abi_version() != 1:
+                raise ImportError("libtristage ABI version mismatch")
+            _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise TristageError(rc, (lib().ts_last_error() or b"").decode("utf-8", "replace"))
+
+
+def _stream_ptr(device_index: int):
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+def _torch_dtype(code: int):
+    import torch
+
+    return {TS_F32: torch.float32, TS_BF16: torch.bfloat16, TS_F16: torch.float16}[code]
+
+
+def _code_of_torch(dt) -> int:
+    import torch
+
+    return {torch.float32: TS_F32, torch.bfloat16: TS_BF16, torch.float16: TS_F16}[dt]
+
+
+class Index:
+    """One Stage-1 corpus shard on one GPU (``ts_index``)."""
+
+    def __init__(self, dim: int, dtype: str = "bf16", metric: str = "ip", device: int = 0,
+                 reserve_rows: int = 0, _handle=None):
+        self.dim, self.device = int(dim), int(device)
+        self.dtype = DTYPES[dtype]
+        self.metric = TS_METRIC_COSINE if metric in ("cosine", "cos") else TS_METRIC_IP
+        if _handle is not None:
+            self._h = _handle
+        else:
+            h = C.c_void_p()
+            check(lib().ts_index_create(C.byref(h), self.device, self.dim, self.dtype, self.metric, int(reserve_rows)))
+            self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and _lib is not None:
+            _lib.ts_index_destroy(h)
+
+    @property
+    def ntotal(self) -> int:
+        return int(lib().ts_index_ntotal(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(lib().ts_index_launch_count(self._h))
+
+    def set_id_base(self, base: int) -> None:
+        check(lib().ts_index_set_id_base(self._h, int(base)))
+
+    def reset(self) -> None:
+        check(lib().ts_index_reset(self._h))
+
+    def add(self, x, normalize: bool = False) -> None:
+        """x: numpy fp32 [n, dim] (host) or torch tensor (cuda: fp32 / storage dtype; cpu: fp32)."""
+        import numpy as np
+        import torch
+
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            assert x.ndim == 2 and x.shape[1] == self.dim, x.shape
+            check(lib().ts_index_add(self._h, C.c_void_p(x.ctypes.data), x.shape[0], TS_F32, 0, int(normalize),
+                                     _stream_ptr(self.device)))
+            return
+        assert isinstance(x, torch.Tensor) and x.dim() == 2 and x.shape[1] == self.dim, x.shape
+        x = x.contiguous()
+        on_dev = 1 if x.is_cuda else 0
+        if on_dev:
+            assert x.device.index == self.device
+        check(lib().ts_index_add(self._h, C.c_void_p(x.data_ptr()), x.shape[0], _code_of_torch(x.dtype), on_dev,
+                                 int(normalize), _stream_ptr(self.device)))
+        if on_dev:
+            torch.cuda.current_stream(self.device).synchronize()   # x may be freed by the caller
+
+    def search(self, q, k: int, normalize_q: bool = False, path: str = "auto"):
+        """q: cuda tensor [B, dim] (fp32 or storage dtype) -> (scores[B,k] f32, ids[B,k] i64) on the device.
+        Asynchronous on the current stream."""
+        import torch
+
+        assert q.is_cuda and q.dim() == 2 and q.shape[1] == self.dim, (q.shape, self.dim)
+        q = q.contiguous()
+        B = q.shape[0]
+        dev = torch.device("cuda", self.device)
+        scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+        ids = torch.empty((B, k), dtype=torch.int64, device=dev)
+        check(lib().ts_index_search(self._h, C.c_void_p(q.data_ptr()), _code_of_torch(q.dtype), B, int(k),
+                                    TS_FLAG_NORMALIZE_Q if normalize_q else 0, PATHS[path],
+                                    C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()),
+                                    _stream_ptr(self.device)))
+        return scores, ids
+
+    def search_host(self, q, k: int, normalize_q: bool = False, path: str = "auto"):
+        """q: numpy fp32 [B, dim] -> (D[B,k] f32, I[B,k] i64) numpy -- the faiss call shape."""
+        import numpy as np
+
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        assert q.ndim == 2 and q.shape[1] == self.dim, (q.shape, self.dim)
+        B = q.shape[0]
+        D = np.empty((B, k), np.float32)
+        I = np.empty((B, k), np.int64)
+        check(lib().ts_index_search_host(self._h, C.c_void_p(q.ctypes.data), TS_F32, B, int(k),
+                                         TS_FLAG_NORMALIZE_Q if normalize_q else 0, PATHS[path],
+                                         C.c_void_p(D.ctypes.data), C.c_void_p(I.ctypes.data),
+                                         _stream_ptr(self.device)))
+        return D, I
+
+    def get_rows(self, start: int, n: int):
+        import numpy as np
+
+        out = np.empty((n, self.dim), np.float32)
+        check(lib().ts_index_get_rows(self._h, int(start), int(n), C.c_void_p(out.ctypes.data)))
+        return out
+
+    def save(self, path: str) -> None:
+        check(lib().ts_index_save(self._h, path.encode()))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0) -> "Index":
+        h = C.c_void_p()
+        check(lib().ts_index_load(C.byref(h), int(device), path.encode()))
+        dim = int(lib().ts_index_dim(h))
+        obj = cls.__new__(cls)
+        obj.dim, obj.device, obj._h = dim, int(device), h
+        obj.dtype, obj.metric = None, None
+        return obj
+
+
+def topk_merge(scores, ids, device: int = 0):
+    """[L, B, k] per-shard results (cuda tensors) -> merged ([B,k], [B,k])."""
+    import torch
+
+    L, B, k = scores.shape
+    scores, ids = scores.contiguous(), ids.contiguous()
+    dev = torch.device("cuda", device)
+    out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+    check(lib().ts_topk_merge(device, C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()), L, B, k,
+                              C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()), _stream_ptr(device)))
+    return out_s, out_i
+
+
+def rank_desc(scores, top_k: int, n_cand=None, device: int = 0):
+    """Stable descending top_k positions per row of scores[B, C] (cuda)."""
+    import torch
+
+    B, Cn = scores.shape
+    scores = scores.contiguous()
+    dev = torch.device("cuda", device)
+    out_s = torch.empty((B, top_k), dtype=torch.float32, device=dev)
+    out_p = torch.empty((B, top_k), dtype=torch.int32, device=dev)
+    nc = C.c_void_p(n_cand.data_ptr()) if n_cand is not None else None
+    check(lib().ts_rank_desc(device, C.c_void_p(scores.data_ptr()), nc, B, Cn, int(top_k),
+                             C.c_void_p(out_s.data_ptr()), C.c_void_p(out_p.data_ptr()), _stream_ptr(device)))
+    return out_s, out_p
+
+
+class TokStore:
+    """One Stage-2 token-embedding shard on one GPU (``ts_tokstore``)."""
+
+    def __init__(self, dim: int, dtype: str = "bf16", device: int = 0, reserve_docs: int = 0,
+                 reserve_tokens: int = 0):
+        self.dim, self.device = int(dim), int(device)
+        self.dtype = DTYPES[dtype]
+        h = C.c_void_p()
+        check(lib().ts_tokstore_create(C.byref(h), self.device, self.dim, self.dtype, int(reserve_docs),
+                                       int(reserve_tokens)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and _lib is not None:
+            _lib.ts_tokstore_destroy(h)
+
+    @property
+    def ndocs(self) -> int:
+        return int(lib().ts_tokstore_ndocs(self._h))
+
+    @property
+    def ntokens(self) -> int:
+        return int(lib().ts_tokstore_ntokens(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(lib().ts_tokstore_launch_count(self._h))
+
+    def set_id_base(self, base: int) -> None:
+        check(lib().ts_tokstore_set_id_base(self._h, int(base)))
+
+    def reset(self) -> None:
+        check(lib().ts_tokstore_reset(self._h))
+
+    def add(self, tok, lens, normalize: bool = True) -> None:
+        """tok: [sum(lens), dim] numpy fp32 (host) or torch tensor; lens: int sequence."""
+        import numpy as np
+        import torch
+
+        lens = np.ascontiguousarray(np.asarray(lens, dtype=np.int32))
+        total = int(lens.sum())
+        if isinstance(tok, np.ndarray):
+            tok = np.ascontiguousarray(tok, dtype=np.float32)
+            assert tok.shape == (total, self.dim), (tok.shape, total, self.dim)
+            check(lib().ts_tokstore_add(self._h, C.c_void_p(tok.ctypes.data), TS_F32, 0,
+                                        C.c_void_p(lens.ctypes.data), len(lens), int(normalize),
+                                        _stream_ptr(self.device)))
+            return
+        assert isinstance(tok, torch.Tensor) and tuple(tok.shape) == (total, self.dim), (tok.shape, total)
+        tok = tok.contiguous()
+        check(lib().ts_tokstore_add(self._h, C.c_void_p(tok.data_ptr()), _code_of_torch(tok.dtype),
+                                    1 if tok.is_cuda else 0, C.c_void_p(lens.ctypes.data), len(lens),
+                                    int(normalize), _stream_ptr(self.device)))
+
+    def maxsim(self, q_tok, cand, q_len=None, n_cand=None, mode: int = TS_S2_MAXSIM, normalize_q: bool = True):
+        """q_tok [B, Lq, dim] cuda, cand [B, C] int64 cuda -> scores [B, C] f32 cuda (async)."""
+        import torch
+
+        assert q_tok.is_cuda and q_tok.dim() == 3 and q_tok.shape[2] == self.dim
+        q_tok, cand = q_tok.contiguous(), cand.contiguous()
+        B, Lq, _ = q_tok.shape
+        Cn = cand.shape[1]
+        out = torch.empty((B, Cn), dtype=torch.float32, device=q_tok.device)
+        check(lib().ts_maxsim(self._h, C.c_void_p(q_tok.data_ptr()), _code_of_torch(q_tok.dtype),
+                              C.c_void_p(q_len.data_ptr()) if q_len is not None else None, B, Lq,
+                              C.c_void_p(cand.data_ptr()),
+                              C.c_void_p(n_cand.data_ptr()) if n_cand is not None else None, Cn, int(mode),
+                              TS_FLAG_NORMALIZE_Q if normalize_q else 0, C.c_void_p(out.data_ptr()),
+                              _stream_ptr(self.device)))
+        return out
+
+    def maxsim_host(self, q_tok, cand, q_len=None, n_cand=None, mode: int = TS_S2_MAXSIM,
+                    normalize_q: bool = True):
+        """numpy in / numpy out variant (copies inside the call, synchronises)."""
+        import numpy as np
+
+        q_tok = np.ascontiguousarray(q_tok, dtype=np.float32)
+        cand = np.ascontiguousarray(cand, dtype=np.int64)
+        B, Lq, _ = q_tok.shape
+        Cn = cand.shape[1]
+        out = np.empty((B, Cn), np.float32)
+        ql = np.ascontiguousarray(q_len, dtype=np.int32) if q_len is not None else None
+        nc = np.ascontiguousarray(n_cand, dtype=np.int32) if n_cand is not None else None
+        check(lib().ts_maxsim_host(self._h, C.c_void_p(q_tok.ctypes.data), TS_F32,
+                                   C.c_void_p(ql.ctypes.data) if ql is not None else None, B, Lq,
+                                   C.c_void_p(cand.ctypes.data),
+                                   C.c_void_p(nc.ctypes.data) if nc is not None else None, Cn, int(mode),
+                                   TS_FLAG_NORMALIZE_Q if normalize_q else 0, C.c_void_p(out.ctypes.data),
+                                   _stream_ptr(self.device)))
+        return out

@@ -1,0 +1,580 @@
+// C ABI of libtristage.so (see include/tristage.h for the contract and the
+// reference call sites each entry point replaces).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "ts_internal.h"
+
+namespace ts {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int get_device_info(int device, DeviceInfo* out) {
+  cudaDeviceProp prop;
+  TS_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  out->sm_count = prop.multiProcessorCount;
+  out->cc_major = prop.major;
+  out->cc_minor = prop.minor;
+  out->smem_optin = prop.sharedMemPerBlockOptin;
+  return TS_OK;
+}
+
+// grow-only device scratch
+static int ensure_bytes(void** p, size_t* cur, size_t need) {
+  if (need <= *cur) return TS_OK;
+  if (*p) { cudaFree(*p); *p = nullptr; *cur = 0; }
+  cudaError_t e = cudaMalloc(p, need);
+  if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); return TS_ERR_NOMEM; }
+  *cur = need;
+  return TS_OK;
+}
+
+}  // namespace ts
+
+using namespace ts;
+
+struct ts_index {
+  int device, dim, ld, dtype, metric;
+  int64_t n, cap, id_base;
+  void* rows;
+  float* inv_norm;
+  DeviceInfo info;
+  int64_t launches;
+  // scratch (grow-only)
+  void* qbuf; size_t qbuf_b;
+  void* lists; size_t lists_b;
+  void* partial; size_t partial_b;
+  void* tmp0; size_t tmp0_b;
+  void* tmp1; size_t tmp1_b;
+  void* stage; size_t stage_b;       // staging for host inputs (add / search_host)
+  void* hout; size_t hout_b;         // device result buffers for search_host
+};
+
+struct ts_tokstore {
+  int device, dim, dtype;
+  int64_t ndocs, nrows, cap_docs, cap_rows, id_base, ntokens;
+  int64_t hint_docs, hint_rows;     // reservation hints honoured by the first add
+  void* tok;
+  int64_t* doc_off;
+  int32_t* doc_len;
+  DeviceInfo info;
+  int64_t launches;
+  void* qbuf; size_t qbuf_b;
+  void* stage; size_t stage_b;
+  void* meta; size_t meta_b;         // per-add src offsets scratch / host-variant buffers
+  void* hbuf; size_t hbuf_b;
+};
+
+namespace {
+
+int check_device(int device, DeviceInfo* info) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s); libtristage has no CPU fallback", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+    return TS_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) { set_error("device %d out of range (%d visible)", device, n); return TS_ERR_INVALID; }
+  int rc = get_device_info(device, info);
+  if (rc) return rc;
+  if (info->cc_major != 10) {
+    set_error("device %d is sm_%d%d; libtristage is built for sm_100a only", device, info->cc_major, info->cc_minor);
+    return TS_ERR_UNSUPPORTED;
+  }
+  TS_CUDA_OK(cudaSetDevice(device));
+  return TS_OK;
+}
+
+bool valid_storage(int dt) { return dt == TS_F32 || dt == TS_BF16 || dt == TS_F16; }
+
+int index_reserve(ts_index* h, int64_t rows, cudaStream_t st) {
+  if (rows <= h->cap) return TS_OK;
+  int64_t ncap = h->cap > 0 ? h->cap : 1024;
+  while (ncap < rows) ncap *= 2;
+  const size_t row_b = (size_t)h->ld * dtype_size(h->dtype);
+  void* nrows = nullptr;
+  cudaError_t e = cudaMalloc(&nrows, (size_t)ncap * row_b);
+  if (e != cudaSuccess) {
+    // retry with the exact size before giving up (doubling can overshoot HBM)
+    ncap = rows;
+    e = cudaMalloc(&nrows, (size_t)ncap * row_b);
+    if (e != cudaSuccess) { set_error("cudaMalloc of %lld corpus rows failed: %s", (long long)ncap, cudaGetErrorString(e)); return TS_ERR_NOMEM; }
+  }
+  float* ninv = nullptr;
+  if (h->metric == TS_METRIC_COSINE) {
+    e = cudaMalloc((void**)&ninv, (size_t)ncap * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(nrows); set_error("cudaMalloc inv_norm failed"); return TS_ERR_NOMEM; }
+  }
+  if (h->n > 0) {
+    TS_CUDA_OK(cudaMemcpyAsync(nrows, h->rows, (size_t)h->n * row_b, cudaMemcpyDeviceToDevice, st));
+    if (ninv) TS_CUDA_OK(cudaMemcpyAsync(ninv, h->inv_norm, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TS_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  if (h->rows) cudaFree(h->rows);
+  if (h->inv_norm) cudaFree(h->inv_norm);
+  h->rows = nrows; h->inv_norm = ninv; h->cap = ncap;
+  return TS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ts_abi_version(void) { return TS_ABI_VERSION; }
+const char* ts_last_error(void) { return ts::get_error(); }
+
+int ts_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+// ------------------------------------------------------------------ Stage 1
+int ts_index_create(ts_index** out, int device, int dim, int storage_dtype, int metric, int64_t reserve_rows) {
+  if (!out || dim <= 0 || dim > 8192 || !valid_storage(storage_dtype) ||
+      (metric != TS_METRIC_IP && metric != TS_METRIC_COSINE) || reserve_rows < 0) {
+    set_error("ts_index_create: invalid argument");
+    return TS_ERR_INVALID;
+  }
+  DeviceInfo info;
+  int rc = check_device(device, &info);
+  if (rc) return rc;
+  ts_index* h = new ts_index();
+  memset(h, 0, sizeof(*h));
+  h->device = device; h->dim = dim; h->dtype = storage_dtype; h->metric = metric;
+  h->ld = row_pitch(dim, storage_dtype);
+  h->info = info;
+  if (reserve_rows > 0) {
+    h->cap = 0;
+    // exact reservation (no doubling) for the first allocation
+    const size_t row_b = (size_t)h->ld * dtype_size(h->dtype);
+    cudaError_t e = cudaMalloc(&h->rows, (size_t)reserve_rows * row_b);
+    if (e != cudaSuccess) { set_error("cudaMalloc of %lld rows failed: %s", (long long)reserve_rows, cudaGetErrorString(e)); delete h; return TS_ERR_NOMEM; }
+    if (metric == TS_METRIC_COSINE) {
+      e = cudaMalloc((void**)&h->inv_norm, (size_t)reserve_rows * sizeof(float));
+      if (e != cudaSuccess) { cudaFree(h->rows); set_error("cudaMalloc inv_norm failed"); delete h; return TS_ERR_NOMEM; }
+    }
+    h->cap = reserve_rows;
+  }
+  *out = h;
+  return TS_OK;
+}
+
+int ts_index_destroy(ts_index* h) {
+  if (!h) return TS_OK;
+  cudaSetDevice(h->device);
+  void* ptrs[] = {h->rows, h->inv_norm, h->qbuf, h->lists, h->partial, h->tmp0, h->tmp1, h->stage, h->hout};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete h;
+  return TS_OK;
+}
+
+int ts_index_add(ts_index* h, const void* rows, int64_t n, int src_dtype, int src_on_device, int normalize, void* stream) {
+  if (!h || n < 0 || (n > 0 && !rows)) { set_error("ts_index_add: invalid argument"); return TS_ERR_INVALID; }
+  if (src_dtype != TS_F32 && src_dtype != h->dtype) { set_error("ts_index_add: src dtype must be f32 or the storage dtype"); return TS_ERR_INVALID; }
+  if (n == 0) return TS_OK;
+  if (h->n + n > 0xFFFFFFF0ll) { set_error("ts_index_add: shard limited to 2^32 rows"); return TS_ERR_UNSUPPORTED; }
+  cudaStream_t st = (cudaStream_t)stream;
+  TS_CUDA_OK(cudaSetDevice(h->device));
+  int rc = index_reserve(h, h->n + n, st);
+  if (rc) return rc;
+  const int ssz = dtype_size(src_dtype);
+  const size_t row_b = (size_t)h->ld * dtype_size(h->dtype);
+  const int norm_mode = (h->metric == TS_METRIC_COSINE || normalize) ? kNormStage1 : kNormNone;
+  const int64_t chunk = src_on_device ? n : (int64_t)((256ull << 20) / ((size_t)h->dim * ssz) + 1);
+  for (int64_t s = 0; s < n; s += chunk) {
+    const int64_t m = (n - s) < chunk ? (n - s) : chunk;
+    const char* src = (const char*)rows + (size_t)s * h->dim * ssz;
+    const void* dsrc = src;
+    if (!src_on_device) {
+      rc = ensure_bytes(&h->stage, &h->stage_b, (size_t)m * h->dim * ssz);
+      if (rc) return rc;
+      TS_CUDA_OK(cudaMemcpyAsync(h->stage, src, (size_t)m * h->dim * ssz, cudaMemcpyHostToDevice, st));
+      dsrc = h->stage;
+    }
+    float* inv = (h->metric == TS_METRIC_COSINE) ? h->inv_norm + h->n + s : nullptr;
+    rc = launch_convert_rows(dsrc, src_dtype, h->dim, (char*)h->rows + (size_t)(h->n + s) * row_b, h->dtype, h->ld, m,
+                             h->dim, norm_mode, inv, st);
+    if (rc) return rc;
+    ++h->launches;
+    if (!src_on_device) TS_CUDA_OK(cudaStreamSynchronize(st));  // staging buffer is reused
+  }
+  h->n += n;
+  return TS_OK;
+}
+
+int64_t ts_index_ntotal(const ts_index* h) { return h ? h->n : -1; }
+int ts_index_dim(const ts_index* h) { return h ? h->dim : -1; }
+int ts_index_reset(ts_index* h) { if (!h) return TS_ERR_INVALID; h->n = 0; return TS_OK; }
+int ts_index_set_id_base(ts_index* h, int64_t b) { if (!h) return TS_ERR_INVALID; h->id_base = b; return TS_OK; }
+int64_t ts_index_launch_count(const ts_index* h) { return h ? h->launches : -1; }
+
+int ts_index_search(ts_index* h, const void* q_dev, int q_dtype, int B, int k, unsigned flags, int path,
+                    float* out_scores, int64_t* out_ids, void* stream) {
+  if (!h || !q_dev || !out_scores || !out_ids || B <= 0) { set_error("ts_index_search: invalid argument"); return TS_ERR_INVALID; }
+  if (k <= 0 || k > TS_MAX_K) { set_error("ts_index_search: k=%d outside 1..%d", k, TS_MAX_K); return TS_ERR_INVALID; }
+  if (q_dtype != TS_F32 && q_dtype != h->dtype) { set_error("ts_index_search: query dtype must be f32 or the storage dtype"); return TS_ERR_INVALID; }
+  if (h->n == 0) { set_error("No documents indexed. Call add_documents() first."); return TS_ERR_EMPTY; }
+  cudaStream_t st = (cudaStream_t)stream;
+  TS_CUDA_OK(cudaSetDevice(h->device));
+  int use = path;
+  if (use == TS_PATH_AUTO) use = (B <= 4 || h->dtype == TS_F32) ? TS_PATH_STREAM : TS_PATH_UMMA;
+  if (use == TS_PATH_UMMA && h->dtype == TS_F32) { set_error("umma path needs bf16/fp16 storage"); return TS_ERR_UNSUPPORTED; }
+  if (use != TS_PATH_STREAM && use != TS_PATH_UMMA) { set_error("ts_index_search: bad path %d", path); return TS_ERR_INVALID; }
+
+  const int esz = dtype_size(h->dtype);
+  const int chunkB = 1024;
+  for (int b0 = 0; b0 < B; b0 += chunkB) {
+    const int Bc = (B - b0) < chunkB ? (B - b0) : chunkB;
+    int rc = ensure_bytes(&h->qbuf, &h->qbuf_b, (size_t)chunkB * h->ld * esz);
+    if (rc) return rc;
+    rc = launch_convert_rows((const char*)q_dev + (size_t)b0 * h->dim * dtype_size(q_dtype), q_dtype, h->dim, h->qbuf,
+                             h->dtype, h->ld, Bc, h->dim, (flags & TS_FLAG_NORMALIZE_Q) ? kNormStage1 : kNormNone,
+                             nullptr, st);
+    if (rc) return rc;
+    ++h->launches;
+    ScanArgs a{};
+    a.rows = h->rows; a.n = h->n; a.dim = h->dim; a.ld = h->ld; a.dtype = h->dtype;
+    a.inv_norm = (h->metric == TS_METRIC_COSINE) ? h->inv_norm : nullptr;
+    a.q = h->qbuf; a.B = Bc; a.k = k; a.sm_count = h->info.sm_count;
+    int L = 0; size_t lists_keys = 0;
+    rc = (use == TS_PATH_STREAM) ? s1_stream_plan(a, &L, &lists_keys) : s1_umma_plan(a, &L, &lists_keys);
+    if (rc) return rc;
+    if ((rc = ensure_bytes(&h->lists, &h->lists_b, lists_keys * 8))) return rc;
+    const size_t partial_keys = (size_t)L * Bc * k;
+    if ((rc = ensure_bytes(&h->partial, &h->partial_b, partial_keys * 8))) return rc;
+    const size_t tmpk = merge_tmp_keys(L, Bc, k);
+    if (tmpk) {
+      if ((rc = ensure_bytes(&h->tmp0, &h->tmp0_b, tmpk * 8))) return rc;
+      if ((rc = ensure_bytes(&h->tmp1, &h->tmp1_b, tmpk * 8))) return rc;
+    }
+    a.lists = (uint64_t*)h->lists; a.lists_keys = lists_keys;
+    a.partial = (uint64_t*)h->partial; a.partial_keys = partial_keys;
+    int launches = 0;
+    rc = (use == TS_PATH_STREAM) ? launch_s1_stream(a, st, &launches) : launch_s1_umma(a, st, &launches);
+    if (rc) return rc;
+    rc = launch_merge_keys((const uint64_t*)h->partial, L, Bc, k, h->id_base, (uint64_t*)h->tmp0, (uint64_t*)h->tmp1,
+                           out_scores + (size_t)b0 * k, out_ids + (size_t)b0 * k, st, &launches);
+    if (rc) return rc;
+    h->launches += launches;
+  }
+  return TS_OK;
+}
+
+int ts_index_search_host(ts_index* h, const void* q_host, int q_dtype, int B, int k, unsigned flags, int path,
+                         float* out_scores_host, int64_t* out_ids_host, void* stream) {
+  if (!h || !q_host || !out_scores_host || !out_ids_host || B <= 0 || k <= 0 || k > TS_MAX_K) {
+    set_error("ts_index_search_host: invalid argument");
+    return TS_ERR_INVALID;
+  }
+  if (h->n == 0) { set_error("No documents indexed. Call add_documents() first."); return TS_ERR_EMPTY; }
+  cudaStream_t st = (cudaStream_t)stream;
+  TS_CUDA_OK(cudaSetDevice(h->device));
+  const size_t qb = (size_t)B * h->dim * dtype_size(q_dtype);
+  int rc = ensure_bytes(&h->stage, &h->stage_b, qb);
+  if (rc) return rc;
+  const size_t sb = (size_t)B * k * sizeof(float), ib = (size_t)B * k * sizeof(int64_t);
+  if ((rc = ensure_bytes(&h->hout, &h->hout_b, sb + ib + 256))) return rc;
+  float* ds = (float*)h->hout;
+  int64_t* di = (int64_t*)((char*)h->hout + ((sb + 255) / 256) * 256);
+  TS_CUDA_OK(cudaMemcpyAsync(h->stage, q_host, qb, cudaMemcpyHostToDevice, st));
+  rc = ts_index_search(h, h->stage, q_dtype, B, k, flags, path, ds, di, stream);
+  if (rc) return rc;
+  TS_CUDA_OK(cudaMemcpyAsync(out_scores_host, ds, sb, cudaMemcpyDeviceToHost, st));
+  TS_CUDA_OK(cudaMemcpyAsync(out_ids_host, di, ib, cudaMemcpyDeviceToHost, st));
+  TS_CUDA_OK(cudaStreamSynchronize(st));
+  return TS_OK;
+}
+
+int ts_topk_merge(int device, const float* scores, const int64_t* ids, int n_lists, int B, int k, float* out_scores,
+                  int64_t* out_ids, void* stream) {
+  if (!scores || !ids || !out_scores || !out_ids) { set_error("ts_topk_merge: null pointer"); return TS_ERR_INVALID; }
+  TS_CUDA_OK(cudaSetDevice(device));
+  return launch_merge_pairs(scores, ids, n_lists, B, k, out_scores, out_ids, (cudaStream_t)stream);
+}
+
+int ts_index_get_rows(const ts_index* h, int64_t start, int64_t n, float* out_host) {
+  if (!h || start < 0 || n < 0 || start + n > h->n || (n > 0 && !out_host)) { set_error("ts_index_get_rows: bad range"); return TS_ERR_INVALID; }
+  if (n == 0) return TS_OK;
+  TS_CUDA_OK(cudaSetDevice(h->device));
+  float* tmp = nullptr;
+  TS_CUDA_OK(cudaMalloc((void**)&tmp, (size_t)n * h->dim * sizeof(float)));
+  const size_t row_b = (size_t)h->ld * dtype_size(h->dtype);
+  int rc = launch_convert_rows((const char*)h->rows + (size_t)start * row_b, h->dtype, h->ld, tmp, TS_F32, h->dim, n,
+                               h->dim, kNormNone, nullptr, 0);
+  if (rc == TS_OK) {
+    cudaError_t e = cudaMemcpy(out_host, tmp, (size_t)n * h->dim * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("copy back failed: %s", cudaGetErrorString(e)); rc = TS_ERR_CUDA; }
+  }
+  cudaFree(tmp);
+  return rc;
+}
+
+// ---- persistence: header + raw storage rows (+ inverse norms) -------------
+struct TsFileHeader {
+  char magic[8];
+  int32_t version, dim, ld, dtype, metric, pad;
+  int64_t n, id_base;
+};
+
+int ts_index_save(const ts_index* h, const char* path) {
+  if (!h || !path) { set_error("ts_index_save: invalid argument"); return TS_ERR_INVALID; }
+  TS_CUDA_OK(cudaSetDevice(h->device));
+  FILE* f = fopen(path, "wb");
+  if (!f) { set_error("cannot open %s for writing", path); return TS_ERR_IO; }
+  TsFileHeader hd{};
+  memcpy(hd.magic, "TSIDX01", 8);
+  hd.version = 1; hd.dim = h->dim; hd.ld = h->ld; hd.dtype = h->dtype; hd.metric = h->metric; hd.n = h->n; hd.id_base = h->id_base;
+  int rc = TS_OK;
+  if (fwrite(&hd, sizeof(hd), 1, f) != 1) rc = TS_ERR_IO;
+  const size_t row_b = (size_t)h->ld * dtype_size(h->dtype);
+  const int64_t chunk = (int64_t)((64ull << 20) / row_b) + 1;
+  std::vector<char> buf((size_t)chunk * row_b);
+  for (int64_t s = 0; s < h->n && rc == TS_OK; s += chunk) {
+    const int64_t m = (h->n - s) < chunk ? (h->n - s) : chunk;
+    if (cudaMemcpy(buf.data(), (const char*)h->rows + (size_t)s * row_b, (size_t)m * row_b, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = TS_ERR_CUDA; break; }
+    if (fwrite(buf.data(), row_b, (size_t)m, f) != (size_t)m) rc = TS_ERR_IO;
+  }
+  if (rc == TS_OK && h->metric == TS_METRIC_COSINE && h->n > 0) {
+    std::vector<float> inv((size_t)h->n);
+    if (cudaMemcpy(inv.data(), h->inv_norm, (size_t)h->n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = TS_ERR_CUDA;
+    else if (fwrite(inv.data(), 4, (size_t)h->n, f) != (size_t)h->n) rc = TS_ERR_IO;
+  }
+  fclose(f);
+  if (rc) set_error("ts_index_save(%s) failed (%d)", path, rc);
+  return rc;
+}
+
+int ts_index_load(ts_index** out, int device, const char* path) {
+  if (!out || !path) { set_error("ts_index_load: invalid argument"); return TS_ERR_INVALID; }
+  FILE* f = fopen(path, "rb");
+  if (!f) { set_error("cannot open %s", path); return TS_ERR_IO; }
+  TsFileHeader hd{};
+  if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "TSIDX01", 8) != 0 || hd.version != 1) {
+    fclose(f); set_error("%s is not a tristage index file", path); return TS_ERR_IO;
+  }
+  ts_index* h = nullptr;
+  int rc = ts_index_create(&h, device, hd.dim, hd.dtype, hd.metric, hd.n > 0 ? hd.n : 0);
+  if (rc) { fclose(f); return rc; }
+  if (h->ld != hd.ld) { fclose(f); ts_index_destroy(h); set_error("row pitch mismatch in %s", path); return TS_ERR_IO; }
+  h->id_base = hd.id_base;
+  const size_t row_b = (size_t)h->ld * dtype_size(h->dtype);
+  const int64_t chunk = (int64_t)((64ull << 20) / row_b) + 1;
+  std::vector<char> buf((size_t)chunk * row_b);
+  for (int64_t s = 0; s < hd.n && rc == TS_OK; s += chunk) {
+    const int64_t m = (hd.n - s) < chunk ? (hd.n - s) : chunk;
+    if (fread(buf.data(), row_b, (size_t)m, f) != (size_t)m) { rc = TS_ERR_IO; break; }
+    if (cudaMemcpy((char*)h->rows + (size_t)s * row_b, buf.data(), (size_t)m * row_b, cudaMemcpyHostToDevice) != cudaSuccess) rc = TS_ERR_CUDA;
+  }
+  if (rc == TS_OK && hd.metric == TS_METRIC_COSINE && hd.n > 0) {
+    std::vector<float> inv((size_t)hd.n);
+    if (fread(inv.data(), 4, (size_t)hd.n, f) != (size_t)hd.n) rc = TS_ERR_IO;
+    else if (cudaMemcpy(h->inv_norm, inv.data(), (size_t)hd.n * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = TS_ERR_CUDA;
+  }
+  fclose(f);
+  if (rc) { ts_index_destroy(h); set_error("ts_index_load(%s) failed (%d)", path, rc); return rc; }
+  h->n = hd.n;
+  *out = h;
+  return TS_OK;
+}
+
+// ------------------------------------------------------------------ Stage 2
+int ts_tokstore_create(ts_tokstore** out, int device, int dim, int storage_dtype, int64_t reserve_docs,
+                       int64_t reserve_tokens) {
+  if (!out || dim <= 0 || dim > 4096 || !valid_storage(storage_dtype) || reserve_docs < 0 || reserve_tokens < 0) {
+    set_error("ts_tokstore_create: invalid argument");
+    return TS_ERR_INVALID;
+  }
+  DeviceInfo info;
+  int rc = check_device(device, &info);
+  if (rc) return rc;
+  ts_tokstore* h = new ts_tokstore();
+  memset(h, 0, sizeof(*h));
+  h->device = device; h->dim = dim; h->dtype = storage_dtype; h->info = info;
+  h->hint_docs = reserve_docs;
+  h->hint_rows = reserve_tokens + 8 * reserve_docs;  // every doc is padded to 8 rows
+  *out = h;
+  return TS_OK;
+}
+
+int ts_tokstore_destroy(ts_tokstore* h) {
+  if (!h) return TS_OK;
+  cudaSetDevice(h->device);
+  void* ptrs[] = {h->tok, h->doc_off, h->doc_len, h->qbuf, h->stage, h->meta, h->hbuf};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete h;
+  return TS_OK;
+}
+
+static int tok_reserve(ts_tokstore* h, int64_t docs, int64_t rows, cudaStream_t st) {
+  const int64_t hint_docs = h->hint_docs, hint_rows = h->hint_rows;
+  const int64_t cur_docs = h->cap_docs, cur_rows = h->cap_rows;
+  if (docs > cur_docs) {
+    int64_t nc = cur_docs > 0 ? cur_docs : (hint_docs > 1024 ? hint_docs : 1024);
+    while (nc < docs) nc *= 2;
+    int64_t* noff = nullptr; int32_t* nlen = nullptr;
+    if (cudaMalloc((void**)&noff, (size_t)nc * 8) != cudaSuccess || cudaMalloc((void**)&nlen, (size_t)nc * 4) != cudaSuccess) {
+      set_error("tokstore: cudaMalloc doc tables failed"); return TS_ERR_NOMEM;
+    }
+    if (h->ndocs > 0) {
+      TS_CUDA_OK(cudaMemcpyAsync(noff, h->doc_off, (size_t)h->ndocs * 8, cudaMemcpyDeviceToDevice, st));
+      TS_CUDA_OK(cudaMemcpyAsync(nlen, h->doc_len, (size_t)h->ndocs * 4, cudaMemcpyDeviceToDevice, st));
+      TS_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    if (h->doc_off) cudaFree(h->doc_off);
+    if (h->doc_len) cudaFree(h->doc_len);
+    h->doc_off = noff; h->doc_len = nlen; h->cap_docs = nc;
+  }
+  if (rows > cur_rows) {
+    int64_t nc = cur_rows > 0 ? cur_rows : (hint_rows > 8192 ? hint_rows : 8192);
+    while (nc < rows) nc *= 2;
+    const size_t row_b = (size_t)h->dim * dtype_size(h->dtype);
+    void* nt = nullptr;
+    cudaError_t e = cudaMalloc(&nt, (size_t)nc * row_b);
+    if (e != cudaSuccess) {
+      nc = rows;
+      e = cudaMalloc(&nt, (size_t)nc * row_b);
+      if (e != cudaSuccess) { set_error("tokstore: cudaMalloc of %lld token rows failed: %s", (long long)nc, cudaGetErrorString(e)); return TS_ERR_NOMEM; }
+    }
+    if (h->nrows > 0) {
+      TS_CUDA_OK(cudaMemcpyAsync(nt, h->tok, (size_t)h->nrows * row_b, cudaMemcpyDeviceToDevice, st));
+      TS_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    if (h->tok) cudaFree(h->tok);
+    h->tok = nt; h->cap_rows = nc;
+  }
+  return TS_OK;
+}
+
+}  // extern "C"
+
+namespace ts {
+// scatter ragged docs into the 8-row padded store (defined in tok_ingest.cu)
+int launch_tok_ingest(const void* src, int src_dtype, const int64_t* src_off_dev, const int64_t* dst_off_dev,
+                      const int32_t* len_dev, int n_docs, void* dst, int dst_dtype, int dim, int normalize,
+                      cudaStream_t st);
+}
+
+extern "C" {
+
+int ts_tokstore_add(ts_tokstore* h, const void* tok, int src_dtype, int src_on_device, const int32_t* lens_host,
+                    int n_docs, int normalize, void* stream) {
+  if (!h || n_docs < 0 || (n_docs > 0 && (!tok || !lens_host))) { set_error("ts_tokstore_add: invalid argument"); return TS_ERR_INVALID; }
+  if (src_dtype != TS_F32 && src_dtype != h->dtype) { set_error("ts_tokstore_add: src dtype must be f32 or the storage dtype"); return TS_ERR_INVALID; }
+  if (n_docs == 0) return TS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  TS_CUDA_OK(cudaSetDevice(h->device));
+  std::vector<int64_t> src_off((size_t)n_docs), dst_off((size_t)n_docs);
+  int64_t sum = 0, rows = h->nrows;
+  for (int i = 0; i < n_docs; ++i) {
+    const int L = lens_host[i];
+    if (L < 1 || L > TS_S2_MAX_LD) { set_error("ts_tokstore_add: doc %d has %d tokens (allowed 1..%d)", i, L, TS_S2_MAX_LD); return TS_ERR_INVALID; }
+    src_off[i] = sum; dst_off[i] = rows;
+    sum += L; rows += (L + 7) & ~7;
+  }
+  if (rows > 0x7FFFFF00ll) { set_error("ts_tokstore_add: shard limited to 2^31 token rows"); return TS_ERR_UNSUPPORTED; }
+  int rc = tok_reserve(h, h->ndocs + n_docs, rows, st);
+  if (rc) return rc;
+  // upload per-doc tables (src offsets are scratch; dst offsets + lens append to the store)
+  if ((rc = ensure_bytes(&h->meta, &h->meta_b, (size_t)n_docs * 8))) return rc;
+  TS_CUDA_OK(cudaMemcpyAsync(h->meta, src_off.data(), (size_t)n_docs * 8, cudaMemcpyHostToDevice, st));
+  TS_CUDA_OK(cudaMemcpyAsync(h->doc_off + h->ndocs, dst_off.data(), (size_t)n_docs * 8, cudaMemcpyHostToDevice, st));
+  TS_CUDA_OK(cudaMemcpyAsync(h->doc_len + h->ndocs, lens_host, (size_t)n_docs * 4, cudaMemcpyHostToDevice, st));
+  const void* dsrc = tok;
+  if (!src_on_device) {
+    const size_t nb = (size_t)sum * h->dim * dtype_size(src_dtype);
+    if ((rc = ensure_bytes(&h->stage, &h->stage_b, nb))) return rc;
+    TS_CUDA_OK(cudaMemcpyAsync(h->stage, tok, nb, cudaMemcpyHostToDevice, st));
+    dsrc = h->stage;
+  }
+  rc = launch_tok_ingest(dsrc, src_dtype, (const int64_t*)h->meta, h->doc_off + h->ndocs, h->doc_len + h->ndocs, n_docs,
+                         h->tok, h->dtype, h->dim, normalize, st);
+  if (rc) return rc;
+  ++h->launches;
+  TS_CUDA_OK(cudaStreamSynchronize(st));  // host vectors / staging are reused
+  h->ndocs += n_docs; h->nrows = rows; h->ntokens += sum;
+  return TS_OK;
+}
+
+int64_t ts_tokstore_ndocs(const ts_tokstore* h) { return h ? h->ndocs : -1; }
+int64_t ts_tokstore_ntokens(const ts_tokstore* h) { return h ? h->ntokens : -1; }
+int ts_tokstore_reset(ts_tokstore* h) { if (!h) return TS_ERR_INVALID; h->ndocs = 0; h->nrows = 0; h->ntokens = 0; return TS_OK; }
+int ts_tokstore_set_id_base(ts_tokstore* h, int64_t b) { if (!h) return TS_ERR_INVALID; h->id_base = b; return TS_OK; }
+int64_t ts_tokstore_launch_count(const ts_tokstore* h) { return h ? h->launches : -1; }
+
+int ts_maxsim(ts_tokstore* h, const void* q_tok, int q_dtype, const int32_t* q_len, int B, int lq_stride,
+              const int64_t* cand, const int32_t* n_cand, int C, int mode, unsigned flags, float* out, void* stream) {
+  if (!h || !q_tok || !cand || !out || B <= 0 || C <= 0 || lq_stride <= 0) { set_error("ts_maxsim: invalid argument"); return TS_ERR_INVALID; }
+  if ((mode & 0xff) != TS_S2_MAXSIM && (mode & 0xff) != TS_S2_COLBERT) { set_error("ts_maxsim: bad mode %d", mode); return TS_ERR_INVALID; }
+  if (q_dtype != TS_F32 && q_dtype != h->dtype) { set_error("ts_maxsim: query dtype must be f32 or the storage dtype"); return TS_ERR_INVALID; }
+  if ((int64_t)B * C > 0x7FFFFFFFll) { set_error("ts_maxsim: B*C too large"); return TS_ERR_UNSUPPORTED; }
+  cudaStream_t st = (cudaStream_t)stream;
+  TS_CUDA_OK(cudaSetDevice(h->device));
+  const int64_t qrows = (int64_t)B * lq_stride;
+  // +128 rows of slack: a 128-row TMA box of the last query may run past the end
+  int rc = ensure_bytes(&h->qbuf, &h->qbuf_b, (size_t)(qrows + 128) * h->dim * dtype_size(h->dtype));
+  if (rc) return rc;
+  rc = launch_convert_rows(q_tok, q_dtype, h->dim, h->qbuf, h->dtype, h->dim, qrows, h->dim,
+                           (flags & TS_FLAG_NORMALIZE_Q) ? kNormStage2 : kNormNone, nullptr, st);
+  if (rc) return rc;
+  ++h->launches;
+  MaxSimArgs a{};
+  a.tok = h->tok; a.doc_off = h->doc_off; a.doc_len = h->doc_len; a.ndocs = h->ndocs; a.id_base = h->id_base;
+  a.ntok_rows = h->nrows; a.dim = h->dim; a.dtype = h->dtype; a.q = h->qbuf; a.q_len = q_len; a.B = B;
+  a.lq_stride = lq_stride; a.cand = cand; a.n_cand = n_cand; a.C = C; a.mode = mode; a.out = out;
+  a.sm_count = h->info.sm_count;
+  int launches = 0;
+  rc = launch_maxsim(a, st, &launches);
+  h->launches += launches;
+  return rc;
+}
+
+int ts_maxsim_host(ts_tokstore* h, const void* q_tok, int q_dtype, const int32_t* q_len, int B, int lq_stride,
+                   const int64_t* cand, const int32_t* n_cand, int C, int mode, unsigned flags, float* out,
+                   void* stream) {
+  if (!h || !q_tok || !cand || !out || B <= 0 || C <= 0 || lq_stride <= 0) { set_error("ts_maxsim_host: invalid argument"); return TS_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  TS_CUDA_OK(cudaSetDevice(h->device));
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t qb = up((size_t)B * lq_stride * h->dim * dtype_size(q_dtype));
+  const size_t cb = up((size_t)B * C * 8), lb = up((size_t)B * 4), ob = up((size_t)B * C * 4);
+  int rc = ensure_bytes(&h->hbuf, &h->hbuf_b, qb + cb + 2 * lb + ob);
+  if (rc) return rc;
+  char* base = (char*)h->hbuf;
+  void* dq = base; int64_t* dc = (int64_t*)(base + qb);
+  int32_t* dql = (int32_t*)(base + qb + cb); int32_t* dnc = (int32_t*)(base + qb + cb + lb);
+  float* dout = (float*)(base + qb + cb + 2 * lb);
+  TS_CUDA_OK(cudaMemcpyAsync(dq, q_tok, (size_t)B * lq_stride * h->dim * dtype_size(q_dtype), cudaMemcpyHostToDevice, st));
+  TS_CUDA_OK(cudaMemcpyAsync(dc, cand, (size_t)B * C * 8, cudaMemcpyHostToDevice, st));
+  if (q_len) TS_CUDA_OK(cudaMemcpyAsync(dql, q_len, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  if (n_cand) TS_CUDA_OK(cudaMemcpyAsync(dnc, n_cand, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  rc = ts_maxsim(h, dq, q_dtype, q_len ? dql : nullptr, B, lq_stride, dc, n_cand ? dnc : nullptr, C, mode, flags, dout, stream);
+  if (rc) return rc;
+  TS_CUDA_OK(cudaMemcpyAsync(out, dout, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));
+  TS_CUDA_OK(cudaStreamSynchronize(st));
+  return TS_OK;
+}
+
+int ts_rank_desc(int device, const float* scores, const int32_t* n_cand, int B, int C, int top_k, float* out_scores,
+                 int32_t* out_pos, void* stream) {
+  if (!scores || !out_scores || !out_pos) { set_error("ts_rank_desc: null pointer"); return TS_ERR_INVALID; }
+  TS_CUDA_OK(cudaSetDevice(device));
+  return launch_rank_desc(scores, n_cand, B, C, top_k, out_scores, out_pos, (cudaStream_t)stream);
+}
+
+}  // extern "C"

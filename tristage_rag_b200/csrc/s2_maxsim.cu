@@ -1,0 +1,450 @@
+// Stage-2 late-interaction scoring ("S2-maxsim"): one launch scores every
+// (query, candidate) pair of a batch.
+//
+// Replaces the per-candidate Python loop of ColBERTScorer.rescore_candidates
+// (/root/reference/src/stage2_rescorer.py:268-273) around _maxsim_score
+// (:167-183: cosine sim matrix, max over doc tokens, MEAN over query tokens)
+// and _colbert_score (:185-201: softmax-weighted sum of the row maxima).
+// Tokens are L2-normalised once at ingest (convert_rows.cu), so the kernel is
+// a plain contraction + fused reductions.
+//
+// Roofline: HBM -- algorithmic bytes per candidate = pad8(Ld)*dim*2 (doc
+// tokens read once; the query tile is re-read from L2), 2*Lq*Ld*dim flop,
+// i.e. ~Lq flop/byte: far below the ridge, but only the tensor pipe sustains
+// it (~210 TFLOP/s at 6.5 TB/s for Lq = 32).
+//
+// Tensor path (maxsim_umma_kernel)
+//   Token store: docs concatenated row-wise, each padded to a multiple of 8
+//   rows, [rows][dim] bf16/fp16.  A work item is (query b, 32 consecutive
+//   candidates).  The producer warp looks the candidates up (offset, length),
+//   greedily packs their padded token rows into B tiles of <= 256 rows and,
+//   per 64-wide K chunk, gathers them with TMA boxes of 128/64/32/16/8 rows
+//   (binary decomposition of the padded length -- the ragged docs are staged
+//   side by side in SWIZZLE_128B shared memory).  A = the query's token rows
+//   (8-row TMA boxes).  One thread issues tcgen05.mma M128 x N(used) x K16
+//   into one of two TMEM accumulators: query tokens on lanes, doc tokens on
+//   columns.  Epilogue: each thread (one query token) takes the max over each
+//   doc's valid columns (pad columns masked), the per-doc maxima go through
+//   shared memory and a warp reduces them to mean (maxsim) or softmax-weighted
+//   sum (colbert) and writes out[b][j].  Tile layout travels producer ->
+//   MMA/epilogue through an 8-slot shared-memory ring guarded by mbarriers.
+//
+// CUDA-core path (maxsim_simt_kernel): one CTA per (query, candidate); used
+//   for shapes the tensor path does not take (dim % 8 != 0, Lq > 128) and as
+//   an independent on-device cross-check in the tests.
+#include "ts_common.cuh"
+#include "ts_internal.h"
+#include "ts_ptx.cuh"
+
+namespace ts {
+
+int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, int dim, int ld, int box_rows);
+
+namespace {
+
+using namespace ts::ptx;
+
+// ============================================================ SIMT path ====
+template <typename T>
+__global__ void __launch_bounds__(128)
+    maxsim_simt_kernel(const T* __restrict__ tok, const int64_t* __restrict__ doc_off,
+                       const int32_t* __restrict__ doc_len, int64_t ndocs, int64_t id_base, int dim,
+                       const T* __restrict__ q, const int32_t* __restrict__ q_len, int lq_stride,
+                       const int64_t* __restrict__ cand, const int32_t* __restrict__ n_cand, int C, int mode,
+                       float* __restrict__ out) {
+  extern __shared__ float sm[];  // m[lq_stride]
+  const int b = blockIdx.y, j = blockIdx.x;
+  const int nc = n_cand ? n_cand[b] : C;
+  if (j >= nc) return;
+  const int64_t id = cand[(size_t)b * C + j] - id_base;
+  if (id < 0 || id >= ndocs) return;
+  const int Lq = q_len ? q_len[b] : lq_stride;
+  const int Ld = doc_len[id];
+  const T* d = tok + doc_off[id] * dim;
+  const T* qb = q + (size_t)b * lq_stride * dim;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < Lq; i += nw) {
+    float best = -INFINITY;
+    for (int t = 0; t < Ld; ++t) {
+      float acc = 0.f;
+      for (int c = lane; c < dim; c += 32)
+        acc = fmaf(Elem<T>::to_f32(qb[(size_t)i * dim + c]), Elem<T>::to_f32(d[(size_t)t * dim + c]), acc);
+      acc = warp_sum(acc);
+      best = fmaxf(best, acc);
+    }
+    if (lane == 0) sm[i] = best;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float res;
+    if (mode == TS_S2_MAXSIM) {
+      float s = 0.f;
+      for (int i = lane; i < Lq; i += 32) s += sm[i];
+      res = warp_sum(s) / (float)Lq;
+    } else {
+      float mx = -INFINITY;
+      for (int i = lane; i < Lq; i += 32) mx = fmaxf(mx, sm[i]);
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float z = 0.f, s = 0.f;
+      for (int i = lane; i < Lq; i += 32) { const float e = __expf(sm[i] - mx); z += e; s += e * sm[i]; }
+      z = warp_sum(z); s = warp_sum(s);
+      res = s / z;
+    }
+    if (lane == 0) out[(size_t)b * C + j] = res;
+  }
+}
+
+// ========================================================== tensor path ====
+constexpr int kThreads = 192;
+constexpr int kStages = 4;
+constexpr int kTileM = 128, kTileN = 256, kChunkK = 64;
+constexpr int kABytes = kTileM * kChunkK * 2;
+constexpr int kBBytes = kTileN * kChunkK * 2;
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kMetaSlots = 8;
+constexpr int kMaxDocsPerTile = 32;   // 256 columns / 8
+constexpr int kItemCands = 32;        // candidates per work item (one per producer lane)
+constexpr int kTmemCols = 512;
+
+struct TileMeta {
+  int used;        // columns in use (multiple of 8); 0 = end of work
+  int ndocs;
+  int lq;          // real query tokens of this item's query
+  int pad_;
+  int out_idx[kMaxDocsPerTile];          // b*C + j per doc
+  int seg_col[kMaxDocsPerTile];          // first column of doc d
+  int seg_len[kMaxDocsPerTile];          // real token count of doc d
+  long long seg_row[kMaxDocsPerTile];    // first store row of doc d
+  int q_row;       // first row of the query's tokens in the Q tensor
+  int pad2_[3];
+};
+
+constexpr int kMvalsBytes = kMaxDocsPerTile * kTileM * 4;  // 16 KB
+constexpr int kMetaBytes = kMetaSlots * (int)sizeof(TileMeta);
+constexpr int kBarBytes = 512;
+constexpr int kSmemBytes = kStages * kStageBytes + kMvalsBytes + kMetaBytes + kBarBytes + 1024;
+
+struct MaxSimParams {
+  const int64_t* doc_off;
+  const int32_t* doc_len;
+  int64_t ndocs, id_base;
+  const int32_t* q_len;
+  int B, lq_stride, nK;
+  const int64_t* cand;
+  const int32_t* n_cand;
+  int C, mode, n_chunks, n_items;
+  float* out;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+    maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmQ8, const __grid_constant__ CUtensorMap tmQ128,
+                       const __grid_constant__ CUtensorMap tmT8, const __grid_constant__ CUtensorMap tmT16,
+                       const __grid_constant__ CUtensorMap tmT32, const __grid_constant__ CUtensorMap tmT64,
+                       const __grid_constant__ CUtensorMap tmT128, const MaxSimParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* mvals = reinterpret_cast<float*>(smem + kStages * kStageBytes);                 // [32][128]
+  TileMeta* metas = reinterpret_cast<TileMeta*>(smem + kStages * kStageBytes + kMvalsBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kMvalsBytes + kMetaBytes);
+  uint64_t* full_bar = bars;                           // [kStages]
+  uint64_t* empty_bar = bars + kStages;                // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;            // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;       // [2]
+  uint64_t* mfull_bar = bars + 2 * kStages + 4;        // [kMetaSlots]
+  uint64_t* mempty_bar = mfull_bar + kMetaSlots;       // [kMetaSlots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mempty_bar + kMetaSlots);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int s = 0; s < kMetaSlots; ++s) { mbar_init(&mfull_bar[s], 1); mbar_init(&mempty_bar[s], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------ producer (whole warp) -----
+    if (lane == 0) {
+      prefetch_tmap(&tmQ8); prefetch_tmap(&tmQ128); prefetch_tmap(&tmT8); prefetch_tmap(&tmT16);
+      prefetch_tmap(&tmT32); prefetch_tmap(&tmT64); prefetch_tmap(&tmT128);
+    }
+    int stage = 0; uint32_t phase = 0;
+    uint32_t seq = 0;  // tiles emitted by this CTA
+
+    // emit the tile described by metas[seq % slots] (already filled in)
+    auto emit_tile = [&](TileMeta* m) {
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&mfull_bar[seq % kMetaSlots]);   // release meta to MMA + epilogue
+        const int lq = m->lq;
+        const int a_groups = (lq + 7) >> 3;
+        const bool a_boxes8 = lq <= 64;
+        const uint32_t tx = (a_boxes8 ? (uint32_t)a_groups * 1024u : (uint32_t)kABytes) + (uint32_t)m->used * 128u;
+        for (int kc = 0; kc < p.nK; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 11);
+          unsigned char* sA = smem + stage * kStageBytes;
+          unsigned char* sB = sA + kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], tx);
+          if (a_boxes8) {
+            for (int g = 0; g < a_groups; ++g)
+              tma_load_2d(sA + g * 1024, &tmQ8, &full_bar[stage], kc * kChunkK, m->q_row + g * 8, kEvictLast);
+          } else {
+            tma_load_2d(sA, &tmQ128, &full_bar[stage], kc * kChunkK, m->q_row, kEvictLast);
+          }
+          for (int d = 0; d < m->ndocs; ++d) {
+            int rows = (m->seg_len[d] + 7) & ~7;
+            long long r = m->seg_row[d];
+            unsigned char* dst = sB + m->seg_col[d] * 128;
+            while (rows >= 128) { tma_load_2d(dst, &tmT128, &full_bar[stage], kc * kChunkK, (int)r, kEvictFirst); rows -= 128; r += 128; dst += 128 * 128; }
+            if (rows >= 64) { tma_load_2d(dst, &tmT64, &full_bar[stage], kc * kChunkK, (int)r, kEvictFirst); rows -= 64; r += 64; dst += 64 * 128; }
+            if (rows >= 32) { tma_load_2d(dst, &tmT32, &full_bar[stage], kc * kChunkK, (int)r, kEvictFirst); rows -= 32; r += 32; dst += 32 * 128; }
+            if (rows >= 16) { tma_load_2d(dst, &tmT16, &full_bar[stage], kc * kChunkK, (int)r, kEvictFirst); rows -= 16; r += 16; dst += 16 * 128; }
+            if (rows >= 8) { tma_load_2d(dst, &tmT8, &full_bar[stage], kc * kChunkK, (int)r, kEvictFirst); }
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+      ++seq;
+      __syncwarp();
+    };
+    auto begin_tile = [&]() -> TileMeta* {
+      const uint32_t slot = seq % kMetaSlots;
+      mbar_wait(&mempty_bar[slot], ((seq / kMetaSlots) & 1u) ^ 1u, 12);
+      return &metas[slot];
+    };
+
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int b = item / p.n_chunks, j0 = (item % p.n_chunks) * kItemCands;
+      const int nc = p.n_cand ? min(max(p.n_cand[b], 0), p.C) : p.C;
+      const int lq = p.q_len ? min(max(p.q_len[b], 1), min(p.lq_stride, kTileM)) : min(p.lq_stride, kTileM);
+      // one candidate per lane: look up offset / length
+      const int j = j0 + lane;
+      bool valid = false; long long off = 0; int len = 0;
+      if (j < nc) {
+        const int64_t id = p.cand[(size_t)b * p.C + j] - p.id_base;
+        if (id >= 0 && id < p.ndocs) { off = p.doc_off[id]; len = p.doc_len[id]; valid = len > 0; }
+      }
+      unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      if (!vmask) continue;
+      TileMeta* m = begin_tile();
+      int cols = 0, nd = 0;
+      while (vmask) {
+        const int src = __ffs(vmask) - 1;
+        vmask &= vmask - 1;
+        const int L = __shfl_sync(0xffffffffu, len, src);
+        const long long o = __shfl_sync(0xffffffffu, off, src);
+        const int pad = (L + 7) & ~7;
+        if (cols + pad > kTileN) {
+          if (lane == 0) { m->used = cols; m->ndocs = nd; m->lq = lq; m->q_row = b * p.lq_stride; }
+          emit_tile(m);
+          m = begin_tile();
+          cols = 0; nd = 0;
+        }
+        if (lane == 0) {
+          m->out_idx[nd] = b * p.C + j0 + src;
+          m->seg_col[nd] = cols;
+          m->seg_len[nd] = L;
+          m->seg_row[nd] = o;
+        }
+        cols += pad; ++nd;
+      }
+      if (lane == 0) { m->used = cols; m->ndocs = nd; m->lq = lq; m->q_row = b * p.lq_stride; }
+      emit_tile(m);
+    }
+    // end-of-work sentinel
+    {
+      TileMeta* m = begin_tile();
+      if (lane == 0) { m->used = 0; m->ndocs = 0; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mfull_bar[seq % kMetaSlots]);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------ MMA issuer --------
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (uint32_t seq = 0;; ++seq) {
+        const uint32_t slot = seq % kMetaSlots;
+        mbar_wait(&mfull_bar[slot], (seq / kMetaSlots) & 1u, 21);
+        const int used = *reinterpret_cast<volatile int*>(&metas[slot].used);
+        if (used == 0) break;
+        const int n_mma = used < 16 ? 16 : ((used + 15) & ~15);
+        const uint32_t idesc = make_idesc_f16(kTileM, n_mma, BF16);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 22);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTileN);
+        for (int kc = 0; kc < p.nK; ++kc) {
+          mbar_wait(&full_bar[stage], phase, 23);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+          const uint64_t adesc = make_desc_kmajor_sw128(a_addr);
+          const uint64_t bdesc = make_desc_kmajor_sw128(a_addr + kABytes);
+#pragma unroll
+          for (int ks = 0; ks < kChunkK / 16; ++ks)
+            umma_f16_ss(d_tmem, adesc + ks * kDescKStep, bdesc + ks * kDescKStep, idesc, (kc | ks) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // -------------------------------------------------- epilogue ----------
+    const int quarter = warp & 3;
+    const int ew = warp - 2;  // 0..3: finalize docs d with d % 4 == ew
+    const int lane_row = quarter * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (uint32_t seq = 0;; ++seq) {
+      const uint32_t slot = seq % kMetaSlots;
+      mbar_wait(&mfull_bar[slot], (seq / kMetaSlots) & 1u, 31);
+      const TileMeta* m = &metas[slot];
+      const int used = m->used;
+      if (used == 0) break;
+      const int nd = m->ndocs, lq = m->lq;
+      mbar_wait(&tfull_bar[acc], acc_phase, 32);
+      tc_fence_after();
+      const bool warp_active = quarter * 32 < lq;
+      if (warp_active) {
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kTileN);
+        int d = 0;
+        int seg_end = m->seg_col[0] + m->seg_len[0];          // first masked column of doc d
+        int seg_next = m->seg_col[0] + ((m->seg_len[0] + 7) & ~7);  // first column of doc d+1
+        float best = -INFINITY;
+        for (int c0 = 0; c0 < used; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_addr + (uint32_t)c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int cu = c0 + u * 8;
+            if (cu < used) {                   // warp-uniform
+              if (cu >= seg_next) {            // warp-uniform: next doc starts at this 8-column unit
+                mvals[d * kTileM + lane_row] = best;
+                ++d;
+                best = -INFINITY;
+                seg_end = m->seg_col[d] + m->seg_len[d];
+                seg_next = m->seg_col[d] + ((m->seg_len[d] + 7) & ~7);
+              }
+#pragma unroll
+              for (int j2 = 0; j2 < 8; ++j2) {
+                const float v = __uint_as_float(r[u * 8 + j2]);
+                best = (cu + j2 < seg_end) ? fmaxf(best, v) : best;
+              }
+            }
+          }
+        }
+        mvals[d * kTileM + lane_row] = best;
+      }
+      // accumulator fully read -> hand TMEM back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      named_bar_sync(1, 128);   // all per-doc maxima are in mvals
+      for (int d = ew; d < nd; d += 4) {
+        float res;
+        if (p.mode == TS_S2_MAXSIM) {
+          float s = 0.f;
+          for (int i = lane; i < lq; i += 32) s += mvals[d * kTileM + i];
+          res = warp_sum(s) / (float)lq;
+        } else {
+          float mx = -INFINITY;
+          for (int i = lane; i < lq; i += 32) mx = fmaxf(mx, mvals[d * kTileM + i]);
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          float z = 0.f, s = 0.f;
+          for (int i = lane; i < lq; i += 32) {
+            const float v = mvals[d * kTileM + i];
+            const float e = __expf(v - mx);
+            z += e; s += e * v;
+          }
+          z = warp_sum(z); s = warp_sum(s);
+          res = s / z;
+        }
+        if (lane == 0) p.out[m->out_idx[d]] = res;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mempty_bar[slot]);   // meta slot reusable
+      named_bar_sync(2, 128);   // mvals reusable
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace
+
+int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
+  if (a.B <= 0 || a.C <= 0) { set_error("maxsim: empty batch"); return TS_ERR_INVALID; }
+  TS_CUDA_OK(cudaMemsetAsync(a.out, 0, (size_t)a.B * a.C * sizeof(float), st));
+  if (a.ndocs == 0) return TS_OK;
+  const bool tensor_ok = (a.dtype == TS_BF16 || a.dtype == TS_F16) && (a.dim % 8 == 0) && a.lq_stride >= 1 &&
+                         a.lq_stride <= TS_S2_MAX_LQ && !(a.mode & 0x100);
+  const int mode = a.mode & 0xff;
+  if (!tensor_ok) {
+    if (a.lq_stride > 4096) { set_error("maxsim: lq_stride too large"); return TS_ERR_UNSUPPORTED; }
+    dim3 grid(a.C, a.B);
+    const size_t smem = (size_t)a.lq_stride * sizeof(float);
+#define TS_SIMT(T)                                                                                         \
+  maxsim_simt_kernel<T><<<grid, 128, smem, st>>>((const T*)a.tok, a.doc_off, a.doc_len, a.ndocs, a.id_base, \
+                                                 a.dim, (const T*)a.q, a.q_len, a.lq_stride, a.cand,       \
+                                                 a.n_cand, a.C, mode, a.out)
+    if (a.dtype == TS_BF16) TS_SIMT(__nv_bfloat16);
+    else if (a.dtype == TS_F16) TS_SIMT(__half);
+    else TS_SIMT(float);
+#undef TS_SIMT
+    TS_CUDA_OK(cudaGetLastError());
+    if (launches) ++*launches;
+    return TS_OK;
+  }
+  CUtensorMap tq8, tq128, t8, t16, t32, t64, t128;
+  int rc;
+  const int64_t qrows = (int64_t)a.B * a.lq_stride;
+  if ((rc = make_tmap_2d(&tq8, a.q, a.dtype, qrows, a.dim, a.dim, 8))) return rc;
+  if ((rc = make_tmap_2d(&tq128, a.q, a.dtype, qrows, a.dim, a.dim, 128))) return rc;
+  if ((rc = make_tmap_2d(&t8, a.tok, a.dtype, a.ntok_rows, a.dim, a.dim, 8))) return rc;
+  if ((rc = make_tmap_2d(&t16, a.tok, a.dtype, a.ntok_rows, a.dim, a.dim, 16))) return rc;
+  if ((rc = make_tmap_2d(&t32, a.tok, a.dtype, a.ntok_rows, a.dim, a.dim, 32))) return rc;
+  if ((rc = make_tmap_2d(&t64, a.tok, a.dtype, a.ntok_rows, a.dim, a.dim, 64))) return rc;
+  if ((rc = make_tmap_2d(&t128, a.tok, a.dtype, a.ntok_rows, a.dim, a.dim, 128))) return rc;
+  MaxSimParams p{};
+  p.doc_off = a.doc_off; p.doc_len = a.doc_len; p.ndocs = a.ndocs; p.id_base = a.id_base;
+  p.q_len = a.q_len; p.B = a.B; p.lq_stride = a.lq_stride; p.nK = (a.dim + kChunkK - 1) / kChunkK;
+  p.cand = a.cand; p.n_cand = a.n_cand; p.C = a.C; p.mode = mode;
+  p.n_chunks = (a.C + kItemCands - 1) / kItemCands;
+  p.n_items = a.B * p.n_chunks;
+  p.out = a.out;
+  int grid = a.sm_count < p.n_items ? a.sm_count : p.n_items;
+  if (a.dtype == TS_BF16) {
+    auto kern = maxsim_umma_kernel<true>;
+    TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    kern<<<grid, kThreads, kSmemBytes, st>>>(tq8, tq128, t8, t16, t32, t64, t128, p);
+  } else {
+    auto kern = maxsim_umma_kernel<false>;
+    TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    kern<<<grid, kThreads, kSmemBytes, st>>>(tq8, tq128, t8, t16, t32, t64, t128, p);
+  }
+  TS_CUDA_OK(cudaGetLastError());
+  if (launches) ++*launches;
+  return TS_OK;
+}
+
+}  // namespace ts

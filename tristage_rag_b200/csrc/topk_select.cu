@@ -1,0 +1,158 @@
+// Exact top-k selection over candidate keys (one CTA per query and group).
+//
+// Replaces, on the device:
+//   * FAISS's result heap/reservoir merge inside IndexFlatIP.search
+//     (call site /root/reference/src/stage1_retriever.py:380) -- mode KEYS:
+//     per-CTA partial top-k lists of the scan kernels -> final [B,k];
+//   * the G*k -> k merge after the multi-GPU all-gather --
+//     mode PAIRS;
+//   * scored_candidates.sort(reverse=True)[:top_k]
+//     (/root/reference/src/stage2_rescorer.py:294-297) -- mode RANK.
+//
+// Bound: latency (a few thousand keys per query in shared memory); HBM
+// traffic is L*B*k*8 bytes read once.
+#include "ts_common.cuh"
+#include "ts_internal.h"
+
+namespace ts {
+
+namespace {
+
+constexpr int kSelThreads = 512;
+constexpr int kSelCap = 4096;  // keys of shared memory per CTA (32 KB)
+
+enum SelMode { kKeys = 0, kPairs = 1, kRank = 2 };
+
+struct SelectParams {
+  int mode;
+  const uint64_t* keys;   // kKeys: [L][B][k_in]
+  const float* scores;    // kPairs: [L][B][k_in]; kRank: [B][C]
+  const int64_t* ids;     // kPairs: [L][B][k_in]
+  const int32_t* n_cand;  // kRank: [B] or null
+  int L, B, k_in, group, k_out, C;
+  int final_pass;
+  uint64_t* keys_out;     // !final: [n_groups][B][k_out]
+  float* out_scores;      // final: [B][k_out]
+  int64_t* out_ids;       // final kKeys / kPairs
+  int32_t* out_pos;       // final kRank
+  int64_t id_base;
+};
+
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
+  extern __shared__ __align__(16) uint64_t sbuf[];
+  const int b = blockIdx.x, g = blockIdx.y;
+  int total;
+  const int l0 = g * p.group;
+  if (p.mode == kRank) {
+    total = p.n_cand ? min(max(p.n_cand[b], 0), p.C) : p.C;
+  } else {
+    total = (min(p.L, l0 + p.group) - l0) * p.k_in;
+  }
+  auto load = [&](int i) -> uint64_t {
+    if (p.mode == kKeys) {
+      const int l = l0 + i / p.k_in, r = i % p.k_in;
+      return p.keys[((size_t)l * p.B + b) * p.k_in + r];
+    } else if (p.mode == kPairs) {
+      const int l = l0 + i / p.k_in, r = i % p.k_in;
+      const size_t at = ((size_t)l * p.B + b) * p.k_in + r;
+      const int64_t id = p.ids[at];
+      // position across lists keeps "id ascending" among equal scores when
+      // lists are ordered by ascending id range
+      return id < 0 ? 0ull : make_key(p.scores[at], (uint32_t)(l * p.k_in + r));
+    } else {
+      return make_key(p.scores[(size_t)b * p.C + i], (uint32_t)i);
+    }
+  };
+  block_select_topk(sbuf, kSelCap, p.k_out, total, load);
+  // sbuf[0..k_out) sorted descending, zero padded
+  for (int r = threadIdx.x; r < p.k_out; r += blockDim.x) {
+    const uint64_t key = sbuf[r];
+    if (!p.final_pass) {
+      p.keys_out[((size_t)g * p.B + b) * p.k_out + r] = key;
+      continue;
+    }
+    const size_t o = (size_t)b * p.k_out + r;
+    if (key == 0ull) {
+      p.out_scores[o] = kLowestF32;
+      if (p.mode == kRank) p.out_pos[o] = -1; else p.out_ids[o] = -1;
+    } else {
+      p.out_scores[o] = key_score(key);
+      const uint32_t idx = key_idx(key);
+      if (p.mode == kKeys) {
+        p.out_ids[o] = p.id_base + (int64_t)idx;
+      } else if (p.mode == kPairs) {
+        const int l = idx / p.k_in, r2 = idx % p.k_in;
+        p.out_ids[o] = p.ids[((size_t)l * p.B + b) * p.k_in + r2];
+      } else {
+        p.out_pos[o] = (int32_t)idx;
+      }
+    }
+  }
+}
+
+int launch_select(const SelectParams& p, int n_groups, cudaStream_t st) {
+  dim3 grid(p.B, n_groups);
+  select_kernel<<<grid, kSelThreads, kSelCap * sizeof(uint64_t), st>>>(p);
+  TS_CUDA_OK(cudaGetLastError());
+  return TS_OK;
+}
+
+}  // namespace
+
+size_t merge_tmp_keys(int L, int B, int k) {
+  const int room = kSelCap - k;
+  if ((long long)L * k <= room) return 0;
+  const int group = max(2, room / k);
+  return (size_t)((L + group - 1) / group) * B * k;
+}
+
+int launch_merge_keys(const uint64_t* keys, int L, int B, int k, int64_t id_base, uint64_t* tmp0, uint64_t* tmp1,
+                      float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches) {
+  if (k <= 0 || k > TS_MAX_K || B <= 0 || L <= 0) { set_error("merge: bad L/B/k"); return TS_ERR_INVALID; }
+  const int room = kSelCap - k;
+  const uint64_t* cur = keys;
+  uint64_t* bufs[2] = {tmp0, tmp1};
+  int which = 0;
+  while ((long long)L * k > room) {
+    const int group = max(2, room / k);
+    const int ng = (L + group - 1) / group;
+    if (!bufs[which]) { set_error("merge: missing tmp buffer"); return TS_ERR_INVALID; }
+    SelectParams p{};
+    p.mode = kKeys; p.keys = cur; p.L = L; p.B = B; p.k_in = k; p.group = group; p.k_out = k;
+    p.final_pass = 0; p.keys_out = bufs[which];
+    int rc = launch_select(p, ng, st);
+    if (rc) return rc;
+    if (launches) ++*launches;
+    cur = bufs[which];
+    which ^= 1;
+    L = ng;
+  }
+  SelectParams p{};
+  p.mode = kKeys; p.keys = cur; p.L = L; p.B = B; p.k_in = k; p.group = L; p.k_out = k;
+  p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids; p.id_base = id_base;
+  int rc = launch_select(p, 1, st);
+  if (rc) return rc;
+  if (launches) ++*launches;
+  return TS_OK;
+}
+
+int launch_merge_pairs(const float* scores, const int64_t* ids, int L, int B, int k, float* out_scores,
+                       int64_t* out_ids, cudaStream_t st) {
+  if (k <= 0 || k > TS_MAX_K || B <= 0 || L <= 0) { set_error("merge: bad L/B/k"); return TS_ERR_INVALID; }
+  if ((long long)L * k > 65536) { set_error("merge: n_lists*k too large (%d*%d)", L, k); return TS_ERR_UNSUPPORTED; }
+  SelectParams p{};
+  p.mode = kPairs; p.scores = scores; p.ids = ids; p.L = L; p.B = B; p.k_in = k; p.group = L; p.k_out = k;
+  p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids;
+  return launch_select(p, 1, st);
+}
+
+int launch_rank_desc(const float* scores, const int32_t* n_cand, int B, int C, int top_k, float* out_scores,
+                     int32_t* out_pos, cudaStream_t st) {
+  if (top_k <= 0 || top_k > TS_MAX_K || B <= 0 || C <= 0) { set_error("rank: bad B/C/top_k"); return TS_ERR_INVALID; }
+  SelectParams p{};
+  p.mode = kRank; p.scores = scores; p.n_cand = n_cand; p.B = B; p.C = C; p.k_out = top_k; p.L = 1; p.group = 1;
+  p.k_in = C; p.final_pass = 1; p.out_scores = out_scores; p.out_pos = out_pos;
+  return launch_select(p, 1, st);
+}
+
+}  // namespace ts

@@ -1,0 +1,93 @@
+// Internal (non-ABI) declarations shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tristage.h"
+
+namespace ts {
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define TS_CUDA_OK(expr)                                                                   \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ts::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return TS_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+inline int dtype_size(int dt) { return dt == TS_F32 ? 4 : 2; }
+// row pitch in elements: rows are 16-byte aligned (TMA / 128-bit loads)
+inline int row_pitch(int dim, int dt) { return dt == TS_F32 ? ((dim + 3) / 4) * 4 : ((dim + 7) / 8) * 8; }
+inline int cap_for_k(int k) { return k <= 128 ? 256 : 1024; }
+
+struct DeviceInfo {
+  int sm_count;
+  int cc_major, cc_minor;
+  size_t smem_optin;
+};
+int get_device_info(int device, DeviceInfo* out);
+
+// ---- convert / normalise rows (ingest K1/K3 and query prep) ---------------
+enum NormMode { kNormNone = 0, kNormStage1 = 1 /* x/(|x|+1e-8) */, kNormStage2 = 2 /* x/max(|x|,1e-12) */ };
+// src [n, dim] (pitch src_ld) of src_dtype -> dst [n, dst_ld] of dst_dtype, pad
+// columns zeroed.  norm_mode applies to the stored values unless inv_norm_out
+// is given, in which case values are stored un-normalised and 1/(|x|+eps) is
+// written to inv_norm_out[n] (METRIC_COSINE).
+int launch_convert_rows(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld,
+                        int64_t n, int dim, int norm_mode, float* inv_norm_out, cudaStream_t st);
+
+// ---- Stage-1 scans -> partial keys [L][B][k] ------------------------------
+struct ScanArgs {
+  const void* rows;       // [n][ld] storage dtype
+  int64_t n;
+  int dim, ld, dtype;
+  const float* inv_norm;  // nullptr unless METRIC_COSINE
+  const void* q;          // [B][ld] storage dtype (prepared)
+  int B, k;
+  uint64_t* lists;        // scratch candidate lists
+  size_t lists_keys;      // capacity in keys
+  uint64_t* partial;      // out: [L][B][k] keys
+  size_t partial_keys;    // capacity in keys
+  int sm_count;
+};
+// number of partial lists L a scan will emit / scratch it needs
+int s1_stream_plan(const ScanArgs& a, int* L, size_t* lists_keys);
+int s1_umma_plan(const ScanArgs& a, int* L, size_t* lists_keys);
+int launch_s1_stream(const ScanArgs& a, cudaStream_t st, int* launches);
+int launch_s1_umma(const ScanArgs& a, cudaStream_t st, int* launches);
+
+// ---- top-k selection / merge ----------------------------------------------
+// keys [L][B][k] -> final (scores, ids) [B][k]; tmp0/tmp1 each hold
+// ceil(L/2)*B*k keys (only used when L*k exceeds one selection pass).
+int launch_merge_keys(const uint64_t* keys, int L, int B, int k, int64_t id_base, uint64_t* tmp0, uint64_t* tmp1,
+                      float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches);
+size_t merge_tmp_keys(int L, int B, int k);
+int launch_merge_pairs(const float* scores, const int64_t* ids, int L, int B, int k, float* out_scores,
+                       int64_t* out_ids, cudaStream_t st);
+int launch_rank_desc(const float* scores, const int32_t* n_cand, int B, int C, int top_k, float* out_scores,
+                     int32_t* out_pos, cudaStream_t st);
+
+// ---- Stage-2 ---------------------------------------------------------------
+struct MaxSimArgs {
+  const void* tok;         // [ntok_pad][dim] storage dtype, docs padded to 8 rows
+  const int64_t* doc_off;  // [ndocs] first row of each doc (multiple of 8)
+  const int32_t* doc_len;  // [ndocs]
+  int64_t ndocs, id_base;
+  int64_t ntok_rows;       // rows allocated in tok (for the tensor map)
+  int dim, dtype;
+  const void* q;           // [B][lq_stride][dim] storage dtype, normalised
+  const int32_t* q_len;    // [B] or nullptr
+  int B, lq_stride;
+  const int64_t* cand;     // [B][C]
+  const int32_t* n_cand;   // [B] or nullptr
+  int C, mode;
+  float* out;              // [B][C]
+  int sm_count;
+};
+int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches);
+
+}  // namespace ts

@@ -1,0 +1,97 @@
+"""Row-sharded multi-GPU wrappers: one process per GPU, ``torch.distributed``.
+
+The reference has no parallelism at all; this is the sharding
+BASELINE.json's north_star asks for:
+
+* Stage 1 -- rank r owns corpus rows ``[lo_r, hi_r)`` (contiguous), computes a
+  local exact top-k with GLOBAL ids, the ``[B, k]`` (score, id) pairs are
+  all-gathered (NCCL over NVLink; ``gloo`` in the CPU tests) and every rank
+  merges ``G*k -> k`` with ``ts_topk_merge``.  Exact: the global top-k is a
+  subset of the union of the local top-k lists.
+* Stage 2 -- the token store is partitioned by the same row ranges.  After the
+  Stage-1 merge every rank holds the full candidate list, so "scatter to the
+  owning shard" is a local ownership filter inside ``ts_maxsim`` (unowned ids
+  score 0.0) followed by one all-reduce(SUM) of the ``[B, C]`` score matrix.
+
+Only the exchange step is a collective; the scan/scoring kernels never wait on
+another rank.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous balanced partition: the first ``n_total % world`` ranks get one extra row."""
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def owner_of(ids: torch.Tensor, n_total: int, world: int) -> torch.Tensor:
+    """Rank owning each global id under ``shard_range`` (load-balance reporting)."""
+    base, rem = divmod(int(n_total), int(world))
+    cut = rem * (base + 1)
+    big = torch.div(ids, base + 1, rounding_mode="floor")
+    small = rem + torch.div(ids - cut, max(base, 1), rounding_mode="floor")
+    return torch.where(ids < cut, big, small)
+
+
+def gather_topk(scores: torch.Tensor, ids: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """all-gather per-rank [B, k] results into [G, B, k] (rank-major = ascending id ranges)."""
+    world = dist.get_world_size(group)
+    B, k = scores.shape
+    # dim-0 concatenation is the layout every backend (nccl, gloo) accepts
+    all_s = torch.empty((world * B, k), dtype=scores.dtype, device=scores.device)
+    all_i = torch.empty((world * B, k), dtype=ids.dtype, device=ids.device)
+    dist.all_gather_into_tensor(all_s, scores.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, ids.contiguous(), group=group)
+    return all_s.view(world, B, k), all_i.view(world, B, k)
+
+
+class ShardedIndex:
+    """Stage-1 index whose rows are split across the ranks of a process group."""
+
+    def __init__(self, local_index, n_total: int, group=None,
+                 merge_fn: Optional[Callable] = None):
+        self.local = local_index
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_total = int(n_total)
+        self.lo, self.hi = shard_range(self.n_total, self.rank, self.world)
+        self.local.set_id_base(self.lo)
+        if merge_fn is None:
+            from ._lib import topk_merge
+
+            merge_fn = lambda s, i: topk_merge(s, i, device=s.device.index)  # noqa: E731
+        self.merge_fn = merge_fn
+
+    def search(self, q: torch.Tensor, k: int, **kw) -> Tuple[torch.Tensor, torch.Tensor]:
+        """q replicated on every rank -> identical merged (scores, ids) on every rank."""
+        s, i = self.local.search(q, k, **kw)
+        if self.world == 1:
+            return s, i
+        all_s, all_i = gather_topk(s, i, self.group)
+        return self.merge_fn(all_s, all_i)
+
+
+class ShardedTokStore:
+    """Stage-2 token store partitioned by the same doc-id ranges."""
+
+    def __init__(self, local_store, n_total: int, group=None):
+        self.local = local_store
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.lo, self.hi = shard_range(int(n_total), self.rank, self.world)
+        self.local.set_id_base(self.lo)
+
+    def maxsim(self, q_tok: torch.Tensor, cand: torch.Tensor, **kw) -> torch.Tensor:
+        out = self.local.maxsim(q_tok, cand, **kw)        # 0.0 for ids this shard does not own
+        if self.world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+        return out

@@ -1,0 +1,381 @@
+"""Drop-in ``Stage1Config`` / ``BM25Index`` / ``Stage1Retriever`` for
+``/root/reference/src/stage1_retriever.py`` with the dense scoring on a B200.
+
+Same names, fields, methods, return shapes and error behaviour as the
+reference class that ``src/retrieval_pipeline.py:244-256,316,358`` and
+``non_mcp/main.py:167-177,224,254`` drive.  What changes underneath:
+
+* ``faiss.IndexFlatIP.add/search`` (:270,277,313,380) -> ``libtristage.so``
+  (``ts_index_add`` / ``ts_index_search_host``): hand-written sm_100a kernels,
+  corpus resident in HBM as bf16 (``storage_dtype``), fp32 accumulate, exact
+  top-k fused into the scan.  No CPU fallback: without the library or a B200
+  the constructor's first device call raises.
+* search is ALWAYS exact.  The reference silently switches to an approximate
+  ``IndexIVFFlat(nlist=100, nprobe=10)`` when the first batch has more than
+  1000 rows (:262-273); BASELINE.json pins exact search, so that switch is not
+  reproduced (``get_stats()['faiss_index_type']`` is always ``IndexFlatIP``).
+* the encoder (SentenceTransformer, :137-254) stays the reference's PyTorch
+  model and is outside the hot path; pass ``model=`` to inject one (tests use
+  ``oracle/fakes.py``), otherwise it is loaded like the reference does.
+* BM25 / RRF / weighted fusion (:35-112, :326-366) are lexical Python work,
+  not part of the accelerated path; they are re-implemented here with the
+  same arithmetic so hybrid results match (an inverted index replaces the
+  O(N) per-query Python scan, scores are bit-identical).
+
+Extra (not in the reference): ``search_batch`` and ``add_embeddings`` expose the
+batched regime the reference's batch-1 API cannot reach.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import os
+import pickle
+import re
+from collections import defaultdict
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+
+
+@dataclass
+class Stage1Config:
+    """Field-for-field the reference dataclass (src/stage1_retriever.py:16-33),
+    plus ``storage_dtype`` / ``gpu_index`` for the B200 index."""
+    model_name: str = "google/embeddinggemma-300m"
+    device: str = "auto"
+    cache_dir: str = "./models"
+    index_dir: str = "./faiss_index"
+    top_k_candidates: int = 500
+    batch_size: int = 32
+    max_text_length: int = 512
+    enable_bm25: bool = True
+    bm25_top_k: int = 300
+    fusion_method: str = "rrf"
+    rrf_k: int = 60
+    dense_weight: float = 0.7
+    bm25_weight: float = 0.3
+    use_fp16: bool = True
+    nlist: int = 100
+    nprobe: int = 10
+    storage_dtype: str = "bf16"   # HBM corpus dtype: bf16 | fp16 | fp32
+    gpu_index: int = 0
+
+
+class BM25Index:
+    """BM25 with the reference's arithmetic (src/stage1_retriever.py:35-112).
+
+    Reference behaviours kept on purpose:
+    * ``fit`` appends to ``doc_freqs`` / ``doc_lens`` without clearing them, so a
+      second ``fit`` (every later ``add_documents`` call, :316-322) leaves stale
+      rows that skew ``avg_doc_len`` and the document frequencies;
+    * a query token that occurs twice is counted twice (:93-99);
+    * ``search`` ranks EVERY document, zero scores included, with a stable
+      descending sort (:105-112).
+    """
+
+    def __init__(self, k1: float = 1.2, b: float = 0.75):
+        self.k1 = k1
+        self.b = b
+        self.doc_freqs: List[Dict[str, int]] = []
+        self.idf: Dict[str, float] = {}
+        self.doc_lens: List[int] = []
+        self.avg_doc_len = 0
+        self.corpus_size = 0
+        self.vocabulary = set()
+        self.documents: List[str] = []
+        self._postings: Optional[Dict[str, List[int]]] = None
+
+    def tokenize(self, text: str) -> List[str]:
+        return re.sub(r"[^a-z0-9\s]", " ", text.lower()).split()
+
+    def fit(self, documents: List[str]):
+        self.documents = documents
+        self.corpus_size = len(documents)
+        for doc in documents:
+            tokens = self.tokenize(doc)
+            self.vocabulary.update(tokens)
+            tf: Dict[str, int] = defaultdict(int)
+            for t in tokens:
+                tf[t] += 1
+            self.doc_freqs.append(tf)
+            self.doc_lens.append(len(tokens))
+        self.avg_doc_len = sum(self.doc_lens) / self.corpus_size if self.corpus_size > 0 else 0
+        df: Dict[str, int] = defaultdict(int)
+        for tf in self.doc_freqs:              # one pass instead of |V| passes; same counts
+            for t in tf:
+                df[t] += 1
+        for token in self.vocabulary:
+            d = df.get(token, 0)
+            self.idf[token] = math.log((self.corpus_size - d + 0.5) / (d + 0.5) + 1.0)
+        self._postings = None
+
+    def score(self, query: str, doc_idx: int) -> float:
+        if doc_idx >= len(self.doc_freqs):
+            return 0.0
+        tf_map = self.doc_freqs[doc_idx]
+        dl = self.doc_lens[doc_idx]
+        s = 0.0
+        for token in self.tokenize(query):
+            if token in tf_map and token in self.idf:
+                tf = tf_map[token]
+                s += self.idf[token] * ((tf * (self.k1 + 1)) / (tf + self.k1 * (1 - self.b + self.b * dl / self.avg_doc_len)))
+        return s
+
+    def _build_postings(self):
+        post: Dict[str, List[int]] = defaultdict(list)
+        for idx in range(min(len(self.documents), len(self.doc_freqs))):
+            for t in self.doc_freqs[idx]:
+                post[t].append(idx)
+        self._postings = post
+
+    def search(self, query: str, top_k: int = 10) -> List[Tuple[int, float]]:
+        if getattr(self, "_postings", None) is None:
+            self._build_postings()
+        n = len(self.documents)
+        scores = [0.0] * n
+        for token in self.tokenize(query):     # same accumulation order as score()
+            if token not in self.idf:
+                continue
+            idf = self.idf[token]
+            for idx in self._postings.get(token, ()):
+                tf = self.doc_freqs[idx][token]
+                dl = self.doc_lens[idx]
+                scores[idx] += idf * ((tf * (self.k1 + 1)) / (tf + self.k1 * (1 - self.b + self.b * dl / self.avg_doc_len)))
+        ranked = sorted(enumerate(scores), key=lambda x: x[1], reverse=True)
+        return ranked[:top_k]
+
+
+class IndexFlatIP:
+    """The ``faiss.IndexFlatIP`` surface the reference touches (``d``, ``ntotal``,
+    ``add``, ``search``), backed by one ``ts_index`` shard on the GPU."""
+
+    def __init__(self, d: int, storage_dtype: str = "bf16", device: int = 0, reserve_rows: int = 0):
+        self.d = int(d)
+        self.storage_dtype = storage_dtype
+        self.device = device
+        self._index = _lib.Index(self.d, storage_dtype, "ip", device, reserve_rows)
+        self.is_trained = True
+
+    @property
+    def ntotal(self) -> int:
+        return self._index.ntotal
+
+    def add(self, x: np.ndarray) -> None:
+        self._index.add(np.ascontiguousarray(x, dtype=np.float32), normalize=False)
+
+    def search(self, q: np.ndarray, k: int, path: str = "auto"):
+        if k > _lib.TS_MAX_K:
+            raise ValueError(f"top_k={k} exceeds the fused top-k limit {_lib.TS_MAX_K}")
+        return self._index.search_host(q, k, normalize_q=False, path=path)
+
+    def save(self, path: str) -> None:
+        self._index.save(path)
+
+    @classmethod
+    def load(cls, path: str, storage_dtype: str = "bf16", device: int = 0) -> "IndexFlatIP":
+        obj = cls.__new__(cls)
+        obj._index = _lib.Index.load(path, device)
+        obj.d, obj.storage_dtype, obj.device, obj.is_trained = obj._index.dim, storage_dtype, device, True
+        return obj
+
+
+class Stage1Retriever:
+    """Stage 1: dense embeddings + exact GPU top-k (+ optional BM25 fusion)."""
+
+    def __init__(self, config: Stage1Config, model=None):
+        self.config = config
+        self.logger = logging.getLogger(__name__)
+        self.model = model
+        self.embedding_dim = None
+        self.faiss_index = None
+        self.bm25_index = None
+        self.documents: List[str] = []
+        self.doc_metadata: List[Dict[str, Any]] = []
+        os.makedirs(self.config.cache_dir, exist_ok=True)
+        os.makedirs(self.config.index_dir, exist_ok=True)
+        _lib.lib()                       # fail loudly now if the CUDA library is missing
+        self._load_model()
+
+    # -- encoder: outside the hot path (reference :137-254) ------------------
+    def _load_model(self):
+        if self.model is None:
+            from sentence_transformers import SentenceTransformer  # not in this image: inject model=
+
+            device = self.config.device
+            if device == "auto":
+                import torch
+
+                device = "cuda" if torch.cuda.is_available() else "cpu"
+            base = os.path.join(self.config.cache_dir, os.path.basename(self.config.model_name))
+            legacy = os.path.join(self.config.cache_dir, self.config.model_name)
+            source = base if os.path.isdir(base) else (legacy if os.path.isdir(legacy) else self.config.model_name)
+            self.model = SentenceTransformer(source, device=device, cache_folder=self.config.cache_dir)
+        if hasattr(self.model, "get_sentence_embedding_dimension"):
+            self.embedding_dim = self.model.get_sentence_embedding_dimension()
+        else:
+            self.embedding_dim = self.model.encode("sample text", convert_to_numpy=True).shape[0]
+        self.logger.info(f"Model loaded successfully. Embedding dimension: {self.embedding_dim}")
+
+    def _encode_batch(self, texts: List[str]) -> np.ndarray:
+        emb = self.model.encode(texts, batch_size=self.config.batch_size, convert_to_numpy=True,
+                                show_progress_bar=False)
+        return np.asarray(emb).astype(np.float32)
+
+    def _normalize_embeddings(self, embeddings: np.ndarray) -> np.ndarray:
+        """x / (|x| + 1e-8), fp32 numpy -- reference :285-288."""
+        norms = np.linalg.norm(embeddings, axis=1, keepdims=True)
+        return embeddings / (norms + 1e-8)
+
+    def _create_faiss_index(self, embeddings: np.ndarray):
+        self.faiss_index = IndexFlatIP(embeddings.shape[1], self.config.storage_dtype, self.config.gpu_index)
+        self.faiss_index.add(embeddings)
+        self.logger.info(f"GPU flat index created with {len(embeddings)} vectors")
+
+    # -- ingest ---------------------------------------------------------------
+    def add_documents(self, documents: List[str], metadata: Optional[List[Dict[str, Any]]] = None):
+        if not documents:
+            return
+        self.documents.extend(documents)
+        if metadata is None:
+            metadata = [{}] * len(documents)   # one shared dict, like the reference (:302)
+        self.doc_metadata.extend(metadata)
+        embeddings = self._normalize_embeddings(self._encode_batch(documents)).astype(np.float32)
+        self._add_normalized(embeddings)
+        self._refit_bm25()
+
+    def add_embeddings(self, embeddings: np.ndarray, documents: Optional[List[str]] = None,
+                       metadata: Optional[List[Dict[str, Any]]] = None, normalize: bool = True):
+        """Ingest pre-computed embeddings (synthetic corpora, offline encoders)."""
+        n = len(embeddings)
+        docs = list(documents) if documents is not None else [f"doc-{len(self.documents) + i}" for i in range(n)]
+        assert len(docs) == n
+        self.documents.extend(docs)
+        self.doc_metadata.extend(metadata if metadata is not None else [{}] * n)
+        e = np.asarray(embeddings, dtype=np.float32)
+        self._add_normalized(self._normalize_embeddings(e).astype(np.float32) if normalize else e)
+        if documents is not None:
+            self._refit_bm25()
+
+    def _add_normalized(self, embeddings: np.ndarray):
+        if self.faiss_index is None:
+            self._create_faiss_index(embeddings)
+        else:
+            self.faiss_index.add(embeddings)
+
+    def _refit_bm25(self):
+        if self.config.enable_bm25:
+            if self.bm25_index is None:
+                self.bm25_index = BM25Index()
+            self.bm25_index.fit(self.documents)
+
+    # -- fusion (reference :326-366) -----------------------------------------
+    def _reciprocal_rank_fusion(self, dense_results, bm25_results):
+        scores: Dict[int, float] = defaultdict(float)
+        for rank, (doc_idx, _) in enumerate(dense_results):
+            scores[doc_idx] += 1.0 / (self.config.rrf_k + rank + 1)
+        for rank, (doc_idx, _) in enumerate(bm25_results):
+            scores[doc_idx] += 1.0 / (self.config.rrf_k + rank + 1)
+        fused = list(scores.items())
+        fused.sort(key=lambda x: x[1], reverse=True)
+        return fused
+
+    def _weighted_fusion(self, dense_results, bm25_results):
+        scores: Dict[int, float] = defaultdict(float)
+        if dense_results:
+            mx = max(s for _, s in dense_results)
+            for doc_idx, s in dense_results:
+                scores[doc_idx] += self.config.dense_weight * (s / mx)
+        if bm25_results:
+            mx = max(s for _, s in bm25_results)
+            for doc_idx, s in bm25_results:
+                scores[doc_idx] += self.config.bm25_weight * (s / mx)
+        fused = list(scores.items())
+        fused.sort(key=lambda x: x[1], reverse=True)
+        return fused
+
+    # -- search ---------------------------------------------------------------
+    def _format(self, final_results) -> List[Dict[str, Any]]:
+        out = []
+        for doc_idx, score in final_results:
+            if doc_idx < len(self.documents):
+                out.append({"doc_id": doc_idx, "document": self.documents[doc_idx], "score": score,
+                            "stage1_score": score, "metadata": self.doc_metadata[doc_idx], "stage": "stage1"})
+        return out
+
+    def _fuse(self, query: str, dense_results, top_k: int):
+        bm25_results = []
+        if self.config.enable_bm25 and self.bm25_index is not None:
+            bm25_results = self.bm25_index.search(query, self.config.bm25_top_k)
+        if self.config.enable_bm25 and bm25_results:
+            fused = (self._reciprocal_rank_fusion(dense_results, bm25_results)
+                     if self.config.fusion_method == "rrf" else self._weighted_fusion(dense_results, bm25_results))
+            return fused[:top_k]
+        return dense_results[:top_k]
+
+    def search(self, query: str, top_k: Optional[int] = None) -> List[Dict[str, Any]]:
+        if self.faiss_index is None:
+            raise ValueError("No documents indexed. Call add_documents() first.")
+        top_k = top_k or self.config.top_k_candidates
+        q = self._normalize_embeddings(self._encode_batch([query]))
+        D, I = self.faiss_index.search(q, top_k)
+        dense = [(int(i), float(s)) for i, s in zip(I[0], D[0]) if i >= 0]
+        return self._format(self._fuse(query, dense, top_k))
+
+    def search_batch(self, queries, top_k: Optional[int] = None, path: str = "auto") -> List[List[Dict[str, Any]]]:
+        """Batched search: ``queries`` is a list of strings or an fp32 [B, d]
+        embedding matrix (already encoded).  One GPU call for the whole batch."""
+        if self.faiss_index is None:
+            raise ValueError("No documents indexed. Call add_documents() first.")
+        top_k = top_k or self.config.top_k_candidates
+        texts = list(queries) if not isinstance(queries, np.ndarray) else None
+        emb = self._encode_batch(texts) if texts is not None else np.asarray(queries, np.float32)
+        D, I = self.faiss_index.search(self._normalize_embeddings(emb), top_k, path=path)
+        results = []
+        for b in range(len(D)):
+            dense = [(int(i), float(s)) for i, s in zip(I[b], D[b]) if i >= 0]
+            final = self._fuse(texts[b], dense, top_k) if texts is not None else dense[:top_k]
+            results.append(self._format(final))
+        return results
+
+    # -- persistence (reference :421-465; same file names and quirks) ---------
+    def save_index(self, index_path: Optional[str] = None):
+        if index_path is None:
+            index_path = os.path.join(self.config.index_dir, "stage1_index.pkl")
+        data = {"documents": self.documents, "doc_metadata": self.doc_metadata,
+                "config": self.config.__dict__, "bm25_index": self.bm25_index}
+        faiss_path = os.path.join(self.config.index_dir, "stage1_faiss.index")   # fixed location, like :434
+        if self.faiss_index is not None:
+            self.faiss_index.save(faiss_path)
+        with open(index_path, "wb") as f:
+            pickle.dump(data, f)
+        self.logger.info(f"Stage 1 index saved to {index_path}")
+
+    def load_index(self, index_path: Optional[str] = None):
+        if index_path is None:
+            index_path = os.path.join(self.config.index_dir, "stage1_index.pkl")
+        if not os.path.exists(index_path):
+            self.logger.warning(f"Index file not found: {index_path}")
+            return
+        with open(index_path, "rb") as f:
+            data = pickle.load(f)
+        self.documents = data["documents"]
+        self.doc_metadata = data["doc_metadata"]
+        self.bm25_index = data.get("bm25_index")
+        faiss_path = os.path.join(self.config.index_dir, "stage1_faiss.index")
+        if os.path.exists(faiss_path):
+            self.faiss_index = IndexFlatIP.load(faiss_path, self.config.storage_dtype, self.config.gpu_index)
+        self.logger.info(f"Stage 1 index loaded from {index_path}")
+
+    def get_stats(self) -> Dict[str, Any]:
+        return {
+            "total_documents": len(self.documents),
+            "embedding_dimension": self.embedding_dim,
+            "faiss_index_type": type(self.faiss_index).__name__ if self.faiss_index else None,
+            "bm25_enabled": self.config.enable_bm25,
+            "bm25_vocabulary_size": len(self.bm25_index.vocabulary) if self.bm25_index else 0,
+            "config": self.config.__dict__,
+        }

@@ -1,0 +1,244 @@
+"""Drop-in ``Stage2Config`` / ``ColBERTScorer`` for
+``/root/reference/src/stage2_rescorer.py`` with MaxSim scoring on a B200.
+
+Same names, fields, methods and return shapes as the reference class driven by
+``src/retrieval_pipeline.py:260-270,375`` and ``non_mcp/main.py:181-190,271``.
+What changes underneath:
+
+* the per-candidate loop over ``_maxsim_score`` / ``_colbert_score``
+  (:167-201, :268-273) -> ONE ``ts_maxsim`` launch over all candidates
+  (hand-written sm_100a kernel: TMA gather of ragged docs, tcgen05 contraction,
+  fused row-max + mean/softmax epilogue);
+* the reference re-encodes every candidate document on every query
+  (:255-259); here token embeddings are kept in a GPU token store
+  (``ts_tokstore``), filled the first time a document is seen -- or ahead of
+  time with ``index_documents`` / ``add_token_embeddings`` -- so a query only
+  pays for its own encoding;
+* the final stable descending sort + truncate (:294-297) runs on the device
+  (``ts_rank_desc``).
+
+The HF tokenizer/model (:54-165, :207-242) stay the reference's PyTorch
+encoder, outside the hot path; pass ``tokenizer=`` / ``model=`` to inject them
+(tests use ``oracle/fakes.py``).  No CPU fallback for the scoring.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from dataclasses import dataclass
+from typing import Any, Dict, Hashable, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+@dataclass
+class Stage2Config:
+    """Field-for-field the reference dataclass (src/stage2_rescorer.py:15-27),
+    plus ``storage_dtype`` / ``gpu_index`` for the B200 token store."""
+    model_name: str = "lightonai/GTE-ModernColBERT-v1"
+    device: str = "auto"
+    cache_dir: str = "./models"
+    max_seq_length: int = 192
+    batch_size: int = 16
+    top_k_candidates: int = 100
+    use_fp16: bool = True
+    pooling_method: str = "cls"
+    normalize_embeddings: bool = True
+    scoring_method: str = "maxsim"   # "maxsim" or "colbert"
+    use_gpu_if_available: bool = True
+    storage_dtype: str = "bf16"      # HBM token-store dtype: bf16 | fp16 | fp32
+    gpu_index: int = 0
+
+
+class ColBERTScorer:
+    """ColBERT-style late-interaction rescoring with GPU-resident token embeddings."""
+
+    def __init__(self, config: Stage2Config, tokenizer=None, model=None):
+        self.config = config
+        self.logger = logging.getLogger(__name__)
+        self.model = model
+        self.tokenizer = tokenizer
+        self.device = self._get_device()
+        self.use_amp = False
+        _lib.lib()                        # fail loudly if the CUDA library is missing
+        self._store: Optional[_lib.TokStore] = None
+        self._slot: Dict[Hashable, int] = {}      # doc key -> position in the token store
+        self._load_model()
+
+    # -- encoder side: outside the hot path -----------------------------------
+    def _get_device(self) -> str:
+        if self.config.device == "auto":
+            return "cuda" if (torch.cuda.is_available() and self.config.use_gpu_if_available) else "cpu"
+        return self.config.device
+
+    def _load_model(self):
+        if self.model is None or self.tokenizer is None:
+            from transformers import AutoModel, AutoTokenizer
+
+            base = os.path.join(self.config.cache_dir, os.path.basename(self.config.model_name))
+            legacy = os.path.join(self.config.cache_dir, self.config.model_name)
+            source = base if os.path.isdir(base) else (legacy if os.path.isdir(legacy) else self.config.model_name)
+            self.tokenizer = AutoTokenizer.from_pretrained(source, cache_dir=self.config.cache_dir)
+            self.model = AutoModel.from_pretrained(source, cache_dir=self.config.cache_dir)
+            self.model.to(self.device)
+            self.model.eval()
+            self.use_amp = self.config.use_fp16 and self.device == "cuda"
+
+    def _forward(self, encoded):
+        with torch.no_grad():
+            if self.use_amp:
+                with torch.autocast("cuda"):
+                    return self.model(**encoded)
+            return self.model(**encoded)
+
+    def _encode_single_text(self, text: str) -> torch.Tensor:
+        """[1, L, H] hidden states of the un-padded text (reference :134-165)."""
+        if not text or not text.strip():
+            text = "empty"
+        encoded = self.tokenizer(text, truncation=True, max_length=self.config.max_seq_length,
+                                 return_tensors="pt", padding=False)
+        encoded = {k: v.to(self.device) for k, v in encoded.items()}
+        out = self._forward(encoded)
+        n = int(encoded["attention_mask"].sum().item())
+        return out.last_hidden_state[:, :n, :]
+
+    def encode_query(self, query: str) -> torch.Tensor:
+        return self._encode_single_text(query)
+
+    def encode_single_document(self, document: str) -> torch.Tensor:
+        return self._encode_single_text(document)
+
+    def encode_documents_batch(self, documents: List[str]) -> List[torch.Tensor]:
+        """List of [L_i, H] hidden states, padding removed (reference :207-242)."""
+        all_emb = []
+        for i in range(0, len(documents), self.config.batch_size):
+            batch = [t if t and t.strip() else "empty" for t in documents[i:i + self.config.batch_size]]
+            encoded = self.tokenizer(batch, truncation=True, padding=True,
+                                     max_length=self.config.max_seq_length, return_tensors="pt")
+            encoded = {k: v.to(self.device) for k, v in encoded.items()}
+            out = self._forward(encoded)
+            for j in range(len(batch)):
+                n = int(encoded["attention_mask"][j].sum().item())
+                all_emb.append(out.last_hidden_state[j, :n, :])
+        return all_emb
+
+    # -- token store -----------------------------------------------------------
+    def _ensure_store(self, dim: int) -> _lib.TokStore:
+        if self._store is None:
+            self._store = _lib.TokStore(dim, self.config.storage_dtype, self.config.gpu_index)
+        elif self._store.dim != dim:
+            raise ValueError(f"token dim {dim} != store dim {self._store.dim}")
+        return self._store
+
+    def add_token_embeddings(self, keys: List[Hashable], token_embeddings: List[Any]) -> None:
+        """Insert pre-computed per-document token matrices ([L_i, H] each, raw
+        hidden states: they are L2-normalised on the device at ingest)."""
+        mats = [np.asarray(t.detach().float().cpu().numpy() if isinstance(t, torch.Tensor) else t, np.float32)
+                .reshape(-1, np.shape(t)[-1]) for t in token_embeddings]
+        if not mats:
+            return
+        mats = [m[: _lib.TS_S2_MAX_LD] for m in mats]
+        store = self._ensure_store(mats[0].shape[1])
+        base = store.ndocs
+        store.add(np.concatenate(mats, axis=0), [m.shape[0] for m in mats], normalize=True)
+        for i, key in enumerate(keys):
+            self._slot[key] = base + i
+
+    def index_documents(self, documents: List[str], doc_ids: Optional[List[Hashable]] = None) -> None:
+        """Encode documents once and keep their token embeddings on the GPU."""
+        keys = [(i, d) for i, d in zip(doc_ids, documents)] if doc_ids is not None else [("text", d) for d in documents]
+        todo = [(k, d) for k, d in zip(keys, documents) if k not in self._slot]
+        if todo:
+            self.add_token_embeddings([k for k, _ in todo], self.encode_documents_batch([d for _, d in todo]))
+
+    @staticmethod
+    def _key(candidate: Dict[str, Any]) -> Hashable:
+        # the text is part of the key: doc ids are reused after a clear_index
+        return (candidate.get("doc_id", "text"), candidate["document"])
+
+    def _mode(self) -> int:
+        return _lib.TS_S2_MAXSIM if self.config.scoring_method == "maxsim" else _lib.TS_S2_COLBERT
+
+    def _score_slots(self, query_embeddings: torch.Tensor, slots: List[int]) -> np.ndarray:
+        q = query_embeddings.detach().float().cpu().numpy().reshape(1, -1, query_embeddings.shape[-1])
+        cand = np.asarray(slots, dtype=np.int64).reshape(1, -1)
+        return self._store.maxsim_host(q, cand, mode=self._mode(), normalize_q=True)[0]
+
+    # -- the two scoring functions, one pair at a time (reference :167-201) ----
+    def _pair_score(self, query_embeddings, doc_embeddings, mode: int) -> torch.Tensor:
+        d = doc_embeddings
+        d = d.reshape(-1, d.shape[-1])
+        store = _lib.TokStore(d.shape[-1], self.config.storage_dtype, self.config.gpu_index)
+        store.add(d.detach().float().cpu().numpy(), [d.shape[0]], normalize=True)
+        q = query_embeddings.detach().float().cpu().numpy().reshape(1, -1, d.shape[-1])
+        s = store.maxsim_host(q, np.zeros((1, 1), np.int64), mode=mode, normalize_q=True)
+        return torch.tensor(float(s[0, 0]))
+
+    def _maxsim_score(self, query_embeddings: torch.Tensor, doc_embeddings: torch.Tensor) -> torch.Tensor:
+        return self._pair_score(query_embeddings, doc_embeddings, _lib.TS_S2_MAXSIM)
+
+    def _colbert_score(self, query_embeddings: torch.Tensor, doc_embeddings: torch.Tensor) -> torch.Tensor:
+        return self._pair_score(query_embeddings, doc_embeddings, _lib.TS_S2_COLBERT)
+
+    # -- the call the pipeline makes -------------------------------------------
+    def rescore_candidates(self, query: str, candidates: List[Dict[str, Any]]) -> List[Dict[str, Any]]:
+        if not candidates:
+            return []
+        query_embeddings = self.encode_query(query)
+        try:
+            keys = [self._key(c) for c in candidates]
+            missing = [(k, c["document"]) for k, c in zip(keys, candidates) if k not in self._slot]
+            if missing:
+                seen, uniq = set(), []
+                for k, d in missing:
+                    if k not in seen:
+                        seen.add(k)
+                        uniq.append((k, d))
+                self.add_token_embeddings([k for k, _ in uniq], self.encode_documents_batch([d for _, d in uniq]))
+        except Exception as e:                         # reference :260-263
+            self.logger.error(f"Error encoding documents: {e}")
+            return candidates
+        scores = self._score_slots(query_embeddings, [self._slot[k] for k in keys])
+        scored = []
+        for c, s in zip(candidates, scores):
+            u = c.copy()
+            u["stage2_score"] = float(s)
+            u["stage"] = "stage2"
+            scored.append(u)
+        # stable descending sort + truncate on the device (reference :294-297)
+        top_k = min(self.config.top_k_candidates, len(scored), _lib.TS_MAX_K)
+        dev = torch.device("cuda", self.config.gpu_index)
+        _, pos = _lib.rank_desc(torch.from_numpy(scores.reshape(1, -1)).to(dev), top_k, device=self.config.gpu_index)
+        order = [int(p) for p in pos[0].cpu().tolist() if p >= 0]
+        if self.config.top_k_candidates > _lib.TS_MAX_K and len(scored) > _lib.TS_MAX_K:
+            taken = set(order)
+            rest = sorted((i for i in range(len(scored)) if i not in taken),
+                          key=lambda i: scored[i]["stage2_score"], reverse=True)
+            order += rest[: self.config.top_k_candidates - len(order)]
+        return [scored[i] for i in order]
+
+    def compute_similarity_matrix(self, query: str, documents: List[str]) -> np.ndarray:
+        query_embeddings = self.encode_query(query)
+        self.index_documents(documents)
+        slots = [self._slot[("text", d)] for d in documents]
+        return np.array([float(s) for s in self._score_slots(query_embeddings, slots)])
+
+    def get_model_info(self) -> Dict[str, Any]:
+        return {
+            "model_name": self.config.model_name,
+            "device": self.device,
+            "max_seq_length": self.config.max_seq_length,
+            "use_fp16": self.use_amp,
+            "pooling_method": self.config.pooling_method,
+            "scoring_method": self.config.scoring_method,
+            "batch_size": self.config.batch_size,
+            "embedding_dim": self.model.config.hidden_size if self.model else None,
+        }
+
+    def clear_gpu_memory(self):
+        """Best-effort cache release; the token store is index state and stays."""
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
