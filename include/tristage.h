@@ -148,6 +148,14 @@ int ts_index_get_rows(const ts_index* h, int64_t start, int64_t n, float* out_ho
 /* kernels launched by this handle since creation (bench.py gpu_launches)     */
 int64_t ts_index_launch_count(const ts_index* h);
 
+/* Measurement aid (bench.py roofline): while enabled, every search brackets its
+ * SCAN kernel (stream or umma, not the query prep / merge) with CUDA events on
+ * the launching stream.  ts_index_scan_time reports the mean duration (ms) of
+ * the scans recorded since the last call (at most 256) and clears the record;
+ * it synchronises on the last event.                                         */
+int ts_index_set_profiling(ts_index* h, int enable);
+int ts_index_scan_time(ts_index* h, float* mean_ms_out, int* n_out);
+
 /* ---------------------------------------------------------------- Stage 2 -- */
 
 /* Token-embedding shard: the reference re-encodes every candidate per query
@@ -168,6 +176,9 @@ int64_t ts_tokstore_ntokens(const ts_tokstore* h);
 int ts_tokstore_reset(ts_tokstore* h);
 int ts_tokstore_set_id_base(ts_tokstore* h, int64_t id_base);
 int64_t ts_tokstore_launch_count(const ts_tokstore* h);
+/* same measurement aid for the MaxSim kernel                                 */
+int ts_tokstore_set_profiling(ts_tokstore* h, int enable);
+int ts_tokstore_scan_time(ts_tokstore* h, float* mean_ms_out, int* n_out);
 
 /* _maxsim_score / _colbert_score for every (query, candidate) pair in one
  * launch (replaces the loop at stage2_rescorer.py:268-273).

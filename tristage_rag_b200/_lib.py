@@ -52,6 +52,8 @@ SYMBOLS = {
     "ts_index_load": (_i, [C.POINTER(_vp), _i, C.c_char_p]),
     "ts_index_get_rows": (_i, [_vp, _i64, _i64, _vp]),
     "ts_index_launch_count": (_i64, [_vp]),
+    "ts_index_set_profiling": (_i, [_vp, _i]),
+    "ts_index_scan_time": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(_i)]),
     "ts_tokstore_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i64, _i64]),
     "ts_tokstore_destroy": (_i, [_vp]),
     "ts_tokstore_add": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp]),
@@ -60,6 +62,8 @@ SYMBOLS = {
     "ts_tokstore_reset": (_i, [_vp]),
     "ts_tokstore_set_id_base": (_i, [_vp, _i64]),
     "ts_tokstore_launch_count": (_i64, [_vp]),
+    "ts_tokstore_set_profiling": (_i, [_vp, _i]),
+    "ts_tokstore_scan_time": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(_i)]),
     "ts_maxsim": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _u, _vp, _vp]),
     "ts_maxsim_host": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _u, _vp, _vp]),
     "ts_rank_desc": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
@@ -162,6 +166,15 @@ class Index:
 
     def set_id_base(self, base: int) -> None:
         check(lib().ts_index_set_id_base(self._h, int(base)))
+
+    def set_profiling(self, on: bool) -> None:
+        check(lib().ts_index_set_profiling(self._h, int(on)))
+
+    def scan_time_ms(self):
+        """(mean ms, count) of the scan kernels recorded since the last call."""
+        ms, n = C.c_float(), C.c_int()
+        check(lib().ts_index_scan_time(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     def reset(self) -> None:
         check(lib().ts_index_reset(self._h))
@@ -300,6 +313,14 @@ class TokStore:
 
     def set_id_base(self, base: int) -> None:
         check(lib().ts_tokstore_set_id_base(self._h, int(base)))
+
+    def set_profiling(self, on: bool) -> None:
+        check(lib().ts_tokstore_set_profiling(self._h, int(on)))
+
+    def scan_time_ms(self):
+        ms, n = C.c_float(), C.c_int()
+        check(lib().ts_tokstore_scan_time(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     def reset(self) -> None:
         check(lib().ts_tokstore_reset(self._h))

@@ -43,6 +43,41 @@ static int ensure_bytes(void** p, size_t* cur, size_t need) {
 
 using namespace ts;
 
+namespace {
+// ring of CUDA event pairs around the dominant kernel (measurement aid)
+struct ScanTimer {
+  static constexpr int kMax = 256;
+  bool on = false;
+  int n = 0;
+  cudaEvent_t e0[kMax], e1[kMax];
+  bool made = false;
+  void begin(cudaStream_t st) {
+    if (!on || n >= kMax) return;
+    if (!made) { for (int i = 0; i < kMax; ++i) { cudaEventCreate(&e0[i]); cudaEventCreate(&e1[i]); } made = true; }
+    cudaEventRecord(e0[n], st);
+  }
+  void end(cudaStream_t st) {
+    if (!on || n >= kMax) return;
+    cudaEventRecord(e1[n], st);
+    ++n;
+  }
+  int report(float* mean_ms, int* count) {
+    float tot = 0.f;
+    for (int i = 0; i < n; ++i) {
+      if (cudaEventSynchronize(e1[i]) != cudaSuccess) { set_error("event sync failed"); return TS_ERR_CUDA; }
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0[i], e1[i]);
+      tot += ms;
+    }
+    if (mean_ms) *mean_ms = n ? tot / n : 0.f;
+    if (count) *count = n;
+    n = 0;
+    return TS_OK;
+  }
+  void destroy() { if (made) { for (int i = 0; i < kMax; ++i) { cudaEventDestroy(e0[i]); cudaEventDestroy(e1[i]); } made = false; } }
+};
+}  // namespace
+
 struct ts_index {
   int device, dim, ld, dtype, metric;
   int64_t n, cap, id_base;
@@ -58,6 +93,7 @@ struct ts_index {
   void* tmp1; size_t tmp1_b;
   void* stage; size_t stage_b;       // staging for host inputs (add / search_host)
   void* hout; size_t hout_b;         // device result buffers for search_host
+  ScanTimer* timer;
 };
 
 struct ts_tokstore {
@@ -73,6 +109,7 @@ struct ts_tokstore {
   void* stage; size_t stage_b;
   void* meta; size_t meta_b;         // per-add src offsets scratch / host-variant buffers
   void* hbuf; size_t hbuf_b;
+  ScanTimer* timer;
 };
 
 namespace {
@@ -159,6 +196,7 @@ int ts_index_create(ts_index** out, int device, int dim, int storage_dtype, int 
   h->device = device; h->dim = dim; h->dtype = storage_dtype; h->metric = metric;
   h->ld = row_pitch(dim, storage_dtype);
   h->info = info;
+  h->timer = new ScanTimer();
   if (reserve_rows > 0) {
     h->cap = 0;
     // exact reservation (no doubling) for the first allocation
@@ -180,9 +218,13 @@ int ts_index_destroy(ts_index* h) {
   cudaSetDevice(h->device);
   void* ptrs[] = {h->rows, h->inv_norm, h->qbuf, h->lists, h->partial, h->tmp0, h->tmp1, h->stage, h->hout};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->timer) { h->timer->destroy(); delete h->timer; }
   delete h;
   return TS_OK;
 }
+
+int ts_index_set_profiling(ts_index* h, int enable) { if (!h) return TS_ERR_INVALID; h->timer->on = enable != 0; h->timer->n = 0; return TS_OK; }
+int ts_index_scan_time(ts_index* h, float* mean_ms, int* n) { if (!h) return TS_ERR_INVALID; cudaSetDevice(h->device); return h->timer->report(mean_ms, n); }
 
 int ts_index_add(ts_index* h, const void* rows, int64_t n, int src_dtype, int src_on_device, int normalize, void* stream) {
   if (!h || n < 0 || (n > 0 && !rows)) { set_error("ts_index_add: invalid argument"); return TS_ERR_INVALID; }
@@ -266,7 +308,9 @@ int ts_index_search(ts_index* h, const void* q_dev, int q_dtype, int B, int k, u
     a.lists = (uint64_t*)h->lists; a.lists_keys = lists_keys;
     a.partial = (uint64_t*)h->partial; a.partial_keys = partial_keys;
     int launches = 0;
+    h->timer->begin(st);
     rc = (use == TS_PATH_STREAM) ? launch_s1_stream(a, st, &launches) : launch_s1_umma(a, st, &launches);
+    h->timer->end(st);
     if (rc) return rc;
     rc = launch_merge_keys((const uint64_t*)h->partial, L, Bc, k, h->id_base, (uint64_t*)h->tmp0, (uint64_t*)h->tmp1,
                            out_scores + (size_t)b0 * k, out_ids + (size_t)b0 * k, st, &launches);
@@ -406,6 +450,7 @@ int ts_tokstore_create(ts_tokstore** out, int device, int dim, int storage_dtype
   ts_tokstore* h = new ts_tokstore();
   memset(h, 0, sizeof(*h));
   h->device = device; h->dim = dim; h->dtype = storage_dtype; h->info = info;
+  h->timer = new ScanTimer();
   h->hint_docs = reserve_docs;
   h->hint_rows = reserve_tokens + 8 * reserve_docs;  // every doc is padded to 8 rows
   *out = h;
@@ -417,9 +462,13 @@ int ts_tokstore_destroy(ts_tokstore* h) {
   cudaSetDevice(h->device);
   void* ptrs[] = {h->tok, h->doc_off, h->doc_len, h->qbuf, h->stage, h->meta, h->hbuf};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->timer) { h->timer->destroy(); delete h->timer; }
   delete h;
   return TS_OK;
 }
+
+int ts_tokstore_set_profiling(ts_tokstore* h, int enable) { if (!h) return TS_ERR_INVALID; h->timer->on = enable != 0; h->timer->n = 0; return TS_OK; }
+int ts_tokstore_scan_time(ts_tokstore* h, float* mean_ms, int* n) { if (!h) return TS_ERR_INVALID; cudaSetDevice(h->device); return h->timer->report(mean_ms, n); }
 
 static int tok_reserve(ts_tokstore* h, int64_t docs, int64_t rows, cudaStream_t st) {
   const int64_t hint_docs = h->hint_docs, hint_rows = h->hint_rows;
@@ -539,7 +588,9 @@ int ts_maxsim(ts_tokstore* h, const void* q_tok, int q_dtype, const int32_t* q_l
   a.lq_stride = lq_stride; a.cand = cand; a.n_cand = n_cand; a.C = C; a.mode = mode; a.out = out;
   a.sm_count = h->info.sm_count;
   int launches = 0;
+  h->timer->begin(st);
   rc = launch_maxsim(a, st, &launches);
+  h->timer->end(st);
   h->launches += launches;
   return rc;
 }
