@@ -61,7 +61,7 @@ typedef enum ts_metric { TS_METRIC_IP = 0, TS_METRIC_COSINE = 1 } ts_metric;
 
 /* which Stage-1 scan kernel serves a search call */
 typedef enum ts_path {
-  TS_PATH_AUTO = 0,   /* B <= 4 -> stream, else umma                         */
+  TS_PATH_AUTO = 0,   /* umma for bf16/fp16 storage (faster at every B on B200), stream for fp32 */
   TS_PATH_STREAM = 1, /* CUDA-core 128-bit streaming scan (bandwidth path)   */
   TS_PATH_UMMA = 2    /* TMA -> smem -> tcgen05.mma -> TMEM (tensor path)    */
 } ts_path;

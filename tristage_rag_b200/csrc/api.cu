@@ -91,6 +91,8 @@ struct ts_index {
   void* partial; size_t partial_b;
   void* tmp0; size_t tmp0_b;
   void* tmp1; size_t tmp1_b;
+  void* counts; size_t counts_b;
+  void* pub; size_t pub_b;
   void* stage; size_t stage_b;       // staging for host inputs (add / search_host)
   void* hout; size_t hout_b;         // device result buffers for search_host
   ScanTimer* timer;
@@ -216,7 +218,7 @@ int ts_index_create(ts_index** out, int device, int dim, int storage_dtype, int 
 int ts_index_destroy(ts_index* h) {
   if (!h) return TS_OK;
   cudaSetDevice(h->device);
-  void* ptrs[] = {h->rows, h->inv_norm, h->qbuf, h->lists, h->partial, h->tmp0, h->tmp1, h->stage, h->hout};
+  void* ptrs[] = {h->rows, h->inv_norm, h->qbuf, h->lists, h->partial, h->tmp0, h->tmp1, h->counts, h->pub, h->stage, h->hout};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->timer) { h->timer->destroy(); delete h->timer; }
   delete h;
@@ -275,7 +277,8 @@ int ts_index_search(ts_index* h, const void* q_dev, int q_dtype, int B, int k, u
   cudaStream_t st = (cudaStream_t)stream;
   TS_CUDA_OK(cudaSetDevice(h->device));
   int use = path;
-  if (use == TS_PATH_AUTO) use = (B <= 4 || h->dtype == TS_F32) ? TS_PATH_STREAM : TS_PATH_UMMA;
+  // measured on B200: the TMA/tcgen05 scan streams faster than the CUDA-core scan at every batch size
+  if (use == TS_PATH_AUTO) use = (h->dtype == TS_F32) ? TS_PATH_STREAM : TS_PATH_UMMA;
   if (use == TS_PATH_UMMA && h->dtype == TS_F32) { set_error("umma path needs bf16/fp16 storage"); return TS_ERR_UNSUPPORTED; }
   if (use != TS_PATH_STREAM && use != TS_PATH_UMMA) { set_error("ts_index_search: bad path %d", path); return TS_ERR_INVALID; }
 
@@ -294,27 +297,43 @@ int ts_index_search(ts_index* h, const void* q_dev, int q_dtype, int B, int k, u
     a.rows = h->rows; a.n = h->n; a.dim = h->dim; a.ld = h->ld; a.dtype = h->dtype;
     a.inv_norm = (h->metric == TS_METRIC_COSINE) ? h->inv_norm : nullptr;
     a.q = h->qbuf; a.B = Bc; a.k = k; a.sm_count = h->info.sm_count;
-    int L = 0; size_t lists_keys = 0;
-    rc = (use == TS_PATH_STREAM) ? s1_stream_plan(a, &L, &lists_keys) : s1_umma_plan(a, &L, &lists_keys);
-    if (rc) return rc;
-    if ((rc = ensure_bytes(&h->lists, &h->lists_b, lists_keys * 8))) return rc;
-    const size_t partial_keys = (size_t)L * Bc * k;
-    if ((rc = ensure_bytes(&h->partial, &h->partial_b, partial_keys * 8))) return rc;
-    const size_t tmpk = merge_tmp_keys(L, Bc, k);
-    if (tmpk) {
-      if ((rc = ensure_bytes(&h->tmp0, &h->tmp0_b, tmpk * 8))) return rc;
-      if ((rc = ensure_bytes(&h->tmp1, &h->tmp1_b, tmpk * 8))) return rc;
-    }
-    a.lists = (uint64_t*)h->lists; a.lists_keys = lists_keys;
-    a.partial = (uint64_t*)h->partial; a.partial_keys = partial_keys;
     int launches = 0;
-    h->timer->begin(st);
-    rc = (use == TS_PATH_STREAM) ? launch_s1_stream(a, st, &launches) : launch_s1_umma(a, st, &launches);
-    h->timer->end(st);
-    if (rc) return rc;
-    rc = launch_merge_keys((const uint64_t*)h->partial, L, Bc, k, h->id_base, (uint64_t*)h->tmp0, (uint64_t*)h->tmp1,
-                           out_scores + (size_t)b0 * k, out_ids + (size_t)b0 * k, st, &launches);
-    if (rc) return rc;
+    if (use == TS_PATH_STREAM) {
+      int L = 0; size_t lists_keys = 0;
+      if ((rc = s1_stream_plan(a, &L, &lists_keys))) return rc;
+      if ((rc = ensure_bytes(&h->lists, &h->lists_b, lists_keys * 8))) return rc;
+      const size_t partial_keys = (size_t)L * Bc * k;
+      if ((rc = ensure_bytes(&h->partial, &h->partial_b, partial_keys * 8))) return rc;
+      const size_t tmpk = merge_tmp_keys(L, Bc, k);
+      if (tmpk) {
+        if ((rc = ensure_bytes(&h->tmp0, &h->tmp0_b, tmpk * 8))) return rc;
+        if ((rc = ensure_bytes(&h->tmp1, &h->tmp1_b, tmpk * 8))) return rc;
+      }
+      a.lists = (uint64_t*)h->lists; a.lists_keys = lists_keys;
+      a.partial = (uint64_t*)h->partial; a.partial_keys = partial_keys;
+      h->timer->begin(st);
+      rc = launch_s1_stream(a, st, &launches);
+      h->timer->end(st);
+      if (rc) return rc;
+      rc = launch_merge_keys((const uint64_t*)h->partial, L, Bc, k, h->id_base, (uint64_t*)h->tmp0, (uint64_t*)h->tmp1,
+                             out_scores + (size_t)b0 * k, out_ids + (size_t)b0 * k, st, &launches);
+      if (rc) return rc;
+    } else {
+      UmmaLayout lay{};
+      if ((rc = s1_umma_plan(a, &lay))) return rc;
+      if ((rc = ensure_bytes(&h->lists, &h->lists_b, lay.lists_keys * 8))) return rc;
+      if ((rc = ensure_bytes(&h->counts, &h->counts_b, lay.counts_n * sizeof(int)))) return rc;
+      if ((rc = ensure_bytes(&h->pub, &h->pub_b, lay.pub_n * sizeof(float)))) return rc;
+      a.lists = (uint64_t*)h->lists; a.lists_keys = lay.lists_keys;
+      a.counts = (int*)h->counts; a.pub = (float*)h->pub;
+      h->timer->begin(st);
+      rc = launch_s1_umma(a, lay, st, &launches);
+      h->timer->end(st);
+      if (rc) return rc;
+      rc = launch_merge_lists((const uint64_t*)h->lists, (const int*)h->counts, lay, Bc, k, h->id_base,
+                              out_scores + (size_t)b0 * k, out_ids + (size_t)b0 * k, st, &launches);
+      if (rc) return rc;
+    }
     h->launches += launches;
   }
   return TS_OK;

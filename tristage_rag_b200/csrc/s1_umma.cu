@@ -33,6 +33,8 @@
 // Small batches (B <= 64): the queries are spread over the four TMEM lane
 //   quarters in groups of 8 rows (8-row TMA boxes), so all four epilogue warps
 //   share the list maintenance instead of one.
+#include <stdlib.h>
+
 #include "ts_common.cuh"
 #include "ts_internal.h"
 #include "ts_ptx.cuh"
@@ -43,44 +45,215 @@ namespace {
 using namespace ts::ptx;
 
 constexpr int kThreads = 192;
-constexpr int kStages = 4;
 constexpr int kTileM = 128, kTileN = 256, kChunkK = 64;
 constexpr int kABytes = kTileM * kChunkK * 2;  // 16 KB
 constexpr int kBBytes = kTileN * kChunkK * 2;  // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kRingBytes = 192 * 1024;         // 4 x (A + B) or 3 x (A0 + A1 + B)
 constexpr int kBarBytes = 256;
-constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+constexpr int kSmemBytes = kRingBytes + kBarBytes + 1024;  // + alignment slack
 constexpr int kTmemCols = 512;
+constexpr int kMaxStages = 4;
 
 struct UmmaParams {
   int64_t N;
   int nK, B, k;
   int n_slices, n_tiles;
   int spread, n_qgroups, cap;
-  uint64_t* lists;
-  uint64_t* partial;
+  int dual;        // 1: the CTA owns TWO query tiles (2*mp, 2*mp+1) that share every corpus chunk
+  int dbg_notopk;
+  int mode;        // 0 = threshold pre-pass (first tile of every slice, publishes pub), 1 = scan
+  int jrank;       // j = ceil(k / n_slices) if <= 8, else 0 (threshold sharing off)
+  int bpad;        // row pitch of pub
+  uint64_t* lists; // [grid][rows_per_cta][cap] candidate keys
+  int* counts;     // [grid][rows_per_cta] entries per list (out)
+  float* pub;      // [n_slices][bpad] per-slice j-th best score per query
+  float* tau_g;    // [bpad] min over slices of pub, refreshed by slice 0
   const float* inv_norm;
+  unsigned long long* stats;  // debug: [0] appends [1] prunes [2] slow-path chunks (null = off)
 };
+
+// per-thread state of one query (one TMEM lane of one accumulator)
+struct QState {
+  float tau, tjJ, pub_last;
+  float tj[8];       // best 8 scores appended so far, descending
+  int cnt, q;
+  int n_app, n_prune, n_slow;   // debug counters
+  bool active;
+  uint64_t* lst;
+};
+
+__device__ __forceinline__ float min_over_slices(const UmmaParams& p, int q) {
+  float m = INFINITY;
+  int c = 0;
+  for (; c + 8 <= p.n_slices; c += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(p.pub + (size_t)(c + u) * p.bpad + q);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) m = fminf(m, v[u]);
+  }
+  for (; c < p.n_slices; ++c) m = fminf(m, __ldcg(p.pub + (size_t)c * p.bpad + q));
+  return m;
+}
+
+__device__ __forceinline__ void topj_insert(QState& s, float v, int J) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float hi = fmaxf(s.tj[i], v);
+    v = fminf(s.tj[i], v);
+    s.tj[i] = hi;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i == J - 1) s.tjJ = s.tj[i];
+}
+
+// one accumulator (this warp's 32 lanes x ncols columns) -> candidates of this thread's query
+__device__ __forceinline__ void drain_acc(const UmmaParams& p, QState& s, uint32_t t_addr, int64_t n0, int ncols,
+                                          bool warp_active, bool prepass, int J, int CAP, int lane) {
+  if (!warp_active) return;
+  for (int c0 = 0; c0 < ncols; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_addr + (uint32_t)c0, r);
+    tmem_ld_wait();
+    if (s.active) {
+      const bool whole = (c0 + 32 <= ncols);
+      if (p.inv_norm) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          r[j] = __float_as_uint(__uint_as_float(r[j]) * __ldg(p.inv_norm + n0 + ((c0 + j < ncols) ? c0 + j : 0)));
+      }
+      // fast path: one max over the 32 scores, compared once
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) m = fmaxf(m, (whole || c0 + j < ncols) ? __uint_as_float(r[j]) : -INFINITY);
+      const float thr = prepass ? s.tjJ : s.tau;
+      if (m > thr) {
+        // slow path (a few percent of the chunks): bit mask of the survivors,
+        // then one short loop iteration per survivor.  The 32 scores are
+        // spilled to a local array here so the loop can index them.
+        ++s.n_slow;
+        uint32_t mask = 0;
+        float loc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = __uint_as_float(r[j]);
+          loc[j] = v;
+          mask |= (v > thr && (whole || c0 + j < ncols)) ? (1u << j) : 0u;
+        }
+        while (mask) {
+          const int j = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float v = loc[j];
+          if (prepass) {
+            if (v > s.tjJ) topj_insert(s, v, J);
+          } else {
+            s.lst[s.cnt++] = make_key(v, (uint32_t)(n0 + c0 + j));
+            ++s.n_app;
+            if (J > 0 && v > s.tjJ) topj_insert(s, v, J);
+          }
+        }
+      }
+    }
+    if (!prepass) {
+      unsigned full = __ballot_sync(0xffffffffu, s.active && s.cnt > CAP - 32);
+      while (full) {
+        const int L = __ffs(full) - 1;
+        full &= full - 1;
+        uint64_t* lp = reinterpret_cast<uint64_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(s.lst), L));
+        const int lc = __shfl_sync(0xffffffffu, s.cnt, L);
+        const uint64_t kth = warp_prune_list(lp, lc, p.k, lane, CAP);
+        if (lane == L) { s.cnt = p.k; s.tau = fmaxf(s.tau, key_score(kth)); ++s.n_prune; }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void init_state(const UmmaParams& p, QState& s, int a, int mt0, int quarter, int lane,
+                                           int lane_row, int rows_per_cta, int CAP, bool present) {
+  const int qi = p.spread ? ((((lane >> 3) * 4 + quarter) * 8) + (lane & 7)) : lane_row;
+  s.q = (mt0 + a) * kTileM + qi;
+  s.active = present && s.q < p.B;
+  s.lst = p.lists + ((size_t)blockIdx.x * rows_per_cta + a * kTileM + lane_row) * CAP;
+  s.cnt = 0;
+  s.n_app = s.n_prune = s.n_slow = 0;
+  s.tjJ = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s.tj[i] = -INFINITY;
+  s.tau = p.dbg_notopk ? INFINITY : -INFINITY;
+  s.pub_last = -INFINITY;
+}
+
+// threshold sharing, start of kernel (J > 0)
+__device__ __forceinline__ void start_state(const UmmaParams& p, QState& s, int slice, bool prepass) {
+  if (!s.active) return;
+  if (prepass) {
+    if (slice == 0) p.tau_g[s.q] = -INFINITY;   // reset before the scan kernel reads it
+  } else {
+    // never publish below what the pre-pass already published for this slot
+    s.pub_last = __ldcg(p.pub + (size_t)slice * p.bpad + s.q);
+    const float m = min_over_slices(p, s.q);
+    if (slice == 0) p.tau_g[s.q] = m;
+    if (!p.dbg_notopk) s.tau = nextafterf(m, -INFINITY);   // keep rows that tie with the bound
+  }
+}
+
+// threshold sharing, after every tile of the scan (J > 0)
+__device__ __forceinline__ void share_state(const UmmaParams& p, QState& s, int slice, int iter) {
+  if (!s.active) return;
+  if (s.tjJ > s.pub_last) { p.pub[(size_t)slice * p.bpad + s.q] = s.tjJ; s.pub_last = s.tjJ; }
+  float m;
+  if (slice == 0 && (iter & 1)) {          // designated refresher of the shared bound
+    m = min_over_slices(p, s.q);
+    p.tau_g[s.q] = m;
+  } else {
+    m = __ldcg(p.tau_g + s.q);
+  }
+  if (!p.dbg_notopk) s.tau = fmaxf(s.tau, nextafterf(m, -INFINITY));
+}
+
+__device__ __forceinline__ void finish_state(const UmmaParams& p, QState& s, int a, int slice, bool prepass, int J,
+                                             int rows_per_cta, int lane_row, bool present) {
+  if (!present) return;
+  if (prepass) {
+    if (s.active && J > 0) p.pub[(size_t)slice * p.bpad + s.q] = s.tjJ;
+  } else {
+    // lists stay unsorted: the select kernel merges them (no in-kernel final sort)
+    p.counts[(size_t)blockIdx.x * rows_per_cta + a * kTileM + lane_row] = s.active ? s.cnt : 0;
+    if (p.stats && s.active) {
+      atomicAdd(p.stats + 0, (unsigned long long)s.n_app);
+      atomicAdd(p.stats + 1, (unsigned long long)s.n_prune);
+      atomicAdd(p.stats + 2, (unsigned long long)s.n_slow);
+    }
+  }
+}
 
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1)
     s1_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ8,
                    const __grid_constant__ CUtensorMap tmX, const UmmaParams p) {
   const int CAP = p.cap;
+  const bool dual = p.dual != 0;
+  const int n_stages = dual ? 3 : 4;
+  const int stage_bytes = dual ? (2 * kABytes + kBBytes) : (kABytes + kBBytes);
+  const int b_off = dual ? 2 * kABytes : kABytes;     // B chunk offset inside a stage
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* full_bar = bars;                  // [kStages] TMA -> MMA
-  uint64_t* empty_bar = bars + kStages;       // [kStages] MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * kStages;   // [2] MMA -> epilogue
-  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes);
+  uint64_t* full_bar = bars;                        // [kMaxStages] TMA -> MMA
+  uint64_t* empty_bar = bars + kMaxStages;          // [kMaxStages] MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;      // [2] MMA -> epilogue (per accumulator)
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2; // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x / p.n_slices, slice = blockIdx.x % p.n_slices;
+  const int mg = blockIdx.x / p.n_slices, slice = blockIdx.x % p.n_slices;   // mg: query tile (or pair of tiles)
+  const int mt0 = dual ? 2 * mg : mg;
+  // the pre-pass looks at the first tile of the slice only
+  const int t_end = (p.mode == 0) ? ((slice + 1 < p.n_tiles) ? slice + 1 : p.n_tiles) : p.n_tiles;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     fence_mbar_init();
   }
@@ -97,14 +270,15 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       // ------------------------------------------------ TMA producer ------
       prefetch_tmap(&tmQ); prefetch_tmap(&tmQ8); prefetch_tmap(&tmX);
-      const uint32_t tx = (p.spread ? (uint32_t)p.n_qgroups * 1024u : (uint32_t)kABytes) + (uint32_t)kBBytes;
+      const bool has1 = dual && ((mt0 + 1) * kTileM < p.B);
+      const uint32_t tx = (p.spread ? (uint32_t)p.n_qgroups * 1024u : (uint32_t)kABytes * (has1 ? 2u : 1u)) + (uint32_t)kBBytes;
       const uint64_t x_policy = (gridDim.x > (unsigned)p.n_slices) ? kEvictNormal : kEvictFirst;
       int stage = 0; uint32_t phase = 0;
-      for (int t = slice; t < p.n_tiles; t += p.n_slices) {
+      for (int t = slice; t < t_end; t += p.n_slices) {
         for (int kc = 0; kc < p.nK; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
-          unsigned char* sA = smem + stage * kStageBytes;
-          unsigned char* sB = sA + kABytes;
+          unsigned char* sA = smem + stage * stage_bytes;
+          unsigned char* sB = sA + b_off;
           mbar_arrive_expect_tx(&full_bar[stage], tx);
           if (p.spread) {
             for (int g = 0; g < p.n_qgroups; ++g) {
@@ -112,10 +286,11 @@ __global__ void __launch_bounds__(kThreads, 1)
               tma_load_2d(sA + row * 128, &tmQ8, &full_bar[stage], kc * kChunkK, g * 8, kEvictLast);
             }
           } else {
-            tma_load_2d(sA, &tmQ, &full_bar[stage], kc * kChunkK, mt * kTileM, kEvictLast);
+            tma_load_2d(sA, &tmQ, &full_bar[stage], kc * kChunkK, mt0 * kTileM, kEvictLast);
+            if (has1) tma_load_2d(sA + kABytes, &tmQ, &full_bar[stage], kc * kChunkK, (mt0 + 1) * kTileM, kEvictLast);
           }
           tma_load_2d(sB, &tmX, &full_bar[stage], kc * kChunkK, t * kTileN, x_policy);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -124,87 +299,89 @@ __global__ void __launch_bounds__(kThreads, 1)
       // ------------------------------------------------ MMA issuer --------
       constexpr uint32_t idesc = make_idesc_f16(kTileM, kTileN, BF16);
       int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int t = slice; t < p.n_tiles; t += p.n_slices) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 2);
+      int iter = 0;
+      for (int t = slice; t < t_end; t += p.n_slices, ++iter) {
+        // single: accumulators alternate per tile.  dual: both are written every tile.
+        const int acc = dual ? 0 : (iter & 1);
+        const uint32_t par = dual ? (uint32_t)(iter & 1) : (uint32_t)((iter >> 1) & 1);
+        mbar_wait(&tempty_bar[acc], par ^ 1u, 2);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTileN);
         for (int kc = 0; kc < p.nK; ++kc) {
           mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint64_t adesc = make_desc_kmajor_sw128(a_addr);
-          const uint64_t bdesc = make_desc_kmajor_sw128(a_addr + kABytes);
+          const uint64_t bdesc = make_desc_kmajor_sw128(a_addr + b_off);
 #pragma unroll
           for (int ks = 0; ks < kChunkK / 16; ++ks)
-            umma_f16_ss(d_tmem, adesc + ks * kDescKStep, bdesc + ks * kDescKStep, idesc, (kc | ks) ? 1u : 0u);
+            umma_f16_ss(tmem_base + (uint32_t)(acc * kTileN), adesc + ks * kDescKStep, bdesc + ks * kDescKStep, idesc,
+                        (kc | ks) ? 1u : 0u);
+          if (dual) {
+            if (kc == 0) { mbar_wait(&tempty_bar[1], par ^ 1u, 5); tc_fence_after(); }
+            const uint64_t adesc1 = make_desc_kmajor_sw128(a_addr + kABytes);
+#pragma unroll
+            for (int ks = 0; ks < kChunkK / 16; ++ks)
+              umma_f16_ss(tmem_base + (uint32_t)kTileN, adesc1 + ks * kDescKStep, bdesc + ks * kDescKStep, idesc,
+                          (kc | ks) ? 1u : 0u);
+          }
           umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[acc]);      // accumulator complete
-        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        umma_commit(&tfull_bar[acc]);      // accumulator(s) complete
+        if (dual) umma_commit(&tfull_bar[1]);
       }
     }
   } else {
     // -------------------------------------------------- epilogue ----------
     const int quarter = warp & 3;
     const int lane_row = quarter * 32 + lane;
-    int qi;
-    if (p.spread) qi = (((lane >> 3) * 4 + quarter) * 8) + (lane & 7);
-    else qi = lane_row;
-    const int q_global = mt * kTileM + qi;
-    const bool active = q_global < p.B;
-    const bool warp_active = __any_sync(0xffffffffu, active);
-    uint64_t* lst = p.lists + ((size_t)blockIdx.x * kTileM + lane_row) * CAP;
-    float tau = -INFINITY;
-    int cnt = 0;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int t = slice; t < p.n_tiles; t += p.n_slices) {
-      mbar_wait(&tfull_bar[acc], acc_phase, 4);
-      tc_fence_after();
-      if (warp_active) {
-        const int64_t n0 = (int64_t)t * kTileN;
-        const int ncols = (int)((p.N - n0) < (int64_t)kTileN ? (p.N - n0) : (int64_t)kTileN);
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kTileN);
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_addr + (uint32_t)c0, r);
-          tmem_ld_wait();
-          if (active) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float s = __uint_as_float(r[j]);
-              const int col = c0 + j;
-              if (p.inv_norm) s *= __ldg(p.inv_norm + n0 + (col < ncols ? col : 0));
-              if (col < ncols && s > tau) lst[cnt++] = make_key(s, (uint32_t)(n0 + col));
-            }
-          }
-          unsigned full = __ballot_sync(0xffffffffu, active && cnt > CAP - 32);
-          while (full) {
-            const int L = __ffs(full) - 1;
-            full &= full - 1;
-            uint64_t* lp = reinterpret_cast<uint64_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(lst), L));
-            const int lc = __shfl_sync(0xffffffffu, cnt, L);
-            const uint64_t kth = warp_prune_list(lp, lc, p.k, lane, CAP);
-            if (lane == L) { cnt = p.k; tau = key_score(kth); }
-          }
-        }
+    const int rows_per_cta = dual ? 2 * kTileM : kTileM;
+    const bool prepass = (p.mode == 0);
+    const int J = p.jrank;
+    QState s0, s1;
+    init_state(p, s0, 0, mt0, quarter, lane, lane_row, rows_per_cta, CAP, true);
+    init_state(p, s1, 1, mt0, quarter, lane, lane_row, rows_per_cta, CAP, dual);
+    if (J > 0) {
+      start_state(p, s0, slice, prepass);
+      start_state(p, s1, slice, prepass);
+    }
+
+    const bool wact0 = __any_sync(0xffffffffu, s0.active);
+    const bool wact1 = __any_sync(0xffffffffu, s1.active);
+    int iter = 0;
+    for (int t = slice; t < t_end; t += p.n_slices, ++iter) {
+      const int64_t n0 = (int64_t)t * kTileN;
+      const int ncols = (int)((p.N - n0) < (int64_t)kTileN ? (p.N - n0) : (int64_t)kTileN);
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      if (!dual) {
+        const int acc = iter & 1;
+        mbar_wait(&tfull_bar[acc], (uint32_t)((iter >> 1) & 1), 4);
+        tc_fence_after();
+        drain_acc(p, s0, lane_addr + (uint32_t)(acc * kTileN), n0, ncols, wact0, prepass, J, CAP, lane);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      } else {
+        mbar_wait(&tfull_bar[0], (uint32_t)(iter & 1), 4);
+        tc_fence_after();
+        drain_acc(p, s0, lane_addr, n0, ncols, wact0, prepass, J, CAP, lane);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[0]);
+        mbar_wait(&tfull_bar[1], (uint32_t)(iter & 1), 6);
+        tc_fence_after();
+        drain_acc(p, s1, lane_addr + (uint32_t)kTileN, n0, ncols, wact1, prepass, J, CAP, lane);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[1]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      if (!prepass && J > 0) {
+        share_state(p, s0, slice, iter);
+        share_state(p, s1, slice, iter);
+      }
     }
-    // final flush: sort every list, emit partial[slice][q][0..k)
-    unsigned act = __ballot_sync(0xffffffffu, active);
-    while (act) {
-      const int L = __ffs(act) - 1;
-      act &= act - 1;
-      uint64_t* lp = reinterpret_cast<uint64_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(lst), L));
-      const int lc = __shfl_sync(0xffffffffu, cnt, L);
-      const int qL = __shfl_sync(0xffffffffu, q_global, L);
-      warp_prune_list(lp, lc, p.k, lane, CAP, p.partial + ((size_t)slice * p.B + qL) * p.k);
-    }
+    finish_state(p, s0, 0, slice, prepass, J, rows_per_cta, lane_row, true);
+    finish_state(p, s1, 1, slice, prepass, J, rows_per_cta, lane_row, dual);
   }
 
   tc_fence_before();
@@ -247,56 +424,87 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, in
 }
 
 namespace {
-struct UmmaPlan { int n_mt, n_slices, n_tiles, grid; };
+struct UmmaPlan { int n_mt, n_mg, dual, n_slices, n_tiles, grid; };
 UmmaPlan umma_plan(const ScanArgs& a) {
   UmmaPlan pl;
   pl.n_mt = (a.B + kTileM - 1) / kTileM;
+  // Two query tiles per CTA sharing each corpus chunk halve the L2->SM traffic, but the two
+  // accumulators then cannot be double buffered against the epilogue; measured on B200 the
+  // single-tile layout is faster (19.2 vs 21.5 ms at B=1024, 10M x 1024), so it is opt-in.
+  pl.dual = (pl.n_mt >= 2 && getenv("TS_DUAL")) ? 1 : 0;
+  pl.n_mg = pl.dual ? (pl.n_mt + 1) / 2 : pl.n_mt;
   pl.n_tiles = (int)((a.n + kTileN - 1) / kTileN);
-  int s = a.sm_count / pl.n_mt;
+  int s = a.sm_count / pl.n_mg;
   if (s < 1) s = 1;
   if (s > pl.n_tiles) s = pl.n_tiles;
   pl.n_slices = s;
-  pl.grid = pl.n_mt * pl.n_slices;
+  pl.grid = pl.n_mg * pl.n_slices;
   return pl;
 }
 }  // namespace
 
-int s1_umma_plan(const ScanArgs& a, int* L, size_t* lists_keys) {
+int s1_umma_plan(const ScanArgs& a, UmmaLayout* lay) {
   if (a.dtype != TS_BF16 && a.dtype != TS_F16) { set_error("umma path needs bf16/fp16 storage"); return TS_ERR_UNSUPPORTED; }
   if (a.B > 1024) { set_error("umma path: at most 1024 queries per launch"); return TS_ERR_INVALID; }
   const UmmaPlan pl = umma_plan(a);
-  *L = pl.n_slices;
-  *lists_keys = (size_t)pl.grid * kTileM * cap_for_k(a.k);
+  lay->n_slices = pl.n_slices;
+  lay->n_mt = pl.n_mt;
+  lay->dual = pl.dual;
+  lay->rows_per_cta = pl.dual ? 2 * kTileM : kTileM;
+  lay->grid = pl.grid;
+  lay->cap = cap_for_k(a.k);
+  lay->spread = (a.B <= 64 && !getenv("TS_DBG_NOSPREAD")) ? 1 : 0;
+  lay->bpad = pl.n_mt * kTileM;
+  lay->lists_keys = (size_t)pl.grid * lay->rows_per_cta * lay->cap;
+  lay->counts_n = (size_t)pl.grid * lay->rows_per_cta;
+  lay->pub_n = (size_t)(pl.n_slices + 1) * lay->bpad;   // + one row for tau_g
+  const int j = (a.k + pl.n_slices - 1) / pl.n_slices;
+  lay->jrank = (j <= 8 && !getenv("TS_DBG_NOSHARE")) ? j : 0;
   return TS_OK;
 }
 
-int launch_s1_umma(const ScanArgs& a, cudaStream_t st, int* launches) {
-  int L; size_t lk;
-  int rc = s1_umma_plan(a, &L, &lk);
-  if (rc) return rc;
-  const UmmaPlan pl = umma_plan(a);
+int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, int* launches) {
+  int rc;
   CUtensorMap tmQ, tmQ8, tmX;
   if ((rc = make_tmap_2d(&tmQ, a.q, a.dtype, a.B, a.dim, a.ld, kTileM))) return rc;
   if ((rc = make_tmap_2d(&tmQ8, a.q, a.dtype, a.B, a.dim, a.ld, 8))) return rc;
   if ((rc = make_tmap_2d(&tmX, a.rows, a.dtype, a.n, a.dim, a.ld, kTileN))) return rc;
   UmmaParams p{};
   p.N = a.n; p.nK = (a.dim + kChunkK - 1) / kChunkK; p.B = a.B; p.k = a.k;
-  p.n_slices = pl.n_slices; p.n_tiles = pl.n_tiles;
-  p.spread = (a.B <= 64) ? 1 : 0;
+  p.n_slices = lay.n_slices; p.n_tiles = (int)((a.n + kTileN - 1) / kTileN);
+  p.spread = lay.spread;
   p.n_qgroups = (a.B + 7) / 8;
-  p.cap = cap_for_k(a.k);
-  p.lists = a.lists; p.partial = a.partial; p.inv_norm = a.inv_norm;
+  p.cap = lay.cap;
+  p.dbg_notopk = getenv("TS_DBG_NOTOPK") ? 1 : 0;
+  p.jrank = lay.jrank; p.bpad = lay.bpad; p.dual = lay.dual;
+  p.lists = a.lists; p.counts = a.counts; p.pub = a.pub; p.tau_g = a.pub + (size_t)lay.n_slices * lay.bpad;
+  p.inv_norm = a.inv_norm;
+  static unsigned long long* d_stats = nullptr;
+  if (getenv("TS_DBG_STATS")) {
+    if (!d_stats) cudaMalloc((void**)&d_stats, 32);
+    cudaMemsetAsync(d_stats, 0, 32, st);
+    p.stats = d_stats;
+  }
   const bool bf16 = a.dtype == TS_BF16;
-#define TS_LAUNCH(BF)                                                                                 \
-  do {                                                                                                     \
-    auto kern = s1_umma_kernel<BF>;                                                                   \
-    TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));       \
-    kern<<<pl.grid, kThreads, kSmemBytes, st>>>(tmQ, tmQ8, tmX, p);                                        \
-  } while (0)
-  if (bf16) TS_LAUNCH(true); else TS_LAUNCH(false);
-#undef TS_LAUNCH
+  auto kern = bf16 ? s1_umma_kernel<true> : s1_umma_kernel<false>;
+  TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  if (p.jrank > 0) {
+    p.mode = 0;   // threshold pre-pass over the first tile of every slice
+    kern<<<lay.grid, kThreads, kSmemBytes, st>>>(tmQ, tmQ8, tmX, p);
+    TS_CUDA_OK(cudaGetLastError());
+    if (launches) ++*launches;
+  }
+  p.mode = 1;
+  kern<<<lay.grid, kThreads, kSmemBytes, st>>>(tmQ, tmQ8, tmX, p);
   TS_CUDA_OK(cudaGetLastError());
   if (launches) ++*launches;
+  if (p.stats) {
+    unsigned long long h[4];
+    cudaMemcpyAsync(h, d_stats, 32, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[ts stats] B=%d k=%d grid=%d slices=%d dual=%d J=%d: appends=%llu (%.1f/list) prunes=%llu slow_chunks=%llu\n", a.B, a.k, lay.grid,
+            lay.n_slices, lay.dual, lay.jrank, h[0], (double)h[0] / ((double)lay.n_slices * a.B), h[1], h[2]);
+  }
   return TS_OK;
 }
 

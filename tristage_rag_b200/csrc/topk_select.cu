@@ -21,7 +21,8 @@ namespace {
 constexpr int kSelThreads = 512;
 constexpr int kSelCap = 4096;  // keys of shared memory per CTA (32 KB)
 
-enum SelMode { kKeys = 0, kPairs = 1, kRank = 2 };
+enum SelMode { kKeys = 0, kPairs = 1, kRank = 2, kLists = 3 };
+constexpr int kMaxLists = 256;
 
 struct SelectParams {
   int mode;
@@ -36,20 +37,42 @@ struct SelectParams {
   int64_t* out_ids;       // final kKeys / kPairs
   int32_t* out_pos;       // final kRank
   int64_t id_base;
+  // kLists: unsorted candidate lists of the umma scan, lists[(cta*128 + row)*cap .. +counts[cta*128+row])
+  const int* counts;
+  int n_slices, spread, cap, dual, rows_per_cta;
 };
 
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
   extern __shared__ __align__(16) uint64_t sbuf[];
+  __shared__ int pre[kMaxLists + 1];
   const int b = blockIdx.x, g = blockIdx.y;
   int total;
   const int l0 = g * p.group;
-  if (p.mode == kRank) {
+  size_t list_row0 = 0;   // kLists: (first CTA of this query's m-tile)*128 + this query's TMEM lane
+  if (p.mode == kLists) {
+    const int mt = b >> 7, qi = b & 127;
+    int row = qi;
+    if (p.spread) { const int grp = qi >> 3; row = ((grp & 3) * 32) + ((grp >> 2) * 8) + (qi & 7); }
+    const int mg = p.dual ? (mt >> 1) : mt;                 // CTA group owning this query tile
+    list_row0 = (size_t)mg * p.n_slices * p.rows_per_cta + (p.dual ? (mt & 1) * 128 : 0) + row;
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      for (int l = 0; l < p.n_slices; ++l) { pre[l] = acc; acc += min(max(p.counts[list_row0 + (size_t)l * p.rows_per_cta], 0), p.cap); }
+      pre[p.n_slices] = acc;
+    }
+    __syncthreads();
+    total = pre[p.n_slices];
+  } else if (p.mode == kRank) {
     total = p.n_cand ? min(max(p.n_cand[b], 0), p.C) : p.C;
   } else {
     total = (min(p.L, l0 + p.group) - l0) * p.k_in;
   }
   auto load = [&](int i) -> uint64_t {
-    if (p.mode == kKeys) {
+    if (p.mode == kLists) {
+      int lo = 0, hi = p.n_slices;            // largest l with pre[l] <= i
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= i) lo = mid; else hi = mid; }
+      return __ldcg(p.keys + (list_row0 + (size_t)lo * p.rows_per_cta) * p.cap + (i - pre[lo]));
+    } else if (p.mode == kKeys) {
       const int l = l0 + i / p.k_in, r = i % p.k_in;
       return p.keys[((size_t)l * p.B + b) * p.k_in + r];
     } else if (p.mode == kPairs) {
@@ -78,7 +101,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     } else {
       p.out_scores[o] = key_score(key);
       const uint32_t idx = key_idx(key);
-      if (p.mode == kKeys) {
+      if (p.mode == kKeys || p.mode == kLists) {
         p.out_ids[o] = p.id_base + (int64_t)idx;
       } else if (p.mode == kPairs) {
         const int l = idx / p.k_in, r2 = idx % p.k_in;
@@ -129,6 +152,20 @@ int launch_merge_keys(const uint64_t* keys, int L, int B, int k, int64_t id_base
   }
   SelectParams p{};
   p.mode = kKeys; p.keys = cur; p.L = L; p.B = B; p.k_in = k; p.group = L; p.k_out = k;
+  p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids; p.id_base = id_base;
+  int rc = launch_select(p, 1, st);
+  if (rc) return rc;
+  if (launches) ++*launches;
+  return TS_OK;
+}
+
+int launch_merge_lists(const uint64_t* lists, const int* counts, const UmmaLayout& lay, int B, int k, int64_t id_base,
+                       float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches) {
+  if (k <= 0 || k > TS_MAX_K || B <= 0 || lay.n_slices > kMaxLists) { set_error("merge_lists: bad arguments"); return TS_ERR_INVALID; }
+  SelectParams p{};
+  p.mode = kLists; p.keys = lists; p.counts = counts; p.n_slices = lay.n_slices; p.spread = lay.spread; p.cap = lay.cap;
+  p.dual = lay.dual; p.rows_per_cta = lay.rows_per_cta;
+  p.L = lay.n_slices; p.B = B; p.k_in = k; p.group = lay.n_slices; p.k_out = k;
   p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids; p.id_base = id_base;
   int rc = launch_select(p, 1, st);
   if (rc) return rc;

@@ -50,15 +50,22 @@ struct ScanArgs {
   int B, k;
   uint64_t* lists;        // scratch candidate lists
   size_t lists_keys;      // capacity in keys
-  uint64_t* partial;      // out: [L][B][k] keys
+  uint64_t* partial;      // stream path out: [L][B][k] keys
   size_t partial_keys;    // capacity in keys
+  int* counts;            // umma path out: entries per candidate list
+  float* pub;             // umma path scratch: published per-slice thresholds
   int sm_count;
+};
+// where the umma scan leaves its candidates (consumed by launch_merge_lists)
+struct UmmaLayout {
+  int n_slices, n_mt, grid, cap, spread, bpad, jrank, dual, rows_per_cta;
+  size_t lists_keys, counts_n, pub_n;
 };
 // number of partial lists L a scan will emit / scratch it needs
 int s1_stream_plan(const ScanArgs& a, int* L, size_t* lists_keys);
-int s1_umma_plan(const ScanArgs& a, int* L, size_t* lists_keys);
+int s1_umma_plan(const ScanArgs& a, UmmaLayout* lay);
 int launch_s1_stream(const ScanArgs& a, cudaStream_t st, int* launches);
-int launch_s1_umma(const ScanArgs& a, cudaStream_t st, int* launches);
+int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, int* launches);
 
 // ---- top-k selection / merge ----------------------------------------------
 // keys [L][B][k] -> final (scores, ids) [B][k]; tmp0/tmp1 each hold
@@ -66,6 +73,9 @@ int launch_s1_umma(const ScanArgs& a, cudaStream_t st, int* launches);
 int launch_merge_keys(const uint64_t* keys, int L, int B, int k, int64_t id_base, uint64_t* tmp0, uint64_t* tmp1,
                       float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches);
 size_t merge_tmp_keys(int L, int B, int k);
+// unsorted per-(CTA, query) candidate lists of the umma scan -> final (scores, ids) [B][k]
+int launch_merge_lists(const uint64_t* lists, const int* counts, const UmmaLayout& lay, int B, int k, int64_t id_base,
+                       float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches);
 int launch_merge_pairs(const float* scores, const int64_t* ids, int L, int B, int k, float* out_scores,
                        int64_t* out_ids, cudaStream_t st);
 int launch_rank_desc(const float* scores, const int32_t* n_cand, int B, int C, int top_k, float* out_scores,
