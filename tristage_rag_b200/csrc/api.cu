@@ -330,7 +330,7 @@ int ts_index_search(ts_index* h, const void* q_dev, int q_dtype, int B, int k, u
       rc = launch_s1_umma(a, lay, st, &launches);
       h->timer->end(st);
       if (rc) return rc;
-      rc = launch_merge_lists((const uint64_t*)h->lists, (const int*)h->counts, lay, Bc, k, h->id_base,
+      rc = launch_merge_lists((const uint64_t*)h->lists, (const int*)h->counts, (const float*)h->pub, lay, Bc, k, h->id_base,
                               out_scores + (size_t)b0 * k, out_ids + (size_t)b0 * k, st, &launches);
       if (rc) return rc;
     }

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128)
 
 // ========================================================== tensor path ====
 constexpr int kThreads = 192;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kTileM = 128, kTileN = 256, kChunkK = 64;
 constexpr int kABytes = kTileM * kChunkK * 2;
 constexpr int kBBytes = kTileN * kChunkK * 2;
@@ -120,7 +120,8 @@ struct TileMeta {
   int pad2_[3];
 };
 
-constexpr int kMvalsBytes = kMaxDocsPerTile * kTileM * 4;  // 16 KB
+constexpr int kMvalsOne = kMaxDocsPerTile * kTileM;         // floats per buffer
+constexpr int kMvalsBytes = 2 * kMvalsOne * 4;             // two buffers, 32 KB
 constexpr int kMetaBytes = kMetaSlots * (int)sizeof(TileMeta);
 constexpr int kBarBytes = 512;
 constexpr int kSmemBytes = kStages * kStageBytes + kMvalsBytes + kMetaBytes + kBarBytes + 1024;
@@ -143,13 +144,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1)
-    maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmQ8, const __grid_constant__ CUtensorMap tmQ128,
+    maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmQ8, const __grid_constant__ CUtensorMap tmQ32,
+                       const __grid_constant__ CUtensorMap tmQ128,
                        const __grid_constant__ CUtensorMap tmT8, const __grid_constant__ CUtensorMap tmT16,
                        const __grid_constant__ CUtensorMap tmT32, const __grid_constant__ CUtensorMap tmT64,
                        const __grid_constant__ CUtensorMap tmT128, const MaxSimParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* mvals = reinterpret_cast<float*>(smem + kStages * kStageBytes);                 // [32][128]
+  float* mvals_base = reinterpret_cast<float*>(smem + kStages * kStageBytes);           // [2][32][128]
   TileMeta* metas = reinterpret_cast<TileMeta*>(smem + kStages * kStageBytes + kMvalsBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kMvalsBytes + kMetaBytes);
   uint64_t* full_bar = bars;                           // [kStages]
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 0) {
     // ------------------------------------------ producer (whole warp) -----
     if (lane == 0) {
-      prefetch_tmap(&tmQ8); prefetch_tmap(&tmQ128); prefetch_tmap(&tmT8); prefetch_tmap(&tmT16);
+      prefetch_tmap(&tmQ8); prefetch_tmap(&tmQ32); prefetch_tmap(&tmQ128); prefetch_tmap(&tmT8); prefetch_tmap(&tmT16);
       prefetch_tmap(&tmT32); prefetch_tmap(&tmT64); prefetch_tmap(&tmT128);
     }
     int stage = 0; uint32_t phase = 0;
@@ -193,14 +195,19 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_arrive(&mfull_bar[seq % kMetaSlots]);   // release meta to MMA + epilogue
         const int lq = m->lq;
         const int a_groups = (lq + 7) >> 3;
+        const bool rep4 = lq <= 32;          // query tokens replicated into all four TMEM lane quarters
         const bool a_boxes8 = lq <= 64;
-        const uint32_t tx = (a_boxes8 ? (uint32_t)a_groups * 1024u : (uint32_t)kABytes) + (uint32_t)m->used * 128u;
+        const uint32_t tx = (rep4 ? (uint32_t)kABytes : a_boxes8 ? (uint32_t)a_groups * 1024u : (uint32_t)kABytes) +
+                            (uint32_t)m->used * 128u;
         for (int kc = 0; kc < p.nK; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1u, 11);
           unsigned char* sA = smem + stage * kStageBytes;
           unsigned char* sB = sA + kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], tx);
-          if (a_boxes8) {
+          if (rep4) {
+            for (int g = 0; g < 4; ++g)
+              tma_load_2d(sA + g * 4096, &tmQ32, &full_bar[stage], kc * kChunkK, m->q_row, kEvictLast);
+          } else if (a_boxes8) {
             for (int g = 0; g < a_groups; ++g)
               tma_load_2d(sA + g * 1024, &tmQ8, &full_bar[stage], kc * kChunkK, m->q_row + g * 8, kEvictLast);
           } else {
@@ -228,19 +235,29 @@ __global__ void __launch_bounds__(kThreads, 1)
       return &metas[slot];
     };
 
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int b = item / p.n_chunks, j0 = (item % p.n_chunks) * kItemCands;
+    // candidate lookup (one per lane) for a work item; the loads of item i+1
+    // are issued before item i is packed so their latency hides behind the TMA issue
+    struct Look { bool valid; long long off; int len; int lq; };
+    auto lookup = [&](int item) -> Look {
+      Look L{false, 0, 0, 1};
+      if (item >= p.n_items) return L;
+      const int b = item / p.n_chunks, j = (item % p.n_chunks) * kItemCands + lane;
       const int nc = p.n_cand ? min(max(p.n_cand[b], 0), p.C) : p.C;
-      const int lq = p.q_len ? min(max(p.q_len[b], 1), min(p.lq_stride, kTileM)) : min(p.lq_stride, kTileM);
-      // one candidate per lane: look up offset / length
-      const int j = j0 + lane;
-      bool valid = false; long long off = 0; int len = 0;
+      L.lq = p.q_len ? min(max(p.q_len[b], 1), min(p.lq_stride, kTileM)) : min(p.lq_stride, kTileM);
       if (j < nc) {
         const int64_t id = p.cand[(size_t)b * p.C + j] - p.id_base;
-        if (id >= 0 && id < p.ndocs) { off = p.doc_off[id]; len = p.doc_len[id]; valid = len > 0; }
+        if (id >= 0 && id < p.ndocs) { L.off = p.doc_off[id]; L.len = p.doc_len[id]; L.valid = L.len > 0; }
       }
+      return L;
+    };
+    Look cur = lookup(blockIdx.x);
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const Look nxt = lookup(item + gridDim.x);
+      const int b = item / p.n_chunks, j0 = (item % p.n_chunks) * kItemCands;
+      const int lq = cur.lq;
+      const bool valid = cur.valid; const long long off = cur.off; const int len = cur.len;
       unsigned vmask = __ballot_sync(0xffffffffu, valid);
-      if (!vmask) continue;
+      if (!vmask) { cur = nxt; continue; }
       TileMeta* m = begin_tile();
       int cols = 0, nd = 0;
       while (vmask) {
@@ -265,6 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       if (lane == 0) { m->used = cols; m->ndocs = nd; m->lq = lq; m->q_row = b * p.lq_stride; }
       emit_tile(m);
+      cur = nxt;
     }
     // end-of-work sentinel
     {
@@ -306,6 +324,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     // -------------------------------------------------- epilogue ----------
+    // lq <= 32: the query tokens sit in ALL four lane quarters (rep4), so warp
+    // (quarter q) owns columns [64q, 64q+64) of the tile and the four warps
+    // split the drain.  lq > 32: tokens span the quarters, every warp walks
+    // all columns of its 32 tokens.  Per-doc partial maxima meet in mvals
+    // (double buffered: one named barrier per tile).
     const int quarter = warp & 3;
     const int ew = warp - 2;  // 0..3: finalize docs d with d % 4 == ew
     const int lane_row = quarter * 32 + lane;
@@ -317,71 +340,92 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int used = m->used;
       if (used == 0) break;
       const int nd = m->ndocs, lq = m->lq;
+      const bool rep4 = lq <= 32;
+      float* mvals = mvals_base + (seq & 1u) * kMvalsOne;
       mbar_wait(&tfull_bar[acc], acc_phase, 32);
       tc_fence_after();
-      const bool warp_active = quarter * 32 < lq;
+      const int c_lo = rep4 ? quarter * 64 : 0;
+      const int c_hi = rep4 ? ((used < c_lo + 64) ? used : c_lo + 64) : used;
+      const bool warp_active = rep4 ? true : (quarter * 32 < lq);
       if (warp_active) {
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kTileN);
-        int d = 0;
-        int seg_end = m->seg_col[0] + m->seg_len[0];          // first masked column of doc d
-        int seg_next = m->seg_col[0] + ((m->seg_len[0] + 7) & ~7);  // first column of doc d+1
-        float best = -INFINITY;
-        for (int c0 = 0; c0 < used; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_addr + (uint32_t)c0, r);
-          tmem_ld_wait();
+        // docs that do not touch this warp's column range contribute -inf
+        int d = -1;
+        for (int dd = 0; dd < nd; ++dd) {
+          const int col = m->seg_col[dd];
+          const int nxt = col + ((m->seg_len[dd] + 7) & ~7);
+          if (nxt <= c_lo || col >= c_hi) mvals[dd * kTileM + lane_row] = -INFINITY;
+          else if (d < 0) d = dd;                         // first doc overlapping the range
+        }
+        if (d >= 0) {
+          const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kTileN);
+          int seg_end = m->seg_col[d] + m->seg_len[d];                 // first masked column of doc d
+          int seg_next = m->seg_col[d] + ((m->seg_len[d] + 7) & ~7);   // first column of doc d+1
+          float best = -INFINITY;
+          for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_addr + (uint32_t)c0, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int cu = c0 + u * 8;
-            if (cu < used) {                   // warp-uniform
-              if (cu >= seg_next) {            // warp-uniform: next doc starts at this 8-column unit
-                mvals[d * kTileM + lane_row] = best;
-                ++d;
-                best = -INFINITY;
-                seg_end = m->seg_col[d] + m->seg_len[d];
-                seg_next = m->seg_col[d] + ((m->seg_len[d] + 7) & ~7);
-              }
+            for (int u = 0; u < 4; ++u) {
+              const int cu = c0 + u * 8;
+              if (cu < c_hi) {                   // warp-uniform
+                if (cu >= seg_next) {            // warp-uniform: next doc starts at this 8-column unit
+                  mvals[d * kTileM + lane_row] = best;
+                  ++d;
+                  best = -INFINITY;
+                  seg_end = m->seg_col[d] + m->seg_len[d];
+                  seg_next = m->seg_col[d] + ((m->seg_len[d] + 7) & ~7);
+                }
 #pragma unroll
-              for (int j2 = 0; j2 < 8; ++j2) {
-                const float v = __uint_as_float(r[u * 8 + j2]);
-                best = (cu + j2 < seg_end) ? fmaxf(best, v) : best;
+                for (int j2 = 0; j2 < 8; ++j2) {
+                  const float v = __uint_as_float(r[u * 8 + j2]);
+                  best = (cu + j2 < seg_end) ? fmaxf(best, v) : best;
+                }
               }
             }
           }
+          mvals[d * kTileM + lane_row] = best;
         }
-        mvals[d * kTileM + lane_row] = best;
       }
       // accumulator fully read -> hand TMEM back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1u;
-      named_bar_sync(1, 128);   // all per-doc maxima are in mvals
+      named_bar_sync(1, 128);   // all per-doc maxima of this tile are in mvals
       for (int d = ew; d < nd; d += 4) {
+        // m_i = max over doc tokens for query token i (lane i, i + 32, ...)
         float res;
+        float mv[4];
+        int nmv = 0;
+        for (int i = lane; i < lq; i += 32) {
+          float v = mvals[d * kTileM + i];
+          if (rep4) v = fmaxf(fmaxf(v, mvals[d * kTileM + 32 + i]), fmaxf(mvals[d * kTileM + 64 + i], mvals[d * kTileM + 96 + i]));
+          mv[nmv++] = v;
+        }
         if (p.mode == TS_S2_MAXSIM) {
-          float s = 0.f;
-          for (int i = lane; i < lq; i += 32) s += mvals[d * kTileM + i];
-          res = warp_sum(s) / (float)lq;
+          float sacc = 0.f;
+          for (int t = 0; t < nmv; ++t) sacc += mv[t];
+          res = warp_sum(sacc) / (float)lq;
         } else {
           float mx = -INFINITY;
-          for (int i = lane; i < lq; i += 32) mx = fmaxf(mx, mvals[d * kTileM + i]);
+          for (int t = 0; t < nmv; ++t) mx = fmaxf(mx, mv[t]);
 #pragma unroll
           for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-          float z = 0.f, s = 0.f;
-          for (int i = lane; i < lq; i += 32) {
-            const float v = mvals[d * kTileM + i];
-            const float e = __expf(v - mx);
-            z += e; s += e * v;
+          float z = 0.f, sacc = 0.f;
+          for (int t = 0; t < nmv; ++t) {
+            const float e = __expf(mv[t] - mx);
+            z += e; sacc += e * mv[t];
           }
-          z = warp_sum(z); s = warp_sum(s);
-          res = s / z;
+          z = warp_sum(z); sacc = warp_sum(sacc);
+          res = sacc / z;
         }
         if (lane == 0) p.out[m->out_idx[d]] = res;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&mempty_bar[slot]);   // meta slot reusable
-      named_bar_sync(2, 128);   // mvals reusable
+      // mvals[(seq & 1)] is rewritten at tile seq + 2, after the barrier of tile seq + 1,
+      // which every warp reaches only after this finalize
     }
   }
 
@@ -415,10 +459,11 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
     if (launches) ++*launches;
     return TS_OK;
   }
-  CUtensorMap tq8, tq128, t8, t16, t32, t64, t128;
+  CUtensorMap tq8, tq32, tq128, t8, t16, t32, t64, t128;
   int rc;
   const int64_t qrows = (int64_t)a.B * a.lq_stride;
   if ((rc = make_tmap_2d(&tq8, a.q, a.dtype, qrows, a.dim, a.dim, 8))) return rc;
+  if ((rc = make_tmap_2d(&tq32, a.q, a.dtype, qrows, a.dim, a.dim, 32))) return rc;
   if ((rc = make_tmap_2d(&tq128, a.q, a.dtype, qrows, a.dim, a.dim, 128))) return rc;
   if ((rc = make_tmap_2d(&t8, a.tok, a.dtype, a.ntok_rows, a.dim, a.dim, 8))) return rc;
   if ((rc = make_tmap_2d(&t16, a.tok, a.dtype, a.ntok_rows, a.dim, a.dim, 16))) return rc;
@@ -436,11 +481,11 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
   if (a.dtype == TS_BF16) {
     auto kern = maxsim_umma_kernel<true>;
     TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    kern<<<grid, kThreads, kSmemBytes, st>>>(tq8, tq128, t8, t16, t32, t64, t128, p);
+    kern<<<grid, kThreads, kSmemBytes, st>>>(tq8, tq32, tq128, t8, t16, t32, t64, t128, p);
   } else {
     auto kern = maxsim_umma_kernel<false>;
     TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    kern<<<grid, kThreads, kSmemBytes, st>>>(tq8, tq128, t8, t16, t32, t64, t128, p);
+    kern<<<grid, kThreads, kSmemBytes, st>>>(tq8, tq32, tq128, t8, t16, t32, t64, t128, p);
   }
   TS_CUDA_OK(cudaGetLastError());
   if (launches) ++*launches;

@@ -40,11 +40,15 @@ struct SelectParams {
   // kLists: unsorted candidate lists of the umma scan, lists[(cta*128 + row)*cap .. +counts[cta*128+row])
   const int* counts;
   int n_slices, spread, cap, dual, rows_per_cta;
+  const float* pub;       // kLists: final per-slice J-th best scores [n_slices][bpad] (null = no filter)
+  int bpad;
 };
 
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
   extern __shared__ __align__(16) uint64_t sbuf[];
   __shared__ int pre[kMaxLists + 1];
+  __shared__ float s_min[kSelThreads / 32];
+  __shared__ int s_cnt;
   const int b = blockIdx.x, g = blockIdx.y;
   int total;
   const int l0 = g * p.group;
@@ -86,7 +90,40 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
       return make_key(p.scores[(size_t)b * p.C + i], (uint32_t)i);
     }
   };
-  block_select_topk(sbuf, kSelCap, p.k_out, total, load);
+  bool done = false;
+  if (p.mode == kLists && p.pub) {
+    // Every slice's FINAL J-th best score is known now: at least k rows score
+    // >= their minimum, so only keys at or above it can be in the top-k.
+    // Filter + compact first (a few hundred survivors), then one small sort.
+    float m = INFINITY;
+    for (int c = threadIdx.x; c < p.n_slices; c += blockDim.x) m = fminf(m, __ldcg(p.pub + (size_t)c * p.bpad + b));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = m;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    m = s_min[0];
+    for (int w = 1; w < kSelThreads / 32; ++w) m = fminf(m, s_min[w]);
+    const uint64_t thr = (uint64_t)f2ord(m) << 32;      // smallest key with score m
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const uint64_t key = load(i);
+      if (key >= thr && key != 0ull) {
+        const int pos = atomicAdd(&s_cnt, 1);
+        if (pos < kSelCap) sbuf[pos] = key;
+      }
+    }
+    __syncthreads();
+    const int kept = s_cnt;
+    if (kept <= kSelCap) {
+      const int n = next_pow2(max(max(kept, p.k_out), 2));
+      for (int i = kept + threadIdx.x; i < n; i += blockDim.x) sbuf[i] = 0ull;
+      __syncthreads();
+      block_sort_desc(sbuf, n);
+      done = true;
+    }
+    __syncthreads();
+  }
+  if (!done) block_select_topk(sbuf, kSelCap, p.k_out, total, load);
   // sbuf[0..k_out) sorted descending, zero padded
   for (int r = threadIdx.x; r < p.k_out; r += blockDim.x) {
     const uint64_t key = sbuf[r];
@@ -159,12 +196,13 @@ int launch_merge_keys(const uint64_t* keys, int L, int B, int k, int64_t id_base
   return TS_OK;
 }
 
-int launch_merge_lists(const uint64_t* lists, const int* counts, const UmmaLayout& lay, int B, int k, int64_t id_base,
-                       float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches) {
+int launch_merge_lists(const uint64_t* lists, const int* counts, const float* pub, const UmmaLayout& lay, int B, int k,
+                       int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches) {
   if (k <= 0 || k > TS_MAX_K || B <= 0 || lay.n_slices > kMaxLists) { set_error("merge_lists: bad arguments"); return TS_ERR_INVALID; }
   SelectParams p{};
   p.mode = kLists; p.keys = lists; p.counts = counts; p.n_slices = lay.n_slices; p.spread = lay.spread; p.cap = lay.cap;
   p.dual = lay.dual; p.rows_per_cta = lay.rows_per_cta;
+  p.pub = (lay.jrank > 0) ? pub : nullptr; p.bpad = lay.bpad;
   p.L = lay.n_slices; p.B = B; p.k_in = k; p.group = lay.n_slices; p.k_out = k;
   p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids; p.id_base = id_base;
   int rc = launch_select(p, 1, st);

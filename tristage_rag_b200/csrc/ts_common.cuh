@@ -121,10 +121,10 @@ __device__ __forceinline__ uint64_t warp_prune_list(uint64_t* list, int cnt, int
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void block_sort_desc(uint64_t* s, int n) {
   for (int size = 2; size <= n; size <<= 1) {
-    for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+    for (int stride = size >> 1, lg = 31 - __clz(size >> 1); stride >= 1; stride >>= 1, --lg) {
       for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
-        const int e = ((i / stride) * (stride << 1)) + (i % stride);
-        const int p = e + stride;
+        const int e = ((i >> lg) << (lg + 1)) | (i & (stride - 1));   // strides are powers of two
+        const int p = e | stride;
         const bool desc = ((e & size) == 0);
         const uint64_t a = s[e], b = s[p];
         const bool sw = desc ? (a < b) : (a > b);
