@@ -2,10 +2,19 @@
 mkdir -p gpurun_out
 run() { name=$1; shift; timeout 1200 python -m pytest "$@" -q -m gpu -p no:cacheprovider --timeout 900 > gpurun_out/$name.log 2>&1; echo "$name rc=$? $(tail -1 gpurun_out/$name.log)"; }
 run s2 tests/test_gpu_stage2.py
-run s1_umma tests/test_gpu_stage1.py -k "umma_path"
-run s1_rest tests/test_gpu_stage1.py -k "not stream_path and not umma_path"
-run pipe tests/test_gpu_pipeline.py
-python bench.py --steps 50 --warmup 5 --no-cpu > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
-P="python tools/perf_probe.py --paths umma"
-$P --rows 1000000 --dim 768 --batches 1,32,128,1024 --tag v5 > gpurun_out/exp_1M.jsonl 2>> gpurun_out/exp.err
-echo done
+P="python tools/s2_probe.py"
+$P --tag c4 > gpurun_out/s2.jsonl 2> gpurun_out/s2.err
+$P --tag all180 --lo 180 --hi 180 >> gpurun_out/s2.jsonl 2>> gpurun_out/s2.err
+$P --tag all248 --lo 248 --hi 248 >> gpurun_out/s2.jsonl 2>> gpurun_out/s2.err
+$P --tag short --lo 16 --hi 40 >> gpurun_out/s2.jsonl 2>> gpurun_out/s2.err
+$P --tag lq128 --Lq 128 >> gpurun_out/s2.jsonl 2>> gpurun_out/s2.err
+$P --tag dim768 --dim 768 --ndocs 50000 >> gpurun_out/s2.jsonl 2>> gpurun_out/s2.err
+python - <<'PY'
+import json
+for l in open('gpurun_out/s2.jsonl'):
+    r=json.loads(l); print(f"{r['tag']:8s} kernel={r['kernel_ms']:.3f}ms cand/s={r['cand_per_s']/1e6:.1f}M GB/s={r['GBps']:.0f} frac={r['hbm_frac']:.2f}")
+PY
+CMD="python tools/s2_probe.py --steps 3"
+$CMD > gpurun_out/plain_s2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:maxsim_umma -s 2 -c 1 -o gpurun_out/prof_s2 $CMD > gpurun_out/ncu_s2.log 2>&1
+echo "ncu s2 rc=$?"

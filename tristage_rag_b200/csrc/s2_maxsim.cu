@@ -188,43 +188,50 @@ __global__ void __launch_bounds__(kThreads, 1)
     int stage = 0; uint32_t phase = 0;
     uint32_t seq = 0;  // tiles emitted by this CTA
 
-    // emit the tile described by metas[seq % slots] (already filled in)
+    // emit the tile described by metas[seq % slots] (already filled in).
+    // The whole warp issues the TMA traffic: lane d gathers doc d of the tile
+    // (its padded rows as boxes of 128/64/32/16/8), lanes 28-31 (or 24-31 /
+    // 31) bring the query rows -- one warp-wide instruction per box size
+    // instead of a per-doc loop on a single thread.
     auto emit_tile = [&](TileMeta* m) {
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&mfull_bar[seq % kMetaSlots]);   // release meta to MMA + epilogue
-        const int lq = m->lq;
-        const int a_groups = (lq + 7) >> 3;
-        const bool rep4 = lq <= 32;          // query tokens replicated into all four TMEM lane quarters
-        const bool a_boxes8 = lq <= 64;
-        const uint32_t tx = (rep4 ? (uint32_t)kABytes : a_boxes8 ? (uint32_t)a_groups * 1024u : (uint32_t)kABytes) +
-                            (uint32_t)m->used * 128u;
-        for (int kc = 0; kc < p.nK; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u, 11);
-          unsigned char* sA = smem + stage * kStageBytes;
-          unsigned char* sB = sA + kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], tx);
-          if (rep4) {
-            for (int g = 0; g < 4; ++g)
-              tma_load_2d(sA + g * 4096, &tmQ32, &full_bar[stage], kc * kChunkK, m->q_row, kEvictLast);
-          } else if (a_boxes8) {
-            for (int g = 0; g < a_groups; ++g)
-              tma_load_2d(sA + g * 1024, &tmQ8, &full_bar[stage], kc * kChunkK, m->q_row + g * 8, kEvictLast);
-          } else {
-            tma_load_2d(sA, &tmQ128, &full_bar[stage], kc * kChunkK, m->q_row, kEvictLast);
-          }
-          for (int d = 0; d < m->ndocs; ++d) {
-            int rows = (m->seg_len[d] + 7) & ~7;
-            long long r = m->seg_row[d];
-            unsigned char* dst = sB + m->seg_col[d] * 128;
-            while (rows >= 128) { tma_load_2d(dst, &tmT128, &full_bar[stage], kc * kChunkK, (int)r, kEvictFirst); rows -= 128; r += 128; dst += 128 * 128; }
-            if (rows >= 64) { tma_load_2d(dst, &tmT64, &full_bar[stage], kc * kChunkK, (int)r, kEvictFirst); rows -= 64; r += 64; dst += 64 * 128; }
-            if (rows >= 32) { tma_load_2d(dst, &tmT32, &full_bar[stage], kc * kChunkK, (int)r, kEvictFirst); rows -= 32; r += 32; dst += 32 * 128; }
-            if (rows >= 16) { tma_load_2d(dst, &tmT16, &full_bar[stage], kc * kChunkK, (int)r, kEvictFirst); rows -= 16; r += 16; dst += 16 * 128; }
-            if (rows >= 8) { tma_load_2d(dst, &tmT8, &full_bar[stage], kc * kChunkK, (int)r, kEvictFirst); }
-          }
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      if (lane == 0) mbar_arrive(&mfull_bar[seq % kMetaSlots]);   // release meta to MMA + epilogue
+      const int lq = m->lq;
+      const int nd = m->ndocs;
+      const int q_row = m->q_row;
+      const int a_groups = (lq + 7) >> 3;
+      const bool rep4 = lq <= 32;          // query tokens replicated into all four TMEM lane quarters
+      const bool a_boxes8 = lq <= 64;
+      const uint32_t tx = (rep4 ? (uint32_t)kABytes : a_boxes8 ? (uint32_t)a_groups * 1024u : (uint32_t)kABytes) +
+                          (uint32_t)m->used * 128u;
+      const bool has_doc = lane < nd;
+      const int my_rows = has_doc ? ((m->seg_len[lane] + 7) & ~7) : 0;
+      const int my_row0 = has_doc ? (int)m->seg_row[lane] : 0;
+      const int my_col = has_doc ? m->seg_col[lane] : 0;
+      for (int kc = 0; kc < p.nK; ++kc) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u, 11);
+        unsigned char* sA = smem + stage * kStageBytes;
+        unsigned char* sB = sA + kABytes;
+        uint64_t* fb = &full_bar[stage];
+        if (lane == 0) mbar_arrive_expect_tx(fb, tx);
+        __syncwarp();
+        const int kx = kc * kChunkK;
+        if (rep4) {
+          if (lane >= 28) tma_load_2d(sA + (lane - 28) * 4096, &tmQ32, fb, kx, q_row, kEvictLast);
+        } else if (a_boxes8) {
+          if (lane >= 24 && lane - 24 < a_groups) tma_load_2d(sA + (lane - 24) * 1024, &tmQ8, fb, kx, q_row + (lane - 24) * 8, kEvictLast);
+        } else {
+          if (lane == 31) tma_load_2d(sA, &tmQ128, fb, kx, q_row, kEvictLast);
         }
+        int rows = my_rows, r = my_row0;
+        unsigned char* dst = sB + my_col * 128;
+        if (rows >= 256) { tma_load_2d(dst, &tmT128, fb, kx, r, kEvictFirst); rows -= 128; r += 128; dst += 128 * 128; }
+        if (rows >= 128) { tma_load_2d(dst, &tmT128, fb, kx, r, kEvictFirst); rows -= 128; r += 128; dst += 128 * 128; }
+        if (rows >= 64) { tma_load_2d(dst, &tmT64, fb, kx, r, kEvictFirst); rows -= 64; r += 64; dst += 64 * 128; }
+        if (rows >= 32) { tma_load_2d(dst, &tmT32, fb, kx, r, kEvictFirst); rows -= 32; r += 32; dst += 32 * 128; }
+        if (rows >= 16) { tma_load_2d(dst, &tmT16, fb, kx, r, kEvictFirst); rows -= 16; r += 16; dst += 16 * 128; }
+        if (rows >= 8) { tma_load_2d(dst, &tmT8, fb, kx, r, kEvictFirst); }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
       ++seq;
       __syncwarp();
