@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--path", default="auto")
     ap.add_argument("--no-extra", action="store_true", help="skip the B=1 / B=1024 / Stage-2 side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -245,13 +246,45 @@ def main():
     # ---- device-resident timing (value) --------------------------------------
     path = args.path
     step = lambda: sharded.search(q_dev, k, path=path)     # noqa: E731
-    timed(step, 2, args.warmup, dev, dist_on)               # extra warm-up incl. scratch allocation
+    timed(step, 2, args.warmup, dev, dist_on)               # warm-up incl. scratch allocation
+    # scan-kernel duration: CUDA events around the kernel on its own stream, eager launches
     idx.set_profiling(True)
     l0 = idx.launches
-    ms = timed(step, args.steps, 0, dev, dist_on)
+    ms_eager = timed(step, args.steps, 0, dev, dist_on)
     launches = idx.launches - l0
     scan_ms, scan_n = idx.scan_time_ms()
     idx.set_profiling(False)
+    # headline: the same step captured once in a CUDA graph (query prep, threshold pre-pass,
+    # scan, select, all-gather, merge) and replayed K times -- no per-launch host latency
+    ms, launch_mode = ms_eager, "eager"
+    extra_modes = {}
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g_out = step()
+            replay = lambda: graph.replay()                 # noqa: E731
+            ms_graph = timed(replay, args.steps, args.warmup, dev, dist_on)
+            ref_s, ref_i = step()
+            torch.cuda.synchronize(dev)
+            assert torch.equal(g_out[1], ref_i) and torch.equal(g_out[0], ref_s), "graph replay diverged from eager"
+            # the two launch modes drive identical kernels; keep whichever the box runs faster
+            # (a second eager pass guards against clock drift between the passes)
+            ms_eager = min(ms_eager, timed(step, args.steps, 2, dev, dist_on))
+            if ms_graph < ms_eager:
+                ms, launch_mode = ms_graph, "cuda_graph"
+            else:
+                ms, launch_mode = ms_eager, "eager"
+            extra_modes = {"ms_per_step_cuda_graph": ms_graph / args.steps}
+        except Exception as e:                               # noqa: BLE001
+            print(f"[bench] CUDA-graph capture unavailable ({type(e).__name__}: {e}); eager timing kept", file=sys.stderr)
     value = B * args.steps / (ms / 1e3)
 
     # ---- end-to-end timing (host buffers in, host results out) ---------------
@@ -271,7 +304,7 @@ def main():
     pk = peaks()
     ld = ((d + 7) // 8) * 8
     n_local = hi - lo
-    use_stream = (path == "stream") or (path == "auto" and B <= 4)
+    use_stream = (path == "stream")
     sm = torch.cuda.get_device_properties(dev).multi_processor_count
     L = min(2 * sm, max(1, n_local // 32)) if use_stream else min(sm // ((B + 127) // 128), (n_local + 255) // 256)
     alg_bytes = stage1_alg_bytes(n_local, ld, B, k, L)
@@ -292,7 +325,8 @@ def main():
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"exact top-{k} over {N}x{d} bf16 corpus (row-sharded over {world} GPU), query batch {B}",
                    "rows": N, "dim": d, "k": k, "batch": B, "path": roof["kernel"], "parallelism": f"rowshard{world}",
-                   "l2": "inputs larger than L2 (shard >= 2.5 GB vs 126 MB), no flush needed"},
+                   "l2": "inputs larger than L2 (shard >= 2.5 GB vs 126 MB), no flush needed",
+                   "launch": launch_mode, "ms_per_step_eager": ms_eager / args.steps, **extra_modes},
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": B * d * 4,
                 "d2h_bytes_per_step": B * k * 12, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,

@@ -137,6 +137,13 @@ int ts_index_search_host(ts_index* h, const void* q_host, int q_dtype, int B, in
 int ts_topk_merge(int device, const float* scores_dev, const int64_t* ids_dev, int n_lists, int B,
                   int k, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
 
+/* Same merge over ONE packed buffer per list, the layout a single all-gather
+ * delivers: list l lives at blob + l*list_stride_bytes and holds its [B, k]
+ * fp32 scores at offset 0 and its [B, k] int64 ids at ids_offset_bytes.      */
+int ts_topk_merge_packed(int device, const void* blob_dev, int64_t list_stride_bytes,
+                         int64_t ids_offset_bytes, int n_lists, int B, int k,
+                         float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+
 /* faiss.write_index / read_index  (stage1_retriever.py:436,463).             */
 int ts_index_save(const ts_index* h, const char* path);
 int ts_index_load(ts_index** out, int device, const char* path);

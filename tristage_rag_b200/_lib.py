@@ -48,6 +48,7 @@ SYMBOLS = {
     "ts_index_search": (_i, [_vp, _vp, _i, _i, _i, _u, _i, _vp, _vp, _vp]),
     "ts_index_search_host": (_i, [_vp, _vp, _i, _i, _i, _u, _i, _vp, _vp, _vp]),
     "ts_topk_merge": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "ts_topk_merge_packed": (_i, [_i, _vp, _i64, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "ts_index_save": (_i, [_vp, C.c_char_p]),
     "ts_index_load": (_i, [C.POINTER(_vp), _i, C.c_char_p]),
     "ts_index_get_rows": (_i, [_vp, _i64, _i64, _vp]),
@@ -217,6 +218,19 @@ class Index:
                                     _stream_ptr(self.device)))
         return scores, ids
 
+    def search_packed(self, q, k: int, blob, normalize_q: bool = False, path: str = "auto"):
+        """Like search(), but scores and ids land in one uint8 cuda buffer (packed_layout) so a
+        single all-gather moves both."""
+        q = q.contiguous()
+        B = q.shape[0]
+        ids_off, nbytes = packed_layout(B, k)
+        assert blob.is_cuda and blob.numel() >= nbytes and blob.data_ptr() % 8 == 0
+        check(lib().ts_index_search(self._h, C.c_void_p(q.data_ptr()), _code_of_torch(q.dtype), B, int(k),
+                                    TS_FLAG_NORMALIZE_Q if normalize_q else 0, PATHS[path],
+                                    C.c_void_p(blob.data_ptr()), C.c_void_p(blob.data_ptr() + ids_off),
+                                    _stream_ptr(self.device)))
+        return blob
+
     def search_host(self, q, k: int, normalize_q: bool = False, path: str = "auto"):
         """q: numpy fp32 [B, dim] -> (D[B,k] f32, I[B,k] i64) numpy -- the faiss call shape."""
         import numpy as np
@@ -264,6 +278,25 @@ def topk_merge(scores, ids, device: int = 0):
     out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
     check(lib().ts_topk_merge(device, C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()), L, B, k,
                               C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()), _stream_ptr(device)))
+    return out_s, out_i
+
+
+def packed_layout(B: int, k: int):
+    """(ids_offset_bytes, blob_bytes) of one packed [B, k] result: fp32 scores, then int64 ids."""
+    ids_off = (B * k * 4 + 7) // 8 * 8
+    return ids_off, ids_off + B * k * 8
+
+
+def topk_merge_packed(blob, n_lists: int, B: int, k: int, device: int = 0):
+    """blob: uint8 cuda tensor [n_lists * blob_bytes] (one all-gather of packed results)."""
+    import torch
+
+    ids_off, nbytes = packed_layout(B, k)
+    dev = torch.device("cuda", device)
+    out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+    check(lib().ts_topk_merge_packed(device, C.c_void_p(blob.data_ptr()), nbytes, ids_off, n_lists, B, k,
+                                     C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()), _stream_ptr(device)))
     return out_s, out_i
 
 

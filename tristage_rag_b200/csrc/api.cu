@@ -368,7 +368,21 @@ int ts_topk_merge(int device, const float* scores, const int64_t* ids, int n_lis
                   int64_t* out_ids, void* stream) {
   if (!scores || !ids || !out_scores || !out_ids) { set_error("ts_topk_merge: null pointer"); return TS_ERR_INVALID; }
   TS_CUDA_OK(cudaSetDevice(device));
-  return launch_merge_pairs(scores, ids, n_lists, B, k, out_scores, out_ids, (cudaStream_t)stream);
+  return launch_merge_pairs(scores, ids, (long long)B * k, (long long)B * k, n_lists, B, k, out_scores, out_ids,
+                            (cudaStream_t)stream);
+}
+
+int ts_topk_merge_packed(int device, const void* blob, int64_t list_stride_bytes, int64_t ids_offset_bytes, int n_lists,
+                         int B, int k, float* out_scores, int64_t* out_ids, void* stream) {
+  if (!blob || !out_scores || !out_ids || (list_stride_bytes % 8) || (ids_offset_bytes % 8) || ids_offset_bytes < (int64_t)B * k * 4) {
+    set_error("ts_topk_merge_packed: bad layout");
+    return TS_ERR_INVALID;
+  }
+  TS_CUDA_OK(cudaSetDevice(device));
+  const float* scores = (const float*)blob;
+  const int64_t* ids = (const int64_t*)((const char*)blob + ids_offset_bytes);
+  return launch_merge_pairs(scores, ids, list_stride_bytes / 4, list_stride_bytes / 8, n_lists, B, k, out_scores, out_ids,
+                            (cudaStream_t)stream);
 }
 
 int ts_index_get_rows(const ts_index* h, int64_t start, int64_t n, float* out_host) {

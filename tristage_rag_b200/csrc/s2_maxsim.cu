@@ -32,6 +32,8 @@
 // CUDA-core path (maxsim_simt_kernel): one CTA per (query, candidate); used
 //   for shapes the tensor path does not take (dim % 8 != 0, Lq > 128) and as
 //   an independent on-device cross-check in the tests.
+#include <stdlib.h>
+
 #include "ts_common.cuh"
 #include "ts_internal.h"
 #include "ts_ptx.cuh"
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(128)
 
 // ========================================================== tensor path ====
 constexpr int kThreads = 192;
-constexpr int kStages = 3;
+constexpr int kMaxStages = 4;   // 3 stages + double-buffered maxima, or 4 stages + single buffer (p.n_stages)
 constexpr int kTileM = 128, kTileN = 256, kChunkK = 64;
 constexpr int kABytes = kTileM * kChunkK * 2;
 constexpr int kBBytes = kTileN * kChunkK * 2;
@@ -124,7 +126,9 @@ constexpr int kMvalsOne = kMaxDocsPerTile * kTileM;         // floats per buffer
 constexpr int kMvalsBytes = 2 * kMvalsOne * 4;             // two buffers, 32 KB
 constexpr int kMetaBytes = kMetaSlots * (int)sizeof(TileMeta);
 constexpr int kBarBytes = 512;
-constexpr int kSmemBytes = kStages * kStageBytes + kMvalsBytes + kMetaBytes + kBarBytes + 1024;
+constexpr int kRingMvalsBytes = 3 * kStageBytes + kMvalsBytes;   // == 4 * kStageBytes + kMvalsBytes / 2 - 32 KB
+static_assert(4 * kStageBytes + kMvalsBytes / 2 <= kRingMvalsBytes + 32 * 1024, "layout");
+constexpr int kSmemBytes = 4 * kStageBytes + kMvalsBytes / 2 + kMetaBytes + kBarBytes + 1024;
 
 struct MaxSimParams {
   const int64_t* doc_off;
@@ -135,6 +139,7 @@ struct MaxSimParams {
   const int64_t* cand;
   const int32_t* n_cand;
   int C, mode, n_chunks, n_items;
+  int n_stages;   // 3: maxima double buffered (one barrier per tile); 4: single buffer (two barriers)
   float* out;
 };
 
@@ -151,21 +156,24 @@ __global__ void __launch_bounds__(kThreads, 1)
                        const __grid_constant__ CUtensorMap tmT128, const MaxSimParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* mvals_base = reinterpret_cast<float*>(smem + kStages * kStageBytes);           // [2][32][128]
-  TileMeta* metas = reinterpret_cast<TileMeta*>(smem + kStages * kStageBytes + kMvalsBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kMvalsBytes + kMetaBytes);
-  uint64_t* full_bar = bars;                           // [kStages]
-  uint64_t* empty_bar = bars + kStages;                // [kStages]
-  uint64_t* tfull_bar = bars + 2 * kStages;            // [2]
-  uint64_t* tempty_bar = bars + 2 * kStages + 2;       // [2]
-  uint64_t* mfull_bar = bars + 2 * kStages + 4;        // [kMetaSlots]
+  const int kStages = p.n_stages;
+  const int mvals_bufs = (kStages == 3) ? 2 : 1;
+  float* mvals_base = reinterpret_cast<float*>(smem + kStages * kStageBytes);           // [bufs][32][128]
+  unsigned char* after = smem + kStages * kStageBytes + mvals_bufs * kMvalsOne * 4;
+  TileMeta* metas = reinterpret_cast<TileMeta*>(after);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after + kMetaBytes);
+  uint64_t* full_bar = bars;                           // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;             // [kMaxStages]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;         // [2]
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;    // [2]
+  uint64_t* mfull_bar = bars + 2 * kMaxStages + 4;     // [kMetaSlots]
   uint64_t* mempty_bar = mfull_bar + kMetaSlots;       // [kMetaSlots]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mempty_bar + kMetaSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     for (int s = 0; s < kMetaSlots; ++s) { mbar_init(&mfull_bar[s], 1); mbar_init(&mempty_bar[s], 4); }
     fence_mbar_init();
@@ -348,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (used == 0) break;
       const int nd = m->ndocs, lq = m->lq;
       const bool rep4 = lq <= 32;
-      float* mvals = mvals_base + (seq & 1u) * kMvalsOne;
+      float* mvals = mvals_base + ((mvals_bufs == 2) ? (seq & 1u) : 0u) * kMvalsOne;
       mbar_wait(&tfull_bar[acc], acc_phase, 32);
       tc_fence_after();
       const int c_lo = rep4 ? quarter * 64 : 0;
@@ -431,8 +439,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&mempty_bar[slot]);   // meta slot reusable
-      // mvals[(seq & 1)] is rewritten at tile seq + 2, after the barrier of tile seq + 1,
-      // which every warp reaches only after this finalize
+      // two buffers: mvals[(seq & 1)] is rewritten at tile seq + 2, after the barrier of tile
+      // seq + 1, which every warp reaches only after this finalize.  one buffer: wait here.
+      if (mvals_bufs == 1) named_bar_sync(2, 128);
     }
   }
 
@@ -484,6 +493,7 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
   p.n_chunks = (a.C + kItemCands - 1) / kItemCands;
   p.n_items = a.B * p.n_chunks;
   p.out = a.out;
+  { const char* e = getenv("TS_S2_STAGES"); p.n_stages = (e && atoi(e) == 4) ? 4 : 3; }
   int grid = a.sm_count < p.n_items ? a.sm_count : p.n_items;
   if (a.dtype == TS_BF16) {
     auto kern = maxsim_umma_kernel<true>;

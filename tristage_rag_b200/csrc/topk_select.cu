@@ -40,6 +40,8 @@ struct SelectParams {
   // kLists: unsorted candidate lists of the umma scan, lists[(cta*128 + row)*cap .. +counts[cta*128+row])
   const int* counts;
   int n_slices, spread, cap, dual, rows_per_cta;
+  long long pair_stride;  // kPairs: elements between consecutive lists (scores: floats, ids: int64s)
+  long long pair_stride_ids;
   const float* pub;       // kLists: final per-slice J-th best scores [n_slices][bpad] (null = no filter)
   int bpad;
 };
@@ -81,11 +83,11 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
       return p.keys[((size_t)l * p.B + b) * p.k_in + r];
     } else if (p.mode == kPairs) {
       const int l = l0 + i / p.k_in, r = i % p.k_in;
-      const size_t at = ((size_t)l * p.B + b) * p.k_in + r;
-      const int64_t id = p.ids[at];
+      const size_t at = ((size_t)b) * p.k_in + r;
+      const int64_t id = p.ids[(size_t)l * p.pair_stride_ids + at];
       // position across lists keeps "id ascending" among equal scores when
       // lists are ordered by ascending id range
-      return id < 0 ? 0ull : make_key(p.scores[at], (uint32_t)(l * p.k_in + r));
+      return id < 0 ? 0ull : make_key(p.scores[(size_t)l * p.pair_stride + at], (uint32_t)(l * p.k_in + r));
     } else {
       return make_key(p.scores[(size_t)b * p.C + i], (uint32_t)i);
     }
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
         p.out_ids[o] = p.id_base + (int64_t)idx;
       } else if (p.mode == kPairs) {
         const int l = idx / p.k_in, r2 = idx % p.k_in;
-        p.out_ids[o] = p.ids[((size_t)l * p.B + b) * p.k_in + r2];
+        p.out_ids[o] = p.ids[(size_t)l * p.pair_stride_ids + (size_t)b * p.k_in + r2];
       } else {
         p.out_pos[o] = (int32_t)idx;
       }
@@ -211,12 +213,13 @@ int launch_merge_lists(const uint64_t* lists, const int* counts, const float* pu
   return TS_OK;
 }
 
-int launch_merge_pairs(const float* scores, const int64_t* ids, int L, int B, int k, float* out_scores,
-                       int64_t* out_ids, cudaStream_t st) {
+int launch_merge_pairs(const float* scores, const int64_t* ids, long long stride_scores, long long stride_ids, int L,
+                       int B, int k, float* out_scores, int64_t* out_ids, cudaStream_t st) {
   if (k <= 0 || k > TS_MAX_K || B <= 0 || L <= 0) { set_error("merge: bad L/B/k"); return TS_ERR_INVALID; }
   if ((long long)L * k > 65536) { set_error("merge: n_lists*k too large (%d*%d)", L, k); return TS_ERR_UNSUPPORTED; }
   SelectParams p{};
   p.mode = kPairs; p.scores = scores; p.ids = ids; p.L = L; p.B = B; p.k_in = k; p.group = L; p.k_out = k;
+  p.pair_stride = stride_scores; p.pair_stride_ids = stride_ids;
   p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids;
   return launch_select(p, 1, st);
 }

@@ -76,8 +76,9 @@ size_t merge_tmp_keys(int L, int B, int k);
 // unsorted per-(CTA, query) candidate lists of the umma scan -> final (scores, ids) [B][k]
 int launch_merge_lists(const uint64_t* lists, const int* counts, const float* pub, const UmmaLayout& lay, int B, int k,
                        int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches);
-int launch_merge_pairs(const float* scores, const int64_t* ids, int L, int B, int k, float* out_scores,
-                       int64_t* out_ids, cudaStream_t st);
+// strides = elements between consecutive lists (floats for scores, int64s for ids)
+int launch_merge_pairs(const float* scores, const int64_t* ids, long long stride_scores, long long stride_ids, int L,
+                       int B, int k, float* out_scores, int64_t* out_ids, cudaStream_t st);
 int launch_rank_desc(const float* scores, const int32_t* n_cand, int B, int C, int top_k, float* out_scores,
                      int32_t* out_pos, cudaStream_t st);
 

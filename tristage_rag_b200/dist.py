@@ -68,15 +68,37 @@ class ShardedIndex:
             from ._lib import topk_merge
 
             merge_fn = lambda s, i: topk_merge(s, i, device=s.device.index)  # noqa: E731
+            self._packed = hasattr(local_index, "search_packed")
+        else:
+            self._packed = False
+        self._bufs = {}
         self.merge_fn = merge_fn
 
     def search(self, q: torch.Tensor, k: int, **kw) -> Tuple[torch.Tensor, torch.Tensor]:
         """q replicated on every rank -> identical merged (scores, ids) on every rank."""
+        if self.world > 1 and self._packed and q.is_cuda:
+            return self._search_packed(q, k, **kw)
         s, i = self.local.search(q, k, **kw)
         if self.world == 1:
             return s, i
         all_s, all_i = gather_topk(s, i, self.group)
         return self.merge_fn(all_s, all_i)
+
+    def _search_packed(self, q, k, **kw):
+        """GPU fast path: scores + ids in one buffer -> ONE all-gather -> one merge kernel."""
+        from ._lib import packed_layout, topk_merge_packed
+
+        B = q.shape[0]
+        _, nbytes = packed_layout(B, k)
+        key = (B, k)
+        if self._bufs.get("key") != key:
+            self._bufs = {"key": key,
+                          "mine": torch.empty(nbytes, dtype=torch.uint8, device=q.device),
+                          "all": torch.empty(nbytes * self.world, dtype=torch.uint8, device=q.device)}
+        mine, allb = self._bufs["mine"], self._bufs["all"]
+        self.local.search_packed(q, k, mine, **kw)
+        dist.all_gather_into_tensor(allb, mine, group=self.group)
+        return topk_merge_packed(allb, self.world, B, k, device=q.device.index)
 
 
 class ShardedTokStore:
