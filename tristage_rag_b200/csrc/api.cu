@@ -93,6 +93,8 @@ struct ts_index {
   void* tmp1; size_t tmp1_b;
   void* counts; size_t counts_b;
   void* pub; size_t pub_b;
+  unsigned int* grid_bar;            // {counter, generation}, zeroed once
+  int coop;                          // device supports cooperative launch
   void* stage; size_t stage_b;       // staging for host inputs (add / search_host)
   void* hout; size_t hout_b;         // device result buffers for search_host
   ScanTimer* timer;
@@ -199,6 +201,13 @@ int ts_index_create(ts_index** out, int device, int dim, int storage_dtype, int 
   h->ld = row_pitch(dim, storage_dtype);
   h->info = info;
   h->timer = new ScanTimer();
+  {
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    h->coop = coop;
+    if (coop && cudaMalloc((void**)&h->grid_bar, 8) == cudaSuccess) cudaMemset(h->grid_bar, 0, 8);
+    else h->grid_bar = nullptr;
+  }
   if (reserve_rows > 0) {
     h->cap = 0;
     // exact reservation (no doubling) for the first allocation
@@ -218,7 +227,7 @@ int ts_index_create(ts_index** out, int device, int dim, int storage_dtype, int 
 int ts_index_destroy(ts_index* h) {
   if (!h) return TS_OK;
   cudaSetDevice(h->device);
-  void* ptrs[] = {h->rows, h->inv_norm, h->qbuf, h->lists, h->partial, h->tmp0, h->tmp1, h->counts, h->pub, h->stage, h->hout};
+  void* ptrs[] = {h->rows, h->inv_norm, h->qbuf, h->lists, h->partial, h->tmp0, h->tmp1, h->counts, h->pub, h->stage, h->hout, h->grid_bar};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->timer) { h->timer->destroy(); delete h->timer; }
   delete h;
@@ -325,7 +334,7 @@ int ts_index_search(ts_index* h, const void* q_dev, int q_dtype, int B, int k, u
       if ((rc = ensure_bytes(&h->counts, &h->counts_b, lay.counts_n * sizeof(int)))) return rc;
       if ((rc = ensure_bytes(&h->pub, &h->pub_b, lay.pub_n * sizeof(float)))) return rc;
       a.lists = (uint64_t*)h->lists; a.lists_keys = lay.lists_keys;
-      a.counts = (int*)h->counts; a.pub = (float*)h->pub;
+      a.counts = (int*)h->counts; a.pub = (float*)h->pub; a.grid_bar = h->grid_bar;
       h->timer->begin(st);
       rc = launch_s1_umma(a, lay, st, &launches);
       h->timer->end(st);

@@ -61,7 +61,9 @@ struct UmmaParams {
   int spread, n_qgroups, cap;
   int dual;        // 1: the CTA owns TWO query tiles (2*mp, 2*mp+1) that share every corpus chunk
   int dbg_notopk;
-  int mode;        // 0 = threshold pre-pass (first tile of every slice, publishes pub), 1 = scan
+  int mode;        // 0 = threshold pre-pass (first tile of every slice, publishes pub), 1 = scan,
+                   // 2 = both in one cooperative launch (grid barrier after the first tile)
+  unsigned int* grid_bar;  // [0] arrival counter, [1] generation (mode 2)
   int jrank;       // j = ceil(k / n_slices) if <= 8, else 0 (threshold sharing off)
   int bpad;        // row pitch of pub
   uint64_t* lists; // [grid][rows_per_cta][cap] candidate keys
@@ -228,6 +230,38 @@ __device__ __forceinline__ void finish_state(const UmmaParams& p, QState& s, int
   }
 }
 
+__device__ __forceinline__ void named_bar_sync128(int id) {
+  asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+}
+
+// Grid-wide barrier for the epilogue threads of a cooperative launch (all CTAs
+// co-resident).  Self-resetting (arrival counter + generation word), so it
+// also works when the launch is replayed from a CUDA graph.  `gen0` must have
+// been read before this CTA arrives.  Bounded spin: a protocol bug traps.
+__device__ __forceinline__ void grid_barrier_epilogue(unsigned int* bar, unsigned int gen0, int warp, int lane) {
+  __threadfence();
+  named_bar_sync128(1);
+  if (warp == 2 && lane == 0) {
+    __threadfence();
+    const unsigned int old = atomicAdd(bar, 1u);
+    if (old == gridDim.x - 1) {
+      atomicExch(bar, 0u);
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      const long long t0 = clock64();
+      while (*reinterpret_cast<volatile unsigned int*>(bar + 1) == gen0) {
+        if (clock64() - t0 > TS_WAIT_TIMEOUT_CYCLES) {
+          printf("[tristage] grid barrier timeout: block %d\n", (int)blockIdx.x);
+          __trap();
+        }
+      }
+    }
+    __threadfence();
+  }
+  named_bar_sync128(1);
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1)
     s1_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ8,
@@ -337,11 +371,14 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int lane_row = quarter * 32 + lane;
     const int rows_per_cta = dual ? 2 * kTileM : kTileM;
     const bool prepass = (p.mode == 0);
+    const bool fused = (p.mode == 2);          // pre-pass + scan in one cooperative launch (never with dual)
     const int J = p.jrank;
+    unsigned int gen0 = 0;
+    if (fused) gen0 = *reinterpret_cast<volatile unsigned int*>(p.grid_bar + 1);
     QState s0, s1;
     init_state(p, s0, 0, mt0, quarter, lane, lane_row, rows_per_cta, CAP, true);
     init_state(p, s1, 1, mt0, quarter, lane, lane_row, rows_per_cta, CAP, dual);
-    if (J > 0) {
+    if (J > 0 && !fused) {
       start_state(p, s0, slice, prepass);
       start_state(p, s1, slice, prepass);
     }
@@ -357,6 +394,21 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int acc = iter & 1;
         mbar_wait(&tfull_bar[acc], (uint32_t)((iter >> 1) & 1), 4);
         tc_fence_after();
+        if (fused && iter == 0) {
+          // first tile, pass 1: only the thread's J best scores -> publish -> wait for every slice
+          drain_acc(p, s0, lane_addr + (uint32_t)(acc * kTileN), n0, ncols, wact0, true, J, CAP, lane);
+          if (s0.active) {
+            p.pub[(size_t)slice * p.bpad + s0.q] = s0.tjJ;
+            if (slice == 0) p.tau_g[s0.q] = -INFINITY;   // never let a stale bound of an earlier call be read
+          }
+          grid_barrier_epilogue(p.grid_bar, gen0, warp, lane);
+          // pass 2 re-reads the same accumulator with the shared bound in place; the J-best
+          // registers restart from scratch so no row is counted twice
+          s0.tjJ = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s0.tj[i] = -INFINITY;
+          start_state(p, s0, slice, false);
+        }
         drain_acc(p, s0, lane_addr + (uint32_t)(acc * kTileN), n0, ncols, wact0, prepass, J, CAP, lane);
         tc_fence_before();
         __syncwarp();
@@ -460,6 +512,7 @@ int s1_umma_plan(const ScanArgs& a, UmmaLayout* lay) {
   lay->pub_n = (size_t)(pl.n_slices + 1) * lay->bpad;   // + one row for tau_g
   const int j = (a.k + pl.n_slices - 1) / pl.n_slices;
   lay->jrank = (j <= 8 && !getenv("TS_DBG_NOSHARE")) ? j : 0;
+  lay->fused = (lay->jrank > 0 && !pl.dual && !getenv("TS_NOFUSE")) ? 1 : 0;
   return TS_OK;
 }
 
@@ -488,16 +541,25 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
   const bool bf16 = a.dtype == TS_BF16;
   auto kern = bf16 ? s1_umma_kernel<true> : s1_umma_kernel<false>;
   TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  if (p.jrank > 0) {
-    p.mode = 0;   // threshold pre-pass over the first tile of every slice
+  if (p.jrank > 0 && lay.fused && a.grid_bar) {
+    // one cooperative launch (all CTAs co-resident): first tile -> publish -> grid barrier -> scan
+    p.mode = 2;
+    p.grid_bar = a.grid_bar;
+    void* args[] = {(void*)&tmQ, (void*)&tmQ8, (void*)&tmX, (void*)&p};
+    TS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(lay.grid), dim3(kThreads), args, kSmemBytes, st));
+    if (launches) ++*launches;
+  } else {
+    if (p.jrank > 0) {
+      p.mode = 0;   // threshold pre-pass over the first tile of every slice
+      kern<<<lay.grid, kThreads, kSmemBytes, st>>>(tmQ, tmQ8, tmX, p);
+      TS_CUDA_OK(cudaGetLastError());
+      if (launches) ++*launches;
+    }
+    p.mode = 1;
     kern<<<lay.grid, kThreads, kSmemBytes, st>>>(tmQ, tmQ8, tmX, p);
     TS_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
   }
-  p.mode = 1;
-  kern<<<lay.grid, kThreads, kSmemBytes, st>>>(tmQ, tmQ8, tmX, p);
-  TS_CUDA_OK(cudaGetLastError());
-  if (launches) ++*launches;
   if (p.stats) {
     unsigned long long h[4];
     cudaMemcpyAsync(h, d_stats, 32, cudaMemcpyDeviceToHost, st);

@@ -54,11 +54,12 @@ struct ScanArgs {
   size_t partial_keys;    // capacity in keys
   int* counts;            // umma path out: entries per candidate list
   float* pub;             // umma path scratch: published per-slice thresholds
+  unsigned int* grid_bar; // umma path: {arrival counter, generation} of the in-kernel grid barrier
   int sm_count;
 };
 // where the umma scan leaves its candidates (consumed by launch_merge_lists)
 struct UmmaLayout {
-  int n_slices, n_mt, grid, cap, spread, bpad, jrank, dual, rows_per_cta;
+  int n_slices, n_mt, grid, cap, spread, bpad, jrank, dual, rows_per_cta, fused;
   size_t lists_keys, counts_n, pub_n;
 };
 // number of partial lists L a scan will emit / scratch it needs
