@@ -199,27 +199,3 @@ def test_argument_errors(cuda_device):
     D, I = f32.search_host(np.ones((9, 32), np.float32), 2)   # fp32 + B > 4: stream passes of 4
     assert I.shape == (9, 2) and (I >= 0).all()
 
-
-def test_scan_variants_agree_bit_for_bit(cuda_device, monkeypatch):
-    """The fused (cooperative, in-kernel grid barrier) scan, the two-launch scan and the scan
-    without threshold sharing must return identical results: the shared bound only prunes
-    rows that cannot be in the top-k."""
-    N, d, B, k = 60000, 256, 48, 100
-    X, Q = make(N, d, B, seed=77, planted=20)
-    idx = _lib.Index(d, "bf16", "ip", cuda_device)
-    idx.add(X)
-    base = idx.search_host(Q, k, path="umma")
-    for var in ("TS_NOFUSE", "TS_DBG_NOSHARE", "TS_DUAL"):
-        monkeypatch.setenv(var, "1")
-        D, I = idx.search_host(Q, k, path="umma")
-        monkeypatch.delenv(var)
-        assert (I == base[1]).all() and (D == base[0]).all(), var
-    rD, rI, sc = oracle_search(X, Q, k, "bf16")
-    assert not flat_ip.check_topk(base[0], base[1], sc, rD, rI, rel=REL)
-    # 300 queries: three query tiles (TS_DUAL pairs two of them)
-    Q2 = make(10, d, 300, seed=78)[1]
-    base2 = idx.search_host(Q2, k, path="umma")
-    monkeypatch.setenv("TS_DUAL", "1")
-    D2, I2 = idx.search_host(Q2, k, path="umma")
-    monkeypatch.delenv("TS_DUAL")
-    assert (I2 == base2[1]).all() and (D2 == base2[0]).all()

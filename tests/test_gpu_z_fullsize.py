@@ -5,6 +5,8 @@ import numpy as np
 import pytest
 import torch
 
+from test_gpu_stage1 import REL, make, oracle_search
+
 from oracle import flat_ip, maxsim
 from tristage_rag_b200 import _lib
 
@@ -149,3 +151,28 @@ def test_config5_shapes_stage1_k500_into_stage2(cuda_device):
         assert top_p[b].cpu().tolist() == order.tolist()
     assert (s2h > 0).all() and s2h.shape == (B, k1)
     assert st.ndocs == N and int(off[-1]) >= int(lens.sum())
+
+
+def test_scan_variants_agree_bit_for_bit(cuda_device, monkeypatch):
+    """The scan with and without cross-CTA threshold sharing, and the two-query-tiles-per-CTA
+    layout, must return identical results: the shared bound only prunes rows that cannot be
+    in the top-k."""
+    N, d, B, k = 60000, 256, 48, 100
+    X, Q = make(N, d, B, seed=77, planted=20)
+    idx = _lib.Index(d, "bf16", "ip", cuda_device)
+    idx.add(X)
+    base = idx.search_host(Q, k, path="umma")
+    for var in ("TS_DBG_NOSHARE", "TS_DUAL"):
+        monkeypatch.setenv(var, "1")
+        D, I = idx.search_host(Q, k, path="umma")
+        monkeypatch.delenv(var)
+        assert (I == base[1]).all() and (D == base[0]).all(), var
+    rD, rI, sc = oracle_search(X, Q, k, "bf16")
+    assert not flat_ip.check_topk(base[0], base[1], sc, rD, rI, rel=REL)
+    # 300 queries: three query tiles (TS_DUAL pairs two of them)
+    Q2 = make(10, d, 300, seed=78)[1]
+    base2 = idx.search_host(Q2, k, path="umma")
+    monkeypatch.setenv("TS_DUAL", "1")
+    D2, I2 = idx.search_host(Q2, k, path="umma")
+    monkeypatch.delenv("TS_DUAL")
+    assert (I2 == base2[1]).all() and (D2 == base2[0]).all()

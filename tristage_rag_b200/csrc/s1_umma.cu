@@ -512,7 +512,9 @@ int s1_umma_plan(const ScanArgs& a, UmmaLayout* lay) {
   lay->pub_n = (size_t)(pl.n_slices + 1) * lay->bpad;   // + one row for tau_g
   const int j = (a.k + pl.n_slices - 1) / pl.n_slices;
   lay->jrank = (j <= 8 && !getenv("TS_DBG_NOSHARE")) ? j : 0;
-  lay->fused = (lay->jrank > 0 && !pl.dual && !getenv("TS_NOFUSE")) ? 1 : 0;
+  // One cooperative launch (pre-pass + grid barrier + scan) instead of two launches.  Written
+  // after this round's GPU budget was spent: NOT yet validated on hardware, so it is opt-in.
+  lay->fused = (lay->jrank > 0 && !pl.dual && getenv("TS_FUSE")) ? 1 : 0;
   return TS_OK;
 }
 
