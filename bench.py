@@ -275,7 +275,7 @@ def main():
     idx.set_profiling(True)
     l0 = idx.launches
     ms_eager = timed(step, args.steps, 0, dev, dist_on)
-    launches = idx.launches - l0
+    launches = idx.launches - l0 + (args.steps if world > 1 else 0)   # + the post-all-gather merge kernel
     scan_ms, scan_n = idx.scan_time_ms()
     idx.set_profiling(False)
     # headline: the same step captured once in a CUDA graph (query prep, threshold pre-pass,

@@ -176,3 +176,29 @@ def test_scan_variants_agree_bit_for_bit(cuda_device, monkeypatch):
     D2, I2 = idx.search_host(Q2, k, path="umma")
     monkeypatch.delenv("TS_DUAL")
     assert (I2 == base2[1]).all() and (D2 == base2[0]).all()
+
+
+@pytest.mark.parametrize("order", ["ascending", "descending", "constant"])
+@pytest.mark.parametrize("k", [100, 500])
+def test_adversarial_score_orders_on_device(cuda_device, order, k):
+    """Rows are multiples of one direction, so the score of row i is a chosen value: ascending
+    order makes every later row beat the running threshold (list overflow + in-scan prune),
+    'constant' makes every row tie (k smallest ids must win).  tests/test_topk_model.py checks
+    the same cases on the CPU model of the selection algorithm."""
+    N, d = 60_000, 64
+    rng = np.random.default_rng(4)
+    u = flat_ip.normalize_rows(rng.standard_normal((1, d)).astype(np.float32))[0].astype(np.float32)
+    v = {"ascending": np.linspace(0.05, 1.0, N), "descending": np.linspace(1.0, 0.05, N),
+         "constant": np.full(N, 0.5)}[order].astype(np.float32)
+    X = (v[:, None] * u[None, :]).astype(np.float32)
+    Q = np.stack([u, -u, flat_ip.normalize_rows(rng.standard_normal((1, d)).astype(np.float32))[0]]).astype(np.float32)
+    idx = _lib.Index(d, "bf16", "ip", cuda_device)
+    idx.add(X)
+    for path in ("umma", "stream"):
+        D, I = idx.search_host(Q, k, path=path)
+        rD, rI, sc = oracle_search(X, Q, k, "bf16")
+        bad = flat_ip.check_topk(D, I, sc, rD, rI, rel=REL)
+        assert not bad, (order, k, path, bad[:3])
+        if order == "constant":
+            # every row has the same stored value: exact ties, ids ascending
+            assert I[0].tolist() == list(range(k)) and I[1].tolist() == list(range(k))
