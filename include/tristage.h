@@ -183,6 +183,11 @@ int64_t ts_tokstore_ntokens(const ts_tokstore* h);
 int ts_tokstore_reset(ts_tokstore* h);
 int ts_tokstore_set_id_base(ts_tokstore* h, int64_t id_base);
 int64_t ts_tokstore_launch_count(const ts_tokstore* h);
+/* persistence of one token shard (no reference equivalent: the reference
+ * re-encodes at query time, stage2_rescorer.py:255-259): header, doc table,
+ * padded token rows in the storage dtype.                                    */
+int ts_tokstore_save(const ts_tokstore* h, const char* path);
+int ts_tokstore_load(ts_tokstore** out, int device, const char* path);
 /* same measurement aid for the MaxSim kernel                                 */
 int ts_tokstore_set_profiling(ts_tokstore* h, int enable);
 int ts_tokstore_scan_time(ts_tokstore* h, float* mean_ms_out, int* n_out);

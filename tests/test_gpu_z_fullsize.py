@@ -202,3 +202,24 @@ def test_adversarial_score_orders_on_device(cuda_device, order, k):
         if order == "constant":
             # every row has the same stored value: exact ties, ids ascending
             assert I[0].tolist() == list(range(k)) and I[1].tolist() == list(range(k))
+
+
+def test_tokstore_save_load_roundtrip(cuda_device, tmp_path):
+    rng = np.random.default_rng(8)
+    dim, ndocs = 128, 500
+    lens = rng.integers(1, 200, size=ndocs)
+    tok = rng.standard_normal((int(lens.sum()), dim)).astype(np.float32)
+    st = _lib.TokStore(dim, "bf16", cuda_device)
+    st.add(tok, lens, normalize=True)
+    st.set_id_base(40)
+    q = rng.standard_normal((3, 32, dim)).astype(np.float32)
+    cand = (rng.integers(0, ndocs, size=(3, 64)) + 40).astype(np.int64)
+    ref = st.maxsim_host(q, cand)
+    p = str(tmp_path / "tok.tstok")
+    st.save(p)
+    st2 = _lib.TokStore.load(p, dim, "bf16", cuda_device)
+    assert st2.ndocs == ndocs and st2.ntokens == int(lens.sum())
+    got = st2.maxsim_host(q, cand)                    # id_base travels with the file
+    assert np.array_equal(got, ref) and (ref != 0).all()
+    with pytest.raises(_lib.TristageError):
+        _lib.TokStore.load(str(tmp_path / "missing"), dim, "bf16", cuda_device)

@@ -63,6 +63,8 @@ SYMBOLS = {
     "ts_tokstore_reset": (_i, [_vp]),
     "ts_tokstore_set_id_base": (_i, [_vp, _i64]),
     "ts_tokstore_launch_count": (_i64, [_vp]),
+    "ts_tokstore_save": (_i, [_vp, C.c_char_p]),
+    "ts_tokstore_load": (_i, [C.POINTER(_vp), _i, C.c_char_p]),
     "ts_tokstore_set_profiling": (_i, [_vp, _i]),
     "ts_tokstore_scan_time": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(_i)]),
     "ts_maxsim": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _u, _vp, _vp]),
@@ -326,6 +328,17 @@ class TokStore:
         check(lib().ts_tokstore_create(C.byref(h), self.device, self.dim, self.dtype, int(reserve_docs),
                                        int(reserve_tokens)))
         self._h = h
+
+    def save(self, path: str) -> None:
+        check(lib().ts_tokstore_save(self._h, path.encode()))
+
+    @classmethod
+    def load(cls, path: str, dim: int, dtype: str = "bf16", device: int = 0) -> "TokStore":
+        h = C.c_void_p()
+        check(lib().ts_tokstore_load(C.byref(h), int(device), path.encode()))
+        obj = cls.__new__(cls)
+        obj.dim, obj.device, obj.dtype, obj._h = int(dim), int(device), DTYPES[dtype], h
+        return obj
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

@@ -608,6 +608,78 @@ int ts_tokstore_reset(ts_tokstore* h) { if (!h) return TS_ERR_INVALID; h->ndocs 
 int ts_tokstore_set_id_base(ts_tokstore* h, int64_t b) { if (!h) return TS_ERR_INVALID; h->id_base = b; return TS_OK; }
 int64_t ts_tokstore_launch_count(const ts_tokstore* h) { return h ? h->launches : -1; }
 
+struct TsTokHeader {
+  char magic[8];
+  int32_t version, dim, dtype, pad;
+  int64_t ndocs, nrows, ntokens, id_base;
+};
+
+int ts_tokstore_save(const ts_tokstore* h, const char* path) {
+  if (!h || !path) { set_error("ts_tokstore_save: invalid argument"); return TS_ERR_INVALID; }
+  TS_CUDA_OK(cudaSetDevice(h->device));
+  FILE* f = fopen(path, "wb");
+  if (!f) { set_error("cannot open %s for writing", path); return TS_ERR_IO; }
+  TsTokHeader hd{};
+  memcpy(hd.magic, "TSTOK01", 8);
+  hd.version = 1; hd.dim = h->dim; hd.dtype = h->dtype; hd.ndocs = h->ndocs; hd.nrows = h->nrows;
+  hd.ntokens = h->ntokens; hd.id_base = h->id_base;
+  int rc = (fwrite(&hd, sizeof(hd), 1, f) == 1) ? TS_OK : TS_ERR_IO;
+  if (rc == TS_OK && h->ndocs > 0) {
+    std::vector<int64_t> off((size_t)h->ndocs);
+    std::vector<int32_t> len((size_t)h->ndocs);
+    if (cudaMemcpy(off.data(), h->doc_off, (size_t)h->ndocs * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(len.data(), h->doc_len, (size_t)h->ndocs * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = TS_ERR_CUDA;
+    else if (fwrite(off.data(), 8, off.size(), f) != off.size() || fwrite(len.data(), 4, len.size(), f) != len.size()) rc = TS_ERR_IO;
+  }
+  const size_t row_b = (size_t)h->dim * dtype_size(h->dtype);
+  const int64_t chunk = (int64_t)((64ull << 20) / row_b) + 1;
+  std::vector<char> buf((size_t)chunk * row_b);
+  for (int64_t s = 0; s < h->nrows && rc == TS_OK; s += chunk) {
+    const int64_t m = (h->nrows - s) < chunk ? (h->nrows - s) : chunk;
+    if (cudaMemcpy(buf.data(), (const char*)h->tok + (size_t)s * row_b, (size_t)m * row_b, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = TS_ERR_CUDA; break; }
+    if (fwrite(buf.data(), row_b, (size_t)m, f) != (size_t)m) rc = TS_ERR_IO;
+  }
+  fclose(f);
+  if (rc) set_error("ts_tokstore_save(%s) failed (%d)", path, rc);
+  return rc;
+}
+
+int ts_tokstore_load(ts_tokstore** out, int device, const char* path) {
+  if (!out || !path) { set_error("ts_tokstore_load: invalid argument"); return TS_ERR_INVALID; }
+  FILE* f = fopen(path, "rb");
+  if (!f) { set_error("cannot open %s", path); return TS_ERR_IO; }
+  TsTokHeader hd{};
+  if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "TSTOK01", 8) != 0 || hd.version != 1 || hd.ndocs < 0 ||
+      hd.nrows < 0) {
+    fclose(f); set_error("%s is not a tristage token-store file", path); return TS_ERR_IO;
+  }
+  ts_tokstore* h = nullptr;
+  int rc = ts_tokstore_create(&h, device, hd.dim, hd.dtype, hd.ndocs, hd.nrows);
+  if (rc) { fclose(f); return rc; }
+  h->id_base = hd.id_base;
+  if (hd.ndocs > 0) {
+    rc = tok_reserve(h, hd.ndocs, hd.nrows, 0);
+    std::vector<int64_t> off((size_t)hd.ndocs);
+    std::vector<int32_t> len((size_t)hd.ndocs);
+    if (rc == TS_OK && (fread(off.data(), 8, off.size(), f) != off.size() || fread(len.data(), 4, len.size(), f) != len.size())) rc = TS_ERR_IO;
+    if (rc == TS_OK && (cudaMemcpy(h->doc_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+                        cudaMemcpy(h->doc_len, len.data(), len.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)) rc = TS_ERR_CUDA;
+    const size_t row_b = (size_t)h->dim * dtype_size(h->dtype);
+    const int64_t chunk = (int64_t)((64ull << 20) / row_b) + 1;
+    std::vector<char> buf((size_t)chunk * row_b);
+    for (int64_t s = 0; s < hd.nrows && rc == TS_OK; s += chunk) {
+      const int64_t m = (hd.nrows - s) < chunk ? (hd.nrows - s) : chunk;
+      if (fread(buf.data(), row_b, (size_t)m, f) != (size_t)m) { rc = TS_ERR_IO; break; }
+      if (cudaMemcpy((char*)h->tok + (size_t)s * row_b, buf.data(), (size_t)m * row_b, cudaMemcpyHostToDevice) != cudaSuccess) rc = TS_ERR_CUDA;
+    }
+  }
+  fclose(f);
+  if (rc) { ts_tokstore_destroy(h); set_error("ts_tokstore_load(%s) failed (%d)", path, rc); return rc; }
+  h->ndocs = hd.ndocs; h->nrows = hd.nrows; h->ntokens = hd.ntokens;
+  *out = h;
+  return TS_OK;
+}
+
 int ts_maxsim(ts_tokstore* h, const void* q_tok, int q_dtype, const int32_t* q_len, int B, int lq_stride,
               const int64_t* cand, const int32_t* n_cand, int C, int mode, unsigned flags, float* out, void* stream) {
   if (!h || !q_tok || !cand || !out || B <= 0 || C <= 0 || lq_stride <= 0) { set_error("ts_maxsim: invalid argument"); return TS_ERR_INVALID; }

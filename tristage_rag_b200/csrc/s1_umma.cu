@@ -23,16 +23,25 @@
 //   quarter (w % 4) with tcgen05.ld 32x32b.x32, so thread t owns ONE query and
 //   walks its 256 scores of the tile.
 //
-// Fused top-k: thread-private running threshold tau (register) and candidate
-//   count; scores > tau are appended to the thread's candidate list in global
-//   memory (L2 resident).  When a list is within 32 entries of CAP the whole
-//   warp bitonic-sorts it in registers (warp_prune_list), keeps the best k
-//   and raises tau.  At the end every list is sorted once more and written as
-//   partial[slice][query][k]; topk_select.cu merges the n_slices lists.
+// Fused exact top-k (the [B, N] score matrix never exists):
+//   * fast path: per 32-column chunk a thread takes the max of its 32 scores and compares it
+//     ONCE with its threshold tau; 96-99 % of the chunks end here.
+//   * slow path: survivors are appended to the thread's candidate list in global memory (L2
+//     resident).  Within 32 entries of CAP the whole warp bitonic-sorts the list in registers
+//     (warp_prune_list), keeps the best k and raises tau (never needed on the benchmark
+//     configurations; exercised by adversarial score orders).
+//   * shared threshold: each slice c publishes pub[c][q] = the J-th best score it has seen for
+//     query q, J = ceil(k / n_slices) (8 registers per thread).  n_slices * J >= k rows score
+//     >= min_c pub[c][q], so the global k-th best is >= that minimum and every thread may drop
+//     anything below it.  A one-tile pre-pass launch (mode 0) seeds pub; during the scan
+//     (mode 1) slice 0 recomputes the minimum every other tile into tau_g, everybody else reads
+//     tau_g.  Mode 2 (opt-in, TS_FUSE) does both in one cooperative launch with a grid barrier.
+//   * the lists leave the kernel UNSORTED with their counts; topk_select.cu filters them with
+//     the final bound, compacts and sorts a few hundred survivors per query.
 //
 // Small batches (B <= 64): the queries are spread over the four TMEM lane
 //   quarters in groups of 8 rows (8-row TMA boxes), so all four epilogue warps
-//   share the list maintenance instead of one.
+//   share the work instead of one.
 #include <stdlib.h>
 
 #include "ts_common.cuh"
