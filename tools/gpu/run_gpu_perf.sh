@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-./run_gpu_tests.sh
+tools/gpu/run_gpu_tests.sh
 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
 CMD="python bench.py --steps 2 --warmup 1 --no-cpu"
