@@ -223,3 +223,26 @@ def test_tokstore_save_load_roundtrip(cuda_device, tmp_path):
     assert np.array_equal(got, ref) and (ref != 0).all()
     with pytest.raises(_lib.TristageError):
         _lib.TokStore.load(str(tmp_path / "missing"), dim, "bf16", cuda_device)
+
+
+def test_batched_rescoring_equals_per_query(cuda_device):
+    """ColBERTScorer.rescore_candidates_batch (one launch for the batch) == the per-query call."""
+    from oracle import fakes
+    from tristage_rag_b200 import ColBERTScorer, Stage2Config
+
+    docs = [f"document number {i} talks about topic {i % 7} and item {i * 3 % 11} in some detail" for i in range(60)]
+    queries = ["topic 3 item 5", "document number 12", "what about detail", ""]
+    tok = fakes.FakeTokenizer()
+    sc = ColBERTScorer(Stage2Config(device="cpu", top_k_candidates=10, gpu_index=cuda_device), tokenizer=tok,
+                       model=fakes.FakeTokenModel(tok, 64))
+    rng = np.random.default_rng(3)
+    cands = []
+    for n in (25, 7, 0, 60):
+        ids = rng.choice(60, size=n, replace=False)
+        cands.append([{"doc_id": int(i), "document": docs[int(i)], "score": 1.0} for i in ids])
+    batch = sc.rescore_candidates_batch(queries, cands)
+    for q, c, got in zip(queries, cands, batch):
+        ref = sc.rescore_candidates(q, c)
+        assert [x["doc_id"] for x in got] == [x["doc_id"] for x in ref]
+        assert [x["stage2_score"] for x in got] == pytest.approx([x["stage2_score"] for x in ref], rel=1e-6, abs=1e-7)
+        assert all(x["stage"] == "stage2" for x in got) and len(got) == min(10, len(c))

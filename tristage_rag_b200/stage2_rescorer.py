@@ -220,6 +220,67 @@ class ColBERTScorer:
             order += rest[: self.config.top_k_candidates - len(order)]
         return [scored[i] for i in order]
 
+    def rescore_candidates_batch(self, queries: List[str],
+                                 candidates: List[List[Dict[str, Any]]]) -> List[List[Dict[str, Any]]]:
+        """``rescore_candidates`` for a batch of queries with ONE scoring launch (the reference
+        loops over queries, src/retrieval_pipeline.py:444-448).  Per-query results are identical
+        to calling ``rescore_candidates`` query by query."""
+        assert len(queries) == len(candidates)
+        out: List[List[Dict[str, Any]]] = [[] for _ in queries]
+        live = [b for b, c in enumerate(candidates) if c]
+        if not live:
+            return out
+        q_embs = [self.encode_query(queries[b]) for b in live]
+        try:
+            missing, seen = [], set()
+            for b in live:
+                for c in candidates[b]:
+                    k = self._key(c)
+                    if k not in self._slot and k not in seen:
+                        seen.add(k)
+                        missing.append((k, c["document"]))
+            if missing:
+                self.add_token_embeddings([k for k, _ in missing], self.encode_documents_batch([d for _, d in missing]))
+        except Exception as e:                         # reference :260-263, per batch
+            self.logger.error(f"Error encoding documents: {e}")
+            return [list(c) for c in candidates]
+        H = q_embs[0].shape[-1]
+        lq = [int(q.reshape(-1, H).shape[0]) for q in q_embs]
+        if max(lq) > _lib.TS_S2_MAX_LQ:                # rare: very long queries take the per-query path
+            for b in live:
+                out[b] = self.rescore_candidates(queries[b], candidates[b])
+            return out
+        Cmax = max(len(candidates[b]) for b in live)
+        qbuf = np.zeros((len(live), max(lq), H), np.float32)
+        cand = np.full((len(live), Cmax), -1, np.int64)
+        n_cand = np.zeros(len(live), np.int32)
+        for r, b in enumerate(live):
+            qbuf[r, : lq[r]] = q_embs[r].detach().float().cpu().numpy().reshape(-1, H)
+            slots = [self._slot[self._key(c)] for c in candidates[b]]
+            cand[r, : len(slots)] = slots
+            n_cand[r] = len(slots)
+        scores = self._store.maxsim_host(qbuf, cand, q_len=np.asarray(lq, np.int32), n_cand=n_cand,
+                                         mode=self._mode(), normalize_q=True)
+        top_k = min(self.config.top_k_candidates, Cmax, _lib.TS_MAX_K)
+        dev = torch.device("cuda", self.config.gpu_index)
+        _, pos = _lib.rank_desc(torch.from_numpy(scores).to(dev), top_k,
+                                n_cand=torch.from_numpy(n_cand).to(dev), device=self.config.gpu_index)
+        pos = pos.cpu().numpy()
+        for r, b in enumerate(live):
+            if self.config.top_k_candidates > _lib.TS_MAX_K and len(candidates[b]) > _lib.TS_MAX_K:
+                out[b] = self.rescore_candidates(queries[b], candidates[b])
+                continue
+            res = []
+            for p_ in pos[r]:
+                if p_ < 0:
+                    break
+                u = candidates[b][int(p_)].copy()
+                u["stage2_score"] = float(scores[r, int(p_)])
+                u["stage"] = "stage2"
+                res.append(u)
+            out[b] = res
+        return out
+
     def compute_similarity_matrix(self, query: str, documents: List[str]) -> np.ndarray:
         query_embeddings = self.encode_query(query)
         self.index_documents(documents)
