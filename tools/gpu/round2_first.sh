@@ -1,0 +1,21 @@
+#!/bin/bash
+# First GPU call of round 2 (1 GPU, ~6 min): validates everything written after the round-1
+# budget ran out, then re-measures.  Usage: gpurun --timeout 1500 -- tools/gpu/round2_first.sh
+mkdir -p gpurun_out
+run() { name=$1; shift; timeout 900 python -m pytest "$@" -q -m gpu -p no:cacheprovider > gpurun_out/$name.log 2>&1; echo "$name rc=$? $(tail -1 gpurun_out/$name.log)"; }
+run pipe tests/test_gpu_pipeline.py
+run s1 tests/test_gpu_stage1.py
+run s2 tests/test_gpu_stage2.py
+run zfull tests/test_gpu_z_fullsize.py
+# opt-in single-launch scan: parity first, then its effect on small shards
+TS_FUSE=1 run s1_fused tests/test_gpu_stage1.py -k "umma_path or planted or duplicates or cosine or merge_of_shards"
+P="python tools/perf_probe.py --paths umma --rows 1250000 --dim 1024 --batches 1,32,128,1024"
+$P --tag twolaunch > gpurun_out/fuse_probe.jsonl 2> gpurun_out/fuse_probe.err
+TS_FUSE=1 $P --tag fused >> gpurun_out/fuse_probe.jsonl 2>> gpurun_out/fuse_probe.err
+python - <<'PY'
+import json
+for l in open('gpurun_out/fuse_probe.jsonl'):
+    r=json.loads(l); print(f"{r['tag']:10s} B={r['B']:5d} step={r['step_ms']:.3f} scan={r['scan_ms_per_launch']:.3f}")
+PY
+timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; tail -c 600 gpurun_out/bench_n1.json
+timeout 300 python tools/e2e_c5.py --docs 500000 > gpurun_out/e2e_c5_1gpu.json 2> gpurun_out/e2e_c5.err; echo "c5 rc=$?"; cat gpurun_out/e2e_c5_1gpu.json
