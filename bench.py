@@ -183,6 +183,12 @@ def stage1_alg_bytes(n_rows, ld, B, k, L):
     return n_rows * ld * 2 + B * ld * 2 + L * B * k * 8
 
 
+def workload_config(N, d, k, B, world):
+    """The `config` both arms print: same workload keys for the GPU arm and the CPU reference arm."""
+    return {"workload": f"exact top-{k} over {N}x{d} bf16 corpus (row-sharded over {world} GPU), query batch {B}",
+            "rows": N, "dim": d, "k": k, "batch": B}
+
+
 def finish(code: int = 0):
     """Leave without running interpreter/NCCL teardown: destroying a process group (or CUDA
     graphs that captured NCCL work) can block for minutes after the result line is out."""
@@ -223,8 +229,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": args.batch / value * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"exact top-{args.k} over {args.rows}x{args.dim} corpus, query batch {args.batch}",
-                   "note": "each step scans a 500k-row slice; rate scaled linearly to the full corpus"},
+        "config": {**workload_config(args.rows, args.dim, args.k, args.batch, args.gpus),
+                   "path": "cpu: fp32 torch/MKL Q@X.T + topk (restated IndexFlatIP; FAISS not installable here)",
+                   "note": "the reference stores fp32; each step scans a 500k-row slice on all host threads and the "
+                           "rate is scaled linearly to the full corpus (the scan is O(N)); the CPU arm does not "
+                           "shard, so the same number is printed for every --gpus"},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
                          "host": info},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -347,8 +356,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"exact top-{k} over {N}x{d} bf16 corpus (row-sharded over {world} GPU), query batch {B}",
-                   "rows": N, "dim": d, "k": k, "batch": B, "path": roof["kernel"], "parallelism": f"rowshard{world}",
+        "config": {**workload_config(N, d, k, B, world), "path": roof["kernel"], "parallelism": f"rowshard{world}",
                    "l2": "inputs larger than L2 (shard >= 2.5 GB vs 126 MB), no flush needed",
                    "launch": launch_mode, "ms_per_step_eager": ms_eager / args.steps, **extra_modes},
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": B * d * 4,

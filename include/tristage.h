@@ -144,9 +144,19 @@ int ts_topk_merge_packed(int device, const void* blob_dev, int64_t list_stride_b
                          int64_t ids_offset_bytes, int n_lists, int B, int k,
                          float* out_scores_dev, int64_t* out_ids_dev, void* stream);
 
-/* faiss.write_index / read_index  (stage1_retriever.py:436,463).             */
+/* faiss.write_index / read_index  (stage1_retriever.py:436,463): one shard
+ * file per handle (layout: see "shard files" below).  save synchronises the
+ * device; load verifies the file's checksums.                                */
 int ts_index_save(const ts_index* h, const char* path);
 int ts_index_load(ts_index** out, int device, const char* path);
+/* Append rows [row_lo, row_lo + n_rows) of an index shard file to h (same dim,
+ * storage dtype and metric).  This is the primitive behind re-sharding: a
+ * corpus saved by G ranks is loaded by G' ranks, each appending the pieces of
+ * the old files that intersect its new row range.  id_base is NOT taken from
+ * the file (use ts_index_set_id_base).  Synchronises `stream`.               */
+int ts_index_append_file(ts_index* h, const char* path, int64_t row_lo, int64_t n_rows, void* stream);
+int ts_index_dtype(const ts_index* h);
+int ts_index_metric(const ts_index* h);
 
 /* copy stored rows [start, start+n) back as fp32 [n, dim] to host (tests,
  * migration); not on the hot path.                                           */
@@ -184,10 +194,13 @@ int ts_tokstore_reset(ts_tokstore* h);
 int ts_tokstore_set_id_base(ts_tokstore* h, int64_t id_base);
 int64_t ts_tokstore_launch_count(const ts_tokstore* h);
 /* persistence of one token shard (no reference equivalent: the reference
- * re-encodes at query time, stage2_rescorer.py:255-259): header, doc table,
- * padded token rows in the storage dtype.                                    */
+ * re-encodes at query time, stage2_rescorer.py:255-259).                     */
 int ts_tokstore_save(const ts_tokstore* h, const char* path);
 int ts_tokstore_load(ts_tokstore** out, int device, const char* path);
+/* append docs [doc_lo, doc_lo + n_docs) of a token shard file (re-sharding)  */
+int ts_tokstore_append_file(ts_tokstore* h, const char* path, int64_t doc_lo, int64_t n_docs, void* stream);
+int ts_tokstore_dim(const ts_tokstore* h);
+int ts_tokstore_dtype(const ts_tokstore* h);
 /* same measurement aid for the MaxSim kernel                                 */
 int ts_tokstore_set_profiling(ts_tokstore* h, int enable);
 int ts_tokstore_scan_time(ts_tokstore* h, float* mean_ms_out, int* n_out);
@@ -216,6 +229,41 @@ int ts_maxsim_host(ts_tokstore* h, const void* q_tok_host, int q_dtype, const in
  * out_pos [B, top_k] int32 (-1 padded), out_scores [B, top_k].               */
 int ts_rank_desc(int device, const float* scores_dev, const int32_t* n_cand_dev, int B, int C,
                  int top_k, float* out_scores_dev, int32_t* out_pos_dev, void* stream);
+
+/* ------------------------------------------------------------ shard files -- */
+/* On-disk form of one shard, little endian, sections
+ * 4096-byte aligned so the payload can be mmap'ed:
+ *   header page | table (index: inv_norm f32[n] for TS_METRIC_COSINE;
+ *   tokstore: doc_off i64[n] + doc_len i32[n]) | payload (index: rows[n][ld];
+ *   tokstore: tok[nrows][dim], docs padded to 8 rows), storage dtype.
+ * Each section carries an XXH64 digest; files are written to "<path>.tmp" and
+ * renamed into place.  The functions in this block are HOST ONLY (no CUDA
+ * call): tools and CPU tests can inspect, check and produce shard files.     */
+typedef enum ts_file_kind { TS_FILE_INDEX = 1, TS_FILE_TOKSTORE = 2 } ts_file_kind;
+typedef struct ts_file_info {
+  int32_t kind, version, dim, ld, dtype, metric;
+  int64_t n;       /* rows (index) or docs (tokstore)                          */
+  int64_t nrows;   /* payload rows (index: n; tokstore: 8-row padded tokens)   */
+  int64_t ntokens; /* tokstore: real tokens                                    */
+  int64_t id_base; /* global id of row / doc 0 when the shard was saved        */
+  uint64_t table_offset, table_bytes, payload_offset, payload_bytes;
+  uint64_t table_hash, payload_hash;
+} ts_file_info;
+/* parse + validate the header and the section bounds                         */
+int ts_file_probe(const char* path, ts_file_info* out);
+/* recompute both digests (and, for a token shard, check that the doc table
+ * adds up to the payload); TS_ERR_IO on any mismatch                         */
+int ts_file_verify(const char* path);
+/* Write a shard file from HOST memory already in the storage dtype -- no
+ * arithmetic, only layout (migration of an existing matrix, tests).
+ * rows_storage: [n][ld] with ld = dim rounded up to 16 bytes, pad columns 0;
+ * inv_norm: [n] for TS_METRIC_COSINE, else NULL.                             */
+int ts_file_write_index_host(const char* path, int dim, int storage_dtype, int metric, int64_t n,
+                             int64_t id_base, const void* rows_storage, const float* inv_norm);
+/* tok_storage: [sum(lens)][dim] un-padded, already normalised; the writer
+ * inserts the zero rows that pad every doc to a multiple of 8.               */
+int ts_file_write_tokstore_host(const char* path, int dim, int storage_dtype, int64_t n_docs,
+                                int64_t id_base, const int32_t* lens, const void* tok_storage);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,96 @@
+// TEST INFRASTRUCTURE ONLY (see tests/hostsim/cuda_runtime.h).  Stand-ins for the kernel
+// launchers that csrc/api.cu calls: the two INGEST launchers are restated on the CPU so the
+// host-side bookkeeping around them (growth, staging, padding, shard files) can be checked
+// end to end; the scan / scoring / selection launchers are NOT simulated -- they fail with
+// TS_ERR_UNSUPPORTED, there is no CPU compute path for them anywhere in this repository.
+#include <math.h>
+
+#include <vector>
+
+#include "ts_internal.h"
+
+extern "C" {
+long long hostsim_live_allocs = 0;
+long long hostsim_live_pinned = 0;
+long long hostsim_fail_malloc_over = 0;
+int hostsim_is_simulation(void) { return 1; }
+}
+
+namespace {
+uint16_t f32_to_bf16(float f) {          // round to nearest even, NaN kept quiet
+  uint32_t u; memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+float bf16_to_f32(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+uint16_t f32_to_f16(float f) { _Float16 h = (_Float16)f; uint16_t u; memcpy(&u, &h, 2); return u; }
+float f16_to_f32(uint16_t u) { _Float16 h; memcpy(&h, &u, 2); return (float)h; }
+float load(const void* p, int dt, size_t i) {
+  if (dt == TS_F32) return ((const float*)p)[i];
+  return dt == TS_BF16 ? bf16_to_f32(((const uint16_t*)p)[i]) : f16_to_f32(((const uint16_t*)p)[i]);
+}
+void store(void* p, int dt, size_t i, float v) {
+  if (dt == TS_F32) ((float*)p)[i] = v;
+  else ((uint16_t*)p)[i] = dt == TS_BF16 ? f32_to_bf16(v) : f32_to_f16(v);
+}
+}  // namespace
+
+namespace ts {
+
+int launch_convert_rows(const void* src, int sdt, int64_t src_ld, void* dst, int ddt, int64_t dst_ld, int64_t n, int dim,
+                        int norm_mode, float* inv_norm_out, cudaStream_t) {
+  for (int64_t r = 0; r < n; ++r) {
+    float denom = 1.f; bool scale = false;
+    if (norm_mode != kNormNone) {
+      float ss = 0.f;
+      for (int c = 0; c < dim; ++c) { const float v = load(src, sdt, (size_t)(r * src_ld + c)); ss += v * v; }
+      const float nrm = sqrtf(ss);
+      denom = norm_mode == kNormStage1 ? nrm + 1e-8f : fmaxf(nrm, 1e-12f);
+      if (inv_norm_out) inv_norm_out[r] = 1.0f / denom; else scale = true;
+    }
+    for (int64_t c = 0; c < dst_ld; ++c) {
+      float v = c < dim ? load(src, sdt, (size_t)(r * src_ld + c)) : 0.f;
+      if (scale) v /= denom;
+      store(dst, ddt, (size_t)(r * dst_ld + c), v);
+    }
+  }
+  return TS_OK;
+}
+
+int launch_tok_ingest(const void* src, int sdt, const int64_t* so, const int64_t* dof, const int32_t* len, int n_docs,
+                      void* dst, int ddt, int dim, int normalize, cudaStream_t) {
+  for (int d = 0; d < n_docs; ++d) {
+    const int L = len[d], Lp = (L + 7) & ~7;
+    for (int r = 0; r < Lp; ++r) {
+      const size_t o = (size_t)(dof[d] + r) * dim;
+      if (r >= L) { for (int c = 0; c < dim; ++c) store(dst, ddt, o + c, 0.f); continue; }
+      const size_t s = (size_t)(so[d] + r) * dim;
+      float denom = 1.f;
+      if (normalize) {
+        float ss = 0.f;
+        for (int c = 0; c < dim; ++c) { const float v = load(src, sdt, s + c); ss += v * v; }
+        denom = fmaxf(sqrtf(ss), 1e-12f);
+      }
+      for (int c = 0; c < dim; ++c) { float v = load(src, sdt, s + c); if (normalize) v /= denom; store(dst, ddt, o + c, v); }
+    }
+  }
+  return TS_OK;
+}
+
+static int not_simulated(const char* what) {
+  set_error("%s: not simulated -- the scan/scoring kernels only exist for sm_100a (hostsim is test infrastructure)", what);
+  return TS_ERR_UNSUPPORTED;
+}
+int s1_stream_plan(const ScanArgs&, int*, size_t*) { return not_simulated("s1_stream"); }
+int s1_umma_plan(const ScanArgs&, UmmaLayout*) { return not_simulated("s1_umma"); }
+int launch_s1_stream(const ScanArgs&, cudaStream_t, int*) { return not_simulated("s1_stream"); }
+int launch_s1_umma(const ScanArgs&, const UmmaLayout&, cudaStream_t, int*) { return not_simulated("s1_umma"); }
+int launch_merge_keys(const uint64_t*, int, int, int, int64_t, uint64_t*, uint64_t*, float*, int64_t*, cudaStream_t, int*) { return not_simulated("merge_keys"); }
+size_t merge_tmp_keys(int, int, int) { return 0; }
+int launch_merge_lists(const uint64_t*, const int*, const float*, const UmmaLayout&, int, int, int64_t, float*, int64_t*, cudaStream_t, int*) { return not_simulated("merge_lists"); }
+int launch_merge_pairs(const float*, const int64_t*, long long, long long, int, int, int, float*, int64_t*, cudaStream_t) { return not_simulated("merge_pairs"); }
+int launch_rank_desc(const float*, const int32_t*, int, int, int, float*, int32_t*, cudaStream_t) { return not_simulated("rank_desc"); }
+int launch_maxsim(const MaxSimArgs&, cudaStream_t, int*) { return not_simulated("maxsim"); }
+
+}  // namespace ts

@@ -1,6 +1,8 @@
 """GPU: BASELINE.json's full sizes through size-independent properties
 (planted known answers, sortedness, idempotence, shard-merge == full search,
 agreement of the two scan kernels) plus oracle checks on a few queries."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -154,28 +156,29 @@ def test_config5_shapes_stage1_k500_into_stage2(cuda_device):
 
 
 def test_scan_variants_agree_bit_for_bit(cuda_device, monkeypatch):
-    """The scan with and without cross-CTA threshold sharing, and the two-query-tiles-per-CTA
-    layout, must return identical results: the shared bound only prunes rows that cannot be
-    in the top-k."""
+    """The scan with and without cross-CTA threshold sharing must return identical results: the
+    shared bound only prunes rows that cannot be in the top-k.  Experimental layouts that lost
+    on hardware (TS_DUAL, two query tiles per CTA) and the not-yet-validated single-launch scan
+    (TS_FUSE) are compared too when TS_TEST_EXPERIMENTAL=1 (tools/gpu/round2_first.sh)."""
     N, d, B, k = 60000, 256, 48, 100
     X, Q = make(N, d, B, seed=77, planted=20)
     idx = _lib.Index(d, "bf16", "ip", cuda_device)
     idx.add(X)
     base = idx.search_host(Q, k, path="umma")
-    for var in ("TS_DBG_NOSHARE", "TS_DUAL"):
-        monkeypatch.setenv(var, "1")
-        D, I = idx.search_host(Q, k, path="umma")
-        monkeypatch.delenv(var)
-        assert (I == base[1]).all() and (D == base[0]).all(), var
     rD, rI, sc = oracle_search(X, Q, k, "bf16")
     assert not flat_ip.check_topk(base[0], base[1], sc, rD, rI, rel=REL)
-    # 300 queries: three query tiles (TS_DUAL pairs two of them)
-    Q2 = make(10, d, 300, seed=78)[1]
+    Q2 = make(10, d, 300, seed=78)[1]                 # 300 queries: three query tiles
     base2 = idx.search_host(Q2, k, path="umma")
-    monkeypatch.setenv("TS_DUAL", "1")
-    D2, I2 = idx.search_host(Q2, k, path="umma")
-    monkeypatch.delenv("TS_DUAL")
-    assert (I2 == base2[1]).all() and (D2 == base2[0]).all()
+    variants = ["TS_DBG_NOSHARE"]
+    if os.environ.get("TS_TEST_EXPERIMENTAL"):
+        variants += ["TS_DUAL", "TS_FUSE"]
+    for var in variants:
+        monkeypatch.setenv(var, "1")
+        D, I = idx.search_host(Q, k, path="umma")
+        D2, I2 = idx.search_host(Q2, k, path="umma")
+        monkeypatch.delenv(var)
+        assert (I == base[1]).all() and (D == base[0]).all(), var
+        assert (I2 == base2[1]).all() and (D2 == base2[0]).all(), var
 
 
 @pytest.mark.parametrize("order", ["ascending", "descending", "constant"])

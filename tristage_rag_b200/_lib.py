@@ -32,6 +32,23 @@ DTYPES = {"f32": TS_F32, "fp32": TS_F32, "float32": TS_F32,
           "f16": TS_F16, "fp16": TS_F16, "float16": TS_F16}
 PATHS = {"auto": TS_PATH_AUTO, "stream": TS_PATH_STREAM, "umma": TS_PATH_UMMA}
 
+DTYPE_NAMES = {TS_F32: "fp32", TS_BF16: "bf16", TS_F16: "fp16"}
+TS_FILE_INDEX, TS_FILE_TOKSTORE = 1, 2
+
+
+class FileInfo(C.Structure):
+    """``ts_file_info`` (include/tristage.h): the header of one shard file."""
+    _fields_ = [("kind", C.c_int32), ("version", C.c_int32), ("dim", C.c_int32), ("ld", C.c_int32),
+                ("dtype", C.c_int32), ("metric", C.c_int32),
+                ("n", C.c_int64), ("nrows", C.c_int64), ("ntokens", C.c_int64), ("id_base", C.c_int64),
+                ("table_offset", C.c_uint64), ("table_bytes", C.c_uint64),
+                ("payload_offset", C.c_uint64), ("payload_bytes", C.c_uint64),
+                ("table_hash", C.c_uint64), ("payload_hash", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
 # every symbol include/tristage.h declares: name -> (restype, argtypes)
 _vp, _i, _i64, _u = C.c_void_p, C.c_int, C.c_int64, C.c_uint
 SYMBOLS = {
@@ -51,6 +68,9 @@ SYMBOLS = {
     "ts_topk_merge_packed": (_i, [_i, _vp, _i64, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "ts_index_save": (_i, [_vp, C.c_char_p]),
     "ts_index_load": (_i, [C.POINTER(_vp), _i, C.c_char_p]),
+    "ts_index_append_file": (_i, [_vp, C.c_char_p, _i64, _i64, _vp]),
+    "ts_index_dtype": (_i, [_vp]),
+    "ts_index_metric": (_i, [_vp]),
     "ts_index_get_rows": (_i, [_vp, _i64, _i64, _vp]),
     "ts_index_launch_count": (_i64, [_vp]),
     "ts_index_set_profiling": (_i, [_vp, _i]),
@@ -65,11 +85,18 @@ SYMBOLS = {
     "ts_tokstore_launch_count": (_i64, [_vp]),
     "ts_tokstore_save": (_i, [_vp, C.c_char_p]),
     "ts_tokstore_load": (_i, [C.POINTER(_vp), _i, C.c_char_p]),
+    "ts_tokstore_append_file": (_i, [_vp, C.c_char_p, _i64, _i64, _vp]),
+    "ts_tokstore_dim": (_i, [_vp]),
+    "ts_tokstore_dtype": (_i, [_vp]),
     "ts_tokstore_set_profiling": (_i, [_vp, _i]),
     "ts_tokstore_scan_time": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(_i)]),
     "ts_maxsim": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _u, _vp, _vp]),
     "ts_maxsim_host": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _u, _vp, _vp]),
     "ts_rank_desc": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "ts_file_probe": (_i, [C.c_char_p, C.POINTER(FileInfo)]),
+    "ts_file_verify": (_i, [C.c_char_p]),
+    "ts_file_write_index_host": (_i, [C.c_char_p, _i, _i, _i, _i64, _i64, _vp, _vp]),
+    "ts_file_write_tokstore_host": (_i, [C.c_char_p, _i, _i, _i64, _i64, _vp, _vp]),
 }
 
 _lib = None
@@ -256,17 +283,80 @@ class Index:
         return out
 
     def save(self, path: str) -> None:
-        check(lib().ts_index_save(self._h, path.encode()))
+        check(lib().ts_index_save(self._h, os.fsencode(path)))
+
+    def append_file(self, path: str, row_lo: int, n_rows: int) -> None:
+        """Append rows [row_lo, row_lo + n_rows) of an index shard file (re-sharding primitive)."""
+        check(lib().ts_index_append_file(self._h, os.fsencode(path), int(row_lo), int(n_rows),
+                                         _stream_ptr(self.device)))
 
     @classmethod
     def load(cls, path: str, device: int = 0) -> "Index":
         h = C.c_void_p()
-        check(lib().ts_index_load(C.byref(h), int(device), path.encode()))
-        dim = int(lib().ts_index_dim(h))
+        check(lib().ts_index_load(C.byref(h), int(device), os.fsencode(path)))
         obj = cls.__new__(cls)
-        obj.dim, obj.device, obj._h = dim, int(device), h
-        obj.dtype, obj.metric = None, None
+        obj.dim, obj.device, obj._h = int(lib().ts_index_dim(h)), int(device), h
+        obj.dtype, obj.metric = int(lib().ts_index_dtype(h)), int(lib().ts_index_metric(h))
         return obj
+
+
+def file_probe(path: str) -> dict:
+    """Header of a shard file as a dict (host only: works without a GPU)."""
+    fi = FileInfo()
+    check(lib().ts_file_probe(os.fsencode(path), C.byref(fi)))
+    return fi.as_dict()
+
+
+def file_verify(path: str) -> None:
+    """Recompute the section checksums of a shard file; raises TristageError on a mismatch."""
+    check(lib().ts_file_verify(os.fsencode(path)))
+
+
+def _storage_view(a, dtype_code: int):
+    """numpy array already in the storage dtype: float32, or uint16 bit patterns of bf16 / fp16
+    (float16 arrays are accepted for fp16)."""
+    import numpy as np
+
+    a = np.ascontiguousarray(a)
+    if dtype_code == TS_F32:
+        assert a.dtype == np.float32, a.dtype
+    elif dtype_code == TS_F16 and a.dtype == np.float16:
+        a = a.view(np.uint16)
+    else:
+        assert a.dtype == np.uint16, f"pass {DTYPE_NAMES[dtype_code]} rows as uint16 bit patterns, got {a.dtype}"
+    return a
+
+
+def write_index_file(path: str, rows, dtype: str = "bf16", metric: str = "ip", id_base: int = 0, inv_norm=None,
+                     dim: int = None) -> None:
+    """Write an index shard file from host rows ALREADY in the storage dtype ([n, ld] with ld = dim
+    rounded up to 16 bytes).  Layout only, no arithmetic; host only."""
+    import numpy as np
+
+    code = DTYPES[dtype]
+    rows = _storage_view(rows, code)
+    n, ld = rows.shape
+    dim = ld if dim is None else int(dim)
+    per = 4 if code == TS_F32 else 8
+    assert (dim + per - 1) // per * per == ld, (dim, ld)
+    m = TS_METRIC_COSINE if metric in ("cosine", "cos") else TS_METRIC_IP
+    inv = np.ascontiguousarray(inv_norm, np.float32) if inv_norm is not None else None
+    check(lib().ts_file_write_index_host(os.fsencode(path), dim, code, m, n, int(id_base),
+                                         C.c_void_p(rows.ctypes.data) if n else None,
+                                         C.c_void_p(inv.ctypes.data) if inv is not None else None))
+
+
+def write_tokstore_file(path: str, tok, lens, dtype: str = "bf16", id_base: int = 0) -> None:
+    """Write a token shard file from un-padded host token rows already in the storage dtype."""
+    import numpy as np
+
+    code = DTYPES[dtype]
+    tok = _storage_view(tok, code)
+    lens = np.ascontiguousarray(lens, np.int32)
+    assert tok.ndim == 2 and tok.shape[0] == int(lens.sum()), (tok.shape, int(lens.sum()))
+    check(lib().ts_file_write_tokstore_host(os.fsencode(path), tok.shape[1], code, len(lens), int(id_base),
+                                            C.c_void_p(lens.ctypes.data) if len(lens) else None,
+                                            C.c_void_p(tok.ctypes.data) if len(lens) else None))
 
 
 def topk_merge(scores, ids, device: int = 0):
@@ -330,14 +420,23 @@ class TokStore:
         self._h = h
 
     def save(self, path: str) -> None:
-        check(lib().ts_tokstore_save(self._h, path.encode()))
+        check(lib().ts_tokstore_save(self._h, os.fsencode(path)))
+
+    def append_file(self, path: str, doc_lo: int, n_docs: int) -> None:
+        """Append docs [doc_lo, doc_lo + n_docs) of a token shard file (re-sharding primitive)."""
+        check(lib().ts_tokstore_append_file(self._h, os.fsencode(path), int(doc_lo), int(n_docs),
+                                            _stream_ptr(self.device)))
 
     @classmethod
-    def load(cls, path: str, dim: int, dtype: str = "bf16", device: int = 0) -> "TokStore":
+    def load(cls, path: str, dim: int = None, dtype: str = None, device: int = 0) -> "TokStore":
+        """dim / dtype come from the file; when given they are checked against it."""
         h = C.c_void_p()
-        check(lib().ts_tokstore_load(C.byref(h), int(device), path.encode()))
+        check(lib().ts_tokstore_load(C.byref(h), int(device), os.fsencode(path)))
         obj = cls.__new__(cls)
-        obj.dim, obj.device, obj.dtype, obj._h = int(dim), int(device), DTYPES[dtype], h
+        obj.dim, obj.dtype = int(lib().ts_tokstore_dim(h)), int(lib().ts_tokstore_dtype(h))
+        obj.device, obj._h = int(device), h
+        if (dim is not None and int(dim) != obj.dim) or (dtype is not None and DTYPES[dtype] != obj.dtype):
+            raise ValueError(f"{path}: holds dim {obj.dim} {DTYPE_NAMES[obj.dtype]}, expected dim {dim} {dtype}")
         return obj
 
     def __del__(self):

@@ -6,7 +6,7 @@
 
 #include <vector>
 
-#include "ts_internal.h"
+#include "ts_handles.h"
 
 namespace ts {
 
@@ -30,11 +30,11 @@ int get_device_info(int device, DeviceInfo* out) {
 }
 
 // grow-only device scratch
-static int ensure_bytes(void** p, size_t* cur, size_t need) {
+int ensure_bytes(void** p, size_t* cur, size_t need) {
   if (need <= *cur) return TS_OK;
   if (*p) { cudaFree(*p); *p = nullptr; *cur = 0; }
   cudaError_t e = cudaMalloc(p, need);
-  if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); return TS_ERR_NOMEM; }
+  if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); return TS_ERR_NOMEM; }
   *cur = need;
   return TS_OK;
 }
@@ -43,80 +43,7 @@ static int ensure_bytes(void** p, size_t* cur, size_t need) {
 
 using namespace ts;
 
-namespace {
-// ring of CUDA event pairs around the dominant kernel (measurement aid)
-struct ScanTimer {
-  static constexpr int kMax = 256;
-  bool on = false;
-  int n = 0;
-  cudaEvent_t e0[kMax], e1[kMax];
-  bool made = false;
-  void begin(cudaStream_t st) {
-    if (!on || n >= kMax) return;
-    if (!made) { for (int i = 0; i < kMax; ++i) { cudaEventCreate(&e0[i]); cudaEventCreate(&e1[i]); } made = true; }
-    cudaEventRecord(e0[n], st);
-  }
-  void end(cudaStream_t st) {
-    if (!on || n >= kMax) return;
-    cudaEventRecord(e1[n], st);
-    ++n;
-  }
-  int report(float* mean_ms, int* count) {
-    float tot = 0.f;
-    for (int i = 0; i < n; ++i) {
-      if (cudaEventSynchronize(e1[i]) != cudaSuccess) { set_error("event sync failed"); return TS_ERR_CUDA; }
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, e0[i], e1[i]);
-      tot += ms;
-    }
-    if (mean_ms) *mean_ms = n ? tot / n : 0.f;
-    if (count) *count = n;
-    n = 0;
-    return TS_OK;
-  }
-  void destroy() { if (made) { for (int i = 0; i < kMax; ++i) { cudaEventDestroy(e0[i]); cudaEventDestroy(e1[i]); } made = false; } }
-};
-}  // namespace
-
-struct ts_index {
-  int device, dim, ld, dtype, metric;
-  int64_t n, cap, id_base;
-  void* rows;
-  float* inv_norm;
-  DeviceInfo info;
-  int64_t launches;
-  // scratch (grow-only)
-  void* qbuf; size_t qbuf_b;
-  void* lists; size_t lists_b;
-  void* partial; size_t partial_b;
-  void* tmp0; size_t tmp0_b;
-  void* tmp1; size_t tmp1_b;
-  void* counts; size_t counts_b;
-  void* pub; size_t pub_b;
-  unsigned int* grid_bar;            // {counter, generation}, zeroed once
-  int coop;                          // device supports cooperative launch
-  void* stage; size_t stage_b;       // staging for host inputs (add / search_host)
-  void* hout; size_t hout_b;         // device result buffers for search_host
-  ScanTimer* timer;
-};
-
-struct ts_tokstore {
-  int device, dim, dtype;
-  int64_t ndocs, nrows, cap_docs, cap_rows, id_base, ntokens;
-  int64_t hint_docs, hint_rows;     // reservation hints honoured by the first add
-  void* tok;
-  int64_t* doc_off;
-  int32_t* doc_len;
-  DeviceInfo info;
-  int64_t launches;
-  void* qbuf; size_t qbuf_b;
-  void* stage; size_t stage_b;
-  void* meta; size_t meta_b;         // per-add src offsets scratch / host-variant buffers
-  void* hbuf; size_t hbuf_b;
-  ScanTimer* timer;
-};
-
-namespace {
+namespace ts {
 
 int check_device(int device, DeviceInfo* info) {
   int n = 0;
@@ -136,8 +63,6 @@ int check_device(int device, DeviceInfo* info) {
   return TS_OK;
 }
 
-bool valid_storage(int dt) { return dt == TS_F32 || dt == TS_BF16 || dt == TS_F16; }
-
 int index_reserve(ts_index* h, int64_t rows, cudaStream_t st) {
   if (rows <= h->cap) return TS_OK;
   int64_t ncap = h->cap > 0 ? h->cap : 1024;
@@ -147,14 +72,15 @@ int index_reserve(ts_index* h, int64_t rows, cudaStream_t st) {
   cudaError_t e = cudaMalloc(&nrows, (size_t)ncap * row_b);
   if (e != cudaSuccess) {
     // retry with the exact size before giving up (doubling can overshoot HBM)
+    cudaGetLastError();   // a failed cudaMalloc must not surface at the next launch check
     ncap = rows;
     e = cudaMalloc(&nrows, (size_t)ncap * row_b);
-    if (e != cudaSuccess) { set_error("cudaMalloc of %lld corpus rows failed: %s", (long long)ncap, cudaGetErrorString(e)); return TS_ERR_NOMEM; }
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of %lld corpus rows failed: %s", (long long)ncap, cudaGetErrorString(e)); return TS_ERR_NOMEM; }
   }
   float* ninv = nullptr;
   if (h->metric == TS_METRIC_COSINE) {
     e = cudaMalloc((void**)&ninv, (size_t)ncap * sizeof(float));
-    if (e != cudaSuccess) { cudaFree(nrows); set_error("cudaMalloc inv_norm failed"); return TS_ERR_NOMEM; }
+    if (e != cudaSuccess) { cudaGetLastError(); cudaFree(nrows); set_error("cudaMalloc inv_norm failed"); return TS_ERR_NOMEM; }
   }
   if (h->n > 0) {
     TS_CUDA_OK(cudaMemcpyAsync(nrows, h->rows, (size_t)h->n * row_b, cudaMemcpyDeviceToDevice, st));
@@ -167,6 +93,10 @@ int index_reserve(ts_index* h, int64_t rows, cudaStream_t st) {
   return TS_OK;
 }
 
+}  // namespace ts
+
+namespace {
+bool valid_storage(int dt) { return dt == TS_F32 || dt == TS_BF16 || dt == TS_F16; }
 }  // namespace
 
 extern "C" {
@@ -213,10 +143,10 @@ int ts_index_create(ts_index** out, int device, int dim, int storage_dtype, int 
     // exact reservation (no doubling) for the first allocation
     const size_t row_b = (size_t)h->ld * dtype_size(h->dtype);
     cudaError_t e = cudaMalloc(&h->rows, (size_t)reserve_rows * row_b);
-    if (e != cudaSuccess) { set_error("cudaMalloc of %lld rows failed: %s", (long long)reserve_rows, cudaGetErrorString(e)); delete h; return TS_ERR_NOMEM; }
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of %lld rows failed: %s", (long long)reserve_rows, cudaGetErrorString(e)); h->rows = nullptr; ts_index_destroy(h); return TS_ERR_NOMEM; }
     if (metric == TS_METRIC_COSINE) {
       e = cudaMalloc((void**)&h->inv_norm, (size_t)reserve_rows * sizeof(float));
-      if (e != cudaSuccess) { cudaFree(h->rows); set_error("cudaMalloc inv_norm failed"); delete h; return TS_ERR_NOMEM; }
+      if (e != cudaSuccess) { cudaGetLastError(); h->inv_norm = nullptr; set_error("cudaMalloc inv_norm failed"); ts_index_destroy(h); return TS_ERR_NOMEM; }
     }
     h->cap = reserve_rows;
   }
@@ -273,6 +203,8 @@ int ts_index_add(ts_index* h, const void* rows, int64_t n, int src_dtype, int sr
 
 int64_t ts_index_ntotal(const ts_index* h) { return h ? h->n : -1; }
 int ts_index_dim(const ts_index* h) { return h ? h->dim : -1; }
+int ts_index_dtype(const ts_index* h) { return h ? h->dtype : -1; }
+int ts_index_metric(const ts_index* h) { return h ? h->metric : -1; }
 int ts_index_reset(ts_index* h) { if (!h) return TS_ERR_INVALID; h->n = 0; return TS_OK; }
 int ts_index_set_id_base(ts_index* h, int64_t b) { if (!h) return TS_ERR_INVALID; h->id_base = b; return TS_OK; }
 int64_t ts_index_launch_count(const ts_index* h) { return h ? h->launches : -1; }
@@ -411,74 +343,6 @@ int ts_index_get_rows(const ts_index* h, int64_t start, int64_t n, float* out_ho
   return rc;
 }
 
-// ---- persistence: header + raw storage rows (+ inverse norms) -------------
-struct TsFileHeader {
-  char magic[8];
-  int32_t version, dim, ld, dtype, metric, pad;
-  int64_t n, id_base;
-};
-
-int ts_index_save(const ts_index* h, const char* path) {
-  if (!h || !path) { set_error("ts_index_save: invalid argument"); return TS_ERR_INVALID; }
-  TS_CUDA_OK(cudaSetDevice(h->device));
-  FILE* f = fopen(path, "wb");
-  if (!f) { set_error("cannot open %s for writing", path); return TS_ERR_IO; }
-  TsFileHeader hd{};
-  memcpy(hd.magic, "TSIDX01", 8);
-  hd.version = 1; hd.dim = h->dim; hd.ld = h->ld; hd.dtype = h->dtype; hd.metric = h->metric; hd.n = h->n; hd.id_base = h->id_base;
-  int rc = TS_OK;
-  if (fwrite(&hd, sizeof(hd), 1, f) != 1) rc = TS_ERR_IO;
-  const size_t row_b = (size_t)h->ld * dtype_size(h->dtype);
-  const int64_t chunk = (int64_t)((64ull << 20) / row_b) + 1;
-  std::vector<char> buf((size_t)chunk * row_b);
-  for (int64_t s = 0; s < h->n && rc == TS_OK; s += chunk) {
-    const int64_t m = (h->n - s) < chunk ? (h->n - s) : chunk;
-    if (cudaMemcpy(buf.data(), (const char*)h->rows + (size_t)s * row_b, (size_t)m * row_b, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = TS_ERR_CUDA; break; }
-    if (fwrite(buf.data(), row_b, (size_t)m, f) != (size_t)m) rc = TS_ERR_IO;
-  }
-  if (rc == TS_OK && h->metric == TS_METRIC_COSINE && h->n > 0) {
-    std::vector<float> inv((size_t)h->n);
-    if (cudaMemcpy(inv.data(), h->inv_norm, (size_t)h->n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = TS_ERR_CUDA;
-    else if (fwrite(inv.data(), 4, (size_t)h->n, f) != (size_t)h->n) rc = TS_ERR_IO;
-  }
-  fclose(f);
-  if (rc) set_error("ts_index_save(%s) failed (%d)", path, rc);
-  return rc;
-}
-
-int ts_index_load(ts_index** out, int device, const char* path) {
-  if (!out || !path) { set_error("ts_index_load: invalid argument"); return TS_ERR_INVALID; }
-  FILE* f = fopen(path, "rb");
-  if (!f) { set_error("cannot open %s", path); return TS_ERR_IO; }
-  TsFileHeader hd{};
-  if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "TSIDX01", 8) != 0 || hd.version != 1) {
-    fclose(f); set_error("%s is not a tristage index file", path); return TS_ERR_IO;
-  }
-  ts_index* h = nullptr;
-  int rc = ts_index_create(&h, device, hd.dim, hd.dtype, hd.metric, hd.n > 0 ? hd.n : 0);
-  if (rc) { fclose(f); return rc; }
-  if (h->ld != hd.ld) { fclose(f); ts_index_destroy(h); set_error("row pitch mismatch in %s", path); return TS_ERR_IO; }
-  h->id_base = hd.id_base;
-  const size_t row_b = (size_t)h->ld * dtype_size(h->dtype);
-  const int64_t chunk = (int64_t)((64ull << 20) / row_b) + 1;
-  std::vector<char> buf((size_t)chunk * row_b);
-  for (int64_t s = 0; s < hd.n && rc == TS_OK; s += chunk) {
-    const int64_t m = (hd.n - s) < chunk ? (hd.n - s) : chunk;
-    if (fread(buf.data(), row_b, (size_t)m, f) != (size_t)m) { rc = TS_ERR_IO; break; }
-    if (cudaMemcpy((char*)h->rows + (size_t)s * row_b, buf.data(), (size_t)m * row_b, cudaMemcpyHostToDevice) != cudaSuccess) rc = TS_ERR_CUDA;
-  }
-  if (rc == TS_OK && hd.metric == TS_METRIC_COSINE && hd.n > 0) {
-    std::vector<float> inv((size_t)hd.n);
-    if (fread(inv.data(), 4, (size_t)hd.n, f) != (size_t)hd.n) rc = TS_ERR_IO;
-    else if (cudaMemcpy(h->inv_norm, inv.data(), (size_t)hd.n * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = TS_ERR_CUDA;
-  }
-  fclose(f);
-  if (rc) { ts_index_destroy(h); set_error("ts_index_load(%s) failed (%d)", path, rc); return rc; }
-  h->n = hd.n;
-  *out = h;
-  return TS_OK;
-}
-
 // ------------------------------------------------------------------ Stage 2
 int ts_tokstore_create(ts_tokstore** out, int device, int dim, int storage_dtype, int64_t reserve_docs,
                        int64_t reserve_tokens) {
@@ -512,7 +376,10 @@ int ts_tokstore_destroy(ts_tokstore* h) {
 int ts_tokstore_set_profiling(ts_tokstore* h, int enable) { if (!h) return TS_ERR_INVALID; h->timer->on = enable != 0; h->timer->n = 0; return TS_OK; }
 int ts_tokstore_scan_time(ts_tokstore* h, float* mean_ms, int* n) { if (!h) return TS_ERR_INVALID; cudaSetDevice(h->device); return h->timer->report(mean_ms, n); }
 
-static int tok_reserve(ts_tokstore* h, int64_t docs, int64_t rows, cudaStream_t st) {
+}  // extern "C"
+
+namespace ts {
+int tok_reserve(ts_tokstore* h, int64_t docs, int64_t rows, cudaStream_t st) {
   const int64_t hint_docs = h->hint_docs, hint_rows = h->hint_rows;
   const int64_t cur_docs = h->cap_docs, cur_rows = h->cap_rows;
   if (docs > cur_docs) {
@@ -520,6 +387,8 @@ static int tok_reserve(ts_tokstore* h, int64_t docs, int64_t rows, cudaStream_t 
     while (nc < docs) nc *= 2;
     int64_t* noff = nullptr; int32_t* nlen = nullptr;
     if (cudaMalloc((void**)&noff, (size_t)nc * 8) != cudaSuccess || cudaMalloc((void**)&nlen, (size_t)nc * 4) != cudaSuccess) {
+      cudaGetLastError();
+      if (noff) cudaFree(noff);
       set_error("tokstore: cudaMalloc doc tables failed"); return TS_ERR_NOMEM;
     }
     if (h->ndocs > 0) {
@@ -538,9 +407,10 @@ static int tok_reserve(ts_tokstore* h, int64_t docs, int64_t rows, cudaStream_t 
     void* nt = nullptr;
     cudaError_t e = cudaMalloc(&nt, (size_t)nc * row_b);
     if (e != cudaSuccess) {
+      cudaGetLastError();
       nc = rows;
       e = cudaMalloc(&nt, (size_t)nc * row_b);
-      if (e != cudaSuccess) { set_error("tokstore: cudaMalloc of %lld token rows failed: %s", (long long)nc, cudaGetErrorString(e)); return TS_ERR_NOMEM; }
+      if (e != cudaSuccess) { cudaGetLastError(); set_error("tokstore: cudaMalloc of %lld token rows failed: %s", (long long)nc, cudaGetErrorString(e)); return TS_ERR_NOMEM; }
     }
     if (h->nrows > 0) {
       TS_CUDA_OK(cudaMemcpyAsync(nt, h->tok, (size_t)h->nrows * row_b, cudaMemcpyDeviceToDevice, st));
@@ -552,9 +422,7 @@ static int tok_reserve(ts_tokstore* h, int64_t docs, int64_t rows, cudaStream_t 
   return TS_OK;
 }
 
-}  // extern "C"
 
-namespace ts {
 // scatter ragged docs into the 8-row padded store (defined in tok_ingest.cu)
 int launch_tok_ingest(const void* src, int src_dtype, const int64_t* src_off_dev, const int64_t* dst_off_dev,
                       const int32_t* len_dev, int n_docs, void* dst, int dst_dtype, int dim, int normalize,
@@ -604,81 +472,11 @@ int ts_tokstore_add(ts_tokstore* h, const void* tok, int src_dtype, int src_on_d
 
 int64_t ts_tokstore_ndocs(const ts_tokstore* h) { return h ? h->ndocs : -1; }
 int64_t ts_tokstore_ntokens(const ts_tokstore* h) { return h ? h->ntokens : -1; }
+int ts_tokstore_dim(const ts_tokstore* h) { return h ? h->dim : -1; }
+int ts_tokstore_dtype(const ts_tokstore* h) { return h ? h->dtype : -1; }
 int ts_tokstore_reset(ts_tokstore* h) { if (!h) return TS_ERR_INVALID; h->ndocs = 0; h->nrows = 0; h->ntokens = 0; return TS_OK; }
 int ts_tokstore_set_id_base(ts_tokstore* h, int64_t b) { if (!h) return TS_ERR_INVALID; h->id_base = b; return TS_OK; }
 int64_t ts_tokstore_launch_count(const ts_tokstore* h) { return h ? h->launches : -1; }
-
-struct TsTokHeader {
-  char magic[8];
-  int32_t version, dim, dtype, pad;
-  int64_t ndocs, nrows, ntokens, id_base;
-};
-
-int ts_tokstore_save(const ts_tokstore* h, const char* path) {
-  if (!h || !path) { set_error("ts_tokstore_save: invalid argument"); return TS_ERR_INVALID; }
-  TS_CUDA_OK(cudaSetDevice(h->device));
-  FILE* f = fopen(path, "wb");
-  if (!f) { set_error("cannot open %s for writing", path); return TS_ERR_IO; }
-  TsTokHeader hd{};
-  memcpy(hd.magic, "TSTOK01", 8);
-  hd.version = 1; hd.dim = h->dim; hd.dtype = h->dtype; hd.ndocs = h->ndocs; hd.nrows = h->nrows;
-  hd.ntokens = h->ntokens; hd.id_base = h->id_base;
-  int rc = (fwrite(&hd, sizeof(hd), 1, f) == 1) ? TS_OK : TS_ERR_IO;
-  if (rc == TS_OK && h->ndocs > 0) {
-    std::vector<int64_t> off((size_t)h->ndocs);
-    std::vector<int32_t> len((size_t)h->ndocs);
-    if (cudaMemcpy(off.data(), h->doc_off, (size_t)h->ndocs * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(len.data(), h->doc_len, (size_t)h->ndocs * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = TS_ERR_CUDA;
-    else if (fwrite(off.data(), 8, off.size(), f) != off.size() || fwrite(len.data(), 4, len.size(), f) != len.size()) rc = TS_ERR_IO;
-  }
-  const size_t row_b = (size_t)h->dim * dtype_size(h->dtype);
-  const int64_t chunk = (int64_t)((64ull << 20) / row_b) + 1;
-  std::vector<char> buf((size_t)chunk * row_b);
-  for (int64_t s = 0; s < h->nrows && rc == TS_OK; s += chunk) {
-    const int64_t m = (h->nrows - s) < chunk ? (h->nrows - s) : chunk;
-    if (cudaMemcpy(buf.data(), (const char*)h->tok + (size_t)s * row_b, (size_t)m * row_b, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = TS_ERR_CUDA; break; }
-    if (fwrite(buf.data(), row_b, (size_t)m, f) != (size_t)m) rc = TS_ERR_IO;
-  }
-  fclose(f);
-  if (rc) set_error("ts_tokstore_save(%s) failed (%d)", path, rc);
-  return rc;
-}
-
-int ts_tokstore_load(ts_tokstore** out, int device, const char* path) {
-  if (!out || !path) { set_error("ts_tokstore_load: invalid argument"); return TS_ERR_INVALID; }
-  FILE* f = fopen(path, "rb");
-  if (!f) { set_error("cannot open %s", path); return TS_ERR_IO; }
-  TsTokHeader hd{};
-  if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "TSTOK01", 8) != 0 || hd.version != 1 || hd.ndocs < 0 ||
-      hd.nrows < 0) {
-    fclose(f); set_error("%s is not a tristage token-store file", path); return TS_ERR_IO;
-  }
-  ts_tokstore* h = nullptr;
-  int rc = ts_tokstore_create(&h, device, hd.dim, hd.dtype, hd.ndocs, hd.nrows);
-  if (rc) { fclose(f); return rc; }
-  h->id_base = hd.id_base;
-  if (hd.ndocs > 0) {
-    rc = tok_reserve(h, hd.ndocs, hd.nrows, 0);
-    std::vector<int64_t> off((size_t)hd.ndocs);
-    std::vector<int32_t> len((size_t)hd.ndocs);
-    if (rc == TS_OK && (fread(off.data(), 8, off.size(), f) != off.size() || fread(len.data(), 4, len.size(), f) != len.size())) rc = TS_ERR_IO;
-    if (rc == TS_OK && (cudaMemcpy(h->doc_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
-                        cudaMemcpy(h->doc_len, len.data(), len.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)) rc = TS_ERR_CUDA;
-    const size_t row_b = (size_t)h->dim * dtype_size(h->dtype);
-    const int64_t chunk = (int64_t)((64ull << 20) / row_b) + 1;
-    std::vector<char> buf((size_t)chunk * row_b);
-    for (int64_t s = 0; s < hd.nrows && rc == TS_OK; s += chunk) {
-      const int64_t m = (hd.nrows - s) < chunk ? (hd.nrows - s) : chunk;
-      if (fread(buf.data(), row_b, (size_t)m, f) != (size_t)m) { rc = TS_ERR_IO; break; }
-      if (cudaMemcpy((char*)h->tok + (size_t)s * row_b, buf.data(), (size_t)m * row_b, cudaMemcpyHostToDevice) != cudaSuccess) rc = TS_ERR_CUDA;
-    }
-  }
-  fclose(f);
-  if (rc) { ts_tokstore_destroy(h); set_error("ts_tokstore_load(%s) failed (%d)", path, rc); return rc; }
-  h->ndocs = hd.ndocs; h->nrows = hd.nrows; h->ntokens = hd.ntokens;
-  *out = h;
-  return TS_OK;
-}
 
 int ts_maxsim(ts_tokstore* h, const void* q_tok, int q_dtype, const int32_t* q_len, int B, int lq_stride,
               const int64_t* cand, const int32_t* n_cand, int C, int mode, unsigned flags, float* out, void* stream) {

@@ -15,10 +15,20 @@ BASELINE.json's north_star asks for:
 
 Only the exchange step is a collective; the scan/scoring kernels never wait on
 another rank.
+
+Persistence: ``save(dir)`` writes one shard file per rank
+(``ts_index_save`` / ``ts_tokstore_save``, layout in ``include/tristage.h``)
+plus a JSON manifest with the row range of every file; ``load(dir, ...)`` works
+for ANY world size -- each rank appends the pieces of the old files that
+intersect its new range (``plan_reshard`` + ``ts_*_append_file``), so a corpus
+saved by 8 ranks loads on 1, 2 or 4.  This replaces ``faiss.write_index`` /
+``read_index`` (``src/stage1_retriever.py:436,463``) for the sharded layout.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+import json
+import os
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -38,6 +48,69 @@ def owner_of(ids: torch.Tensor, n_total: int, world: int) -> torch.Tensor:
     big = torch.div(ids, base + 1, rounding_mode="floor")
     small = rem + torch.div(ids - cut, max(base, 1), rounding_mode="floor")
     return torch.where(ids < cut, big, small)
+
+
+# ---------------------------------------------------------------- persistence --
+MANIFEST_FORMAT = "tristage-shards-1"
+
+
+def shard_file_name(kind: str, rank: int, world: int) -> str:
+    return f"{kind}.{rank:05d}-of-{world:05d}.tsshard"
+
+
+def manifest_path(directory: str, kind: str) -> str:
+    return os.path.join(directory, f"{kind}.manifest.json")
+
+
+def write_manifest(directory: str, kind: str, n_total: int, world: int, **meta) -> dict:
+    """Manifest of a ``world``-rank save: file name and global [lo, hi) of every shard."""
+    shards = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        shards.append({"file": shard_file_name(kind, r, world), "lo": lo, "hi": hi})
+    man = {"format": MANIFEST_FORMAT, "kind": kind, "n_total": int(n_total), "world_size": int(world),
+           "shards": shards, **meta}
+    tmp = manifest_path(directory, kind) + ".tmp"
+    with open(tmp, "w") as f:
+        json.dump(man, f, indent=1)
+    os.replace(tmp, manifest_path(directory, kind))
+    return man
+
+
+def read_manifest(directory: str, kind: str) -> dict:
+    with open(manifest_path(directory, kind)) as f:
+        man = json.load(f)
+    if man.get("format") != MANIFEST_FORMAT or man.get("kind") != kind:
+        raise ValueError(f"{manifest_path(directory, kind)}: not a {kind} manifest of format {MANIFEST_FORMAT}")
+    return man
+
+
+def plan_reshard(shards: Sequence[Dict], lo: int, hi: int) -> List[Tuple[str, int, int]]:
+    """Pieces ``(file, first_row_in_file, n_rows)`` of saved shards that cover the global range
+    [lo, hi), in ascending id order.  Raises if the saved shards leave a gap inside the range."""
+    pieces, at = [], lo
+    for sh in sorted(shards, key=lambda x: x["lo"]):
+        a, b = max(lo, sh["lo"]), min(hi, sh["hi"])
+        if a >= b:
+            continue
+        if a != at:
+            raise ValueError(f"saved shards do not cover rows [{at}, {a})")
+        pieces.append((sh["file"], a - sh["lo"], b - a))
+        at = b
+    if at != hi and hi > lo:
+        raise ValueError(f"saved shards do not cover rows [{at}, {hi})")
+    return pieces
+
+
+def _rank_world(group) -> Tuple[int, int]:
+    if dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def _barrier(group) -> None:
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.barrier(group=group)
 
 
 def gather_topk(scores: torch.Tensor, ids: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -84,6 +157,37 @@ class ShardedIndex:
         all_s, all_i = gather_topk(s, i, self.group)
         return self.merge_fn(all_s, all_i)
 
+    def save(self, directory: str) -> None:
+        """Every rank writes its shard file; rank 0 writes the manifest once all files are in place."""
+        os.makedirs(directory, exist_ok=True)
+        self.local.save(os.path.join(directory, shard_file_name("index", self.rank, self.world)))
+        _barrier(self.group)
+        if self.rank == 0:
+            write_manifest(directory, "index", self.n_total, self.world)
+        _barrier(self.group)
+
+    @classmethod
+    def load(cls, directory: str, device: int = 0, group=None, make_local: Optional[Callable] = None,
+             merge_fn: Optional[Callable] = None) -> "ShardedIndex":
+        """Load a saved corpus under the CURRENT world size (which may differ from the saving one).
+        ``make_local(info, reserve_rows)`` builds the empty local index (default: ``_lib.Index`` on
+        ``device`` with the dim / dtype / metric of the files)."""
+        from . import _lib
+
+        man = read_manifest(directory, "index")
+        rank, world = _rank_world(group)
+        lo, hi = shard_range(man["n_total"], rank, world)
+        info = _lib.file_probe(os.path.join(directory, man["shards"][0]["file"]))
+        if make_local is None:
+            local = _lib.Index(info["dim"], _lib.DTYPE_NAMES[info["dtype"]],
+                               "cosine" if info["metric"] == _lib.TS_METRIC_COSINE else "ip", device,
+                               reserve_rows=hi - lo)
+        else:
+            local = make_local(info, hi - lo)
+        for fname, first, n in plan_reshard(man["shards"], lo, hi):
+            local.append_file(os.path.join(directory, fname), first, n)
+        return cls(local, man["n_total"], group=group, merge_fn=merge_fn)
+
     def _search_packed(self, q, k, **kw):
         """GPU fast path: scores + ids in one buffer -> ONE all-gather -> one merge kernel."""
         from ._lib import packed_layout, topk_merge_packed
@@ -109,8 +213,35 @@ class ShardedTokStore:
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.lo, self.hi = shard_range(int(n_total), self.rank, self.world)
+        self.n_total = int(n_total)
+        self.lo, self.hi = shard_range(self.n_total, self.rank, self.world)
         self.local.set_id_base(self.lo)
+
+    def save(self, directory: str) -> None:
+        os.makedirs(directory, exist_ok=True)
+        self.local.save(os.path.join(directory, shard_file_name("tokstore", self.rank, self.world)))
+        _barrier(self.group)
+        if self.rank == 0:
+            write_manifest(directory, "tokstore", self.n_total, self.world)
+        _barrier(self.group)
+
+    @classmethod
+    def load(cls, directory: str, device: int = 0, group=None,
+             make_local: Optional[Callable] = None) -> "ShardedTokStore":
+        """Token shards re-partitioned by doc id for the current world size (see ShardedIndex.load)."""
+        from . import _lib
+
+        man = read_manifest(directory, "tokstore")
+        rank, world = _rank_world(group)
+        lo, hi = shard_range(man["n_total"], rank, world)
+        info = _lib.file_probe(os.path.join(directory, man["shards"][0]["file"]))
+        if make_local is None:
+            local = _lib.TokStore(info["dim"], _lib.DTYPE_NAMES[info["dtype"]], device, reserve_docs=hi - lo)
+        else:
+            local = make_local(info, hi - lo)
+        for fname, first, n in plan_reshard(man["shards"], lo, hi):
+            local.append_file(os.path.join(directory, fname), first, n)
+        return cls(local, man["n_total"], group=group)
 
     def maxsim(self, q_tok: torch.Tensor, cand: torch.Tensor, **kw) -> torch.Tensor:
         out = self.local.maxsim(q_tok, cand, **kw)        # 0.0 for ids this shard does not own
