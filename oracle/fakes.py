@@ -11,6 +11,9 @@
   surface ``ColBERTScorer`` calls (src/stage2_rescorer.py:105-111,140-165,
   215-231): per-token hashed embeddings as ``last_hidden_state``.
 
+* ``FakeReranker`` -- the ``rerank`` surface of the Stage-3 cross-encoder wrapper
+  (src/stage3_reranker.py:230-264) with a word-overlap score.
+
 No model weights and no network exist here; these make BASELINE config #1
 (non_mcp/test_docs.json through the pipeline) runnable and reproducible.
 """
@@ -136,6 +139,33 @@ class FakeTokenModel:
             for t in range(L):
                 out[b, t] = self._vec(int(input_ids[b, t])) + 0.1 * _token_vec(f"pos:{t}", H)
         return types.SimpleNamespace(last_hidden_state=torch.from_numpy(out))
+
+
+class FakeReranker:
+    """Stage-3 stand-in with the ``rerank`` flow of the reference's cross-encoder wrapper
+    (src/stage3_reranker.py:230-264: copy, ``stage3_score``, ``stage: "stage3"``, stable sort
+    descending, truncate).  Stage 3 is outside the hot path; the score is a deterministic word
+    overlap so the orchestration around it can be pinned."""
+
+    def __init__(self, top_k_final: int = 20):
+        self.config = types.SimpleNamespace(top_k_final=top_k_final, batch_size=32)
+
+    def predict(self, query: str, documents) -> list:
+        qw = set(_words(query))
+        return [len(qw & set(_words(d))) / (1.0 + len(_words(d))) ** 0.5 for d in documents]
+
+    def rerank(self, query: str, candidates):
+        if not candidates:
+            return []
+        scores = self.predict(query, [c["document"] for c in candidates])
+        out = []
+        for c, s in zip(candidates, scores):
+            u = c.copy()
+            u["stage3_score"] = s
+            u["stage"] = "stage3"
+            out.append(u)
+        out.sort(key=lambda x: x["stage3_score"], reverse=True)
+        return out[: self.config.top_k_final]
 
 
 class _IVFFlatAsExact(flat_ip.IndexFlatIP):

@@ -17,6 +17,8 @@ What is imported from the reference (read-only, never copied):
     mcp/demo.py documents and queries) -> ``pipeline_c1.json``.
   * ``Stage1Retriever._normalize_embeddings`` (stage1_retriever.py:285-288)
     on a seeded matrix -> ``stage1_normalize.json``.
+  * ``src.retrieval_pipeline.RetrievalPipeline.batch_search`` (:426-448) over
+    those classes with ``FakeReranker`` as Stage 3 -> ``pipeline_batch.json``.
 
 Unused third-party imports of the reference (``sentence_transformers``) are
 stubbed in ``sys.modules``; nothing in the reference is modified.
@@ -179,6 +181,65 @@ def gen_pipeline(s1, s2):
     print("pipeline_c1.json:", len(cases), "cases")
 
 
+def gen_pipeline_batch(s1, s2):
+    """Unmodified reference RetrievalPipeline.batch_search (src/retrieval_pipeline.py:426-448, the
+    sequential loop over :323-424) with the reference Stage-1/Stage-2 classes, the fake encoders
+    and FakeReranker as Stage 3 -> pipeline_batch.json.  Pins what tristage_rag_b200/pipeline.py's
+    BatchedPipeline must return."""
+    import src.retrieval_pipeline as rp
+
+    test_docs, demo_docs, demo_queries = demo_fixture_inputs()
+    enc = fakes.FakeSentenceEncoder(768)
+    tok = fakes.FakeTokenizer()
+    tokmodel = fakes.FakeTokenModel(tok, 128)
+
+    def _load_s1(self):
+        self.model = enc
+        self.embedding_dim = enc.get_sentence_embedding_dimension()
+
+    def _load_s2(self):
+        self.tokenizer, self.model, self.use_amp = tok, tokmodel, False
+
+    s1.Stage1Retriever._load_model = _load_s1
+    s2.ColBERTScorer._load_model = _load_s2
+    cases = []
+    queries = list(demo_queries) + ["", "zzzz qqqq unknown words only", demo_queries[0]]
+    for name, docs, kw in (
+            ("demo_rrf_keep3", demo_docs, dict(stage1_top_k=8, stage1_enable_bm25=True, stage1_bm25_top_k=5,
+                                               stage1_fusion_method="rrf", stage2_top_k=5, stage3_top_k=3,
+                                               save_intermediate_results=True)),
+            ("test_docs_dense_keep2", test_docs, dict(stage1_top_k=50, stage1_enable_bm25=False, stage2_top_k=20,
+                                                      stage3_top_k=2, save_intermediate_results=False))):
+        tmp = tempfile.mkdtemp()
+        cfg = rp.PipelineConfig(device="cpu", cache_dir=os.path.join(tmp, "m"), index_dir=os.path.join(tmp, "i"),
+                                log_file=os.path.join(tmp, "log.txt"), stage1_use_fp16=False, stage2_use_fp16=False,
+                                auto_cleanup=False, **kw)
+        pipe = rp.RetrievalPipeline(config=cfg)
+        pipe.stage1 = s1.Stage1Retriever(s1.Stage1Config(
+            device="cpu", cache_dir=cfg.cache_dir, index_dir=cfg.index_dir, top_k_candidates=cfg.stage1_top_k,
+            batch_size=16, enable_bm25=cfg.stage1_enable_bm25, bm25_top_k=cfg.stage1_bm25_top_k,
+            fusion_method=cfg.stage1_fusion_method, use_fp16=False))
+        pipe.stage2 = s2.ColBERTScorer(s2.Stage2Config(
+            device="cpu", cache_dir=cfg.cache_dir, max_seq_length=192, batch_size=8,
+            top_k_candidates=cfg.stage2_top_k, use_fp16=False, scoring_method=cfg.stage2_scoring_method))
+        pipe.stage3 = fakes.FakeReranker(top_k_final=cfg.stage3_top_k)
+        pipe.add_documents(list(docs))
+        res = pipe.batch_search(queries)
+        slim = lambda rows, keys: [{k: r[k] for k in keys if k in r} for r in rows]   # noqa: E731
+        cases.append(dict(
+            name=name, docs="demo_docs" if docs is demo_docs else "test_docs", config=kw,
+            total_queries=pipe.performance_stats["total_queries"],
+            results=[dict(query=r["query"], keys=sorted(r.keys()), timing_keys=sorted(r["timing"].keys()),
+                          results=slim(r["results"], ("doc_id", "score", "stage1_score", "stage2_score", "stage3_score", "stage")),
+                          stage1_ids=[x["doc_id"] for x in r["stage1_results"]],
+                          stage2_ids=[x["doc_id"] for x in r["stage2_results"]]) for r in res]))
+    with open(os.path.join(GOLD, "pipeline_batch.json"), "w") as f:
+        json.dump(dict(source="unmodified reference RetrievalPipeline.batch_search with reference Stage-1/2 classes, "
+                              "oracle/fakes.py encoders + FakeReranker, restated faiss module",
+                       test_docs=test_docs, demo_docs=demo_docs, queries=queries, cases=cases), f, indent=1)
+    print("pipeline_batch.json:", len(cases), "cases")
+
+
 def gen_flat_ip():
     """Oracle-generated regression vectors for the restated IndexFlatIP (FAISS is
     absent: these pin the oracle against itself and document the semantics)."""
@@ -208,6 +269,7 @@ def main():
     os.chdir(tempfile.mkdtemp())
     try:
         gen_pipeline(s1, s2)
+        gen_pipeline_batch(s1, s2)
     finally:
         os.chdir(cwd)
     gen_flat_ip()

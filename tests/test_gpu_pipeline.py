@@ -84,3 +84,62 @@ def test_save_load_and_batch_search(cuda_device, golden_dir):
         b = r2.search("What is machine learning?")
         assert [(x["doc_id"], x["score"]) for x in b] == [(x["doc_id"], x["score"]) for x in a]
         assert r2.doc_metadata[5] == {"i": 5}
+
+
+@pytest.mark.parametrize("storage", ["fp32", "bf16"])
+def test_batched_pipeline_matches_reference_batch_search(cuda_device, golden_dir, storage):
+    """BatchedPipeline (one Stage-1 scan + one Stage-2 launch per batch) over the drop-in stages
+    against the UNMODIFIED reference RetrievalPipeline.batch_search (pipeline_batch.json)."""
+    from tristage_rag_b200.pipeline import BatchedPipeline
+
+    with open(os.path.join(golden_dir, "pipeline_batch.json")) as f:
+        g = json.load(f)
+    tol = 1e-5 if storage == "fp32" else 4e-3
+    for case in g["cases"]:
+        docs, cfg = g[case["docs"]], case["config"]
+        with tempfile.TemporaryDirectory() as tmp:
+            c1 = Stage1Config(device="cpu", cache_dir=os.path.join(tmp, "m"), index_dir=os.path.join(tmp, "i"),
+                              top_k_candidates=cfg["stage1_top_k"], batch_size=16,
+                              enable_bm25=cfg["stage1_enable_bm25"], bm25_top_k=cfg.get("stage1_bm25_top_k", 300),
+                              fusion_method=cfg.get("stage1_fusion_method", "rrf"), use_fp16=False,
+                              storage_dtype=storage, gpu_index=cuda_device)
+            c2 = Stage2Config(device="cpu", cache_dir=os.path.join(tmp, "m"), max_seq_length=192, batch_size=8,
+                              top_k_candidates=cfg["stage2_top_k"], use_fp16=False, storage_dtype=storage,
+                              gpu_index=cuda_device)
+            r1 = Stage1Retriever(c1, model=fakes.FakeSentenceEncoder(768))
+            tok = fakes.FakeTokenizer()
+            r2 = ColBERTScorer(c2, tokenizer=tok, model=fakes.FakeTokenModel(tok, 128))
+            r1.add_documents(list(docs))
+            bp = BatchedPipeline(stage1=r1, stage2=r2, stage3=fakes.FakeReranker(cfg["stage3_top_k"]),
+                                 stage1_top_k=cfg["stage1_top_k"], final_top_k=cfg["stage3_top_k"],
+                                 save_intermediate_results=cfg["save_intermediate_results"])
+            l1 = r1.faiss_index._index.launches
+            out = bp.batch_search(g["queries"])
+            s1_launches = r1.faiss_index._index.launches - l1
+            if storage == "bf16":     # convert + threshold pre-pass + scan + select
+                assert s1_launches <= 4, f"Stage 1 must be one batched search, saw {s1_launches} launches"
+            assert bp.performance_stats["total_queries"] == case["total_queries"]
+            for got, ref in zip(out, case["results"]):
+                assert got["query"] == ref["query"] and sorted(got.keys()) == ref["keys"]
+                assert sorted(got["timing"].keys()) == ref["timing_keys"]
+                if storage == "fp32":
+                    assert [x["doc_id"] for x in got["stage1_results"]] == ref["stage1_ids"]
+                    assert [x["doc_id"] for x in got["stage2_results"]] == ref["stage2_ids"]
+                    assert [x["doc_id"] for x in got["results"]] == [x["doc_id"] for x in ref["results"]]
+                elif ref["results"] and ref["results"][0]["stage3_score"] > 0:
+                    # bf16 storage: near-ties may swap further down, a clear winner must not
+                    assert got["results"][0]["doc_id"] == ref["results"][0]["doc_id"]
+                ref_by_id = {x["doc_id"]: x for x in ref["results"]}
+                for x in got["results"]:
+                    assert x["stage"] == "stage3" and type(x["stage2_score"]) is float
+                    if x["doc_id"] in ref_by_id:
+                        assert x["stage2_score"] == pytest.approx(ref_by_id[x["doc_id"]]["stage2_score"], rel=tol, abs=tol)
+                        assert x["stage3_score"] == pytest.approx(ref_by_id[x["doc_id"]]["stage3_score"])
+                json.dumps(got)
+            # the batched answer equals the per-query path of the same classes, in fewer launches
+            l1 = r1.faiss_index._index.launches
+            for got, q in zip(out, g["queries"]):
+                seq = r2.rescore_candidates(q, r1.search(q, cfg["stage1_top_k"]))
+                seq = fakes.FakeReranker(cfg["stage3_top_k"]).rerank(q, seq)[: cfg["stage3_top_k"]]
+                assert [x["doc_id"] for x in got["results"]] == [x["doc_id"] for x in seq]
+            assert s1_launches < r1.faiss_index._index.launches - l1
