@@ -20,3 +20,15 @@ for l in open('gpurun_out/fuse_probe.jsonl'):
 PY
 timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; tail -c 600 gpurun_out/bench_n1.json
 timeout 300 python tools/e2e_c5.py --docs 500000 > gpurun_out/e2e_c5_1gpu.json 2> gpurun_out/e2e_c5.err; echo "c5 rc=$?"; cat gpurun_out/e2e_c5_1gpu.json
+# opt-in Stage-2 epilogue (V2: LDS/STS, no -inf init, paired tcgen05.ld + max tree): parity, then A/B timing
+TS_S2_V2=1 run s2_v2 tests/test_gpu_stage2.py
+for v in "" 1; do
+  for cfg in "--lo 16 --hi 180" "--lo 180 --hi 180" "--lo 16 --hi 40" "--Lq 128" "--dim 768 --ndocs 50000"; do
+    TS_S2_V2=$v python tools/s2_probe.py $cfg --tag "v2=${v:-0} $cfg" >> gpurun_out/s2_v2_probe.jsonl 2>> gpurun_out/s2_v2_probe.err
+  done
+done
+python - <<'PY'
+import json
+for l in open('gpurun_out/s2_v2_probe.jsonl'):
+    r=json.loads(l); print(f"{r['tag']:45s} kernel={r['kernel_ms']:.3f} ms  {r['cand_per_s']/1e6:.1f} Mcand/s  hbm={r['hbm_frac']:.2f}")
+PY

@@ -492,7 +492,7 @@ UmmaPlan umma_plan(const ScanArgs& a) {
   // Two query tiles per CTA sharing each corpus chunk halve the L2->SM traffic, but the two
   // accumulators then cannot be double buffered against the epilogue; measured on B200 the
   // single-tile layout is faster (19.2 vs 21.5 ms at B=1024, 10M x 1024), so it is opt-in.
-  pl.dual = (pl.n_mt >= 2 && getenv("TS_DUAL")) ? 1 : 0;
+  pl.dual = (pl.n_mt >= 2 && env_on("TS_DUAL")) ? 1 : 0;
   pl.n_mg = pl.dual ? (pl.n_mt + 1) / 2 : pl.n_mt;
   pl.n_tiles = (int)((a.n + kTileN - 1) / kTileN);
   int s = a.sm_count / pl.n_mg;
@@ -514,16 +514,16 @@ int s1_umma_plan(const ScanArgs& a, UmmaLayout* lay) {
   lay->rows_per_cta = pl.dual ? 2 * kTileM : kTileM;
   lay->grid = pl.grid;
   lay->cap = cap_for_k(a.k);
-  lay->spread = (a.B <= 64 && !getenv("TS_DBG_NOSPREAD")) ? 1 : 0;
+  lay->spread = (a.B <= 64 && !env_on("TS_DBG_NOSPREAD")) ? 1 : 0;
   lay->bpad = pl.n_mt * kTileM;
   lay->lists_keys = (size_t)pl.grid * lay->rows_per_cta * lay->cap;
   lay->counts_n = (size_t)pl.grid * lay->rows_per_cta;
   lay->pub_n = (size_t)(pl.n_slices + 1) * lay->bpad;   // + one row for tau_g
   const int j = (a.k + pl.n_slices - 1) / pl.n_slices;
-  lay->jrank = (j <= 8 && !getenv("TS_DBG_NOSHARE")) ? j : 0;
+  lay->jrank = (j <= 8 && !env_on("TS_DBG_NOSHARE")) ? j : 0;
   // One cooperative launch (pre-pass + grid barrier + scan) instead of two launches.  Written
   // after this round's GPU budget was spent: NOT yet validated on hardware, so it is opt-in.
-  lay->fused = (lay->jrank > 0 && !pl.dual && getenv("TS_FUSE")) ? 1 : 0;
+  lay->fused = (lay->jrank > 0 && !pl.dual && env_on("TS_FUSE")) ? 1 : 0;
   return TS_OK;
 }
 
@@ -539,12 +539,12 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
   p.spread = lay.spread;
   p.n_qgroups = (a.B + 7) / 8;
   p.cap = lay.cap;
-  p.dbg_notopk = getenv("TS_DBG_NOTOPK") ? 1 : 0;
+  p.dbg_notopk = env_on("TS_DBG_NOTOPK") ? 1 : 0;
   p.jrank = lay.jrank; p.bpad = lay.bpad; p.dual = lay.dual;
   p.lists = a.lists; p.counts = a.counts; p.pub = a.pub; p.tau_g = a.pub + (size_t)lay.n_slices * lay.bpad;
   p.inv_norm = a.inv_norm;
   static unsigned long long* d_stats = nullptr;
-  if (getenv("TS_DBG_STATS")) {
+  if (env_on("TS_DBG_STATS")) {
     if (!d_stats) cudaMalloc((void**)&d_stats, 32);
     cudaMemsetAsync(d_stats, 0, 32, st);
     p.stats = d_stats;

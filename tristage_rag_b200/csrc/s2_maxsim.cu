@@ -147,7 +147,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <bool BF16>
+// V2 (opt-in, TS_S2_V2=1; written from the round-1 ncu source view, not yet validated on
+// hardware): the same pipeline with a shorter epilogue critical path --
+//   * shared-memory pointers keep their address space (LDS/STS instead of generic LD/ST for the
+//     tile meta and the per-doc maxima),
+//   * no per-tile "-inf" initialisation of the maxima: the producer records the first doc of
+//     every 64-column quarter in the tile meta and the finalize step only reads the quarters a
+//     doc really overlaps,
+//   * the drain keeps two tcgen05.ld in flight and reduces each 8-column unit with a max tree
+//     (unmasked when the unit lies inside a doc) instead of a 32-long dependent FMNMX chain.
+template <bool BF16, bool V2>
 __global__ void __launch_bounds__(kThreads, 1)
     maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmQ8, const __grid_constant__ CUtensorMap tmQ32,
                        const __grid_constant__ CUtensorMap tmQ128,
@@ -155,7 +164,13 @@ __global__ void __launch_bounds__(kThreads, 1)
                        const __grid_constant__ CUtensorMap tmT32, const __grid_constant__ CUtensorMap tmT64,
                        const __grid_constant__ CUtensorMap tmT128, const MaxSimParams p) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem;
+  if constexpr (V2) {
+    // offset arithmetic on the __shared__ array keeps the address space known to the compiler
+    smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  } else {
+    smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  }
   const int kStages = p.n_stages;
   const int mvals_bufs = (kStages == 3) ? 2 : 1;
   float* mvals_base = reinterpret_cast<float*>(smem + kStages * kStageBytes);           // [bufs][32][128]
@@ -275,6 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (!vmask) { cur = nxt; continue; }
       TileMeta* m = begin_tile();
       int cols = 0, nd = 0;
+      int qf1 = -1, qf2 = -1, qf3 = -1;   // V2: first doc reaching into columns >= 64 / 128 / 192
       while (vmask) {
         const int src = __ffs(vmask) - 1;
         vmask &= vmask - 1;
@@ -282,10 +298,19 @@ __global__ void __launch_bounds__(kThreads, 1)
         const long long o = __shfl_sync(0xffffffffu, off, src);
         const int pad = (L + 7) & ~7;
         if (cols + pad > kTileN) {
-          if (lane == 0) { m->used = cols; m->ndocs = nd; m->lq = lq; m->q_row = b * p.lq_stride; }
+          if (lane == 0) {
+            m->used = cols; m->ndocs = nd; m->lq = lq; m->q_row = b * p.lq_stride;
+            if constexpr (V2) { m->pad2_[0] = qf1; m->pad2_[1] = qf2; m->pad2_[2] = qf3; }
+          }
           emit_tile(m);
           m = begin_tile();
           cols = 0; nd = 0;
+          qf1 = qf2 = qf3 = -1;
+        }
+        if constexpr (V2) {
+          if (qf1 < 0 && cols + pad > 64) qf1 = nd;
+          if (qf2 < 0 && cols + pad > 128) qf2 = nd;
+          if (qf3 < 0 && cols + pad > 192) qf3 = nd;
         }
         if (lane == 0) {
           m->out_idx[nd] = b * p.C + j0 + src;
@@ -295,7 +320,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         cols += pad; ++nd;
       }
-      if (lane == 0) { m->used = cols; m->ndocs = nd; m->lq = lq; m->q_row = b * p.lq_stride; }
+      if (lane == 0) {
+        m->used = cols; m->ndocs = nd; m->lq = lq; m->q_row = b * p.lq_stride;
+        if constexpr (V2) { m->pad2_[0] = qf1; m->pad2_[1] = qf2; m->pad2_[2] = qf3; }
+      }
       emit_tile(m);
       cur = nxt;
     }
@@ -362,6 +390,47 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int c_lo = rep4 ? quarter * 64 : 0;
       const int c_hi = rep4 ? ((used < c_lo + 64) ? used : c_lo + 64) : used;
       const bool warp_active = rep4 ? true : (quarter * 32 < lq);
+      if constexpr (V2) {
+        // first doc of this warp's column range comes from the tile meta (no -inf initialisation)
+        int d = rep4 ? (quarter == 0 ? 0 : m->pad2_[quarter - 1]) : 0;
+        if (warp_active && d >= 0 && c_lo < c_hi) {
+          const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kTileN);
+          int seg_end = m->seg_col[d] + m->seg_len[d];
+          int seg_next = m->seg_col[d] + ((m->seg_len[d] + 7) & ~7);
+          float best = -INFINITY;
+          for (int g0 = c_lo; g0 < c_hi; g0 += 64) {
+            uint32_t r0[32], r1[32];
+            const bool two = g0 + 32 < c_hi;           // warp-uniform
+            tmem_ld_32x32b_x32(t_addr + (uint32_t)g0, r0);
+            if (two) tmem_ld_32x32b_x32(t_addr + (uint32_t)(g0 + 32), r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int cu = g0 + u * 8;
+              if (cu < c_hi) {                         // warp-uniform
+                if (cu >= seg_next) {                  // warp-uniform: the next doc starts here
+                  mvals[d * kTileM + lane_row] = best;
+                  ++d;
+                  best = -INFINITY;
+                  seg_end = m->seg_col[d] + m->seg_len[d];
+                  seg_next = m->seg_col[d] + ((m->seg_len[d] + 7) & ~7);
+                }
+                float v[8];
+#pragma unroll
+                for (int j2 = 0; j2 < 8; ++j2) v[j2] = __uint_as_float(u < 4 ? r0[u * 8 + j2] : r1[(u - 4) * 8 + j2]);
+                if (cu + 8 > seg_end) {                // warp-uniform: the doc's last, partly padded unit
+#pragma unroll
+                  for (int j2 = 0; j2 < 8; ++j2) v[j2] = (cu + j2 < seg_end) ? v[j2] : -INFINITY;
+                }
+                const float m01 = fmaxf(v[0], v[1]), m23 = fmaxf(v[2], v[3]);
+                const float m45 = fmaxf(v[4], v[5]), m67 = fmaxf(v[6], v[7]);
+                best = fmaxf(best, fmaxf(fmaxf(m01, m23), fmaxf(m45, m67)));
+              }
+            }
+          }
+          mvals[d * kTileM + lane_row] = best;
+        }
+      } else
       if (warp_active) {
         // docs that do not touch this warp's column range contribute -inf
         int d = -1;
@@ -413,6 +482,17 @@ __global__ void __launch_bounds__(kThreads, 1)
         float res;
         float mv[4];
         int nmv = 0;
+        if constexpr (V2) {
+          // only the lane quarters whose 64-column range the doc overlaps hold a value for it
+          const int col = m->seg_col[d];
+          const int q_lo = rep4 ? (col >> 6) : 0;
+          const int q_hi = rep4 ? ((col + ((m->seg_len[d] + 7) & ~7) - 1) >> 6) : 0;
+          for (int i = lane; i < lq; i += 32) {
+            float v = mvals[d * kTileM + (rep4 ? q_lo * 32 : 0) + i];
+            for (int qq = q_lo + 1; qq <= q_hi; ++qq) v = fmaxf(v, mvals[d * kTileM + qq * 32 + i]);
+            mv[nmv++] = v;
+          }
+        } else
         for (int i = lane; i < lq; i += 32) {
           float v = mvals[d * kTileM + i];
           if (rep4) v = fmaxf(fmaxf(v, mvals[d * kTileM + 32 + i]), fmaxf(mvals[d * kTileM + 64 + i], mvals[d * kTileM + 96 + i]));
@@ -495,15 +575,15 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
   p.out = a.out;
   { const char* e = getenv("TS_S2_STAGES"); p.n_stages = (e && atoi(e) == 4) ? 4 : 3; }
   int grid = a.sm_count < p.n_items ? a.sm_count : p.n_items;
-  if (a.dtype == TS_BF16) {
-    auto kern = maxsim_umma_kernel<true>;
+  const bool v2 = env_on("TS_S2_V2");   // opt-in until validated on hardware
+  auto launch = [&](auto kern) -> int {
     TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     kern<<<grid, kThreads, kSmemBytes, st>>>(tq8, tq32, tq128, t8, t16, t32, t64, t128, p);
-  } else {
-    auto kern = maxsim_umma_kernel<false>;
-    TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    kern<<<grid, kThreads, kSmemBytes, st>>>(tq8, tq32, tq128, t8, t16, t32, t64, t128, p);
-  }
+    return TS_OK;
+  };
+  if (a.dtype == TS_BF16) rc = v2 ? launch(maxsim_umma_kernel<true, true>) : launch(maxsim_umma_kernel<true, false>);
+  else rc = v2 ? launch(maxsim_umma_kernel<false, true>) : launch(maxsim_umma_kernel<false, false>);
+  if (rc) return rc;
   TS_CUDA_OK(cudaGetLastError());
   if (launches) ++*launches;
   return TS_OK;

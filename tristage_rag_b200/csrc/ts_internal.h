@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/tristage.h"
 
@@ -18,6 +19,12 @@ const char* get_error();
       return TS_ERR_CUDA;                                                                  \
     }                                                                                      \
   } while (0)
+
+// experiment switches (TS_FUSE, TS_S2_V2, TS_DBG_*): on when set to anything but "" or "0"
+inline bool env_on(const char* name) {
+  const char* e = getenv(name);
+  return e && e[0] && !(e[0] == '0' && !e[1]);
+}
 
 inline int dtype_size(int dt) { return dt == TS_F32 ? 4 : 2; }
 // row pitch in elements: rows are 16-byte aligned (TMA / 128-bit loads)
