@@ -1,0 +1,287 @@
+"""CPU: the CUDA-core kernels of libtristage EXECUTED on a SIMT emulator (tests/cudasim/: every
+simulated thread is a fiber; __syncthreads and the *_sync warp primitives are rendezvous points)
+and checked against the oracle with the rule the GPU parity tests use.  The kernel sources are
+the product's own (.cu files compiled with g++ under TS_CUDASIM); the tensor-path kernels
+(TMA / tcgen05) cannot be emulated and refuse.  Test infrastructure only -- the emulated library
+is built into build/cudasim/, loaded explicitly here, and never used by the package."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import flat_ip, maxsim
+from tristage_rag_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def sim_lib():
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    out = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cudasim"), "-j", "8"], env=env,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0, out.stdout[-4000:]
+    L = C.CDLL(os.path.join(ROOT, "build", "cudasim", "libtristage_cudasim.so"))
+    assert L.hostsim_is_simulation() == 2
+    for name, (res, args) in _lib.SYMBOLS.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    for name in ("cudasim_launches", "cudasim_blocks", "cudasim_switches"):
+        getattr(L, name).restype = C.c_ulonglong
+    return L
+
+
+@pytest.fixture()
+def sim(sim_lib, monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", sim_lib)
+    monkeypatch.setattr(_lib, "_stream_ptr", lambda device: None)
+    return sim_lib
+
+
+def make(N, d, B, seed=0, planted=0):
+    rng = np.random.default_rng(seed)
+    X = flat_ip.normalize_rows(rng.standard_normal((N, d)).astype(np.float32)).astype(np.float32)
+    Q = flat_ip.normalize_rows(rng.standard_normal((B, d)).astype(np.float32)).astype(np.float32)
+    if planted and N > planted * B:
+        for b in range(B):
+            pos = rng.choice(N, size=planted, replace=False)
+            noise = rng.standard_normal((planted, d)).astype(np.float32) / np.sqrt(d)
+            X[pos] = flat_ip.normalize_rows(Q[b][None, :] + 0.7 * noise)
+    return X, Q
+
+
+def oracle_search(X, Q, k, dtype):
+    Xr, Qr = flat_ip.round_to(X, dtype), flat_ip.round_to(Q, dtype)
+    idx = flat_ip.IndexFlatIP(X.shape[1])
+    idx.add(Xr)
+    D, I = idx.search(Qr, k)
+    return D, I, (lambda b, ids: (Xr[ids].astype(np.float64) @ Qr[b].astype(np.float64)))
+
+
+def p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+# ------------------------------------------------------------------- Stage 1 ---
+@pytest.mark.parametrize("N,d,B,k,dtype", [(5, 40, 1, 50, "bf16"), (700, 64, 3, 10, "bf16"), (900, 100, 2, 7, "fp16"),
+                                           (1500, 32, 4, 128, "fp32"), (1100, 72, 6, 20, "bf16"), (600, 16, 1, 500, "fp32")])
+def test_stream_scan_and_select_match_the_oracle(sim, N, d, B, k, dtype):
+    X, Q = make(N, d, B, seed=N + B, planted=5)
+    idx = _lib.Index(d, dtype, "ip", 0)
+    for part in np.array_split(X, 3):
+        idx.add(part)
+    before = sim.cudasim_launches()
+    D, I = idx.search_host(Q, k, path="stream")
+    assert sim.cudasim_launches() - before >= 3          # query prep, scan pass(es), selection
+    rD, rI, sc = oracle_search(X, Q, k, dtype)
+    assert not flat_ip.check_topk(D, I, sc, rD, rI, rel=REL)
+    if k > N:
+        assert (I[:, N:] == -1).all() and (D[:, N:] == np.float32(flat_ip.LOWEST_F32)).all()
+    idx.set_id_base(10_000_000_000)
+    D2, I2 = idx.search_host(Q, min(k, N), path="stream")
+    assert (I2 == I[:, : min(k, N)] + 10_000_000_000).all()
+
+
+@pytest.mark.parametrize("order", ["ascending", "descending", "constant"])
+def test_adversarial_score_orders_exercise_the_in_scan_prune(sim, order):
+    """Scores chosen per row: ascending order overflows every candidate list (warp bitonic prune in
+    the scan), constant makes every row tie (the k smallest ids must win)."""
+    N, d, k = 2600, 32, 100
+    rng = np.random.default_rng(4)
+    u = flat_ip.normalize_rows(rng.standard_normal((1, d)).astype(np.float32))[0].astype(np.float32)
+    v = {"ascending": np.linspace(0.05, 1.0, N), "descending": np.linspace(1.0, 0.05, N),
+         "constant": np.full(N, 0.5)}[order].astype(np.float32)
+    X = (v[:, None] * u[None, :]).astype(np.float32)
+    Q = np.stack([u, -u]).astype(np.float32)
+    idx = _lib.Index(d, "bf16", "ip", 0)
+    idx.add(X)
+    D, I = idx.search_host(Q, k, path="stream")
+    rD, rI, sc = oracle_search(X, Q, k, "bf16")
+    assert not flat_ip.check_topk(D, I, sc, rD, rI, rel=REL)
+    if order == "constant":
+        assert I[0].tolist() == list(range(k)) and I[1].tolist() == list(range(k))
+
+
+def test_cosine_metric_and_query_normalisation_flags(sim):
+    rng = np.random.default_rng(2)
+    N, d, k = 800, 48, 15
+    X = (rng.standard_normal((N, d)) * rng.uniform(0.1, 5.0, size=(N, 1))).astype(np.float32)
+    Q = (3.0 * rng.standard_normal((3, d))).astype(np.float32)
+    idx = _lib.Index(d, "bf16", "cosine", 0)
+    idx.add(X)
+    D, I = idx.search_host(Q, k, normalize_q=True, path="stream")
+    Xr = flat_ip.round_to(X, "bf16")
+    Qr = flat_ip.round_to(flat_ip.normalize_rows(Q), "bf16")
+    inv = (1.0 / (np.linalg.norm(X, axis=1) + 1e-8)).astype(np.float32)
+    S = (Qr @ Xr.T) * inv[None, :]
+    rD, rI = flat_ip.topk_desc(S, k)
+    sc = lambda b, ids: (Xr[ids].astype(np.float64) @ Qr[b].astype(np.float64)) * inv[ids]   # noqa: E731
+    assert not flat_ip.check_topk(D, I, sc, rD, rI, rel=REL)
+
+
+def test_shard_merge_equals_full_search(sim):
+    """ts_topk_merge / ts_topk_merge_packed: merge of per-shard top-k == top-k over the union, ties by id."""
+    N, d, B, k = 1200, 32, 5, 40
+    X, Q = make(N, d, B, seed=21)
+    X[700] = X[3]
+    X[1100] = X[3]                                           # exact duplicates across shards
+    full = _lib.Index(d, "bf16", "ip", 0)
+    full.add(X)
+    Df, If = full.search_host(Q, k, path="stream")
+    bounds = [0, 401, 402, 900, N]
+    S = np.empty((4, B, k), np.float32)
+    Id = np.empty((4, B, k), np.int64)
+    for i, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
+        sh = _lib.Index(d, "bf16", "ip", 0)
+        sh.add(X[lo:hi])
+        sh.set_id_base(lo)
+        S[i], Id[i] = sh.search_host(Q, k, path="stream")    # 1-row shard: k - 1 slots are -1 padding
+    out_s, out_i = np.empty((B, k), np.float32), np.empty((B, k), np.int64)
+    _lib.check(sim.ts_topk_merge(0, p(S), p(Id), 4, B, k, p(out_s), p(out_i), None))
+    assert (out_i == If).all() and (out_s == Df).all()
+    ids_off, nbytes = _lib.packed_layout(B, k)
+    blob = np.zeros(4 * nbytes, np.uint8)
+    for i in range(4):
+        blob[i * nbytes: i * nbytes + B * k * 4] = S[i].view(np.uint8).ravel()
+        blob[i * nbytes + ids_off: i * nbytes + ids_off + B * k * 8] = Id[i].view(np.uint8).ravel()
+    out_s2, out_i2 = np.empty((B, k), np.float32), np.empty((B, k), np.int64)
+    _lib.check(sim.ts_topk_merge_packed(0, p(blob), nbytes, ids_off, 4, B, k, p(out_s2), p(out_i2), None))
+    assert (out_i2 == If).all() and (out_s2 == Df).all()
+    rD, rI, sc = oracle_search(X, Q, k, "bf16")
+    assert not flat_ip.check_topk(out_s, out_i, sc, rD, rI, rel=REL)
+
+
+def test_rank_desc_is_the_reference_stable_sort(sim):
+    rng = np.random.default_rng(5)
+    B, Cn, top = 4, 300, 100
+    scores = rng.integers(0, 12, size=(B, Cn)).astype(np.float32) / 4          # many exact ties
+    n_cand = np.array([300, 17, 0, 100], np.int32)
+    out_s, out_p = np.empty((B, top), np.float32), np.empty((B, top), np.int32)
+    _lib.check(sim.ts_rank_desc(0, p(scores), p(n_cand), B, Cn, top, p(out_s), p(out_p), None))
+    for b in range(B):
+        order = maxsim.rescore_order(scores[b, : n_cand[b]], top)
+        n = len(order)
+        assert out_p[b, :n].tolist() == order.tolist() and (out_p[b, n:] == -1).all()
+        assert (out_s[b, :n] == scores[b, order]).all()
+
+
+def test_tensor_path_is_not_emulated(sim):
+    idx = _lib.Index(32, "bf16", "ip", 0)
+    idx.add(np.ones((4, 32), np.float32))
+    with pytest.raises(_lib.TristageError, match="cannot be emulated"):
+        idx.search_host(np.ones((1, 32), np.float32), 2, path="umma")
+    with pytest.raises(_lib.TristageError, match="cannot be emulated"):
+        idx.search_host(np.ones((1, 32), np.float32), 2)                       # auto = tensor path for bf16
+
+
+# ------------------------------------------------------------------- Stage 2 ---
+@pytest.mark.parametrize("dtype,mode", [("bf16", _lib.TS_S2_MAXSIM), ("fp32", _lib.TS_S2_COLBERT), ("fp16", _lib.TS_S2_MAXSIM)])
+def test_simt_maxsim_matches_the_oracle(sim, dtype, mode):
+    rng = np.random.default_rng(8)
+    dim, ndocs, Bq, Cn, Lq = 24, 60, 3, 12, 9
+    lens = rng.integers(1, 40, size=ndocs)
+    tok = (rng.standard_normal((int(lens.sum()), dim)) * 2).astype(np.float32)
+    st = _lib.TokStore(dim, dtype, 0)
+    st.add(tok, lens, normalize=True)
+    st.set_id_base(100)
+    q = rng.standard_normal((Bq, Lq, dim)).astype(np.float32)
+    cand = (rng.integers(0, ndocs, size=(Bq, Cn)) + 100).astype(np.int64)
+    cand[0, 3] = 5            # below the shard's id range
+    cand[1, 0] = 100 + ndocs  # above it
+    cand[2, 5] = -1
+    q_len = np.array([9, 4, 1], np.int32)
+    n_cand = np.array([12, 7, 12], np.int32)
+    got = st.maxsim_host(q, cand, q_len=q_len, n_cand=n_cand, mode=mode)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    nr = lambda x: flat_ip.round_to(maxsim.l2_normalize_tokens(x), dtype)      # noqa: E731
+    fn = maxsim.maxsim_score if mode == _lib.TS_S2_MAXSIM else maxsim.colbert_score
+    for b in range(Bq):
+        for j in range(Cn):
+            c = cand[b, j] - 100
+            if j >= n_cand[b] or c < 0 or c >= ndocs:
+                assert got[b, j] == 0.0
+            else:
+                want = fn(nr(q[b, : q_len[b]]), nr(tok[off[c]: off[c + 1]]), normalize=False)
+                assert got[b, j] == pytest.approx(want, rel=1e-3, abs=2e-4)
+
+
+# ------------------------------------------- selection over the tensor-path scan's lists ---
+def f2ord(x):
+    u = np.asarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    return np.where(u & 0x80000000, (~u) & 0xFFFFFFFF, u | 0x80000000).astype(np.uint64)
+
+
+def make_keys(scores, rows):
+    return (f2ord(scores) << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - np.asarray(rows, np.uint64))
+
+
+def scan_output_contract(Sc, n_slices, k, cap, rng, extra_frac=0.5):
+    """What s1_umma_kernel leaves for select_kernel (csrc/s1_umma.cu header): per (slice, query) an
+    UNSORTED list holding at least every row of the slice at or above the final shared bound
+    min_c pub[c][q] (plus rows appended while the bound was still lower), its count, and
+    pub[c][q] = the J-th best score of the slice, J = ceil(k / n_slices) (sharing off when J > 8)."""
+    B, N = Sc.shape
+    n_mt = (B + 127) // 128
+    bpad = n_mt * 128
+    spread = 1 if B <= 64 else 0
+    J = -(-k // n_slices)
+    jrank = J if J <= 8 else 0
+    tiles = np.arange(N) // 256
+    pub = np.full((n_slices, bpad), -np.inf, np.float32)
+    lists = np.zeros((n_mt * n_slices * 128, cap), np.uint64)
+    counts = np.zeros(n_mt * n_slices * 128, np.int32)
+    members = [np.nonzero(tiles % n_slices == c)[0] for c in range(n_slices)]
+    for b in range(B):
+        if jrank:
+            for c in range(n_slices):
+                s = np.sort(Sc[b, members[c]])[::-1]
+                pub[c, b] = s[J - 1] if len(s) >= J else -np.inf
+        bound = pub[:, b].min() if jrank else -np.inf
+        mt, qi = b >> 7, b & 127
+        row = ((qi >> 3) & 3) * 32 + ((qi >> 3) >> 2) * 8 + (qi & 7) if spread else qi
+        for c in range(n_slices):
+            rows = members[c]
+            must = rows[Sc[b, rows] >= bound]
+            rest = rows[Sc[b, rows] < bound]
+            if len(must) > cap:                       # the in-scan prune keeps the best k of an overflowing list
+                order = np.lexsort((must, -Sc[b, must].astype(np.float64)))
+                must = must[order[:k]]
+            take = rng.permutation(rest)[: min(int(len(rest) * extra_frac), cap - len(must))]
+            sel = rng.permutation(np.concatenate([must, take]))
+            at = (mt * n_slices + c) * 128 + row
+            lists[at, : len(sel)] = make_keys(Sc[b, sel], sel)
+            lists[at, len(sel):] = rng.integers(1, 2 ** 63, size=cap - len(sel)).astype(np.uint64)   # stale keys beyond count
+            counts[at] = len(sel)
+    return lists, counts, pub, dict(n_slices=n_slices, n_mt=n_mt, cap=cap, spread=spread, bpad=bpad, jrank=jrank)
+
+
+@pytest.mark.parametrize("N,B,k,n_slices,ties", [(6000, 3, 100, 20, False), (9000, 130, 100, 35, False), (5000, 2, 500, 10, False),
+                                                 (4000, 5, 10, 148, False), (3000, 2, 100, 7, True), (300, 1, 100, 2, False),
+                                                 (40000, 1, 100, 148, True)])   # 14 800 tied survivors: more than the sort buffer holds
+@pytest.mark.parametrize("serial", [False, True])
+def test_select_over_scan_lists_matches_the_oracle(sim, monkeypatch, N, B, k, n_slices, ties, serial):
+    """select_kernel in its kLists mode (parallel count prefix + batched loads by default, the first
+    version with TS_SELECT_V1=1) over lists that satisfy the scan's output contract."""
+    rng = np.random.default_rng(N + B + k)
+    X, Q = make(N, 32, B, seed=N, planted=0)
+    if ties:
+        X[:] = X[0]                                   # every row identical: one giant tie, ids must ascend
+    Sc = (flat_ip.round_to(Q, "bf16") @ flat_ip.round_to(X, "bf16").T).astype(np.float32)
+    n_slices = min(n_slices, (N + 255) // 256)
+    cap = 256 if k <= 128 else 1024
+    lists, counts, pub, lay = scan_output_contract(Sc, n_slices, k, cap, rng)
+    if serial:
+        monkeypatch.setenv("TS_SELECT_V1", "1")
+    out_s, out_i = np.empty((B, k), np.float32), np.empty((B, k), np.int64)
+    sim.cudasim_merge_lists.argtypes = [C.c_void_p] * 3 + [C.c_int] * 8 + [C.c_int64, C.c_void_p, C.c_void_p]
+    rc = sim.cudasim_merge_lists(p(lists), p(counts), p(pub), lay["n_slices"], lay["n_mt"], lay["cap"], lay["spread"],
+                                 lay["bpad"], lay["jrank"], B, k, 7_000_000_000, p(out_s), p(out_i))
+    assert rc == 0, sim.ts_last_error()
+    rD, rI = flat_ip.topk_desc(Sc, k)
+    valid = rI >= 0
+    assert (out_i[valid] == rI[valid] + 7_000_000_000).all() and (out_i[~valid] == -1).all()
+    assert (out_s[valid] == rD[valid]).all()

@@ -8,6 +8,10 @@ run s1 tests/test_gpu_stage1.py
 run s2 tests/test_gpu_stage2.py
 run zfull tests/test_gpu_z_fullsize.py
 TS_TEST_EXPERIMENTAL=1 run zvariants tests/test_gpu_z_fullsize.py -k scan_variants
+# select kernel: parallel count prefix (default since the emulator-validated rewrite) vs the first version
+P8="python tools/perf_probe.py --paths umma --rows 1250000 --dim 1024 --batches 1,32 --steps 50"
+$P8 --tag select_v2 > gpurun_out/select_probe.jsonl 2> gpurun_out/select_probe.err
+TS_SELECT_V1=1 $P8 --tag select_v1 >> gpurun_out/select_probe.jsonl 2>> gpurun_out/select_probe.err
 # opt-in single-launch scan: parity first, then its effect on small shards
 TS_FUSE=1 run s1_fused tests/test_gpu_stage1.py -k "umma_path or planted or duplicates or cosine or merge_of_shards"
 P="python tools/perf_probe.py --paths umma --rows 1250000 --dim 1024 --batches 1,32,128,1024"

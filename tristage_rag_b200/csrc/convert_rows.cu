@@ -56,8 +56,8 @@ int launch_t(const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t
   const int warps_per_block = 8;
   int64_t blocks = (n + warps_per_block - 1) / warps_per_block;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  convert_rows_kernel<TS, TD><<<(unsigned)blocks, 256, 0, st>>>((const TS*)src, src_ld, (TD*)dst, dst_ld, n, dim,
-                                                               norm_mode, inv);
+  auto kern = convert_rows_kernel<TS, TD>;
+  TS_LAUNCH(kern, (unsigned)blocks, 256, 0, st, (const TS*)src, src_ld, (TD*)dst, dst_ld, n, dim, norm_mode, inv);
   TS_CUDA_OK(cudaGetLastError());
   return TS_OK;
 }

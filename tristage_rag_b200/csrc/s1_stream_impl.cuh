@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2)
                      uint64_t* __restrict__ partial, int B_total, int b0) {
   constexpr int R = kRowsPerGroup;
   constexpr int EPC = Elem<T>::kPerChunk;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TS_DYN_SMEM(unsigned char, smem_raw);
   uint64_t* sbuf = reinterpret_cast<uint64_t*>(smem_raw);                       // kCtaMergeCap keys
   float* Qs = reinterpret_cast<float*>(smem_raw + kCtaMergeCap * sizeof(uint64_t));  // [NB][ld]
 
@@ -169,8 +169,8 @@ int launch_nb(const ScanArgs& a, int b0, cudaStream_t st) {
   auto kern = s1_stream_kernel<T, NB>;
   if (smem > 48 * 1024) TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const T* q = reinterpret_cast<const T*>(a.q) + (size_t)b0 * a.ld;
-  kern<<<grid, kStreamThreads, smem, st>>>(reinterpret_cast<const T*>(a.rows), a.n, a.ld, q, a.inv_norm, a.k,
-                                          cap_for_k(a.k), a.lists, a.partial, a.B, b0);
+  TS_LAUNCH(kern, grid, kStreamThreads, smem, st, reinterpret_cast<const T*>(a.rows), a.n, a.ld, q, a.inv_norm, a.k,
+            cap_for_k(a.k), a.lists, a.partial, a.B, b0);
   TS_CUDA_OK(cudaGetLastError());
   return TS_OK;
 }

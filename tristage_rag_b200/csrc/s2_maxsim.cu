@@ -36,15 +36,22 @@
 
 #include "ts_common.cuh"
 #include "ts_internal.h"
+#ifndef TS_CUDASIM   // the tensor path (TMA / tcgen05 inline PTX) only exists for sm_100a
 #include "ts_ptx.cuh"
+#endif
 
 namespace ts {
 
+#ifndef TS_CUDASIM
 int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, int dim, int ld, int box_rows);
+
+#endif
 
 namespace {
 
+#ifndef TS_CUDASIM
 using namespace ts::ptx;
+#endif
 
 // ============================================================ SIMT path ====
 template <typename T>
@@ -54,7 +61,7 @@ __global__ void __launch_bounds__(128)
                        const T* __restrict__ q, const int32_t* __restrict__ q_len, int lq_stride,
                        const int64_t* __restrict__ cand, const int32_t* __restrict__ n_cand, int C, int mode,
                        float* __restrict__ out) {
-  extern __shared__ float sm[];  // m[lq_stride]
+  TS_DYN_SMEM(float, sm);  // m[lq_stride]
   const int b = blockIdx.y, j = blockIdx.x;
   const int nc = n_cand ? n_cand[b] : C;
   if (j >= nc) return;
@@ -98,6 +105,7 @@ __global__ void __launch_bounds__(128)
 }
 
 // ========================================================== tensor path ====
+#ifndef TS_CUDASIM
 constexpr int kThreads = 192;
 constexpr int kMaxStages = 4;   // 3 stages + double-buffered maxima, or 4 stages + single buffer (p.n_stages)
 constexpr int kTileM = 128, kTileN = 256, kChunkK = 64;
@@ -529,6 +537,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
+#endif  // !TS_CUDASIM
 
 }  // namespace
 
@@ -536,17 +545,23 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
   if (a.B <= 0 || a.C <= 0) { set_error("maxsim: empty batch"); return TS_ERR_INVALID; }
   TS_CUDA_OK(cudaMemsetAsync(a.out, 0, (size_t)a.B * a.C * sizeof(float), st));
   if (a.ndocs == 0) return TS_OK;
+#ifdef TS_CUDASIM
+  const bool tensor_ok = false;   // tests/cudasim: only the CUDA-core kernel can be emulated
+#else
   const bool tensor_ok = (a.dtype == TS_BF16 || a.dtype == TS_F16) && (a.dim % 8 == 0) && a.lq_stride >= 1 &&
                          a.lq_stride <= TS_S2_MAX_LQ && !(a.mode & 0x100);
+#endif
   const int mode = a.mode & 0xff;
   if (!tensor_ok) {
     if (a.lq_stride > 4096) { set_error("maxsim: lq_stride too large"); return TS_ERR_UNSUPPORTED; }
     dim3 grid(a.C, a.B);
     const size_t smem = (size_t)a.lq_stride * sizeof(float);
-#define TS_SIMT(T)                                                                                         \
-  maxsim_simt_kernel<T><<<grid, 128, smem, st>>>((const T*)a.tok, a.doc_off, a.doc_len, a.ndocs, a.id_base, \
-                                                 a.dim, (const T*)a.q, a.q_len, a.lq_stride, a.cand,       \
-                                                 a.n_cand, a.C, mode, a.out)
+#define TS_SIMT(T)                                                                                    \
+  do {                                                                                                \
+    auto kern = maxsim_simt_kernel<T>;                                                                \
+    TS_LAUNCH(kern, grid, 128, smem, st, (const T*)a.tok, a.doc_off, a.doc_len, a.ndocs, a.id_base,   \
+              a.dim, (const T*)a.q, a.q_len, a.lq_stride, a.cand, a.n_cand, a.C, mode, a.out);        \
+  } while (0)
     if (a.dtype == TS_BF16) TS_SIMT(__nv_bfloat16);
     else if (a.dtype == TS_F16) TS_SIMT(__half);
     else TS_SIMT(float);
@@ -555,6 +570,7 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
     if (launches) ++*launches;
     return TS_OK;
   }
+#ifndef TS_CUDASIM
   CUtensorMap tq8, tq32, tq128, t8, t16, t32, t64, t128;
   int rc;
   const int64_t qrows = (int64_t)a.B * a.lq_stride;
@@ -586,6 +602,7 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
   if (rc) return rc;
   TS_CUDA_OK(cudaGetLastError());
   if (launches) ++*launches;
+#endif  // !TS_CUDASIM
   return TS_OK;
 }
 

@@ -50,7 +50,8 @@ template <typename TS, typename TD>
 int launch_t(const void* src, const int64_t* so, const int64_t* dof, const int32_t* len, int n_docs, void* dst, int dim,
              int normalize, cudaStream_t st) {
   int grid = n_docs < 148 * 64 ? n_docs : 148 * 64;
-  tok_ingest_kernel<TS, TD><<<grid, 128, 0, st>>>((const TS*)src, so, dof, len, n_docs, (TD*)dst, dim, normalize);
+  auto kern = tok_ingest_kernel<TS, TD>;
+  TS_LAUNCH(kern, grid, 128, 0, st, (const TS*)src, so, dof, len, n_docs, (TD*)dst, dim, normalize);
   TS_CUDA_OK(cudaGetLastError());
   return TS_OK;
 }

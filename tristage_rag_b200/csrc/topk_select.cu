@@ -44,12 +44,14 @@ struct SelectParams {
   long long pair_stride_ids;
   const float* pub;       // kLists: final per-slice J-th best scores [n_slices][bpad] (null = no filter)
   int bpad;
+  int serial_prefix;      // kLists: 1 = first version of the count prefix / filter loop (TS_SELECT_V1)
 };
 
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
-  extern __shared__ __align__(16) uint64_t sbuf[];
+  TS_DYN_SMEM(uint64_t, sbuf);
   __shared__ int pre[kMaxLists + 1];
   __shared__ float s_min[kSelThreads / 32];
+  __shared__ int s_wsum[kSelThreads / 32];
   __shared__ int s_cnt;
   const int b = blockIdx.x, g = blockIdx.y;
   int total;
@@ -61,10 +63,33 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     if (p.spread) { const int grp = qi >> 3; row = ((grp & 3) * 32) + ((grp >> 2) * 8) + (qi & 7); }
     const int mg = p.dual ? (mt >> 1) : mt;                 // CTA group owning this query tile
     list_row0 = (size_t)mg * p.n_slices * p.rows_per_cta + (p.dual ? (mt & 1) * 128 : 0) + row;
-    if (threadIdx.x == 0) {
-      int acc = 0;
-      for (int l = 0; l < p.n_slices; ++l) { pre[l] = acc; acc += min(max(p.counts[list_row0 + (size_t)l * p.rows_per_cta], 0), p.cap); }
-      pre[p.n_slices] = acc;
+    if (p.serial_prefix) {
+      // first version (TS_SELECT_V1=1, kept for A/B timing): thread 0 walks the counts -- n_slices
+      // dependent global loads, ~20 us of the ~30 us this kernel took at B <= 32
+      if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int l = 0; l < p.n_slices; ++l) { pre[l] = acc; acc += min(max(p.counts[list_row0 + (size_t)l * p.rows_per_cta], 0), p.cap); }
+        pre[p.n_slices] = acc;
+      }
+    } else {
+      // one thread per list loads its count (all loads in flight at once), then a block-wide
+      // exclusive scan: shuffle scan inside each warp + the totals of the warps before it
+      const int t = threadIdx.x;
+      const int c = (t < p.n_slices) ? min(max(__ldcg(p.counts + list_row0 + (size_t)t * p.rows_per_cta), 0), p.cap) : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((t & 31) >= o) incl += v;
+      }
+      if ((t & 31) == 31) s_wsum[t >> 5] = incl;
+      __syncthreads();
+      if (t < p.n_slices) {                      // n_slices <= kMaxLists = 256: at most 8 warps carry counts
+        int base = 0;
+        for (int w = 0; w < (t >> 5); ++w) base += s_wsum[w];
+        pre[t] = base + incl - c;
+        if (t == p.n_slices - 1) pre[p.n_slices] = base + incl;
+      }
     }
     __syncthreads();
     total = pre[p.n_slices];
@@ -107,11 +132,30 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     m = s_min[0];
     for (int w = 1; w < kSelThreads / 32; ++w) m = fminf(m, s_min[w]);
     const uint64_t thr = (uint64_t)f2ord(m) << 32;      // smallest key with score m
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      const uint64_t key = load(i);
-      if (key >= thr && key != 0ull) {
-        const int pos = atomicAdd(&s_cnt, 1);
-        if (pos < kSelCap) sbuf[pos] = key;
+    if (p.serial_prefix) {
+      for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const uint64_t key = load(i);
+        if (key >= thr && key != 0ull) {
+          const int pos = atomicAdd(&s_cnt, 1);
+          if (pos < kSelCap) sbuf[pos] = key;
+        }
+      }
+    } else {
+      // four independent key loads in flight per thread before any of them is tested
+      for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+        uint64_t key[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * (int)blockDim.x;
+          key[u] = (i < total) ? load(i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (key[u] >= thr && key[u] != 0ull) {
+            const int pos = atomicAdd(&s_cnt, 1);
+            if (pos < kSelCap) sbuf[pos] = key[u];
+          }
+        }
       }
     }
     __syncthreads();
@@ -154,7 +198,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
 
 int launch_select(const SelectParams& p, int n_groups, cudaStream_t st) {
   dim3 grid(p.B, n_groups);
-  select_kernel<<<grid, kSelThreads, kSelCap * sizeof(uint64_t), st>>>(p);
+  TS_LAUNCH(select_kernel, grid, kSelThreads, kSelCap * sizeof(uint64_t), st, p);
   TS_CUDA_OK(cudaGetLastError());
   return TS_OK;
 }
@@ -205,6 +249,7 @@ int launch_merge_lists(const uint64_t* lists, const int* counts, const float* pu
   p.mode = kLists; p.keys = lists; p.counts = counts; p.n_slices = lay.n_slices; p.spread = lay.spread; p.cap = lay.cap;
   p.dual = lay.dual; p.rows_per_cta = lay.rows_per_cta;
   p.pub = (lay.jrank > 0) ? pub : nullptr; p.bpad = lay.bpad;
+  p.serial_prefix = env_on("TS_SELECT_V1") ? 1 : 0;
   p.L = lay.n_slices; p.B = B; p.k_in = k; p.group = lay.n_slices; p.k_out = k;
   p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids; p.id_base = id_base;
   int rc = launch_select(p, 1, st);

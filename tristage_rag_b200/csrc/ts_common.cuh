@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ts_launch.h"
+
 namespace ts {
 
 constexpr float kLowestF32 = -3.4028234663852886e38f;  // FAISS pad score
@@ -196,10 +198,14 @@ template <> struct Elem<__half> {
 };
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+#ifdef TS_CUDASIM
+  return *p;
+#else
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
+#endif
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

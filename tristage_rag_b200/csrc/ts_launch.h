@@ -1,0 +1,14 @@
+// Kernel-launch and dynamic-shared-memory spelling.  The product build (nvcc) expands these to the
+// ordinary CUDA syntax.  tests/cudasim/ defines TS_CUDASIM and compiles the SAME kernel sources
+// with g++ against a fiber-based SIMT emulator, so the CUDA-core kernels (ingest, stream scan,
+// selection, SIMT MaxSim) can be executed and checked on a machine without a GPU; that build is
+// test infrastructure and is never loaded by the package.
+#pragma once
+#ifdef TS_CUDASIM
+#define TS_LAUNCH(kern, grid, block, smem, stream, ...) \
+  cudasim::launch((grid), (block), (size_t)(smem), [&]() { kern(__VA_ARGS__); })
+#define TS_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(cudasim::dyn_smem())
+#else
+#define TS_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define TS_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#endif
