@@ -93,6 +93,21 @@ def test_bm25_matches_reference_including_refit_quirk():
             assert ours.search(q, 100) == ref.search(q, 100)
             for i in range(len(batch)):
                 assert ours.score(q, i) == ref.score(q, i)
+    # a larger random corpus: the vectorised CSR search must stay bit-identical to the reference's
+    # per-document Python loop (scores as Python floats, stable order, zero-score padding)
+    rng = np.random.default_rng(0)
+    vocab = [f"w{i}" for i in range(300)]
+    zipf = 1.0 / np.arange(1, 301)
+    zipf /= zipf.sum()
+    big = [" ".join(rng.choice(vocab, size=int(rng.integers(0, 60)), p=zipf)) for _ in range(700)]
+    ours, ref = s1.BM25Index(), RefBM25()
+    for batch in (big[:500], big):
+        ours.fit(list(batch))
+        ref.fit(list(batch))
+        assert ours.idf == ref.idf
+        for q in ["w0 w1 w2", "w7 w7 w250", "w299", "w5 unknownword w5 w0", " ".join(vocab[:40])]:
+            for k in (1, 10, 300, 2000):
+                assert ours.search(q, k) == ref.search(q, k), (q, k)
 
 
 def test_drop_in_surface_matches_the_contract():

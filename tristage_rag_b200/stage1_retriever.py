@@ -87,7 +87,7 @@ class BM25Index:
         self.corpus_size = 0
         self.vocabulary = set()
         self.documents: List[str] = []
-        self._postings: Optional[Dict[str, List[int]]] = None
+        self._postings = None          # CSR inverted index, built lazily by search()
 
     def tokenize(self, text: str) -> List[str]:
         return re.sub(r"[^a-z0-9\s]", " ", text.lower()).split()
@@ -126,27 +126,58 @@ class BM25Index:
         return s
 
     def _build_postings(self):
-        post: Dict[str, List[int]] = defaultdict(list)
-        for idx in range(min(len(self.documents), len(self.doc_freqs))):
-            for t in self.doc_freqs[idx]:
-                post[t].append(idx)
-        self._postings = post
+        """Inverted index as CSR arrays: for term t, ``_docs[_off[t]:_off[t+1]]`` are the documents
+        that contain it (ascending) and ``_w`` the per-posting score contribution
+        ``idf * tf*(k1+1) / (tf + k1*(1 - b + b*dl/avgdl))`` -- the reference's expression (:93-99)
+        evaluated once per posting in IEEE double, same operation order, so sums are bit-identical."""
+        n = min(len(self.documents), len(self.doc_freqs))
+        by_term: Dict[str, List[Tuple[int, int]]] = defaultdict(list)
+        for idx in range(n):
+            for t, tf in self.doc_freqs[idx].items():
+                by_term[t].append((idx, tf))
+        self._tid = {t: i for i, t in enumerate(by_term)}
+        off = np.zeros(len(by_term) + 1, np.int64)
+        docs, tfs, idfs = [], [], []
+        for i, (t, plist) in enumerate(by_term.items()):
+            off[i + 1] = off[i] + len(plist)
+            docs.extend(d for d, _ in plist)
+            tfs.extend(tf for _, tf in plist)
+            idfs.extend([self.idf.get(t, 0.0)] * len(plist))
+        self._off = off
+        self._docs = np.asarray(docs, np.int64)
+        tf = np.asarray(tfs, np.int64)
+        idf = np.asarray(idfs, np.float64)
+        dl = np.asarray(self.doc_lens[:n], np.int64)[self._docs] if len(docs) else np.zeros(0, np.int64)
+        if len(docs) and self.avg_doc_len:
+            self._w = idf * ((tf * (self.k1 + 1)) / (tf + self.k1 * (1 - self.b + self.b * dl / self.avg_doc_len)))
+        else:
+            self._w = np.zeros(len(docs), np.float64)
+        self._postings = True
 
     def search(self, query: str, top_k: int = 10) -> List[Tuple[int, float]]:
-        if getattr(self, "_postings", None) is None:
+        """The reference scores EVERY document in a Python loop and sorts all of them (:103-112);
+        here only documents that share a token with the query are touched.  Ranking is the same
+        stable descending sort: equal scores (all the zeros included) keep ascending index order."""
+        if not getattr(self, "_postings", None) or getattr(self, "_tid", None) is None:
             self._build_postings()
         n = len(self.documents)
-        scores = [0.0] * n
-        for token in self.tokenize(query):     # same accumulation order as score()
-            if token not in self.idf:
+        scores = np.zeros(n, np.float64)
+        for token in self.tokenize(query):     # same accumulation order as score(): query-token order
+            t = self._tid.get(token)
+            if t is None or token not in self.idf:
                 continue
-            idf = self.idf[token]
-            for idx in self._postings.get(token, ()):
-                tf = self.doc_freqs[idx][token]
-                dl = self.doc_lens[idx]
-                scores[idx] += idf * ((tf * (self.k1 + 1)) / (tf + self.k1 * (1 - self.b + self.b * dl / self.avg_doc_len)))
-        ranked = sorted(enumerate(scores), key=lambda x: x[1], reverse=True)
-        return ranked[:top_k]
+            sl = slice(self._off[t], self._off[t + 1])
+            scores[self._docs[sl]] += self._w[sl]          # a document occurs once per term
+        top_k = max(int(top_k), 0)
+        if len(self._w) and (self._w <= 0).any():
+            order = np.argsort(-scores, kind="stable")[:top_k]      # stale-fit quirk can make idf <= 0
+        else:
+            hit = np.flatnonzero(scores > 0)
+            order = hit[np.argsort(-scores[hit], kind="stable")][:top_k]
+            if len(order) < min(top_k, n):                          # pad with zero-score docs, ascending index
+                zero = np.flatnonzero(scores[: top_k + len(hit)] <= 0)[: min(top_k, n) - len(order)]
+                order = np.concatenate([order, zero])
+        return [(int(i), float(scores[i])) for i in order]
 
 
 class IndexFlatIP:
