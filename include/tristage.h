@@ -230,6 +230,45 @@ int ts_maxsim_host(ts_tokstore* h, const void* q_tok_host, int q_dtype, const in
 int ts_rank_desc(int device, const float* scores_dev, const int32_t* n_cand_dev, int B, int C,
                  int top_k, float* out_scores_dev, int32_t* out_pos_dev, void* stream);
 
+/* --------------------------------------------------- hybrid (BM25 + dense) -- */
+/* Device-side BM25 search and rank fusion.  The
+ * reference scores every document with a Python loop per query and sorts all
+ * of them (BM25Index.search, stage1_retriever.py:84-112); here the fitted
+ * index lives on the device as CSR postings with one fp64 weight per posting,
+ *   w = idf * tf*(k1+1) / (tf + k1*(1 - b + b*dl/avgdl))          (:93-99)
+ * precomputed by the caller (it depends on the fit, not on the query), and a
+ * query only touches the documents that share a token with it.  Arithmetic
+ * and order are the reference's: fp64 sums in query-token order, stable
+ * descending rank (ties and the zero-score tail by ascending document index). */
+#define TS_BM25_MAX_K 1024
+typedef struct ts_bm25 ts_bm25;
+/* term_off_host [n_terms + 1], post_doc_host / post_w_host [term_off[n_terms]];
+ * every weight must be > 0 (TS_ERR_UNSUPPORTED otherwise: the reference's
+ * stale-refit quirk can make idf <= 0 -- keep the host search for that index) */
+int ts_bm25_create(ts_bm25** out, int device, int64_t n_docs, int64_t n_terms, const int64_t* term_off_host,
+                   const int32_t* post_doc_host, const double* post_w_host);
+int ts_bm25_destroy(ts_bm25* h);
+int64_t ts_bm25_ndocs(const ts_bm25* h);
+int64_t ts_bm25_launch_count(const ts_bm25* h);
+/* BM25Index.search(query, top_k) for B queries.  q_terms_host: term ids of each
+ * query in query-token order (repeated tokens repeated, tokens unknown to the
+ * index left out), query b = [q_off_host[b], q_off_host[b+1]).
+ * out: [B, top_k] fp64 scores and int64 document indices, -1 beyond n_docs.  */
+int ts_bm25_search_host(ts_bm25* h, const int32_t* q_terms_host, const int64_t* q_off_host, int B, int top_k,
+                        double* out_scores_host, int64_t* out_ids_host, void* stream);
+/* _reciprocal_rank_fusion (method 0, :326-343) / _weighted_fusion (method 1,
+ * :345-366) of a dense list ([B, k1] ids + fp32 scores, n_dense[B] valid or
+ * NULL) and a BM25 list ([B, k2] ids + fp64 scores) in fp64; entries keep dict
+ * insertion order (dense first, then BM25-only), stable descending sort, the
+ * best top_k per query go to out_ids/out_scores [B, top_k] (-1 padded), their
+ * number to out_n[B].  k1 + k2 <= 2048.                                      */
+int ts_hybrid_fuse_host(int device, int method, int rrf_k, double w_dense, double w_bm25,
+                        const int64_t* dense_ids_host, const float* dense_scores_host,
+                        const int32_t* n_dense_host, int k1, const int64_t* bm25_ids_host,
+                        const double* bm25_scores_host, const int32_t* n_bm25_host, int k2, int B,
+                        int top_k, int64_t* out_ids_host, double* out_scores_host, int32_t* out_n_host,
+                        void* stream);
+
 /* ------------------------------------------------------------ shard files -- */
 /* On-disk form of one shard, little endian, sections
  * 4096-byte aligned so the payload can be mmap'ed:

@@ -285,3 +285,141 @@ def test_select_over_scan_lists_matches_the_oracle(sim, monkeypatch, N, B, k, n_
     valid = rI >= 0
     assert (out_i[valid] == rI[valid] + 7_000_000_000).all() and (out_i[~valid] == -1).all()
     assert (out_s[valid] == rD[valid]).all()
+
+
+# ------------------------------------------------- hybrid: BM25 search + rank fusion ---
+def _zipf_corpus(n_docs, vocab_size=300, seed=0):
+    rng = np.random.default_rng(seed)
+    vocab = [f"w{i}" for i in range(vocab_size)]
+    zipf = 1.0 / np.arange(1, vocab_size + 1)
+    zipf /= zipf.sum()
+    return [" ".join(rng.choice(vocab, size=int(rng.integers(0, 50)), p=zipf)) for _ in range(n_docs)], vocab
+
+
+def test_device_bm25_is_bit_identical_to_the_host_index(sim):
+    """bm25_score_kernel + bm25_topk_kernel (emulated) == BM25Index.search, itself pinned bit for bit
+    against the reference's BM25Index in tests/test_host.py: fp64 scores, stable order, zero-score tail."""
+    from tristage_rag_b200.stage1_retriever import BM25Index, DeviceBM25
+
+    docs, vocab = _zipf_corpus(1500)
+    bm = BM25Index()
+    bm.fit(docs)
+    dev = DeviceBM25(bm, 0)
+    queries = ["w0 w1 w2", "w7 w7 w250", "w299", "w5 unknownword w5 w0", " ".join(vocab[:30]), "", "nothing known here",
+               "w0 " * 12]
+    for top_k in (1, 10, 300, 1024):
+        got = dev.search_batch(queries, top_k)
+        for q, g in zip(queries, got):
+            assert g == bm.search(q, top_k), (q, top_k)
+    # 2600 touched documents for one query: the selection walks several buffer refills
+    many = [" ".join(["w0", f"w{i % 40 + 1}"] * 3) for i in range(2600)]
+    bm2 = BM25Index()
+    bm2.fit(many)
+    dev2 = DeviceBM25(bm2, 0)
+    for top_k in (5, 700):
+        assert dev2.search_batch(["w0 w3", "w17"], top_k) == [bm2.search("w0 w3", top_k), bm2.search("w17", top_k)]
+    # tiny corpus, top_k beyond it: the list just ends (ids -1 are dropped)
+    bm3 = BM25Index()
+    bm3.fit(["a b", "b c", "zz"])
+    assert DeviceBM25(bm3, 0).search_batch(["b", "q"], 10) == [bm3.search("b", 10), bm3.search("q", 10)]
+
+
+def test_device_bm25_refuses_non_positive_weights(sim):
+    from tristage_rag_b200.stage1_retriever import BM25Index, DeviceBM25
+
+    bm = BM25Index()
+    bm.fit(["a a b", "a c", "a d"])
+    bm._build_postings()
+    bm._w[0] = 0.0                                     # what a stale refit can produce (idf <= 0)
+    with pytest.raises(_lib.TristageError) as e:
+        DeviceBM25(bm, 0)
+    assert e.value.code == -4
+
+
+@pytest.mark.parametrize("method", ["rrf", "weighted"])
+def test_device_fusion_is_bit_identical_to_the_reference_arithmetic(sim, method):
+    """fuse_kernel (emulated) == Stage1Retriever._reciprocal_rank_fusion / _weighted_fusion (same
+    arithmetic as the reference, :326-366): fp64 values, dict insertion order, stable sort."""
+    import types
+
+    from tristage_rag_b200.stage1_retriever import Stage1Retriever
+
+    rng = np.random.default_rng(3)
+    cfg = types.SimpleNamespace(rrf_k=60, dense_weight=0.7, bm25_weight=0.3)
+    host = types.SimpleNamespace(config=cfg)
+    fuse = Stage1Retriever._reciprocal_rank_fusion if method == "rrf" else Stage1Retriever._weighted_fusion
+    B, k1, k2, top_k = 6, 50, 30, 40
+    dense_ids = np.full((B, k1), -1, np.int64)
+    dense_sc = np.full((B, k1), flat_ip.LOWEST_F32, np.float32)
+    bm_ids = np.full((B, k2), -1, np.int64)
+    bm_sc = np.zeros((B, k2), np.float64)
+    want = []
+    for b in range(B):
+        nd = [50, 50, 7, 50, 1, 20][b]
+        nb = [30, 30, 30, 0, 30, 3][b]
+        universe = 60 if b != 1 else 5000                  # b == 1: (almost) no overlap between the lists
+        d_ids = rng.choice(universe, size=nd, replace=False)
+        d_sc = np.sort(rng.random(nd).astype(np.float32))[::-1] + np.float32(0.01)
+        if b == 5:
+            d_sc[:] = d_sc[0]                              # exact ties everywhere
+        m_ids = rng.choice(universe, size=nb, replace=False)
+        m_sc = np.sort(rng.random(nb) * 9)[::-1] + 0.5
+        dense_ids[b, :nd], dense_sc[b, :nd] = d_ids, d_sc
+        bm_ids[b, :nb], bm_sc[b, :nb] = m_ids, m_sc
+        dense = [(int(i), float(s)) for i, s in zip(d_ids, d_sc)]
+        bm25 = [(int(i), float(s)) for i, s in zip(m_ids, m_sc)]
+        want.append((fuse(host, dense, bm25) if bm25 else dense)[:top_k] if bm25 else None)
+    ids, scores, n = _lib.hybrid_fuse(method, 60, 0.7, 0.3, dense_ids, dense_sc, bm_ids, bm_sc, top_k, 0)
+    for b in range(B):
+        got = [(int(ids[b, r]), float(scores[b, r])) for r in range(int(n[b]))]
+        if want[b] is None:                                # empty BM25 list: the kernel still returns the dense part
+            ref = fuse(host, [(int(i), float(s)) for i, s in zip(dense_ids[b], dense_sc[b]) if i >= 0], [])[:top_k]
+            assert got == ref
+        else:
+            assert got == want[b], b
+        assert (ids[b, int(n[b]):] == -1).all()
+
+
+def test_stage1_search_batch_hybrid_on_device_equals_host_path(sim, tmp_path, monkeypatch):
+    """Stage1Retriever.search_batch with hybrid_on_device=True (device BM25 + device fusion, emulated)
+    returns exactly what the host BM25 + fusion path returns; the dense index is the oracle's here.
+    After a second add_documents the reference's stale-refit quirk makes idf negative for common
+    words: the device index refuses such weights and the call takes the host path."""
+    from oracle import fakes
+    from tristage_rag_b200 import stage1_retriever as s1
+
+    monkeypatch.setattr(flat_ip.IndexFlatIP, "search", _search_ignoring_path, raising=True)
+    docs, _ = _zipf_corpus(400, vocab_size=120, seed=5)
+    queries = ["w0 w1", "w3 w3 w40", "", "w119 w2 w7", "unknown"]
+    out = {}
+    for refit in (False, True):
+        for on_device in (False, True):
+            for fusion in ("rrf", "weighted"):
+                cfg = s1.Stage1Config(device="cpu", cache_dir=str(tmp_path / "m"), index_dir=str(tmp_path / "i"),
+                                      top_k_candidates=50, enable_bm25=True, bm25_top_k=30, fusion_method=fusion,
+                                      hybrid_on_device=on_device)
+                r = s1.Stage1Retriever(cfg, model=fakes.FakeSentenceEncoder(64))
+                r._create_faiss_index = lambda emb, r=r: (setattr(r, "faiss_index", flat_ip.IndexFlatIP(emb.shape[1])),
+                                                           r.faiss_index.add(emb))
+                if refit:
+                    r.add_documents(docs[:250])
+                    r.add_documents(docs[250:])
+                else:
+                    r.add_documents(docs)
+                # weighted fusion divides by the best score of each list: the reference raises ZeroDivisionError
+                # when a query has no lexical hit (or, after a stale refit, only negative ones)
+                qs = queries if fusion == "rrf" else (["w3 w3 w40", "w2 w7"] if refit else ["w0 w1", "w3 w3 w40", "w2 w7"])
+                out[(refit, on_device, fusion)] = r.search_batch(qs, 20)
+                if on_device:
+                    assert (getattr(r, "_device_bm25", None) is not None) == (not refit)
+    for refit in (False, True):
+        for fusion in ("rrf", "weighted"):
+            assert out[(refit, True, fusion)] == out[(refit, False, fusion)]
+            assert all(len(x) == 20 for x in out[(refit, True, fusion)])
+
+
+_orig_search = flat_ip.IndexFlatIP.search
+
+
+def _search_ignoring_path(self, q, k, path="auto", **kw):
+    return _orig_search(self, q, k)

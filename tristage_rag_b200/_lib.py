@@ -23,6 +23,8 @@ TS_FLAG_NORMALIZE_Q = 1
 TS_S2_MAXSIM, TS_S2_COLBERT = 0, 1
 TS_S2_FORCE_SIMT = 0x100          # mode bit: take the CUDA-core Stage-2 kernel
 TS_MAX_K = 512
+TS_BM25_MAX_K = 1024
+TS_FUSE_MAX = 2048
 TS_S2_MAX_LQ = 128
 TS_S2_MAX_LD = 256
 TS_ERR_EMPTY = -6
@@ -93,6 +95,13 @@ SYMBOLS = {
     "ts_maxsim": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _u, _vp, _vp]),
     "ts_maxsim_host": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _u, _vp, _vp]),
     "ts_rank_desc": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "ts_bm25_create": (_i, [C.POINTER(_vp), _i, _i64, _i64, _vp, _vp, _vp]),
+    "ts_bm25_destroy": (_i, [_vp]),
+    "ts_bm25_ndocs": (_i64, [_vp]),
+    "ts_bm25_launch_count": (_i64, [_vp]),
+    "ts_bm25_search_host": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "ts_hybrid_fuse_host": (_i, [_i, _i, _i, C.c_double, C.c_double, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i,
+                                 _vp, _vp, _vp, _vp]),
     "ts_file_probe": (_i, [C.c_char_p, C.POINTER(FileInfo)]),
     "ts_file_verify": (_i, [C.c_char_p]),
     "ts_file_write_index_host": (_i, [C.c_char_p, _i, _i, _i, _i64, _i64, _vp, _vp]),
@@ -405,6 +414,78 @@ def rank_desc(scores, top_k: int, n_cand=None, device: int = 0):
     check(lib().ts_rank_desc(device, C.c_void_p(scores.data_ptr()), nc, B, Cn, int(top_k),
                              C.c_void_p(out_s.data_ptr()), C.c_void_p(out_p.data_ptr()), _stream_ptr(device)))
     return out_s, out_p
+
+
+class BM25:
+    """Device-resident BM25 postings (``ts_bm25``): CSR term offsets, document ids and one fp64
+    weight per posting, as built by ``stage1_retriever.BM25Index._build_postings``."""
+
+    def __init__(self, n_docs: int, term_off, post_doc, post_w, device: int = 0):
+        import numpy as np
+
+        self.device = int(device)
+        off = np.ascontiguousarray(term_off, np.int64)
+        docs = np.ascontiguousarray(post_doc, np.int32)
+        w = np.ascontiguousarray(post_w, np.float64)
+        assert len(docs) == len(w) == int(off[-1])
+        self.n_docs, self.n_terms = int(n_docs), len(off) - 1
+        h = C.c_void_p()
+        check(lib().ts_bm25_create(C.byref(h), self.device, self.n_docs, self.n_terms, C.c_void_p(off.ctypes.data),
+                                   C.c_void_p(docs.ctypes.data) if len(docs) else None,
+                                   C.c_void_p(w.ctypes.data) if len(w) else None))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and _lib is not None:
+            _lib.ts_bm25_destroy(h)
+
+    @property
+    def launches(self) -> int:
+        return int(lib().ts_bm25_launch_count(self._h))
+
+    def search(self, query_terms, top_k: int):
+        """query_terms: one int sequence of term ids per query (query-token order, repeats kept).
+        -> (scores [B, top_k] float64, ids [B, top_k] int64, -1 beyond the corpus)."""
+        import numpy as np
+
+        B = len(query_terms)
+        off = np.zeros(B + 1, np.int64)
+        off[1:] = np.cumsum([len(q) for q in query_terms])
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(q, np.int32) for q in query_terms])
+                                    if int(off[-1]) else np.zeros(0, np.int32), np.int32)
+        scores = np.empty((B, top_k), np.float64)
+        ids = np.empty((B, top_k), np.int64)
+        check(lib().ts_bm25_search_host(self._h, C.c_void_p(flat.ctypes.data) if len(flat) else None,
+                                        C.c_void_p(off.ctypes.data), B, int(top_k), C.c_void_p(scores.ctypes.data),
+                                        C.c_void_p(ids.ctypes.data), _stream_ptr(self.device)))
+        return scores, ids
+
+
+def hybrid_fuse(method: str, rrf_k: int, w_dense: float, w_bm25: float, dense_ids, dense_scores, bm25_ids, bm25_scores,
+                top_k: int, device: int = 0):
+    """RRF / weighted fusion on the device.  dense_ids [B, k1] int64 (-1 = unused slot), dense_scores
+    [B, k1] float32, bm25_ids [B, k2] int64, bm25_scores [B, k2] float64 -> (ids [B, top_k] int64,
+    scores [B, top_k] float64, n [B]) in the reference's order (stable descending)."""
+    import numpy as np
+
+    dense_ids = np.ascontiguousarray(dense_ids, np.int64)
+    dense_scores = np.ascontiguousarray(dense_scores, np.float32)
+    bm25_ids = np.ascontiguousarray(bm25_ids, np.int64)
+    bm25_scores = np.ascontiguousarray(bm25_scores, np.float64)
+    B, k1 = dense_ids.shape
+    k2 = bm25_ids.shape[1]
+    n_dense = np.ascontiguousarray((dense_ids >= 0).sum(axis=1), np.int32)      # valid slots lead (FAISS pads the tail)
+    n_bm = np.ascontiguousarray((bm25_ids >= 0).sum(axis=1), np.int32)
+    out_ids = np.empty((B, top_k), np.int64)
+    out_scores = np.empty((B, top_k), np.float64)
+    out_n = np.empty(B, np.int32)
+    vp = lambda a: C.c_void_p(a.ctypes.data) if a.size else None                # noqa: E731
+    check(lib().ts_hybrid_fuse_host(int(device), 0 if method == "rrf" else 1, int(rrf_k), float(w_dense), float(w_bm25),
+                                    vp(dense_ids), vp(dense_scores), vp(n_dense), k1, vp(bm25_ids), vp(bm25_scores),
+                                    vp(n_bm), k2, B, int(top_k), vp(out_ids), vp(out_scores), vp(out_n),
+                                    _stream_ptr(device)))
+    return out_ids, out_scores, out_n
 
 
 class TokStore:

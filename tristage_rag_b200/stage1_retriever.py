@@ -23,7 +23,10 @@ reference class that ``src/retrieval_pipeline.py:244-256,316,358`` and
   O(N) per-query Python scan, scores are bit-identical).
 
 Extra (not in the reference): ``search_batch`` and ``add_embeddings`` expose the
-batched regime the reference's batch-1 API cannot reach.
+batched regime the reference's batch-1 API cannot reach; with
+``Stage1Config.hybrid_on_device`` the BM25 search and the rank fusion of a batch
+also run as GPU kernels (``DeviceBM25``, ``ts_bm25_*`` / ``ts_hybrid_fuse_host``),
+with results identical to the host path.
 """
 from __future__ import annotations
 
@@ -63,6 +66,7 @@ class Stage1Config:
     nprobe: int = 10
     storage_dtype: str = "bf16"   # HBM corpus dtype: bf16 | fp16 | fp32
     gpu_index: int = 0
+    hybrid_on_device: bool = False   # search_batch: BM25 search + RRF/weighted fusion as GPU kernels (ts_bm25_*)
 
 
 class BM25Index:
@@ -180,6 +184,31 @@ class BM25Index:
         return [(int(i), float(scores[i])) for i in order]
 
 
+class DeviceBM25:
+    """``BM25Index.search`` for batches of queries on the GPU (``ts_bm25_*``): the fitted index's CSR
+    postings and per-posting fp64 weights are uploaded once per fit; results are bit-identical to
+    ``BM25Index.search`` (same fp64 sums in query-token order, same stable ranking)."""
+
+    def __init__(self, bm25: BM25Index, device: int = 0):
+        if not getattr(bm25, "_postings", None) or getattr(bm25, "_tid", None) is None:
+            bm25._build_postings()
+        self.bm25 = bm25
+        self.n_docs = len(bm25.documents)
+        self._dev = _lib.BM25(self.n_docs, bm25._off, bm25._docs, bm25._w, device)   # raises if a weight is <= 0
+
+    def term_ids(self, query: str) -> List[int]:
+        tid, idf = self.bm25._tid, self.bm25.idf
+        return [tid[t] for t in self.bm25.tokenize(query) if t in tid and t in idf]
+
+    def search_arrays(self, queries: List[str], top_k: int):
+        """(scores [B, top_k] float64, ids [B, top_k] int64; -1 beyond the corpus)."""
+        return self._dev.search([self.term_ids(q) for q in queries], top_k)
+
+    def search_batch(self, queries: List[str], top_k: int = 10) -> List[List[Tuple[int, float]]]:
+        scores, ids = self.search_arrays(queries, top_k)
+        return [[(int(i), float(s)) for i, s in zip(ids[b], scores[b]) if i >= 0] for b in range(len(queries))]
+
+
 class IndexFlatIP:
     """The ``faiss.IndexFlatIP`` surface the reference touches (``d``, ``ntotal``,
     ``add``, ``search``), backed by one ``ts_index`` shard on the GPU."""
@@ -226,6 +255,7 @@ class Stage1Retriever:
         self.bm25_index = None
         self.documents: List[str] = []
         self.doc_metadata: List[Dict[str, Any]] = []
+        self._device_bm25 = None
         os.makedirs(self.config.cache_dir, exist_ok=True)
         os.makedirs(self.config.index_dir, exist_ok=True)
         _lib.lib()                       # fail loudly now if the CUDA library is missing
@@ -302,6 +332,31 @@ class Stage1Retriever:
             if self.bm25_index is None:
                 self.bm25_index = BM25Index()
             self.bm25_index.fit(self.documents)
+        self._device_bm25 = None           # postings changed: re-upload lazily
+
+    def _hybrid_batch_on_device(self, texts: List[str], D: np.ndarray, I: np.ndarray, top_k: int):
+        """search_batch's BM25 + fusion step as GPU kernels.  Returns per-query fused (doc, score) lists, or
+        None when this index / request has to take the host path (weights <= 0 after a stale refit, list
+        sizes beyond the kernels' limits, a weighted fusion whose normaliser is 0 -- the reference raises
+        ZeroDivisionError there and so does the host path)."""
+        cfg = self.config
+        k2 = cfg.bm25_top_k
+        if k2 < 1 or k2 > _lib.TS_BM25_MAX_K or top_k + k2 > _lib.TS_FUSE_MAX or not self.bm25_index.documents:
+            return None
+        if getattr(self, "_device_bm25", None) is None:
+            try:
+                self._device_bm25 = DeviceBM25(self.bm25_index, cfg.gpu_index)
+            except _lib.TristageError as e:
+                if e.code != -4:                        # TS_ERR_UNSUPPORTED: weights <= 0
+                    raise
+                return None
+        bs, bi = self._device_bm25.search_arrays(texts, k2)
+        if cfg.fusion_method != "rrf":
+            if (D[:, 0] == 0).any() or (bs[:, 0] == 0).any() or (D.max(axis=1) == 0).any():
+                return None
+        ids, scores, n = _lib.hybrid_fuse(cfg.fusion_method, cfg.rrf_k, cfg.dense_weight, cfg.bm25_weight, I, D, bi, bs,
+                                          top_k, cfg.gpu_index)
+        return [[(int(ids[b, r]), float(scores[b, r])) for r in range(int(n[b]))] for b in range(len(texts))]
 
     # -- fusion (reference :326-366) -----------------------------------------
     def _reciprocal_rank_fusion(self, dense_results, bm25_results):
@@ -365,6 +420,11 @@ class Stage1Retriever:
         texts = list(queries) if not isinstance(queries, np.ndarray) else None
         emb = self._encode_batch(texts) if texts is not None else np.asarray(queries, np.float32)
         D, I = self.faiss_index.search(self._normalize_embeddings(emb), top_k, path=path)
+        if (texts is not None and self.config.hybrid_on_device and self.config.enable_bm25
+                and self.bm25_index is not None):
+            fused = self._hybrid_batch_on_device(texts, D, I, top_k)
+            if fused is not None:
+                return [self._format(f) for f in fused]
         results = []
         for b in range(len(D)):
             dense = [(int(i), float(s)) for i, s in zip(I[b], D[b]) if i >= 0]
