@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- scheduler of the SIMT emulator (see cudasim.h).
 #include "cudasim.h"
 
+#include <unordered_map>
 #include <vector>
 
 // Context switch.  x86-64: a 12-instruction stack switch (callee-saved registers only);
@@ -56,7 +57,7 @@ static inline void ctx_make(Context* c, char* stack, size_t bytes, void (*entry)
 namespace cudasim {
 
 ThreadCtx* g_cur = nullptr;
-unsigned long long g_launches = 0, g_blocks = 0, g_switches = 0;
+unsigned long long g_launches = 0, g_blocks_run = 0, g_switches = 0;
 
 namespace {
 
@@ -84,15 +85,24 @@ struct Block {
   int n = 0, live = 0, bar_arrived = 0, cur = 0;
   unsigned bar_gen = 0;
   unsigned long long progress = 0;
-  std::vector<unsigned char> smem;
+  unsigned char* smem = nullptr;         // 1024-byte aligned (swizzle atoms), kSmemMax bytes
   const std::function<void()>* body = nullptr;
+  // tensor-path emulation (ts_ptx_sim.cuh)
+  struct MBar { uint32_t init = 0, pending = 0, phase = 0; long long tx = 0; };
+  struct NamedBar { int arrived = 0; unsigned gen = 0; };
+  std::unordered_map<uint32_t, MBar> mbars;
+  NamedBar named[16];
+  std::vector<uint32_t> tmem;
 };
+constexpr size_t kSmemMax = 232448;
 
-Block g_block;
+std::vector<Block*> g_blocks;     // blocks alive at the same time: 1, or the whole grid of a cooperative launch
+Block* g_blk = nullptr;           // block of the running simulated thread
+bool g_in_launch = false;
 std::vector<char*> g_stacks;
 
 [[noreturn]] void die(const char* what) {
-  Block& B = g_block;
+  Block& B = *g_blk;
   fprintf(stderr, "[cudasim] %s (block %u,%u: %d threads, %d live, %d at __syncthreads)\n", what,
           B.fibers.empty() ? 0 : B.fibers[0].tc.blockIdx_.x, B.fibers.empty() ? 0 : B.fibers[0].tc.blockIdx_.y, B.n, B.live,
           B.bar_arrived);
@@ -105,18 +115,18 @@ std::vector<char*> g_stacks;
 }
 
 void release_barrier_if_complete() {
-  Block& B = g_block;
+  Block& B = *g_blk;
   if (B.bar_arrived > 0 && B.bar_arrived == B.live) { B.bar_arrived = 0; ++B.bar_gen; }
 }
 
 void yield() {
-  Block& B = g_block;
+  Block& B = *g_blk;
   ++g_switches;
   ctx_switch(&B.fibers[B.cur].ctx, &B.sched);
 }
 
 void fiber_main() {
-  Block& B = g_block;
+  Block& B = *g_blk;
   (*B.body)();
   Fiber& f = B.fibers[B.cur];
   f.state = kDone;
@@ -128,12 +138,12 @@ void fiber_main() {
 }
 
 unsigned existing_lanes(int warp) {
-  const int first = warp * 32, n = g_block.n - first;
+  const int first = warp * 32, n = g_blk->n - first;
   return n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
 }
 
 void complete_collective(int warp, unsigned mask) {
-  Block& B = g_block;
+  Block& B = *g_blk;
   Fiber* lanes = &B.fibers[(size_t)warp * 32];
   const int lead = __builtin_ctz(mask);
   unsigned ballot = 0;
@@ -163,10 +173,56 @@ void complete_collective(int warp, unsigned mask) {
 
 }  // namespace
 
-void* dyn_smem() { return g_block.smem.data(); }
+void* dyn_smem() { return g_blk->smem; }
+unsigned char* smem_base() { return g_blk->smem; }
+uint32_t* tmem() { return g_blk->tmem.data(); }
+
+void yield_spin() { yield(); }
+
+static Block::MBar& mbar_at(uint32_t addr) {
+  auto it = g_blk->mbars.find(addr);
+  if (it == g_blk->mbars.end()) { fprintf(stderr, "[cudasim] mbarrier at shared offset %u used before mbarrier.init\n", addr); abort(); }
+  return it->second;
+}
+static void mbar_check_complete(Block::MBar& b) {
+  if (b.pending == 0 && b.tx == 0) { b.phase ^= 1u; b.pending = b.init; }
+}
+void mbar_init(uint32_t addr, uint32_t count) {
+  Block::MBar b;
+  b.init = b.pending = count;
+  g_blk->mbars[addr] = b;
+  ++g_blk->progress;
+}
+void mbar_arrive(uint32_t addr, uint32_t expect_tx_bytes) {
+  Block::MBar& b = mbar_at(addr);
+  if (b.pending == 0) die("mbarrier received more arrivals than its count");
+  b.tx += expect_tx_bytes;
+  --b.pending;
+  mbar_check_complete(b);
+  ++g_blk->progress;
+}
+void mbar_complete_tx(uint32_t addr, uint32_t bytes) {
+  Block::MBar& b = mbar_at(addr);
+  b.tx -= bytes;
+  if (b.tx < 0) die("mbarrier transaction count went negative (more bytes delivered than expected)");
+  mbar_check_complete(b);
+  ++g_blk->progress;
+}
+bool mbar_phase_done(uint32_t addr, uint32_t parity) { return mbar_at(addr).phase != (parity & 1u); }
+
+void named_barrier(int id, int nthreads) {
+  Block& B = *g_blk;
+  if (id < 0 || id >= 16) die("named barrier id out of range");
+  Block::NamedBar& nb = B.named[id];
+  const unsigned gen = nb.gen;
+  ++B.progress;
+  if (++nb.arrived == nthreads) { nb.arrived = 0; ++nb.gen; return; }
+  if (nb.arrived > nthreads) die("named barrier over-subscribed");
+  while (nb.gen == gen) yield();
+}
 
 void sync_threads() {
-  Block& B = g_block;
+  Block& B = *g_blk;
   Fiber& f = B.fibers[B.cur];
   const unsigned gen = B.bar_gen;
   ++B.bar_arrived;
@@ -180,7 +236,7 @@ void sync_threads() {
 }
 
 uint64_t warp_collective(Collective kind, unsigned mask, uint64_t value, int aux) {
-  Block& B = g_block;
+  Block& B = *g_blk;
   Fiber& f = B.fibers[B.cur];
   const int warp = B.cur >> 5, lane = B.cur & 31;
   mask &= existing_lanes(warp);       // a full mask in a partial last warp names only the lanes that exist
@@ -197,56 +253,103 @@ uint64_t warp_collective(Collective kind, unsigned mask, uint64_t value, int aux
   return f.result;
 }
 
-void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body) {
-  Block& B = g_block;
-  if (B.body != nullptr) { fprintf(stderr, "[cudasim] nested launch\n"); abort(); }
+static void setup_block(Block& B, int n, dim3 grid, dim3 block, unsigned bx, unsigned by, unsigned bz, size_t dyn_smem_bytes,
+                        const std::function<void()>* body, size_t stack0) {
+  B.n = B.live = n;
+  B.bar_arrived = 0; B.bar_gen = 0; B.progress = 0;
+  B.body = body;
+  B.fibers.assign((size_t)n, Fiber());
+  B.warp_arrived.assign((size_t)(n + 31) / 32, 0u);
+  if (!B.smem && posix_memalign(reinterpret_cast<void**>(&B.smem), 1024, kSmemMax) != 0) { fprintf(stderr, "[cudasim] smem allocation failed\n"); abort(); }
+  (void)dyn_smem_bytes;
+  memset(B.smem, 0xCD, kSmemMax);               // never zeroed on a GPU either
+  B.mbars.clear();
+  for (auto& nb : B.named) nb = Block::NamedBar();
+  B.tmem.assign(128 * 512, 0x7fc00000u);        // NaN until an MMA overwrites it
+  while (g_stacks.size() < stack0 + (size_t)n) g_stacks.push_back(static_cast<char*>(malloc(kStackBytes)));
+  for (int t = 0; t < n; ++t) {
+    Fiber& f = B.fibers[t];
+    f.tc.threadIdx_ = {(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
+    f.tc.blockIdx_ = {bx, by, bz};
+    f.tc.blockDim_ = block;
+    f.tc.gridDim_ = grid;
+    f.stack = g_stacks[stack0 + (size_t)t];
+    ctx_make(&f.ctx, f.stack, kStackBytes, fiber_main);
+  }
+}
+
+// run the given blocks until every simulated thread has exited (round-robin over all of them)
+static void run_blocks(Block** blocks, int nb) {
+  unsigned long long last_progress = ~0ull;
+  int idle_rounds = 0;
+  for (;;) {
+    unsigned long long progress = 0;
+    int live = 0;
+    for (int i = 0; i < nb; ++i) { progress += blocks[i]->progress; live += blocks[i]->live; }
+    if (live == 0) break;
+    idle_rounds = (progress == last_progress) ? idle_rounds + 1 : 0;
+    g_blk = blocks[0];
+    if (idle_rounds > 3) die("deadlock: no simulated thread can make progress");
+    last_progress = progress;
+    for (int i = 0; i < nb; ++i) {
+      Block& B = *blocks[i];
+      for (int t = 0; t < B.n; ++t) {
+        Fiber& f = B.fibers[t];
+        if (f.state == kDone) continue;
+        if (f.state == kWaitBarrier && B.bar_gen == f.wait_gen) continue;
+        if (f.state == kWaitCollective && !f.result_ready) continue;
+        g_blk = &B;
+        B.cur = t;
+        g_cur = &f.tc;
+        ++g_switches;
+        ctx_switch(&B.sched, &f.ctx);
+      }
+    }
+  }
+}
+
+static void launch_impl(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body, bool cooperative) {
+  if (g_in_launch) { fprintf(stderr, "[cudasim] nested launch\n"); abort(); }
   const int n = (int)(block.x * block.y * block.z);
   if (n <= 0 || n > 1024) { fprintf(stderr, "[cudasim] bad block size %d\n", n); abort(); }
+  if (dyn_smem_bytes > kSmemMax) { fprintf(stderr, "[cudasim] dynamic shared memory request exceeds 227 KB\n"); abort(); }
+  const size_t n_blocks = (size_t)grid.x * grid.y * grid.z;
+  const size_t alive = cooperative ? n_blocks : 1;
+  if (cooperative && n_blocks * (size_t)n > 16384) { fprintf(stderr, "[cudasim] cooperative grid too large to emulate (%zu threads): lower HOSTSIM_SM_COUNT\n", n_blocks * n); abort(); }
+  while (g_blocks.size() < alive) g_blocks.push_back(new Block());
+  g_in_launch = true;
   ++g_launches;
-  while ((int)g_stacks.size() < n) g_stacks.push_back(static_cast<char*>(malloc(kStackBytes)));
-  B.body = &body;
+  size_t bi = 0;
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        ++g_blocks;
-        B.n = B.live = n;
-        B.bar_arrived = 0; B.bar_gen = 0; B.progress = 0;
-        B.fibers.assign((size_t)n, Fiber());
-        B.warp_arrived.assign((size_t)(n + 31) / 32, 0u);
-        B.smem.assign(dyn_smem_bytes + 16, 0xCD);    // never zeroed on a GPU either
-        for (int t = 0; t < n; ++t) {
-          Fiber& f = B.fibers[t];
-          f.tc.threadIdx_ = {(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
-          f.tc.blockIdx_ = {bx, by, bz};
-          f.tc.blockDim_ = block;
-          f.tc.gridDim_ = grid;
-          f.stack = g_stacks[t];
-          ctx_make(&f.ctx, f.stack, kStackBytes, fiber_main);
-        }
-        unsigned long long last_progress = ~0ull;
-        while (B.live > 0) {
-          if (B.progress == last_progress) die("deadlock: no simulated thread can make progress");
-          last_progress = B.progress;
-          for (int t = 0; t < n; ++t) {
-            Fiber& f = B.fibers[t];
-            if (f.state == kDone) continue;
-            if (f.state == kWaitBarrier && B.bar_gen == f.wait_gen) continue;
-            if (f.state == kWaitCollective && !f.result_ready) continue;
-            B.cur = t;
-            g_cur = &f.tc;
-            ++g_switches;
-            ctx_switch(&B.sched, &f.ctx);
-          }
+      for (unsigned bx = 0; bx < grid.x; ++bx, ++bi) {
+        ++g_blocks_run;
+        if (cooperative) {
+          setup_block(*g_blocks[bi], n, grid, block, bx, by, bz, dyn_smem_bytes, &body, bi * (size_t)n);
+        } else {
+          setup_block(*g_blocks[0], n, grid, block, bx, by, bz, dyn_smem_bytes, &body, 0);
+          Block* one = g_blocks[0];
+          run_blocks(&one, 1);
         }
       }
-  B.body = nullptr;
+  if (cooperative) run_blocks(g_blocks.data(), (int)n_blocks);
+  g_in_launch = false;
+  g_blk = nullptr;
   g_cur = nullptr;
+}
+
+void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body) {
+  launch_impl(grid, block, dyn_smem_bytes, body, false);
+}
+// every CTA of the grid is alive at once (cudaLaunchCooperativeKernel): a grid-wide barrier can complete
+void launch_cooperative(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body) {
+  launch_impl(grid, block, dyn_smem_bytes, body, true);
 }
 
 }  // namespace cudasim
 
 extern "C" {
 unsigned long long cudasim_launches(void) { return cudasim::g_launches; }
-unsigned long long cudasim_blocks(void) { return cudasim::g_blocks; }
+unsigned long long cudasim_blocks(void) { return cudasim::g_blocks_run; }
 unsigned long long cudasim_switches(void) { return cudasim::g_switches; }
 }

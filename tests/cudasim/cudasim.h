@@ -38,11 +38,13 @@ struct ThreadCtx {
 };
 extern ThreadCtx* g_cur;   // the running simulated thread
 void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body);
+void launch_cooperative(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body);
+void yield_spin();   // a spinning thread lets the others run (global-memory flags, mbarrier waits)
 void* dyn_smem();
 void sync_threads();
 enum Collective { kShflIdx, kShflXor, kShflUp, kShflDown, kBallot, kSyncWarp };
 uint64_t warp_collective(Collective kind, unsigned mask, uint64_t value, int aux);
-extern unsigned long long g_launches, g_blocks, g_switches;   // statistics the tests read
+extern unsigned long long g_launches, g_blocks_run, g_switches;   // statistics the tests read
 }  // namespace cudasim
 
 #define threadIdx (cudasim::g_cur->threadIdx_)

@@ -35,10 +35,11 @@ static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSucces
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
-  p->multiProcessorCount = 148; p->major = 10; p->minor = 0; p->sharedMemPerBlockOptin = 232448;
+  const char* sms = getenv("HOSTSIM_SM_COUNT");          // tests shrink the "GPU" to keep emulated grids small
+  p->multiProcessorCount = (sms && atoi(sms) > 0) ? atoi(sms) : 148; p->major = 10; p->minor = 0; p->sharedMemPerBlockOptin = 232448;
   return cudaSuccess;
 }
-static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 1; return cudaSuccess; }   // cooperative launch: yes
 static inline cudaError_t cudaMalloc(void** p, size_t n) {
   if (hostsim_fail_malloc_over > 0 && (long long)n > hostsim_fail_malloc_over) { *p = nullptr; return cudaErrorMemoryAllocation; }
   // 0xA5 fill: reading memory the library never wrote shows up in comparisons

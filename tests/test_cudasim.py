@@ -1,9 +1,13 @@
 """CPU: the CUDA-core kernels of libtristage EXECUTED on a SIMT emulator (tests/cudasim/: every
 simulated thread is a fiber; __syncthreads and the *_sync warp primitives are rendezvous points)
 and checked against the oracle with the rule the GPU parity tests use.  The kernel sources are
-the product's own (.cu files compiled with g++ under TS_CUDASIM); the tensor-path kernels
-(TMA / tcgen05) cannot be emulated and refuse.  Test infrastructure only -- the emulated library
-is built into build/cudasim/, loaded explicitly here, and never used by the package."""
+the product's own (.cu files compiled with g++ under TS_CUDASIM).  The tensor-path kernels run
+too, over a functional model of the inline-PTX wrappers (tests/cudasim/ts_ptx_sim.cuh: mbarrier
+phases, TMA boxes with the 128-byte swizzle, UMMA descriptors, TMEM) in which every asynchronous
+operation completes at issue time -- it checks data movement, descriptor arithmetic, phase
+bookkeeping, masks and the fused selection, not latency or the memory model.  Test infrastructure
+only -- the emulated library is built into build/cudasim/, loaded explicitly here, and never used
+by the package."""
 import ctypes as C
 import os
 import subprocess
@@ -169,13 +173,122 @@ def test_rank_desc_is_the_reference_stable_sort(sim):
         assert (out_s[b, :n] == scores[b, order]).all()
 
 
-def test_tensor_path_is_not_emulated(sim):
-    idx = _lib.Index(32, "bf16", "ip", 0)
-    idx.add(np.ones((4, 32), np.float32))
-    with pytest.raises(_lib.TristageError, match="cannot be emulated"):
-        idx.search_host(np.ones((1, 32), np.float32), 2, path="umma")
-    with pytest.raises(_lib.TristageError, match="cannot be emulated"):
-        idx.search_host(np.ones((1, 32), np.float32), 2)                       # auto = tensor path for bf16
+# ------------------------------------------- Stage 1, tensor path (tcgen05 / TMA model) ---
+@pytest.mark.parametrize("N,d,B,k,dtype", [(5, 768, 1, 50, "bf16"), (256, 64, 8, 5, "bf16"), (1000, 768, 32, 100, "bf16"),
+                                           (9000, 128, 32, 100, "bf16"), (4099, 64, 5, 10, "fp16"), (3000, 100, 17, 7, "bf16"),
+                                           (3000, 1024, 64, 100, "bf16"), (4000, 768, 65, 100, "bf16"), (6000, 256, 128, 128, "fp16"),
+                                           (9000, 128, 200, 100, "bf16"), (5000, 256, 33, 500, "bf16"), (20000, 64, 1024, 100, "bf16"),
+                                           (300, 1024, 1, 100, "bf16"), (9000, 128, 16, 500, "bf16"), (12000, 64, 300, 128, "bf16"),
+                                           (38000, 128, 1, 1, "bf16")])
+def test_tensor_scan_matches_the_oracle(sim, N, d, B, k, dtype):
+    """s1_umma_kernel (threshold pre-pass + scan with the fused, threshold-sharing top-k) and
+    select_kernel over its lists, executed on the functional tcgen05 / TMA / mbarrier model; the
+    shapes of tests/test_gpu_stage1.py::test_umma_path at reduced corpus sizes."""
+    X, Q = make(N, d, B, seed=N + B, planted=10 if N > 10 * B else 0)
+    idx = _lib.Index(d, dtype, "ip", 0)
+    for part in np.array_split(X, 2):
+        idx.add(part)
+    D, I = idx.search_host(Q, k, path="umma")
+    rD, rI, sc = oracle_search(X, Q, k, dtype)
+    assert not flat_ip.check_topk(D, I, sc, rD, rI, rel=REL)
+    Da, Ia = idx.search_host(Q, k)                                  # auto = tensor path for 16-bit storage
+    assert (Ia == I).all() and (Da == D).all()
+
+
+@pytest.mark.parametrize("order", ["ascending", "descending", "constant"])
+@pytest.mark.parametrize("k", [100, 500])
+def test_tensor_scan_adversarial_score_orders(sim, order, k):
+    """The cases of tests/test_gpu_z_fullsize.py::test_adversarial_score_orders_on_device: ascending
+    scores overflow every list (in-scan warp prune under a stale shared bound), constant scores tie
+    everywhere (the k smallest ids must win through scan, prune and select)."""
+    N, d = 60_000, 64
+    rng = np.random.default_rng(4)
+    u = flat_ip.normalize_rows(rng.standard_normal((1, d)).astype(np.float32))[0].astype(np.float32)
+    v = {"ascending": np.linspace(0.05, 1.0, N), "descending": np.linspace(1.0, 0.05, N),
+         "constant": np.full(N, 0.5)}[order].astype(np.float32)
+    X = (v[:, None] * u[None, :]).astype(np.float32)
+    Q = np.stack([u, -u, flat_ip.normalize_rows(rng.standard_normal((1, d)).astype(np.float32))[0]]).astype(np.float32)
+    idx = _lib.Index(d, "bf16", "ip", 0)
+    idx.add(X)
+    D, I = idx.search_host(Q, k, path="umma")
+    rD, rI, sc = oracle_search(X, Q, k, "bf16")
+    bad = flat_ip.check_topk(D, I, sc, rD, rI, rel=REL)
+    assert not bad, bad[:3]
+    if order == "constant":
+        assert I[0].tolist() == list(range(k)) and I[1].tolist() == list(range(k))
+
+
+def test_tensor_scan_variants_agree_bit_for_bit(sim, monkeypatch):
+    """tests/test_gpu_z_fullsize.py::test_scan_variants_agree_bit_for_bit on the emulator: without
+    threshold sharing, with two query tiles per CTA (TS_DUAL), without the small-batch spread, and
+    with the first select kernel -- identical ids and scores."""
+    N, d, B, k = 20000, 128, 48, 100
+    X, Q = make(N, d, B, seed=77, planted=20)
+    idx = _lib.Index(d, "bf16", "ip", 0)
+    idx.add(X)
+    base = idx.search_host(Q, k, path="umma")
+    rD, rI, sc = oracle_search(X, Q, k, "bf16")
+    assert not flat_ip.check_topk(base[0], base[1], sc, rD, rI, rel=REL)
+    Q2 = make(10, d, 300, seed=78)[1]
+    base2 = idx.search_host(Q2, k, path="umma")
+    for var in ("TS_DBG_NOSHARE", "TS_DUAL", "TS_DBG_NOSPREAD", "TS_SELECT_V1"):
+        monkeypatch.setenv(var, "1")
+        D, I = idx.search_host(Q, k, path="umma")
+        D2, I2 = idx.search_host(Q2, k, path="umma")
+        monkeypatch.delenv(var)
+        assert (I == base[1]).all() and (D == base[0]).all(), var
+        assert (I2 == base2[1]).all() and (D2 == base2[0]).all(), var
+    # TS_FUSE: pre-pass + grid barrier + scan in ONE cooperative launch.  Every CTA must be alive at once,
+    # so the emulated "GPU" is shrunk to 12 SMs (12 x 192 fibers); the 148-SM layout of `base` differs, so
+    # the comparison is against the two-launch result on the same 12 SMs.
+    monkeypatch.setenv("HOSTSIM_SM_COUNT", "12")
+    small = _lib.Index(d, "bf16", "ip", 0)
+    small.add(X)
+    two = small.search_host(Q, k, path="umma")
+    two2 = small.search_host(Q2, k, path="umma")
+    assert (two[1] == base[1]).all() and (two[0] == base[0]).all()          # the SM count never changes the answer
+    monkeypatch.setenv("TS_FUSE", "1")
+    before = sim.cudasim_launches()
+    D, I = small.search_host(Q, k, path="umma")
+    assert sim.cudasim_launches() - before == 3                             # query prep, ONE scan launch, select
+    assert (I == two[1]).all() and (D == two[0]).all()
+    D2, I2 = small.search_host(Q2, k, path="umma")                          # three query tiles x 4 slices
+    assert (I2 == two2[1]).all() and (D2 == two2[0]).all()
+    D, I = small.search_host(Q, k, path="umma")                             # the barrier resets itself: run it again
+    assert (I == two[1]).all() and (D == two[0]).all()
+
+
+def test_tensor_scan_cosine_metric_ties_and_shards(sim):
+    rng = np.random.default_rng(2)
+    N, d, k = 3000, 72, 50
+    X = (rng.standard_normal((N, d)) * rng.uniform(0.1, 5.0, size=(N, 1))).astype(np.float32)
+    Q = (3.0 * rng.standard_normal((4, d))).astype(np.float32)
+    idx = _lib.Index(d, "bf16", "cosine", 0)
+    idx.add(X)
+    D, I = idx.search_host(Q, k, normalize_q=True, path="umma")
+    Xr = flat_ip.round_to(X, "bf16")
+    Qr = flat_ip.round_to(flat_ip.normalize_rows(Q), "bf16")
+    inv = (1.0 / (np.linalg.norm(X, axis=1) + 1e-8)).astype(np.float32)
+    rD, rI = flat_ip.topk_desc((Qr @ Xr.T) * inv[None, :], k)
+    sc = lambda b, ids: (Xr[ids].astype(np.float64) @ Qr[b].astype(np.float64)) * inv[ids]   # noqa: E731
+    assert not flat_ip.check_topk(D, I, sc, rD, rI, rel=REL)
+    # exact duplicates: ties resolved by ascending id; half shards merged == full scan (what 2 GPUs compute)
+    X2, Q2 = make(2000, 64, 6, seed=3)
+    X2[5] = X2[1500] = X2[900] = X2[17]
+    full = _lib.Index(64, "bf16", "ip", 0)
+    full.add(X2)
+    Df, If = full.search_host(Q2, 20, path="umma")
+    S, Id = np.empty((2, 6, 20), np.float32), np.empty((2, 6, 20), np.int64)
+    for i, (lo, hi) in enumerate(((0, 1000), (1000, 2000))):
+        sh = _lib.Index(64, "bf16", "ip", 0)
+        sh.add(X2[lo:hi])
+        sh.set_id_base(lo)
+        S[i], Id[i] = sh.search_host(Q2, 20, path="umma")
+    out_s, out_i = np.empty((6, 20), np.float32), np.empty((6, 20), np.int64)
+    _lib.check(sim.ts_topk_merge(0, p(S), p(Id), 2, 6, 20, p(out_s), p(out_i), None))
+    assert (out_i == If).all() and (out_s == Df).all()
+    rD2, rI2, sc2 = oracle_search(X2, Q2, 20, "bf16")
+    assert (If == rI2).all()
 
 
 # ------------------------------------------------------------------- Stage 2 ---
@@ -423,3 +536,93 @@ _orig_search = flat_ip.IndexFlatIP.search
 
 def _search_ignoring_path(self, q, k, path="auto", **kw):
     return _orig_search(self, q, k)
+
+
+# ------------------------------------------- Stage 2, tensor path (tcgen05 / TMA model) ---
+def _norm_round(x, dtype):
+    return flat_ip.round_to(maxsim.l2_normalize_tokens(x), dtype)
+
+
+def _make_store(lens, dim, dtype, seed=0):
+    rng = np.random.default_rng(seed)
+    tok = rng.standard_normal((int(np.sum(lens)), dim)).astype(np.float32)
+    st = _lib.TokStore(dim, dtype, 0)
+    cut = len(lens) // 3
+    off = np.concatenate([[0], np.cumsum(lens)])
+    for a, b in ((0, cut), (cut, len(lens))):
+        if b > a:
+            st.add(tok[off[a]:off[b]], lens[a:b], normalize=True)
+    return st, [tok[off[i]:off[i + 1]] for i in range(len(lens))]
+
+
+def _oracle_scores(q, docs, cand, mode, dtype, n_cand=None, q_len=None):
+    B, Cn = cand.shape
+    out = np.zeros((B, Cn), np.float32)
+    for b in range(B):
+        lq = q.shape[1] if q_len is None else int(q_len[b])
+        qb = _norm_round(q[b, :lq], dtype)
+        for j in range(Cn if n_cand is None else int(n_cand[b])):
+            c = int(cand[b, j])
+            if 0 <= c < len(docs):
+                out[b, j] = maxsim.score(qb, _norm_round(docs[c], dtype), mode, normalize=False)
+    return out
+
+
+@pytest.mark.parametrize("dim,Lq,dtype", [(128, 32, "bf16"), (128, 32, "fp16"), (64, 7, "bf16"), (128, 1, "bf16"),
+                                          (96, 33, "bf16"), (128, 128, "bf16"), (256, 32, "bf16"), (128, 70, "bf16")])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_tensor_maxsim_matches_the_oracle_both_epilogues(sim, monkeypatch, dim, Lq, dtype, mode):
+    """maxsim_umma_kernel on the functional model (ragged TMA gather, tile packing, per-quarter drain,
+    finalize): the cases of tests/test_gpu_stage2.py::test_batch_vs_oracle_ragged, for the validated
+    epilogue and for the opt-in TS_S2_V2 one, which must agree bit for bit."""
+    rng = np.random.default_rng(dim + Lq)
+    ndocs, B, Cn = 150, 3, 70
+    lens = rng.integers(1, 181, size=ndocs)
+    lens[:6] = [1, 8, 9, 255, 256, 180]
+    st, docs = _make_store(lens, dim, dtype, seed=dim)
+    q = rng.standard_normal((B, Lq, dim)).astype(np.float32)
+    cand = rng.integers(0, ndocs, size=(B, Cn)).astype(np.int64)
+    cand[0, :6] = np.arange(6)
+    ref = _oracle_scores(q, docs, cand, mode, dtype)
+    got = st.maxsim_host(q, cand, mode=mode)
+    np.testing.assert_allclose(got, ref, rtol=1e-3, atol=2e-4)
+    monkeypatch.setenv("TS_S2_V2", "1")
+    got2 = st.maxsim_host(q, cand, mode=mode)
+    assert np.array_equal(got2, got)
+    monkeypatch.setenv("TS_S2_STAGES", "4")                          # 4-stage ring, single maxima buffer
+    assert np.array_equal(st.maxsim_host(q, cand, mode=mode), got)
+    monkeypatch.delenv("TS_S2_V2")
+    assert np.array_equal(st.maxsim_host(q, cand, mode=mode), got)
+
+
+@pytest.mark.parametrize("v2", [False, True])
+def test_tensor_maxsim_n_cand_q_len_unowned_and_length_mixes(sim, monkeypatch, v2):
+    if v2:
+        monkeypatch.setenv("TS_S2_V2", "1")
+    rng = np.random.default_rng(2)
+    dim, ndocs, B, Cn, Lq = 128, 200, 6, 64, 32
+    lens = rng.integers(16, 181, size=ndocs)
+    st, docs = _make_store(lens, dim, "bf16", seed=4)
+    q = rng.standard_normal((B, Lq, dim)).astype(np.float32)
+    cand = rng.integers(0, ndocs, size=(B, Cn)).astype(np.int64)
+    cand[1, 5] = -1
+    cand[2, 7] = ndocs + 10
+    n_cand = np.array([64, 10, 0, 33, 1, 64], np.int32)
+    q_len = np.array([32, 5, 32, 17, 1, 31], np.int32)
+    for mode in (0, 1):
+        got = st.maxsim_host(q, cand, q_len=q_len, n_cand=n_cand, mode=mode)
+        ref = _oracle_scores(q, docs, cand, mode, "bf16", n_cand=n_cand, q_len=q_len)
+        np.testing.assert_allclose(got, ref, rtol=1e-3, atol=2e-4)
+        assert got[1, 5] == 0.0 and (got[2] == 0.0).all() and (got[1, 10:] == 0.0).all()
+    st.set_id_base(1000)
+    np.testing.assert_allclose(st.maxsim_host(q, cand + 1000, mode=0), _oracle_scores(q, docs, cand, 0, "bf16"),
+                               rtol=1e-3, atol=2e-4)
+    assert (st.maxsim_host(q, cand, mode=0) == 0.0).all()
+    # doc-length mixes that stress the packing: only tiny docs (32 per tile), only 256-token docs, quarter straddlers
+    for name, ln in (("tiny", np.full(90, 3)), ("max", np.full(12, 256)), ("eights", np.full(70, 8)),
+                     ("straddle", np.array([60, 10, 120, 7, 59, 130, 3, 3, 3, 250, 5, 1, 63, 1, 64, 1, 127, 129] * 3))):
+        st2, docs2 = _make_store(ln, 64, "bf16", seed=len(ln))
+        q2 = rng.standard_normal((2, 20, 64)).astype(np.float32)
+        c2 = np.stack([rng.permutation(len(ln))[: min(len(ln), 40)] for _ in range(2)]).astype(np.int64)
+        np.testing.assert_allclose(st2.maxsim_host(q2, c2), _oracle_scores(q2, docs2, c2, 0, "bf16"), rtol=1e-3, atol=2e-4,
+                                   err_msg=name)

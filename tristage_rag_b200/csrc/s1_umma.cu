@@ -239,9 +239,7 @@ __device__ __forceinline__ void finish_state(const UmmaParams& p, QState& s, int
   }
 }
 
-__device__ __forceinline__ void named_bar_sync128(int id) {
-  asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
-}
+__device__ __forceinline__ void named_bar_sync128(int id) { named_bar_sync(id, 128); }
 
 // Grid-wide barrier for the epilogue threads of a cooperative launch (all CTAs
 // co-resident).  Self-resetting (arrival counter + generation word), so it
@@ -260,6 +258,7 @@ __device__ __forceinline__ void grid_barrier_epilogue(unsigned int* bar, unsigne
     } else {
       const long long t0 = clock64();
       while (*reinterpret_cast<volatile unsigned int*>(bar + 1) == gen0) {
+        TS_SPIN_YIELD();
         if (clock64() - t0 > TS_WAIT_TIMEOUT_CYCLES) {
           printf("[tristage] grid barrier timeout: block %d\n", (int)blockIdx.x);
           __trap();
@@ -280,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int n_stages = dual ? 3 : 4;
   const int stage_bytes = dual ? (2 * kABytes + kBBytes) : (kABytes + kBBytes);
   const int b_off = dual ? 2 * kABytes : kABytes;     // B chunk offset inside a stage
-  extern __shared__ unsigned char smem_raw[];
+  TS_DYN_SMEM(unsigned char, smem_raw);
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes);
   uint64_t* full_bar = bars;                        // [kMaxStages] TMA -> MMA
@@ -451,6 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 // ------------------------------------------------------------------ host ---
+#ifndef TS_CUDASIM
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -466,11 +466,15 @@ EncodeTiledFn get_encode_fn() {
   fn = reinterpret_cast<EncodeTiledFn>(p);
   return fn;
 }
+#endif  // !TS_CUDASIM
 
 }  // namespace
 
 // 2-D row-major [rows][dim] (pitch ld elements) 16-bit tensor, box = 64 x box_rows, SWIZZLE_128B
 int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, int dim, int ld, int box_rows) {
+#ifdef TS_CUDASIM
+  return ptx::sim_make_tmap_2d(out, base, dtype, rows, dim, ld, kChunkK, box_rows);
+#else
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return TS_ERR_CUDA; }
   cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
@@ -482,6 +486,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, in
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows %lld dim %d ld %d box %d)", (int)r, (long long)rows, dim, ld, box_rows); return TS_ERR_CUDA; }
   return TS_OK;
+#endif
 }
 
 namespace {
@@ -556,18 +561,22 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
     // one cooperative launch (all CTAs co-resident): first tile -> publish -> grid barrier -> scan
     p.mode = 2;
     p.grid_bar = a.grid_bar;
+#ifdef TS_CUDASIM
+    cudasim::launch_cooperative(lay.grid, kThreads, kSmemBytes, [&]() { kern(tmQ, tmQ8, tmX, p); });
+#else
     void* args[] = {(void*)&tmQ, (void*)&tmQ8, (void*)&tmX, (void*)&p};
     TS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(lay.grid), dim3(kThreads), args, kSmemBytes, st));
+#endif
     if (launches) ++*launches;
   } else {
     if (p.jrank > 0) {
       p.mode = 0;   // threshold pre-pass over the first tile of every slice
-      kern<<<lay.grid, kThreads, kSmemBytes, st>>>(tmQ, tmQ8, tmX, p);
+      TS_LAUNCH(kern, lay.grid, kThreads, kSmemBytes, st, tmQ, tmQ8, tmX, p);
       TS_CUDA_OK(cudaGetLastError());
       if (launches) ++*launches;
     }
     p.mode = 1;
-    kern<<<lay.grid, kThreads, kSmemBytes, st>>>(tmQ, tmQ8, tmX, p);
+    TS_LAUNCH(kern, lay.grid, kThreads, kSmemBytes, st, tmQ, tmQ8, tmX, p);
     TS_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
   }

@@ -36,22 +36,16 @@
 
 #include "ts_common.cuh"
 #include "ts_internal.h"
-#ifndef TS_CUDASIM   // the tensor path (TMA / tcgen05 inline PTX) only exists for sm_100a
 #include "ts_ptx.cuh"
-#endif
 
 namespace ts {
 
-#ifndef TS_CUDASIM
 int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, int dim, int ld, int box_rows);
 
-#endif
 
 namespace {
 
-#ifndef TS_CUDASIM
 using namespace ts::ptx;
-#endif
 
 // ============================================================ SIMT path ====
 template <typename T>
@@ -105,7 +99,6 @@ __global__ void __launch_bounds__(128)
 }
 
 // ========================================================== tensor path ====
-#ifndef TS_CUDASIM
 constexpr int kThreads = 192;
 constexpr int kMaxStages = 4;   // 3 stages + double-buffered maxima, or 4 stages + single buffer (p.n_stages)
 constexpr int kTileM = 128, kTileN = 256, kChunkK = 64;
@@ -151,10 +144,6 @@ struct MaxSimParams {
   float* out;
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 // V2 (opt-in, TS_S2_V2=1; written from the round-1 ncu source view, not yet validated on
 // hardware): the same pipeline with a shorter epilogue critical path --
 //   * shared-memory pointers keep their address space (LDS/STS instead of generic LD/ST for the
@@ -171,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                        const __grid_constant__ CUtensorMap tmT8, const __grid_constant__ CUtensorMap tmT16,
                        const __grid_constant__ CUtensorMap tmT32, const __grid_constant__ CUtensorMap tmT64,
                        const __grid_constant__ CUtensorMap tmT128, const MaxSimParams p) {
-  extern __shared__ unsigned char smem_raw[];
+  TS_DYN_SMEM(unsigned char, smem_raw);
   unsigned char* smem;
   if constexpr (V2) {
     // offset arithmetic on the __shared__ array keeps the address space known to the compiler
@@ -537,7 +526,6 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
-#endif  // !TS_CUDASIM
 
 }  // namespace
 
@@ -545,12 +533,8 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
   if (a.B <= 0 || a.C <= 0) { set_error("maxsim: empty batch"); return TS_ERR_INVALID; }
   TS_CUDA_OK(cudaMemsetAsync(a.out, 0, (size_t)a.B * a.C * sizeof(float), st));
   if (a.ndocs == 0) return TS_OK;
-#ifdef TS_CUDASIM
-  const bool tensor_ok = false;   // tests/cudasim: only the CUDA-core kernel can be emulated
-#else
   const bool tensor_ok = (a.dtype == TS_BF16 || a.dtype == TS_F16) && (a.dim % 8 == 0) && a.lq_stride >= 1 &&
                          a.lq_stride <= TS_S2_MAX_LQ && !(a.mode & 0x100);
-#endif
   const int mode = a.mode & 0xff;
   if (!tensor_ok) {
     if (a.lq_stride > 4096) { set_error("maxsim: lq_stride too large"); return TS_ERR_UNSUPPORTED; }
@@ -570,7 +554,6 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
     if (launches) ++*launches;
     return TS_OK;
   }
-#ifndef TS_CUDASIM
   CUtensorMap tq8, tq32, tq128, t8, t16, t32, t64, t128;
   int rc;
   const int64_t qrows = (int64_t)a.B * a.lq_stride;
@@ -594,7 +577,7 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
   const bool v2 = env_on("TS_S2_V2");   // opt-in until validated on hardware
   auto launch = [&](auto kern) -> int {
     TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    kern<<<grid, kThreads, kSmemBytes, st>>>(tq8, tq32, tq128, t8, t16, t32, t64, t128, p);
+    TS_LAUNCH(kern, grid, kThreads, kSmemBytes, st, tq8, tq32, tq128, t8, t16, t32, t64, t128, p);
     return TS_OK;
   };
   if (a.dtype == TS_BF16) rc = v2 ? launch(maxsim_umma_kernel<true, true>) : launch(maxsim_umma_kernel<true, false>);
@@ -602,7 +585,6 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
   if (rc) return rc;
   TS_CUDA_OK(cudaGetLastError());
   if (launches) ++*launches;
-#endif  // !TS_CUDASIM
   return TS_OK;
 }
 

@@ -5,6 +5,11 @@
 // cute/arch/mma_sm100_desc.hpp in the vendored CUTLASS tree, used here only as
 // documentation).
 #pragma once
+#ifdef TS_CUDASIM
+// tests/cudasim: functional stand-ins with the same names (mbarrier phases, TMA boxes with the
+// 128-byte swizzle, UMMA descriptors, TMEM) so the tensor-path kernels can be executed on the CPU
+#include "ts_ptx_sim.cuh"
+#else
 #include <cuda.h>  // CUtensorMap (type only; the encoder is fetched at run time)
 #include <stdint.h>
 #include <stdio.h>
@@ -60,6 +65,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
       __trap();
     }
   }
+}
+
+// named barrier over a subset of the CTA (the epilogue warps)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ------------------------------------------------------------------ TMA ----
@@ -163,3 +173,4 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool bf16) {
 
 }  // namespace ptx
 }  // namespace ts
+#endif  // !TS_CUDASIM
