@@ -269,15 +269,22 @@ class Index:
                                     _stream_ptr(self.device)))
         return blob
 
-    def search_host(self, q, k: int, normalize_q: bool = False, path: str = "auto"):
-        """q: numpy fp32 [B, dim] -> (D[B,k] f32, I[B,k] i64) numpy -- the faiss call shape."""
+    def search_host(self, q, k: int, normalize_q: bool = False, path: str = "auto", out=None):
+        """q: numpy fp32 [B, dim] -> (D[B,k] f32, I[B,k] i64) numpy -- the faiss call shape.
+        ``out=(D, I)`` reuses caller-owned result arrays (e.g. views of pinned memory, which makes the
+        device-to-host copies asynchronous up to the final synchronise)."""
         import numpy as np
 
         q = np.ascontiguousarray(q, dtype=np.float32)
         assert q.ndim == 2 and q.shape[1] == self.dim, (q.shape, self.dim)
         B = q.shape[0]
-        D = np.empty((B, k), np.float32)
-        I = np.empty((B, k), np.int64)
+        if out is None:
+            D = np.empty((B, k), np.float32)
+            I = np.empty((B, k), np.int64)
+        else:
+            D, I = out
+            assert D.shape == (B, k) and D.dtype == np.float32 and D.flags.c_contiguous
+            assert I.shape == (B, k) and I.dtype == np.int64 and I.flags.c_contiguous
         check(lib().ts_index_search_host(self._h, C.c_void_p(q.ctypes.data), TS_F32, B, int(k),
                                          TS_FLAG_NORMALIZE_Q if normalize_q else 0, PATHS[path],
                                          C.c_void_p(D.ctypes.data), C.c_void_p(I.ctypes.data),
