@@ -109,15 +109,16 @@ class ClockSampler:
         return out
 
 
-def build_shard(idx, lo, hi, dim, dev, seed, chunk=500_000):
+def build_shard(idx, lo, hi, dim, dev, seed, chunk=500_000, dtype="bf16"):
     import torch
 
     g = torch.Generator(device=dev).manual_seed(seed)
+    tdt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[dtype]
     for s in range(lo, hi, chunk):
         n = min(chunk, hi - s)
         x = torch.randn((n, dim), generator=g, device=dev, dtype=torch.float32)
         x /= x.norm(dim=1, keepdim=True) + 1e-8          # reference formula, stage1_retriever.py:287-288
-        idx.add(x.to(torch.bfloat16), normalize=False)
+        idx.add(x.to(tdt), normalize=False)
         del x
 
 

@@ -36,3 +36,5 @@ import json
 for l in open('gpurun_out/s2_v2_probe.jsonl'):
     r=json.loads(l); print(f"{r['tag']:45s} kernel={r['kernel_ms']:.3f} ms  {r['cand_per_s']/1e6:.1f} Mcand/s  hbm={r['hbm_frac']:.2f}")
 PY
+# BASELINE configs[1] with the reference's own storage dtype (fp32 corpus, CUDA-core stream scan): not timed in round 1
+python tools/perf_probe.py --rows 1000000 --dim 768 --dtype fp32 --paths stream --batches 1,2,4 --tag c2_fp32 > gpurun_out/c2_fp32.jsonl 2> gpurun_out/c2_fp32.err; cat gpurun_out/c2_fp32.jsonl

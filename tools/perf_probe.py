@@ -22,15 +22,18 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--paths", default="stream,umma")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"],
+                    help="corpus storage dtype (fp32 = the reference's; stream path only)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     pk = bench.peaks()
-    idx = _lib.Index(args.dim, "bf16", "ip", 0, reserve_rows=args.rows)
-    bench.build_shard(idx, 0, args.rows, args.dim, dev, 1234)
-    ld = (args.dim + 7) // 8 * 8
+    idx = _lib.Index(args.dim, args.dtype, "ip", 0, reserve_rows=args.rows)
+    bench.build_shard(idx, 0, args.rows, args.dim, dev, 1234, dtype=args.dtype)
+    esz = 4 if args.dtype == "fp32" else 2
+    ld = (args.dim + 3) // 4 * 4 if args.dtype == "fp32" else (args.dim + 7) // 8 * 8
     for B in [int(b) for b in args.batches.split(",")]:
         for path in args.paths.split(","):
-            if path == "stream" and B > 8:
+            if (path == "stream" and B > 8) or (path == "umma" and args.dtype == "fp32"):
                 continue
             _, q = bench.make_queries(B, args.dim, dev, seed=B)
             fn = lambda: idx.search(q, args.k, path=path)  # noqa: E731
@@ -40,9 +43,9 @@ def main():
             kms, n = idx.scan_time_ms()
             idx.set_profiling(False)
             n_scans = n / args.steps
-            gb = args.rows * ld * 2 * n_scans / (kms * n_scans / 1e3) / 1e9
+            gb = args.rows * ld * esz * n_scans / (kms * n_scans / 1e3) / 1e9
             tf = 2.0 * B * args.rows * ld / (kms * n_scans / 1e3) / 1e12
-            print(json.dumps({"tag": args.tag, "rows": args.rows, "dim": args.dim, "B": B, "path": path, "step_ms": ms / args.steps,
+            print(json.dumps({"tag": args.tag, "rows": args.rows, "dim": args.dim, "dtype": args.dtype, "B": B, "path": path, "step_ms": ms / args.steps,
                               "scan_ms_per_launch": kms, "scans_per_step": n_scans,
                               "qps": B * args.steps / (ms / 1e3), "corpus_GBps_per_scan": gb,
                               "hbm_frac": gb / pk["hbm_gbs"], "TFLOPs": tf,
