@@ -175,6 +175,18 @@ def _code_of_torch(dt) -> int:
     return {torch.float32: TS_F32, torch.bfloat16: TS_BF16, torch.float16: TS_F16}[dt]
 
 
+def _locked(fn):
+    """Serialise calls on one handle: the library keeps per-handle scratch (include/tristage.h: "a handle is
+    not re-entrant"); the reference's callers are single threaded except the Flask dev server."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        with self._lock:
+            return fn(self, *a, **kw)
+    return wrapper
+
+
 class Index:
     """One Stage-1 corpus shard on one GPU (``ts_index``)."""
 
@@ -183,6 +195,7 @@ class Index:
         self.dim, self.device = int(dim), int(device)
         self.dtype = DTYPES[dtype]
         self.metric = TS_METRIC_COSINE if metric in ("cosine", "cos") else TS_METRIC_IP
+        self._lock = threading.RLock()     # include/tristage.h: one call at a time per handle
         if _handle is not None:
             self._h = _handle
         else:
@@ -215,9 +228,11 @@ class Index:
         check(lib().ts_index_scan_time(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    @_locked
     def reset(self) -> None:
         check(lib().ts_index_reset(self._h))
 
+    @_locked
     def add(self, x, normalize: bool = False) -> None:
         """x: numpy fp32 [n, dim] (host) or torch tensor (cuda: fp32 / storage dtype; cpu: fp32)."""
         import numpy as np
@@ -239,6 +254,7 @@ class Index:
         if on_dev:
             torch.cuda.current_stream(self.device).synchronize()   # x may be freed by the caller
 
+    @_locked
     def search(self, q, k: int, normalize_q: bool = False, path: str = "auto"):
         """q: cuda tensor [B, dim] (fp32 or storage dtype) -> (scores[B,k] f32, ids[B,k] i64) on the device.
         Asynchronous on the current stream."""
@@ -256,6 +272,7 @@ class Index:
                                     _stream_ptr(self.device)))
         return scores, ids
 
+    @_locked
     def search_packed(self, q, k: int, blob, normalize_q: bool = False, path: str = "auto"):
         """Like search(), but scores and ids land in one uint8 cuda buffer (packed_layout) so a
         single all-gather moves both."""
@@ -269,6 +286,7 @@ class Index:
                                     _stream_ptr(self.device)))
         return blob
 
+    @_locked
     def search_host(self, q, k: int, normalize_q: bool = False, path: str = "auto", out=None):
         """q: numpy fp32 [B, dim] -> (D[B,k] f32, I[B,k] i64) numpy -- the faiss call shape.
         ``out=(D, I)`` reuses caller-owned result arrays (e.g. views of pinned memory, which makes the
@@ -291,6 +309,7 @@ class Index:
                                          _stream_ptr(self.device)))
         return D, I
 
+    @_locked
     def get_rows(self, start: int, n: int):
         import numpy as np
 
@@ -298,9 +317,11 @@ class Index:
         check(lib().ts_index_get_rows(self._h, int(start), int(n), C.c_void_p(out.ctypes.data)))
         return out
 
+    @_locked
     def save(self, path: str) -> None:
         check(lib().ts_index_save(self._h, os.fsencode(path)))
 
+    @_locked
     def append_file(self, path: str, row_lo: int, n_rows: int) -> None:
         """Append rows [row_lo, row_lo + n_rows) of an index shard file (re-sharding primitive)."""
         check(lib().ts_index_append_file(self._h, os.fsencode(path), int(row_lo), int(n_rows),
@@ -313,6 +334,7 @@ class Index:
         obj = cls.__new__(cls)
         obj.dim, obj.device, obj._h = int(lib().ts_index_dim(h)), int(device), h
         obj.dtype, obj.metric = int(lib().ts_index_dtype(h)), int(lib().ts_index_metric(h))
+        obj._lock = threading.RLock()
         return obj
 
 
@@ -431,6 +453,7 @@ class BM25:
         import numpy as np
 
         self.device = int(device)
+        self._lock = threading.RLock()     # per-handle scratch: one call at a time
         off = np.ascontiguousarray(term_off, np.int64)
         docs = np.ascontiguousarray(post_doc, np.int32)
         w = np.ascontiguousarray(post_w, np.float64)
@@ -451,6 +474,7 @@ class BM25:
     def launches(self) -> int:
         return int(lib().ts_bm25_launch_count(self._h))
 
+    @_locked
     def search(self, query_terms, top_k: int):
         """query_terms: one int sequence of term ids per query (query-token order, repeats kept).
         -> (scores [B, top_k] float64, ids [B, top_k] int64, -1 beyond the corpus)."""
@@ -502,14 +526,17 @@ class TokStore:
                  reserve_tokens: int = 0):
         self.dim, self.device = int(dim), int(device)
         self.dtype = DTYPES[dtype]
+        self._lock = threading.RLock()     # one call at a time per handle
         h = C.c_void_p()
         check(lib().ts_tokstore_create(C.byref(h), self.device, self.dim, self.dtype, int(reserve_docs),
                                        int(reserve_tokens)))
         self._h = h
 
+    @_locked
     def save(self, path: str) -> None:
         check(lib().ts_tokstore_save(self._h, os.fsencode(path)))
 
+    @_locked
     def append_file(self, path: str, doc_lo: int, n_docs: int) -> None:
         """Append docs [doc_lo, doc_lo + n_docs) of a token shard file (re-sharding primitive)."""
         check(lib().ts_tokstore_append_file(self._h, os.fsencode(path), int(doc_lo), int(n_docs),
@@ -523,6 +550,7 @@ class TokStore:
         obj = cls.__new__(cls)
         obj.dim, obj.dtype = int(lib().ts_tokstore_dim(h)), int(lib().ts_tokstore_dtype(h))
         obj.device, obj._h = int(device), h
+        obj._lock = threading.RLock()
         if (dim is not None and int(dim) != obj.dim) or (dtype is not None and DTYPES[dtype] != obj.dtype):
             raise ValueError(f"{path}: holds dim {obj.dim} {DTYPE_NAMES[obj.dtype]}, expected dim {dim} {dtype}")
         return obj
@@ -555,9 +583,11 @@ class TokStore:
         check(lib().ts_tokstore_scan_time(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    @_locked
     def reset(self) -> None:
         check(lib().ts_tokstore_reset(self._h))
 
+    @_locked
     def add(self, tok, lens, normalize: bool = True) -> None:
         """tok: [sum(lens), dim] numpy fp32 (host) or torch tensor; lens: int sequence."""
         import numpy as np
@@ -578,6 +608,7 @@ class TokStore:
                                     1 if tok.is_cuda else 0, C.c_void_p(lens.ctypes.data), len(lens),
                                     int(normalize), _stream_ptr(self.device)))
 
+    @_locked
     def maxsim(self, q_tok, cand, q_len=None, n_cand=None, mode: int = TS_S2_MAXSIM, normalize_q: bool = True):
         """q_tok [B, Lq, dim] cuda, cand [B, C] int64 cuda -> scores [B, C] f32 cuda (async)."""
         import torch
@@ -595,6 +626,7 @@ class TokStore:
                               _stream_ptr(self.device)))
         return out
 
+    @_locked
     def maxsim_host(self, q_tok, cand, q_len=None, n_cand=None, mode: int = TS_S2_MAXSIM,
                     normalize_q: bool = True):
         """numpy in / numpy out variant (copies inside the call, synchronises)."""
