@@ -1,0 +1,92 @@
+"""CPU: the binding stub printed in INTEGRATION.md really drives the C ABI (executed here against the
+CPU emulator build of the library, tests/cudasim -- test infrastructure), and the host-side helpers
+of bench.py (contract fields, clock-sample parsing, algorithmic bytes) behave as documented."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from oracle import flat_ip
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_integration_md_binding_stub_runs_against_the_abi(monkeypatch):
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"```python\n# src/_tristage\.py.*?\n(.*?)```", text, flags=re.S)
+    assert m, "INTEGRATION.md lost its binding stub"
+    code = m.group(1)
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cudasim"), "-j", "8"], env=env, stdout=subprocess.DEVNULL)
+    sim = os.path.join(ROOT, "build", "cudasim", "libtristage_cudasim.so")
+    real_cdll = C.CDLL
+    monkeypatch.setattr(C, "CDLL", lambda name, *a, **kw: real_cdll(sim if name == "libtristage.so" else name, *a, **kw))
+    mod = types.ModuleType("_tristage_stub")
+    exec(compile(code, "INTEGRATION.md", "exec"), mod.__dict__)
+    rng = np.random.default_rng(0)
+    X = flat_ip.normalize_rows(rng.standard_normal((700, 48)).astype(np.float32)).astype(np.float32)
+    Q = flat_ip.normalize_rows(rng.standard_normal((3, 48)).astype(np.float32)).astype(np.float32)
+    idx = mod.IndexFlatIP(48)
+    with pytest.raises(ValueError, match=r"No documents indexed\. Call add_documents\(\) first\."):
+        idx.search(Q, 5)                                  # TS_ERR_EMPTY carries the reference's message
+    idx.add(X[:300])
+    idx.add(X[300:])
+    assert idx.ntotal == 700
+    D, I = idx.search(Q, 10)
+    Xr, Qr = flat_ip.round_to(X, "bf16"), flat_ip.round_to(Q, "bf16")
+    rD, rI = flat_ip.topk_desc(Qr @ Xr.T, 10)
+    assert not flat_ip.check_topk(D, I, lambda b, ids: Xr[ids].astype(np.float64) @ Qr[b].astype(np.float64), rD, rI)
+    with pytest.raises(RuntimeError):
+        idx.search(Q, 10_000)                             # k beyond TS_MAX_K
+
+
+def test_bench_contract_helpers():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    cfg = bench.workload_config(10_000_000, 1024, 100, 32, 8)
+    assert cfg["rows"] == 10_000_000 and cfg["batch"] == 32 and "row-sharded over 8 GPU" in cfg["workload"]
+    # algorithmic bytes of one search per GPU: shard once + queries + candidate lists
+    assert bench.stage1_alg_bytes(1_250_000, 1024, 32, 100, 148) == 1_250_000 * 2048 + 32 * 2048 + 148 * 32 * 100 * 8
+    pk = bench.peaks()
+    assert pk["hbm_gbs"] > 1000 and pk["bf16_tflops"] >= pk["bf16_tflops_sustained"] > 100
+
+
+def test_clock_sampler_parses_nvidia_smi_rows(tmp_path, monkeypatch):
+    sys.path.insert(0, ROOT)
+    import bench
+
+    fake = tmp_path / "nvidia-smi"
+    rows = ["1965, 1965, 310.5, 3, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active",
+            "1620, 1965, 998.1, 100, 0x0000000000000004, Not Active, Not Active, Not Active, Active",
+            "1590, 1965, 1001.0, 100, 0x0000000000000004, Not Active, Not Active, Not Active, Active",
+            "garbage line"]
+    fake.write_text("#!/bin/sh\n" + "".join(f"echo '{r}'\n" for r in rows) + "sleep 30\n")
+    fake.chmod(0o755)
+    monkeypatch.setenv("PATH", f"{tmp_path}:{os.environ['PATH']}")
+    s = bench.ClockSampler("GPU-00000000")
+    import time
+    time.sleep(0.5)
+    out = s.stop()
+    assert out["sm_max_mhz"] == 1965.0 and out["sm_mhz"] == 1605.0 and out["samples"] == 2     # median of the busy samples
+    assert out["reasons"] == ["sw_power_cap"]
+
+
+def test_reference_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--rows", "200000", "--dim", "64", "--batch", "4"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["config"]["rows"] == 200000 and line["config"]["batch"] == 4
