@@ -93,6 +93,11 @@ struct Block {
   std::unordered_map<uint32_t, MBar> mbars;
   NamedBar named[16];
   std::vector<uint32_t> tmem;
+  // thread-block cluster (launch_cluster): rank inside the cluster and the cluster's blocks
+  int cluster_rank = 0, cluster_size = 1;
+  Block** cluster = nullptr;
+  int cl_arrived = 0;            // cluster barrier state lives in rank 0's block
+  unsigned cl_gen = 0;
 };
 constexpr size_t kSmemMax = 232448;
 
@@ -179,9 +184,28 @@ uint32_t* tmem() { return g_blk->tmem.data(); }
 
 void yield_spin() { yield(); }
 
-static Block::MBar& mbar_at(uint32_t addr) {
-  auto it = g_blk->mbars.find(addr);
-  if (it == g_blk->mbars.end()) { fprintf(stderr, "[cudasim] mbarrier at shared offset %u used before mbarrier.init\n", addr); abort(); }
+int cluster_rank() { return g_blk->cluster_rank; }
+static Block& block_of(int cta) {
+  Block& B = *g_blk;
+  if (cta < 0 || cta >= B.cluster_size) die("cluster rank out of range");
+  return B.cluster_size == 1 ? B : *B.cluster[cta];
+}
+unsigned char* smem_base_of(int cta) { return block_of(cta).smem; }
+uint32_t* tmem_of(int cta) { return block_of(cta).tmem.data(); }
+void cluster_barrier() {
+  Block& B = *g_blk;
+  Block& R = block_of(0);
+  const unsigned gen = R.cl_gen;
+  const int want = B.cluster_size * B.n;
+  ++B.progress;
+  if (++R.cl_arrived == want) { R.cl_arrived = 0; ++R.cl_gen; return; }
+  while (R.cl_gen == gen) yield();
+}
+
+static Block::MBar& mbar_at(uint32_t addr, int cta = -1) {
+  Block& T = cta < 0 ? *g_blk : block_of(cta);
+  auto it = T.mbars.find(addr);
+  if (it == T.mbars.end()) { fprintf(stderr, "[cudasim] mbarrier at shared offset %u used before mbarrier.init\n", addr); abort(); }
   return it->second;
 }
 static void mbar_check_complete(Block::MBar& b) {
@@ -192,6 +216,22 @@ void mbar_init(uint32_t addr, uint32_t count) {
   b.init = b.pending = count;
   g_blk->mbars[addr] = b;
   ++g_blk->progress;
+}
+void mbar_arrive_at(int cta, uint32_t addr, uint32_t expect_tx_bytes) {
+  Block::MBar& b = mbar_at(addr, cta);
+  if (b.pending == 0) die("mbarrier received more arrivals than its count");
+  b.tx += expect_tx_bytes;
+  --b.pending;
+  mbar_check_complete(b);
+  ++g_blk->progress;
+  ++block_of(cta).progress;
+}
+void mbar_complete_tx_at(int cta, uint32_t addr, uint32_t bytes) {
+  Block::MBar& b = mbar_at(addr, cta);
+  b.tx -= bytes;                 // may run ahead of the expect_tx of the same phase (partner CTA's loads)
+  mbar_check_complete(b);
+  ++g_blk->progress;
+  ++block_of(cta).progress;
 }
 void mbar_arrive(uint32_t addr, uint32_t expect_tx_bytes) {
   Block::MBar& b = mbar_at(addr);
@@ -266,6 +306,7 @@ static void setup_block(Block& B, int n, dim3 grid, dim3 block, unsigned bx, uns
   B.mbars.clear();
   for (auto& nb : B.named) nb = Block::NamedBar();
   B.tmem.assign(128 * 512, 0x7fc00000u);        // NaN until an MMA overwrites it
+  B.cluster_rank = 0; B.cluster_size = 1; B.cluster = nullptr; B.cl_arrived = 0; B.cl_gen = 0;
   while (g_stacks.size() < stack0 + (size_t)n) g_stacks.push_back(static_cast<char*>(malloc(kStackBytes)));
   for (int t = 0; t < n; ++t) {
     Fiber& f = B.fibers[t];
@@ -340,6 +381,29 @@ static void launch_impl(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std:
 
 void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body) {
   launch_impl(grid, block, dyn_smem_bytes, body, false);
+}
+// clusters of `csize` consecutive blocks (1-D grid) run together: distributed shared memory, remote
+// mbarrier arrives and the cluster barrier work inside a cluster; clusters run one after another
+void launch_cluster(dim3 grid, dim3 block, size_t dyn_smem_bytes, int csize, const std::function<void()>& body) {
+  if (g_in_launch) { fprintf(stderr, "[cudasim] nested launch\n"); abort(); }
+  const int n = (int)(block.x * block.y * block.z);
+  if (grid.y != 1 || grid.z != 1 || csize < 1 || csize > 8 || grid.x % (unsigned)csize) {
+    fprintf(stderr, "[cudasim] launch_cluster: grid %u not a multiple of cluster size %d\n", grid.x, csize); abort();
+  }
+  while ((int)g_blocks.size() < csize) g_blocks.push_back(new Block());
+  g_in_launch = true;
+  ++g_launches;
+  for (unsigned b0 = 0; b0 < grid.x; b0 += (unsigned)csize) {
+    for (int r = 0; r < csize; ++r) {
+      ++g_blocks_run;
+      setup_block(*g_blocks[r], n, grid, block, b0 + (unsigned)r, 0, 0, dyn_smem_bytes, &body, (size_t)r * (size_t)n);
+      g_blocks[r]->cluster_rank = r; g_blocks[r]->cluster_size = csize; g_blocks[r]->cluster = g_blocks.data();
+    }
+    run_blocks(g_blocks.data(), csize);
+  }
+  g_in_launch = false;
+  g_blk = nullptr;
+  g_cur = nullptr;
 }
 // every CTA of the grid is alive at once (cudaLaunchCooperativeKernel): a grid-wide barrier can complete
 void launch_cooperative(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body) {

@@ -39,6 +39,7 @@ struct ThreadCtx {
 extern ThreadCtx* g_cur;   // the running simulated thread
 void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body);
 void launch_cooperative(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body);
+void launch_cluster(dim3 grid, dim3 block, size_t dyn_smem_bytes, int cluster_size, const std::function<void()>& body);
 void yield_spin();   // a spinning thread lets the others run (global-memory flags, mbarrier waits)
 void* dyn_smem();
 void sync_threads();

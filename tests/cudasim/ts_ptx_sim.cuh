@@ -38,6 +38,13 @@ void mbar_arrive(uint32_t addr, uint32_t expect_tx_bytes);
 void mbar_complete_tx(uint32_t addr, uint32_t bytes);
 bool mbar_phase_done(uint32_t addr, uint32_t parity);
 void named_barrier(int id, int nthreads);
+// thread-block clusters (launch_cluster)
+int cluster_rank();
+void cluster_barrier();
+unsigned char* smem_base_of(int cta);
+uint32_t* tmem_of(int cta);
+void mbar_arrive_at(int cta, uint32_t addr, uint32_t expect_tx_bytes);
+void mbar_complete_tx_at(int cta, uint32_t addr, uint32_t bytes);
 void yield_spin();                       // give the other simulated threads a turn (no progress made)
 }  // namespace cudasim
 
@@ -159,6 +166,77 @@ inline void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   memcpy(r, cudasim::tmem() + (size_t)lane * 512 + col, 32 * 4);
 }
 inline void tmem_ld_wait() {}
+
+// ------------------------------------------------ CTA pair (cta_group::2) ----
+// Model (assumptions spelled out; they follow the CUTLASS 2-SM GEMM data flow): every CTA of the
+// pair holds ITS 128 rows of A and ITS N/2 rows of B at the descriptor offsets in its own shared
+// memory; CTA r's TMEM lane m receives A_r[m] . B[n] for all N columns, where columns [0, N/2)
+// come from rank 0's B rows and [N/2, N) from rank 1's.  tcgen05.commit multicasts its arrive to
+// the barrier at the same offset in every CTA of the mask; a 2-SM TMA load credits the leader's barrier.
+inline uint32_t cluster_ctarank() { return (uint32_t)cudasim::cluster_rank(); }
+inline void cluster_sync() { cudasim::cluster_barrier(); }
+inline void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) { cudasim::mbar_arrive_at((int)cta, smem_u32(bar), 0); }
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+inline void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint64_t) {
+  const uint32_t dst = smem_u32(smem_dst);
+  if (dst & 1023u) { fprintf(stderr, "[cudasim] TMA destination %u is not 1024-byte aligned\n", dst); abort(); }
+  unsigned char* sm = cudasim::smem_base();               // data lands in the ISSUER's shared memory
+  const uint16_t* g = static_cast<const uint16_t*>(m->base);
+  for (int r = 0; r < m->box_rows; ++r) {
+    const int64_t row = (int64_t)c1 + r;
+    for (int c = 0; c < m->box_cols; ++c) {
+      const int col = c0 + c;
+      uint16_t v = 0;
+      if (row >= 0 && row < m->rows && col >= 0 && col < m->dim) v = g[row * m->ld + col];
+      memcpy(sm + sw128(dst + (uint32_t)r * 128u + (uint32_t)c * 2u), &v, 2);
+    }
+  }
+  cudasim::mbar_complete_tx_at(0, smem_u32(bar), (uint32_t)m->box_rows * 128u);   // ... the bytes count on the LEADER's barrier
+}
+inline void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) { tmem_alloc(smem_dst, ncols); }
+inline void tmem_relinquish_2sm() {}
+inline void tmem_dealloc_2sm(uint32_t, uint32_t) {}
+
+inline float sim_elem_of(int cta, uint32_t addr, bool bf16) {
+  uint16_t h;
+  memcpy(&h, cudasim::smem_base_of(cta) + addr, 2);
+  if (bf16) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+  _Float16 x; memcpy(&x, &h, 2); return (float)x;
+}
+inline void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (cudasim::cluster_rank() != 0) { fprintf(stderr, "[cudasim] cta_group::2 MMA issued by the non-leader CTA\n"); abort(); }
+  const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
+  const bool bf16 = ((idesc >> 7) & 7) == 1;
+  if (M != 256 || N < 32 || N > 256 || (N & 31)) { fprintf(stderr, "[cudasim] unsupported cta_group::2 descriptor (M %d N %d)\n", M, N); abort(); }
+  const uint32_t a0 = (uint32_t)(adesc & 0x3FFF) << 4, b0 = (uint32_t)(bdesc & 0x3FFF) << 4;
+  const uint32_t a_sbo = (uint32_t)((adesc >> 32) & 0x3FFF) << 4, b_sbo = (uint32_t)((bdesc >> 32) & 0x3FFF) << 4;
+  const uint32_t col0 = tmem_d & 0xFFFFu;
+  for (int cta = 0; cta < 2; ++cta) {
+    uint32_t* T = cudasim::tmem_of(cta);
+    float a[128][16];
+    for (int m = 0; m < 128; ++m)
+      for (int k = 0; k < 16; ++k) a[m][k] = sim_elem_of(cta, sw128(a0 + (uint32_t)(m >> 3) * a_sbo + (uint32_t)(m & 7) * 128u + (uint32_t)k * 2u), bf16);
+    for (int n = 0; n < N; ++n) {
+      const int src = n / (N / 2), nn = n % (N / 2);       // which CTA's B rows feed this column
+      float b[16];
+      for (int k = 0; k < 16; ++k) b[k] = sim_elem_of(src, sw128(b0 + (uint32_t)(nn >> 3) * b_sbo + (uint32_t)(nn & 7) * 128u + (uint32_t)k * 2u), bf16);
+      for (int m = 0; m < 128; ++m) {
+        float acc = 0.f;
+        for (int k = 0; k < 16; ++k) acc += a[m][k] * b[k];
+        uint32_t* cell = T + (size_t)m * 512 + col0 + (uint32_t)n;
+        float prev;
+        memcpy(&prev, cell, 4);
+        const float out = accumulate ? prev + acc : acc;
+        memcpy(cell, &out, 4);
+      }
+    }
+  }
+}
+inline void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  for (int cta = 0; cta < 2; ++cta)
+    if (cta_mask & (1u << cta)) cudasim::mbar_arrive_at(cta, smem_u32(bar), 0);
+}
 
 inline uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
   uint64_t d = 0;

@@ -258,6 +258,28 @@ def test_tensor_scan_variants_agree_bit_for_bit(sim, monkeypatch):
     assert (I == two[1]).all() and (D == two[0]).all()
 
 
+@pytest.mark.parametrize("N,d,B,k,dtype", [(3000, 64, 200, 10, "bf16"), (5000, 128, 300, 100, "bf16"), (600, 100, 129, 7, "fp16"),
+                                           (9000, 64, 1024, 100, "bf16"), (4000, 256, 256, 500, "bf16"), (5, 72, 130, 50, "bf16")])
+def test_cta_pair_scan_equals_the_single_cta_scan(sim, monkeypatch, N, d, B, k, dtype):
+    """s1_pair_kernel (TS_PAIR=1: tcgen05.mma cta_group::2 over a 2-CTA cluster, each CTA loading half of
+    every corpus chunk, remote mbarrier arrives, multicast commits) on the emulator's cluster model:
+    same ids and scores as the single-CTA scan, bit for bit, and parity with the oracle.  Odd numbers
+    of query tiles (B = 300, 129, 130) exercise the padded idle tile."""
+    X, Q = make(N, d, B, seed=N + B, planted=5 if N > 5 * B else 0)
+    idx = _lib.Index(d, dtype, "ip" if N > 10 else "cosine", 0)
+    idx.add(X)
+    D0, I0 = idx.search_host(Q, k, path="umma")
+    monkeypatch.setenv("TS_PAIR", "1")
+    D, I = idx.search_host(Q, k, path="umma")
+    assert (I == I0).all() and (D == D0).all()
+    if N > 10:
+        rD, rI, sc = oracle_search(X, Q, k, dtype)
+        assert not flat_ip.check_topk(D, I, sc, rD, rI, rel=REL)
+    monkeypatch.setenv("TS_DBG_NOSHARE", "1")                       # no pre-pass launch, private thresholds only
+    D2, I2 = idx.search_host(Q, k, path="umma")
+    assert (I2 == I0).all() and (D2 == D0).all()
+
+
 def test_tensor_scan_cosine_metric_ties_and_shards(sim):
     rng = np.random.default_rng(2)
     N, d, k = 3000, 72, 50

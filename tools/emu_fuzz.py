@@ -58,7 +58,14 @@ def stage1_case(rng):
             idx.add(part)
     base = int(rng.choice([0, 0, 12345, 5_000_000_000]))
     idx.set_id_base(base)
-    D, I = idx.search_host(Q, k, path=path)
+    variant = str(rng.choice(["", "", "TS_PAIR", "TS_DUAL", "TS_DBG_NOSHARE", "TS_SELECT_V1"]))
+    if variant:
+        os.environ[variant] = "1"
+    try:
+        D, I = idx.search_host(Q, k, path=path)
+    finally:
+        if variant:
+            os.environ[variant] = "0"
     Xr, Qr = flat_ip.round_to(X, dtype), flat_ip.round_to(Q, dtype)
     inv = (1.0 / (np.linalg.norm(X, axis=1) + 1e-8)).astype(np.float32) if metric == "cosine" else np.ones(N, np.float32)
     rD, rI = flat_ip.topk_desc((Qr @ Xr.T) * inv[None, :], k)
@@ -75,7 +82,7 @@ def stage1_case(rng):
                 continue
         keep.append(msg)
     bad = keep
-    return f"S1 N={N} d={d} B={B} k={k} {dtype} {metric} {path} {flavour} base={base}", bad
+    return f"S1 N={N} d={d} B={B} k={k} {dtype} {metric} {path} {flavour} base={base} variant={variant}", bad
 
 
 def stage2_case(rng):

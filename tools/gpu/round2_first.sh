@@ -38,3 +38,13 @@ for l in open('gpurun_out/s2_v2_probe.jsonl'):
 PY
 # BASELINE configs[1] with the reference's own storage dtype (fp32 corpus, CUDA-core stream scan): not timed in round 1
 python tools/perf_probe.py --rows 1000000 --dim 768 --dtype fp32 --paths stream --batches 1,2,4 --tag c2_fp32 > gpurun_out/c2_fp32.jsonl 2> gpurun_out/c2_fp32.err; cat gpurun_out/c2_fp32.jsonl
+# CTA pairs (cta_group::2) for B >= 129: parity, then A/B at the tensor-bound batch sizes
+TS_PAIR=1 run s1_pair tests/test_gpu_stage1.py -k "umma_path"
+PP="python tools/perf_probe.py --paths umma --rows 10000000 --dim 1024 --batches 256,512,1024 --steps 5"
+$PP --tag single > gpurun_out/pair_probe.jsonl 2> gpurun_out/pair_probe.err
+TS_PAIR=1 $PP --tag pair >> gpurun_out/pair_probe.jsonl 2>> gpurun_out/pair_probe.err
+python - <<'PY'
+import json
+for l in open('gpurun_out/pair_probe.jsonl'):
+    r=json.loads(l); print(f"{r['tag']:8s} B={r['B']:5d} scan={r['scan_ms_per_launch']:.3f} ms  {r['TFLOPs']:.0f} TFLOP/s  ({r['tensor_frac_sustained']:.2f} of sustained)")
+PY

@@ -181,11 +181,11 @@ __device__ __forceinline__ void drain_acc(const UmmaParams& p, QState& s, uint32
 }
 
 __device__ __forceinline__ void init_state(const UmmaParams& p, QState& s, int a, int mt0, int quarter, int lane,
-                                           int lane_row, int rows_per_cta, int CAP, bool present) {
+                                           int lane_row, int rows_per_cta, int CAP, bool present, int cta_id) {
   const int qi = p.spread ? ((((lane >> 3) * 4 + quarter) * 8) + (lane & 7)) : lane_row;
   s.q = (mt0 + a) * kTileM + qi;
   s.active = present && s.q < p.B;
-  s.lst = p.lists + ((size_t)blockIdx.x * rows_per_cta + a * kTileM + lane_row) * CAP;
+  s.lst = p.lists + ((size_t)cta_id * rows_per_cta + a * kTileM + lane_row) * CAP;
   s.cnt = 0;
   s.n_app = s.n_prune = s.n_slow = 0;
   s.tjJ = -INFINITY;
@@ -224,13 +224,13 @@ __device__ __forceinline__ void share_state(const UmmaParams& p, QState& s, int 
 }
 
 __device__ __forceinline__ void finish_state(const UmmaParams& p, QState& s, int a, int slice, bool prepass, int J,
-                                             int rows_per_cta, int lane_row, bool present) {
+                                             int rows_per_cta, int lane_row, bool present, int cta_id) {
   if (!present) return;
   if (prepass) {
     if (s.active && J > 0) p.pub[(size_t)slice * p.bpad + s.q] = s.tjJ;
   } else {
     // lists stay unsorted: the select kernel merges them (no in-kernel final sort)
-    p.counts[(size_t)blockIdx.x * rows_per_cta + a * kTileM + lane_row] = s.active ? s.cnt : 0;
+    p.counts[(size_t)cta_id * rows_per_cta + a * kTileM + lane_row] = s.active ? s.cnt : 0;
     if (p.stats && s.active) {
       atomicAdd(p.stats + 0, (unsigned long long)s.n_app);
       atomicAdd(p.stats + 1, (unsigned long long)s.n_prune);
@@ -384,8 +384,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     unsigned int gen0 = 0;
     if (fused) gen0 = *reinterpret_cast<volatile unsigned int*>(p.grid_bar + 1);
     QState s0, s1;
-    init_state(p, s0, 0, mt0, quarter, lane, lane_row, rows_per_cta, CAP, true);
-    init_state(p, s1, 1, mt0, quarter, lane, lane_row, rows_per_cta, CAP, dual);
+    init_state(p, s0, 0, mt0, quarter, lane, lane_row, rows_per_cta, CAP, true, (int)blockIdx.x);
+    init_state(p, s1, 1, mt0, quarter, lane, lane_row, rows_per_cta, CAP, dual, (int)blockIdx.x);
     if (J > 0 && !fused) {
       start_state(p, s0, slice, prepass);
       start_state(p, s1, slice, prepass);
@@ -440,13 +440,148 @@ __global__ void __launch_bounds__(kThreads, 1)
         share_state(p, s1, slice, iter);
       }
     }
-    finish_state(p, s0, 0, slice, prepass, J, rows_per_cta, lane_row, true);
-    finish_state(p, s1, 1, slice, prepass, J, rows_per_cta, lane_row, dual);
+    finish_state(p, s0, 0, slice, prepass, J, rows_per_cta, lane_row, true, (int)blockIdx.x);
+    finish_state(p, s1, 1, slice, prepass, J, rows_per_cta, lane_row, dual, (int)blockIdx.x);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------
+// CTA-pair variant (opt-in TS_PAIR=1, B >= 129; written without a GPU -- the instruction forms are
+// CUTLASS's and assemble for sm_100a, the protocol is checked on the emulator, hardware pending).
+//
+// Why: for B >= 256 the scan is bound by L2->SM throughput (each CTA pulls 16 KB of Q and 32 KB of X
+// per K chunk: ~12.5 TB/s chip-wide at the measured rate, the LTS cap).  A cluster of two CTAs on one
+// TPC takes two query tiles (mt = 2*pair + rank) of the SAME slice and runs ONE tcgen05.mma
+// cta_group::2 (M 256 x N 256 x K 16) per step: every CTA loads its own 128 x 64 of Q and only HALF
+// of the corpus chunk (rows t*256 + 128*rank ..), 32 KB per chunk instead of 48 KB; the tensor cores
+// read the other half from the partner's shared memory.  Each CTA's TMEM still holds 128 queries x
+// 256 corpus rows per accumulator, double buffered, so the epilogue and the fused top-k are the
+// single-CTA ones.  Stages shrink to 32 KB: a 6-deep ring.
+//
+// Protocol (per stage s, accumulator a):
+//   full[s]   leader's barrier, count 2: the leader's producer arrives with expect_tx(2 x 32 KB), the
+//             partner's producer arrives remotely; BOTH CTAs' TMA loads credit the leader's barrier;
+//   empty[s]  one per CTA, count 1: the leader's tcgen05.commit multicasts to both;
+//   tfull[a]  one per CTA, count 1: commit multicast after the last K chunk;
+//   tempty[a] leader's barrier, count 8: the four epilogue warps of both CTAs (partner: remote arrive).
+constexpr int kPairStages = 6;
+constexpr int kPairStageBytes = kABytes + kBBytes / 2;   // 32 KB
+static_assert(kPairStages * kPairStageBytes <= kRingBytes, "pair ring must fit the ring area");
+
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+    s1_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmXh, const UmmaParams p) {
+  const int CAP = p.cap;
+  TS_DYN_SMEM(unsigned char, smem_raw);
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes);
+  uint64_t* full_bar = bars;                           // [kPairStages]
+  uint64_t* empty_bar = bars + kPairStages;            // [kPairStages]
+  uint64_t* tfull_bar = bars + 2 * kPairStages;        // [2]
+  uint64_t* tempty_bar = bars + 2 * kPairStages + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = (int)(blockIdx.x >> 1) / p.n_slices, slice = (int)(blockIdx.x >> 1) % p.n_slices;
+  const int mt = 2 * pair + (int)rank;
+  const int cta_id = mt * p.n_slices + slice;          // logical id: the list layout select_kernel expects
+  const int t_end = (p.mode == 0) ? ((slice + 1 < p.n_tiles) ? slice + 1 : p.n_tiles) : p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPairStages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync();                                      // both CTAs' barriers exist before any remote arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA producer (both CTAs) ------
+      prefetch_tmap(&tmQ); prefetch_tmap(&tmXh);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = slice; t < t_end; t += p.n_slices) {
+        for (int kc = 0; kc < p.nK; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+          unsigned char* sA = smem + stage * kPairStageBytes;
+          unsigned char* sB = sA + kABytes;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)kPairStageBytes);
+          else mbar_arrive_cluster(&full_bar[stage], 0);
+          tma_load_2d_2sm(sA, &tmQ, &full_bar[stage], kc * kChunkK, mt * kTileM, kEvictLast);
+          tma_load_2d_2sm(sB, &tmXh, &full_bar[stage], kc * kChunkK, t * kTileN + (int)rank * (kTileN / 2), kEvictNormal);
+          if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ------------------------------------------------ MMA issuer (leader only) ------
+      constexpr uint32_t idesc = make_idesc_f16(2 * kTileM, kTileN, BF16);
+      int stage = 0; uint32_t phase = 0;
+      int iter = 0;
+      for (int t = slice; t < t_end; t += p.n_slices, ++iter) {
+        const int acc = iter & 1;
+        mbar_wait(&tempty_bar[acc], (uint32_t)((iter >> 1) & 1) ^ 1u, 2);
+        tc_fence_after();
+        for (int kc = 0; kc < p.nK; ++kc) {
+          mbar_wait(&full_bar[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * kPairStageBytes);
+          const uint64_t adesc = make_desc_kmajor_sw128(a_addr);
+          const uint64_t bdesc = make_desc_kmajor_sw128(a_addr + kABytes);
+#pragma unroll
+          for (int ks = 0; ks < kChunkK / 16; ++ks)
+            umma_f16_ss_2sm(tmem_base + (uint32_t)(acc * kTileN), adesc + ks * kDescKStep, bdesc + ks * kDescKStep, idesc,
+                            (kc | ks) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage], 3);       // both CTAs' stage is reusable once these MMAs retire
+          if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(&tfull_bar[acc], 3);           // both CTAs' accumulator halves are complete
+      }
+    }
+  } else {
+    // -------------------------------------------------- epilogue (both CTAs) ----------
+    const int quarter = warp & 3;
+    const int lane_row = quarter * 32 + lane;
+    const bool prepass = (p.mode == 0);
+    const int J = p.jrank;
+    QState s0;
+    init_state(p, s0, 0, mt, quarter, lane, lane_row, kTileM, CAP, true, cta_id);
+    if (J > 0) start_state(p, s0, slice, prepass);
+    const bool wact0 = __any_sync(0xffffffffu, s0.active);
+    int iter = 0;
+    for (int t = slice; t < t_end; t += p.n_slices, ++iter) {
+      const int64_t n0 = (int64_t)t * kTileN;
+      const int ncols = (int)((p.N - n0) < (int64_t)kTileN ? (p.N - n0) : (int64_t)kTileN);
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const int acc = iter & 1;
+      mbar_wait(&tfull_bar[acc], (uint32_t)((iter >> 1) & 1), 4);
+      tc_fence_after();
+      drain_acc(p, s0, lane_addr + (uint32_t)(acc * kTileN), n0, ncols, wact0, prepass, J, CAP, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tempty_bar[acc]); else mbar_arrive_cluster(&tempty_bar[acc], 0);
+      }
+      if (!prepass && J > 0) share_state(p, s0, slice, iter);
+    }
+    finish_state(p, s0, 0, slice, prepass, J, kTileM, lane_row, true, cta_id);
+  }
+
+  tc_fence_before();
+  cluster_sync();                                      // nobody leaves while the partner may still read its smem / TMEM
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------ host ---
@@ -490,7 +625,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, in
 }
 
 namespace {
-struct UmmaPlan { int n_mt, n_mg, dual, n_slices, n_tiles, grid; };
+struct UmmaPlan { int n_mt, n_mg, dual, n_slices, n_tiles, grid, pair; };
 UmmaPlan umma_plan(const ScanArgs& a) {
   UmmaPlan pl;
   pl.n_mt = (a.B + kTileM - 1) / kTileM;
@@ -498,6 +633,9 @@ UmmaPlan umma_plan(const ScanArgs& a) {
   // accumulators then cannot be double buffered against the epilogue; measured on B200 the
   // single-tile layout is faster (19.2 vs 21.5 ms at B=1024, 10M x 1024), so it is opt-in.
   pl.dual = (pl.n_mt >= 2 && env_on("TS_DUAL")) ? 1 : 0;
+  // CTA pairs (cta_group::2): two query tiles per cluster; an odd tile count is padded with an idle tile
+  pl.pair = (pl.n_mt >= 2 && !pl.dual && a.sm_count >= 2 && env_on("TS_PAIR")) ? 1 : 0;
+  if (pl.pair) pl.n_mt = (pl.n_mt + 1) & ~1;
   pl.n_mg = pl.dual ? (pl.n_mt + 1) / 2 : pl.n_mt;
   pl.n_tiles = (int)((a.n + kTileN - 1) / kTileN);
   int s = a.sm_count / pl.n_mg;
@@ -519,6 +657,7 @@ int s1_umma_plan(const ScanArgs& a, UmmaLayout* lay) {
   lay->rows_per_cta = pl.dual ? 2 * kTileM : kTileM;
   lay->grid = pl.grid;
   lay->cap = cap_for_k(a.k);
+  lay->pair = pl.pair;
   lay->spread = (a.B <= 64 && !env_on("TS_DBG_NOSPREAD")) ? 1 : 0;
   lay->bpad = pl.n_mt * kTileM;
   lay->lists_keys = (size_t)pl.grid * lay->rows_per_cta * lay->cap;
@@ -528,7 +667,7 @@ int s1_umma_plan(const ScanArgs& a, UmmaLayout* lay) {
   lay->jrank = (j <= 8 && !env_on("TS_DBG_NOSHARE")) ? j : 0;
   // One cooperative launch (pre-pass + grid barrier + scan) instead of two launches.  Written
   // after this round's GPU budget was spent: NOT yet validated on hardware, so it is opt-in.
-  lay->fused = (lay->jrank > 0 && !pl.dual && env_on("TS_FUSE")) ? 1 : 0;
+  lay->fused = (lay->jrank > 0 && !pl.dual && !pl.pair && env_on("TS_FUSE")) ? 1 : 0;
   return TS_OK;
 }
 
@@ -555,6 +694,28 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
     p.stats = d_stats;
   }
   const bool bf16 = a.dtype == TS_BF16;
+  if (lay.pair) {
+    CUtensorMap tmXh;
+    if ((rc = make_tmap_2d(&tmXh, a.rows, a.dtype, a.n, a.dim, a.ld, kTileN / 2))) return rc;
+    auto pk = bf16 ? s1_pair_kernel<true> : s1_pair_kernel<false>;
+    TS_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    for (int mode = (p.jrank > 0 ? 0 : 1); mode <= 1; ++mode) {
+      p.mode = mode;
+#ifdef TS_CUDASIM
+      cudasim::launch_cluster(lay.grid, kThreads, kSmemBytes, 2, [&]() { pk(tmQ, tmXh, p); });
+#else
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(lay.grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      TS_CUDA_OK(cudaLaunchKernelEx(&cfg, pk, tmQ, tmXh, p));
+#endif
+      if (launches) ++*launches;
+    }
+    return TS_OK;
+  }
   auto kern = bf16 ? s1_umma_kernel<true> : s1_umma_kernel<false>;
   TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   if (p.jrank > 0 && lay.fused && a.grid_bar) {

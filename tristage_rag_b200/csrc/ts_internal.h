@@ -66,7 +66,7 @@ struct ScanArgs {
 };
 // where the umma scan leaves its candidates (consumed by launch_merge_lists)
 struct UmmaLayout {
-  int n_slices, n_mt, grid, cap, spread, bpad, jrank, dual, rows_per_cta, fused;
+  int n_slices, n_mt, grid, cap, spread, bpad, jrank, dual, rows_per_cta, fused, pair;
   size_t lists_keys, counts_n, pub_n;
 };
 // number of partial lists L a scan will emit / scratch it needs
