@@ -159,7 +159,8 @@ def test_scan_variants_agree_bit_for_bit(cuda_device, monkeypatch):
     """The scan with and without cross-CTA threshold sharing must return identical results: the
     shared bound only prunes rows that cannot be in the top-k.  Experimental layouts that lost
     on hardware (TS_DUAL, two query tiles per CTA) and the not-yet-validated single-launch scan
-    (TS_FUSE) are compared too when TS_TEST_EXPERIMENTAL=1 (tools/gpu/round2_first.sh)."""
+    (TS_FUSE) and CTA-pair scan (TS_PAIR) are compared too when TS_TEST_EXPERIMENTAL=1
+    (tools/gpu/round2_variants.sh)."""
     N, d, B, k = 60000, 256, 48, 100
     X, Q = make(N, d, B, seed=77, planted=20)
     idx = _lib.Index(d, "bf16", "ip", cuda_device)
@@ -171,7 +172,7 @@ def test_scan_variants_agree_bit_for_bit(cuda_device, monkeypatch):
     base2 = idx.search_host(Q2, k, path="umma")
     variants = ["TS_DBG_NOSHARE"]
     if os.environ.get("TS_TEST_EXPERIMENTAL"):
-        variants += ["TS_DUAL", "TS_FUSE"]
+        variants += ["TS_DUAL", "TS_FUSE", "TS_PAIR"]
     for var in variants:
         monkeypatch.setenv(var, "1")
         D, I = idx.search_host(Q, k, path="umma")
