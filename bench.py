@@ -285,14 +285,15 @@ def main():
     idx.set_profiling(True)
     l0 = idx.launches
     ms_eager = timed(step, args.steps, 0, dev, dist_on)
-    launches = idx.launches - l0 + (args.steps if world > 1 else 0)   # + the post-all-gather merge kernel
+    # + the post-all-gather merge kernel (or push + wait-merge of the peer-memory exchange)
+    launches = idx.launches - l0 + (args.steps * (2 if getattr(sharded, "_p2p", False) else 1) if world > 1 else 0)
     scan_ms, scan_n = idx.scan_time_ms()
     idx.set_profiling(False)
     # headline: the same step captured once in a CUDA graph (query prep, threshold pre-pass,
     # scan, select, all-gather, merge) and replayed K times -- no per-launch host latency
     ms, launch_mode = ms_eager, "eager"
     extra_modes = {}
-    if args.graph:
+    if args.graph and not getattr(sharded, "_p2p", False):    # the exchange's step counter comes from the host
         try:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -365,7 +366,9 @@ def main():
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {**workload_config(N, d, k, B, world), "path": roof["kernel"], "parallelism": f"rowshard{world}",
                    "l2": "inputs larger than L2 (shard >= 2.5 GB vs 126 MB), no flush needed",
-                   "launch": launch_mode, "ms_per_step_eager": ms_eager / args.steps, **extra_modes},
+                   "launch": launch_mode, "ms_per_step_eager": ms_eager / args.steps, **extra_modes,
+                   "merge": ("peer-memory exchange" if getattr(sharded, "_p2p", False) else
+                             ("nccl all-gather + merge kernel" if world > 1 else "none"))},
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": B * d * 4,
                 "d2h_bytes_per_step": B * k * 12, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,

@@ -144,6 +144,23 @@ int ts_topk_merge_packed(int device, const void* blob_dev, int64_t list_stride_b
                          int64_t ids_offset_bytes, int n_lists, int B, int k,
                          float* out_scores_dev, int64_t* out_ids_dev, void* stream);
 
+/* Multi-GPU exchange over PEER MEMORY (NVLink / NVSwitch) instead of an all-gather followed by
+ * ts_topk_merge_packed.  Every rank owns one symmetric receive buffer, mapped into all ranks:
+ *   [parity 0: n_ranks slots of slot_bytes][parity 1: n_ranks slots] ... [flags: 2 * n_ranks u32 at flags_offset]
+ * Step s uses parity s & 1 and sequence number seq = s + 1 (never 0).  ts_exchange_push writes this
+ * rank's packed [B,k] result (the ts_index_search packed layout: fp32 scores at 0, int64 ids at
+ * ids_offset) into slot `rank` of EVERY rank's buffer with 16-byte stores and then publishes seq in
+ * that rank's flag (system-scope release).  ts_exchange_wait_merge spins (system-scope acquire,
+ * bounded: a missing peer traps after ~4 s) until all n_ranks flags of its own buffer show seq and
+ * merges the n_ranks lists into out [B,k].  Two parities suffice: a rank can only be one step ahead
+ * of the slowest peer, because its next wait needs that peer's next push.
+ * peer_bases_dev: device array [n_ranks] of the buffers' base addresses as seen from this rank.    */
+int ts_exchange_push(int device, const void* blob_dev, int64_t nbytes, const int64_t* peer_bases_dev, int n_ranks,
+                     int rank, int64_t slot_bytes, int64_t flags_offset, int parity, uint32_t seq, void* stream);
+int ts_exchange_wait_merge(int device, const void* local_base_dev, int n_ranks, int B, int k, int64_t slot_bytes,
+                           int64_t ids_offset, int64_t flags_offset, int parity, uint32_t seq,
+                           float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+
 /* faiss.write_index / read_index  (stage1_retriever.py:436,463): one shard
  * file per handle (layout: see "shard files" below).  save synchronises the
  * device; load verifies the file's checksums.                                */

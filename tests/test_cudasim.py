@@ -648,3 +648,58 @@ def test_tensor_maxsim_n_cand_q_len_unowned_and_length_mixes(sim, monkeypatch, v
         c2 = np.stack([rng.permutation(len(ln))[: min(len(ln), 40)] for _ in range(2)]).astype(np.int64)
         np.testing.assert_allclose(st2.maxsim_host(q2, c2), _oracle_scores(q2, docs2, c2, 0, "bf16"), rtol=1e-3, atol=2e-4,
                                    err_msg=name)
+
+
+# ------------------------------------------- multi-GPU exchange over peer memory ---
+def test_peer_memory_exchange_equals_gather_and_merge(sim):
+    """ts_exchange_push / ts_exchange_wait_merge with G ranks living in one process (every rank's receive
+    buffer is plain host memory here, so "peer" pointers are ordinary pointers): after all ranks pushed step
+    s, every rank's wait+merge returns what ts_topk_merge_packed returns over the gathered lists; steps
+    alternate the two parities and the sequence numbers."""
+    G, B, k = 3, 5, 40
+    ids_off, nbytes = _lib.packed_layout(B, k)
+    slot = (nbytes + 15) // 16 * 16
+    flags_off = 2 * G * slot
+    bufs = [np.zeros(flags_off + 2 * G * 4 + 16, np.uint8) for _ in range(G)]
+    bases = np.array([b.ctypes.data for b in bufs], np.int64)
+    N, d = 1500, 32
+    X, _ = make(N, d, 1, seed=4)
+    X[700] = X[3]
+    X[1400] = X[3]                                             # exact ties across shards: ids must ascend
+    shards = []
+    for r in range(G):
+        lo, hi = r * N // G, (r + 1) * N // G
+        sh = _lib.Index(d, "bf16", "ip", 0)
+        sh.add(X[lo:hi])
+        sh.set_id_base(lo)
+        shards.append(sh)
+    rng = np.random.default_rng(9)
+    for step in range(4):
+        Q = flat_ip.normalize_rows(rng.standard_normal((B, d)).astype(np.float32)).astype(np.float32)
+        parity, seq = step & 1, step + 1
+        blobs = []
+        for r in range(G):
+            D, I = shards[r].search_host(Q, k, path="stream")
+            blob = np.zeros(slot, np.uint8)
+            blob[: B * k * 4] = D.view(np.uint8).ravel()
+            blob[ids_off: ids_off + B * k * 8] = I.view(np.uint8).ravel()
+            blobs.append(blob)
+        for r in range(G):                                     # every rank publishes its list into every buffer
+            _lib.check(sim.ts_exchange_push(0, p(blobs[r]), nbytes, p(bases), G, r, slot, flags_off, parity, seq, None))
+        gathered = np.concatenate(blobs)
+        ref_s, ref_i = np.empty((B, k), np.float32), np.empty((B, k), np.int64)
+        _lib.check(sim.ts_topk_merge_packed(0, p(gathered), slot, ids_off, G, B, k, p(ref_s), p(ref_i), None))
+        for r in range(G):
+            out_s, out_i = np.empty((B, k), np.float32), np.empty((B, k), np.int64)
+            _lib.check(sim.ts_exchange_wait_merge(0, p(bufs[r]), G, B, k, slot, ids_off, flags_off, parity, seq, p(out_s), p(out_i), None))
+            assert (out_i == ref_i).all() and (out_s == ref_s).all(), (step, r)
+        full = _lib.Index(d, "bf16", "ip", 0)
+        full.add(X)
+        Df, If = full.search_host(Q, k, path="stream")
+        assert (ref_i == If).all() and (ref_s == Df).all()
+    # flags now hold the sequence numbers of the last step of each parity
+    for b in bufs:
+        assert np.frombuffer(b, np.uint32, 2 * G, flags_off).tolist() == [3] * G + [4] * G
+    # argument checks
+    assert sim.ts_exchange_push(0, p(blobs[0]), nbytes, p(bases), G, G, slot, flags_off, 0, 1, None) == -1       # rank out of range
+    assert sim.ts_exchange_wait_merge(0, p(bufs[0]), G, B, k, slot + 8, ids_off, flags_off, 0, 1, p(out_s), p(out_i), None) == -1

@@ -60,9 +60,37 @@ def main():
     # load balance of candidate ownership
     own = np.bincount(np.searchsorted([shard_range(ndocs, r, world)[1] for r in range(world)], cand.ravel(), side="right"),
                       minlength=world)
+    # sharded persistence: every rank writes its shard, rank 0 the manifest; reload under the same world size
+    # and as ONE shard on rank 0's GPU (re-sharding), both must search like the live index
+    import tempfile
+
+    box = [tempfile.mkdtemp(prefix="ts_shards_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    sh.save(box[0])
+    again = ShardedIndex.load(box[0], local)
+    Q = flat_ip.normalize_rows(rng.standard_normal((8, d)).astype(np.float32)).astype(np.float32)
+    qd = torch.from_numpy(Q).to(dev)
+    s0, i0 = sh.search(qd, k)
+    s1, i1 = again.search(qd, k)
+    torch.cuda.synchronize()
+    assert torch.equal(i0, i1) and torch.equal(s0, s1)
     if rank == 0:
-        print(f"dist_check ok: world={world} stage2 candidates per rank max/mean = {own.max() / own.mean():.3f}")
-    dist.destroy_process_group()
+        from tristage_rag_b200 import dist as tdist
+
+        man = tdist.read_manifest(box[0], "index")
+        one = _lib.Index(d, "bf16", "ip", local, reserve_rows=N)
+        for fname, first, n in tdist.plan_reshard(man["shards"], 0, N):
+            one.append_file(os.path.join(box[0], fname), first, n)
+        s2, i2 = one.search(qd, k)
+        torch.cuda.synchronize()
+        assert torch.equal(i2, i0) and torch.equal(s2, s0)
+    dist.barrier()
+    if rank == 0:
+        mode = "peer-memory exchange" if os.environ.get("TS_P2P", "0") not in ("", "0") and sh._p2p else "nccl all-gather"
+        print(f"dist_check ok: world={world} merge via {mode}; stage2 candidates per rank max/mean = {own.max() / own.mean():.3f}",
+              flush=True)
+    sys.stdout.flush()
+    os._exit(0)          # no NCCL teardown (it can block for minutes after the work is done)
 
 
 if __name__ == "__main__":

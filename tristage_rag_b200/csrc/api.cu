@@ -326,6 +326,34 @@ int ts_topk_merge_packed(int device, const void* blob, int64_t list_stride_bytes
                             (cudaStream_t)stream);
 }
 
+int ts_exchange_push(int device, const void* blob_dev, int64_t nbytes, const int64_t* peer_bases_dev, int n_ranks, int rank,
+                     int64_t slot_bytes, int64_t flags_offset, int parity, uint32_t seq, void* stream) {
+  if (!blob_dev || !peer_bases_dev || n_ranks < 1 || rank < 0 || rank >= n_ranks || (parity != 0 && parity != 1) || nbytes > slot_bytes) {
+    set_error("ts_exchange_push: invalid argument");
+    return TS_ERR_INVALID;
+  }
+  TS_CUDA_OK(cudaSetDevice(device));
+  const long long slot = ((long long)parity * n_ranks + rank) * slot_bytes;
+  const long long flag = flags_offset + ((long long)parity * n_ranks + rank) * 4;
+  return launch_exchange_push(blob_dev, (nbytes + 15) / 16 * 16, (const long long*)peer_bases_dev, n_ranks, slot, flag, seq,
+                              (cudaStream_t)stream);
+}
+
+int ts_exchange_wait_merge(int device, const void* local_base_dev, int n_ranks, int B, int k, int64_t slot_bytes,
+                           int64_t ids_offset, int64_t flags_offset, int parity, uint32_t seq, float* out_scores,
+                           int64_t* out_ids, void* stream) {
+  if (!local_base_dev || !out_scores || !out_ids || n_ranks < 1 || (parity != 0 && parity != 1) || (slot_bytes % 16) ||
+      (ids_offset % 8) || ids_offset < (int64_t)B * k * 4 || ids_offset + (int64_t)B * k * 8 > slot_bytes) {
+    set_error("ts_exchange_wait_merge: bad layout");
+    return TS_ERR_INVALID;
+  }
+  TS_CUDA_OK(cudaSetDevice(device));
+  const char* slots = (const char*)local_base_dev + (size_t)parity * n_ranks * slot_bytes;
+  const unsigned int* flags = (const unsigned int*)((const char*)local_base_dev + flags_offset) + (size_t)parity * n_ranks;
+  return launch_merge_pairs_wait((const float*)slots, (const int64_t*)(slots + ids_offset), slot_bytes / 4, slot_bytes / 8, n_ranks, B,
+                                 k, flags, seq, out_scores, out_ids, (cudaStream_t)stream);
+}
+
 int ts_index_get_rows(const ts_index* h, int64_t start, int64_t n, float* out_host) {
   if (!h || start < 0 || n < 0 || start + n > h->n || (n > 0 && !out_host)) { set_error("ts_index_get_rows: bad range"); return TS_ERR_INVALID; }
   if (n == 0) return TS_OK;

@@ -11,6 +11,8 @@
 //
 // Bound: latency (a few thousand keys per query in shared memory); HBM
 // traffic is L*B*k*8 bytes read once.
+#include <stdio.h>
+
 #include "ts_common.cuh"
 #include "ts_internal.h"
 
@@ -45,7 +47,44 @@ struct SelectParams {
   const float* pub;       // kLists: final per-slice J-th best scores [n_slices][bpad] (null = no filter)
   int bpad;
   int serial_prefix;      // kLists: 1 = first version of the count prefix / filter loop (TS_SELECT_V1)
+  // kPairs after a peer-memory exchange: the lists are written by the other GPUs; flag l holds the sequence
+  // number of the step whose list l is complete (null = lists are already there, e.g. after an NCCL all-gather)
+  const unsigned int* wait_flags;
+  unsigned int wait_seq;
 };
+
+// system-scope flag accesses for the peer-memory exchange (NVLink): the producer's data stores are made
+// visible by __threadfence_system() + st.release.sys, the consumer pairs them with ld.acquire.sys
+constexpr long long kExchangeTimeoutCycles = 8000000000ll;   // ~4 s: a missing peer traps instead of hanging the GPU
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+#ifdef TS_CUDASIM
+  return *reinterpret_cast<const volatile unsigned int*>(p);
+#else
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+#ifdef TS_CUDASIM
+  *reinterpret_cast<volatile unsigned int*>(p) = v;
+#else
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+
+// Exchange, producer side: CTA d copies this GPU's packed [B,k] result into slot `rank` of GPU d's
+// receive buffer (16-byte stores over NVLink; d == rank is the local copy) and then publishes the step.
+__global__ void __launch_bounds__(256)
+    exchange_push_kernel(const uint4* __restrict__ blob, int n16, const long long* __restrict__ peer_bases, long long slot_off,
+                         long long flag_off, unsigned int seq) {
+  char* base = reinterpret_cast<char*>(peer_bases[blockIdx.x]);
+  uint4* dst = reinterpret_cast<uint4*>(base + slot_off);
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = blob[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) st_release_sys(reinterpret_cast<unsigned int*>(base + flag_off), seq);
+}
 
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
   TS_DYN_SMEM(uint64_t, sbuf);
@@ -54,6 +93,21 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   __shared__ int s_wsum[kSelThreads / 32];
   __shared__ int s_cnt;
   const int b = blockIdx.x, g = blockIdx.y;
+  if (p.wait_flags) {
+    // one thread per list spins (system-scope acquire) until its producer GPU has published this step
+    if ((int)threadIdx.x < p.L) {
+      const unsigned int* f = p.wait_flags + threadIdx.x;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(f) != p.wait_seq) {
+        TS_SPIN_YIELD();
+        if (clock64() - t0 > kExchangeTimeoutCycles) {
+          printf("[tristage] exchange timeout: list %d never reached step %u (has %u)\n", (int)threadIdx.x, p.wait_seq, ld_acquire_sys(f));
+          __trap();
+        }
+      }
+    }
+    __syncthreads();
+  }
   int total;
   const int l0 = g * p.group;
   size_t list_row0 = 0;   // kLists: (first CTA of this query's m-tile)*128 + this query's TMEM lane
@@ -266,6 +320,30 @@ int launch_merge_pairs(const float* scores, const int64_t* ids, long long stride
   p.mode = kPairs; p.scores = scores; p.ids = ids; p.L = L; p.B = B; p.k_in = k; p.group = L; p.k_out = k;
   p.pair_stride = stride_scores; p.pair_stride_ids = stride_ids;
   p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids;
+  return launch_select(p, 1, st);
+}
+
+int launch_exchange_push(const void* blob, long long nbytes, const long long* peer_bases_dev, int n_ranks, long long slot_off,
+                         long long flag_off, unsigned int seq, cudaStream_t st) {
+  if (!blob || !peer_bases_dev || n_ranks < 1 || nbytes <= 0 || (nbytes & 15) || (slot_off & 15) || (flag_off & 3)) {
+    set_error("exchange_push: bad arguments (sizes and offsets must be 16-byte multiples)");
+    return TS_ERR_INVALID;
+  }
+  TS_LAUNCH(exchange_push_kernel, n_ranks, 256, 0, st, (const uint4*)blob, (int)(nbytes / 16), peer_bases_dev, slot_off, flag_off, seq);
+  TS_CUDA_OK(cudaGetLastError());
+  return TS_OK;
+}
+
+int launch_merge_pairs_wait(const float* scores, const int64_t* ids, long long stride_scores, long long stride_ids, int L, int B,
+                            int k, const unsigned int* wait_flags, unsigned int wait_seq, float* out_scores, int64_t* out_ids,
+                            cudaStream_t st) {
+  if (k <= 0 || k > TS_MAX_K || B <= 0 || L <= 0 || L > kSelThreads) { set_error("merge: bad L/B/k"); return TS_ERR_INVALID; }
+  if ((long long)L * k > 65536) { set_error("merge: n_lists*k too large (%d*%d)", L, k); return TS_ERR_UNSUPPORTED; }
+  SelectParams p{};
+  p.mode = kPairs; p.scores = scores; p.ids = ids; p.L = L; p.B = B; p.k_in = k; p.group = L; p.k_out = k;
+  p.pair_stride = stride_scores; p.pair_stride_ids = stride_ids;
+  p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids;
+  p.wait_flags = wait_flags; p.wait_seq = wait_seq;
   return launch_select(p, 1, st);
 }
 

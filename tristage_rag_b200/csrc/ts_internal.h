@@ -87,6 +87,12 @@ int launch_merge_lists(const uint64_t* lists, const int* counts, const float* pu
 // strides = elements between consecutive lists (floats for scores, int64s for ids)
 int launch_merge_pairs(const float* scores, const int64_t* ids, long long stride_scores, long long stride_ids, int L,
                        int B, int k, float* out_scores, int64_t* out_ids, cudaStream_t st);
+// peer-memory exchange (multi-GPU merge without a collective library call)
+int launch_exchange_push(const void* blob, long long nbytes, const long long* peer_bases_dev, int n_ranks, long long slot_off,
+                         long long flag_off, unsigned int seq, cudaStream_t st);
+int launch_merge_pairs_wait(const float* scores, const int64_t* ids, long long stride_scores, long long stride_ids, int L, int B,
+                            int k, const unsigned int* wait_flags, unsigned int wait_seq, float* out_scores, int64_t* out_ids,
+                            cudaStream_t st);
 int launch_rank_desc(const float* scores, const int32_t* n_cand, int B, int C, int top_k, float* out_scores,
                      int32_t* out_pos, cudaStream_t st);
 

@@ -146,6 +146,10 @@ class ShardedIndex:
             self._packed = False
         self._bufs = {}
         self.merge_fn = merge_fn
+        # TS_P2P=1: replace all-gather + merge by the peer-memory exchange (ts_exchange_*); opt-in
+        self._p2p = bool(self._packed and self.world > 1 and os.environ.get("TS_P2P", "0") not in ("", "0"))
+        self._p2p_state = None
+        self._step = 0
 
     def search(self, q: torch.Tensor, k: int, **kw) -> Tuple[torch.Tensor, torch.Tensor]:
         """q replicated on every rank -> identical merged (scores, ids) on every rank."""
@@ -188,10 +192,66 @@ class ShardedIndex:
             local.append_file(os.path.join(directory, fname), first, n)
         return cls(local, man["n_total"], group=group, merge_fn=merge_fn)
 
+    def _p2p_setup(self, B: int, k: int, device: torch.device):
+        """Symmetric receive buffer of this rank, mapped into every rank of the group (torch's symmetric
+        memory does the handle exchange): 2 parities x world slots + 2 x world flags (include/tristage.h)."""
+        import torch.distributed._symmetric_memory as symm
+
+        from ._lib import packed_layout
+
+        ids_off, nbytes = packed_layout(B, k)
+        slot = (nbytes + 15) // 16 * 16
+        flags_off = 2 * self.world * slot
+        total = (flags_off + 2 * self.world * 4 + 15) // 16 * 16
+        buf = symm.empty(total, dtype=torch.uint8, device=device)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+        bases = torch.tensor([int(x) for x in hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        torch.cuda.current_stream(device).synchronize()
+        hdl.barrier()                                   # every buffer is zeroed before anybody pushes into it
+        return {"key": (B, k), "buf": buf, "hdl": hdl, "bases": bases, "slot": slot, "ids_off": ids_off,
+                "nbytes": nbytes, "flags_off": flags_off,
+                "mine": torch.zeros(slot, dtype=torch.uint8, device=device)}
+
+    def _search_p2p(self, q, k, **kw):
+        """Local search -> push the packed result into every rank's buffer over NVLink -> wait + merge.
+        Two kernels instead of an NCCL all-gather and a merge; no collective call in the steady state."""
+        import ctypes as C
+
+        from . import _lib
+
+        B = q.shape[0]
+        st = self._p2p_state
+        if st is None or st["key"] != (B, k):
+            st = self._p2p_state = self._p2p_setup(B, k, q.device)
+            self._step = 0
+        dev = q.device.index
+        self.local.search_packed(q, k, st["mine"], **kw)
+        parity, seq = self._step & 1, (self._step % 0x7FFFFFFF) + 1
+        self._step += 1
+        stream = _lib._stream_ptr(dev)
+        _lib.check(_lib.lib().ts_exchange_push(dev, C.c_void_p(st["mine"].data_ptr()), st["nbytes"],
+                                               C.c_void_p(st["bases"].data_ptr()), self.world, self.rank, st["slot"],
+                                               st["flags_off"], parity, seq, stream))
+        out_s = torch.empty((B, k), dtype=torch.float32, device=q.device)
+        out_i = torch.empty((B, k), dtype=torch.int64, device=q.device)
+        _lib.check(_lib.lib().ts_exchange_wait_merge(dev, C.c_void_p(st["buf"].data_ptr()), self.world, B, k, st["slot"],
+                                                     st["ids_off"], st["flags_off"], parity, seq,
+                                                     C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()), stream))
+        return out_s, out_i
+
     def _search_packed(self, q, k, **kw):
         """GPU fast path: scores + ids in one buffer -> ONE all-gather -> one merge kernel."""
         from ._lib import packed_layout, topk_merge_packed
 
+        if self._p2p:
+            try:
+                return self._search_p2p(q, k, **kw)
+            except (ImportError, RuntimeError, AttributeError) as e:      # no symmetric memory on this system: NCCL path
+                import logging
+
+                logging.getLogger(__name__).warning(f"peer-memory exchange unavailable ({e}); using all-gather")
+                self._p2p = False
         B = q.shape[0]
         _, nbytes = packed_layout(B, k)
         key = (B, k)
