@@ -453,6 +453,16 @@ def test_device_bm25_is_bit_identical_to_the_host_index(sim):
     dev2 = DeviceBM25(bm2, 0)
     for top_k in (5, 700):
         assert dev2.search_batch(["w0 w3", "w17"], top_k) == [bm2.search("w0 w3", top_k), bm2.search("w17", top_k)]
+    # documents split over several CTAs per query (grid (B, R)): same sums, same order
+    import os as _os
+    for split in ("3", "7", "64"):
+        _os.environ["TS_BM25_SPLIT"] = split
+        try:
+            for q, g in zip(queries, dev.search_batch(queries, 50)):
+                assert g == bm.search(q, 50), (q, split)
+            assert dev2.search_batch(["w0 w3", "w17"], 700) == [bm2.search("w0 w3", 700), bm2.search("w17", 700)]
+        finally:
+            del _os.environ["TS_BM25_SPLIT"]
     # tiny corpus, top_k beyond it: the list just ends (ids -1 are dropped)
     bm3 = BM25Index()
     bm3.fit(["a b", "b c", "zz"])

@@ -14,8 +14,8 @@
 // tokens in that order with a block barrier in between, so every document's sum is accumulated
 // in the reference's order and is bit-identical to it.
 //
-// bm25_score_kernel   one CTA per query: scores[b][doc] += w over the postings of each query
-//                     token; a document's first hit (score still 0.0 -- all weights are > 0, the
+// bm25_score_kernel   grid (query, document range): scores[b][doc] += w over the postings of each
+//                     query token that fall into the CTA's document range; a document's first hit (score still 0.0 -- all weights are > 0, the
 //                     caller falls back to the host otherwise) appends it to the query's
 //                     "touched" list.  Bound: HBM/L2 latency of the scattered fp64 updates;
 //                     bytes = postings touched * (4 + 8 + 16).
@@ -26,6 +26,7 @@
 // fuse_kernel         one CTA per query: RRF / weighted fusion of the dense top-k and the BM25
 //                     list in fp64, entries kept in dict insertion order (dense first, then
 //                     BM25-only), stable descending sort, truncate.
+#include <stdlib.h>
 #include <string.h>
 
 #include "ts_common.cuh"
@@ -109,18 +110,36 @@ __device__ __forceinline__ int block_rank_of_flag(int z, int* s_wsum, int* total
 constexpr double kWorst = -1.7976931348623157e308;   // pads the sort buffer: ranks after everything
 constexpr int kWorstKey = 0x7fffffff;
 
+// first index in post_doc[lo, hi) whose document is >= d (postings of a term are ascending in document)
+__device__ __forceinline__ int64_t lower_bound_doc(const int32_t* __restrict__ post_doc, int64_t lo, int64_t hi, int64_t d) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (post_doc[mid] < d) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// grid (B, R): CTA (b, r) owns the documents [r*span, (r+1)*span) of query b.  A document belongs to
+// exactly one CTA, so walking the query tokens in order with a block barrier in between keeps every
+// document's fp64 sum in the reference's accumulation order without any cross-CTA synchronisation.
 __global__ void __launch_bounds__(kBmThreads)
     bm25_score_kernel(const int64_t* __restrict__ term_off, const int32_t* __restrict__ post_doc,
                       const double* __restrict__ post_w, const int32_t* __restrict__ q_terms,
-                      const int64_t* __restrict__ q_off, int64_t n_docs, double* __restrict__ scores,
+                      const int64_t* __restrict__ q_off, int64_t n_docs, int64_t span, double* __restrict__ scores,
                       int32_t* __restrict__ touched, int64_t touched_cap, int32_t* __restrict__ touched_cnt) {
   const int b = blockIdx.x;
+  const int64_t d_lo = (int64_t)blockIdx.y * span;
+  const int64_t d_hi = (d_lo + span < n_docs) ? d_lo + span : n_docs;
   double* sc = scores + (size_t)b * n_docs;
   int32_t* tl = touched + (size_t)b * touched_cap;
   for (int64_t ti = q_off[b]; ti < q_off[b + 1]; ++ti) {
     const int t = q_terms[ti];
-    const int64_t p1 = term_off[t + 1];
-    for (int64_t p = term_off[t] + threadIdx.x; p < p1; p += blockDim.x) {
+    int64_t p0 = term_off[t], p1 = term_off[t + 1];
+    if (gridDim.y > 1) {                              // this CTA's slice of the term's postings
+      p0 = lower_bound_doc(post_doc, p0, p1, d_lo);
+      p1 = lower_bound_doc(post_doc, p0, p1, d_hi);
+    }
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
       const int d = post_doc[p];                      // a document occurs once per term: no atomics needed
       const double old = sc[d];
       sc[d] = dadd(old, post_w[p]);
@@ -263,7 +282,7 @@ __global__ void __launch_bounds__(kBmThreads) fuse_kernel(const FuseParams p) {
 using namespace ts;
 
 struct ts_bm25 {
-  int device;
+  int device, sm_count;
   int64_t n_docs, n_terms, nnz;
   int64_t* term_off;
   int32_t* post_doc;
@@ -292,7 +311,7 @@ int ts_bm25_create(ts_bm25** out, int device, int64_t n_docs, int64_t n_terms, c
   if (rc) return rc;
   ts_bm25* h = new ts_bm25();
   memset(h, 0, sizeof(*h));
-  h->device = device; h->n_docs = n_docs; h->n_terms = n_terms; h->nnz = nnz;
+  h->device = device; h->sm_count = info.sm_count; h->n_docs = n_docs; h->n_terms = n_terms; h->nnz = nnz;
   size_t sizes[3] = {(size_t)(n_terms + 1) * 8, (size_t)nnz * 4, (size_t)nnz * 8};
   void** ptrs[3] = {(void**)&h->term_off, (void**)&h->post_doc, (void**)&h->post_w};
   const void* srcs[3] = {term_off_host, post_doc_host, post_w_host};
@@ -362,8 +381,15 @@ int ts_bm25_search_host(ts_bm25* h, const int32_t* q_terms_host, const int64_t* 
   TS_CUDA_OK(cudaMemsetAsync(d_cnt, 0, (size_t)B * 4, st));
   if (nq > 0) TS_CUDA_OK(cudaMemcpyAsync(d_qt, q_terms_host, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
   TS_CUDA_OK(cudaMemcpyAsync(d_qo, q_off_host, (size_t)(B + 1) * 8, cudaMemcpyHostToDevice, st));
-  TS_LAUNCH(bm25_score_kernel, B, kBmThreads, 0, st, h->term_off, h->post_doc, h->post_w, d_qt, d_qo, h->n_docs, d_scores,
-            d_touched, cap, d_cnt);
+  // enough CTAs to fill the GPU: split every query's documents into R contiguous ranges
+  int R = (4 * h->sm_count + B - 1) / B;
+  if (R > 64) R = 64;
+  if ((int64_t)R * 4096 > h->n_docs) R = (int)(h->n_docs / 4096);
+  if (const char* e = getenv("TS_BM25_SPLIT")) { if (atoi(e) > 0) R = atoi(e); }      // tests force a split on tiny corpora
+  if (R < 1) R = 1;
+  const int64_t span = (h->n_docs + R - 1) / R;
+  TS_LAUNCH(bm25_score_kernel, dim3(B, R), kBmThreads, 0, st, h->term_off, h->post_doc, h->post_w, d_qt, d_qo, h->n_docs, span,
+            d_scores, d_touched, cap, d_cnt);
   TS_CUDA_OK(cudaGetLastError());
   TS_LAUNCH(bm25_topk_kernel, B, kBmThreads, 0, st, d_scores, h->n_docs, d_touched, cap, d_cnt, top_k, d_os, d_oi);
   TS_CUDA_OK(cudaGetLastError());
