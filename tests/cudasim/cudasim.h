@@ -10,9 +10,9 @@
 //     __syncthreads, a lane missing from a mask) aborts with a diagnostic instead of hanging;
 //   * "device" memory is host memory (tests/hostsim/cuda_runtime.h).
 // It checks LOGIC (indexing, reductions, selection, tie rules), not memory-model races and not
-// performance.  The tensor-path kernels (TMA / tcgen05 inline PTX) cannot be emulated and are
-// not compiled into this build.  Nothing under tristage_rag_b200/ includes this header unless
-// TS_CUDASIM is defined by tests/cudasim/Makefile.
+// performance.  The tensor-path kernels run on top of it through ts_ptx_sim.cuh, a functional model
+// of the TMA / mbarrier / tcgen05 wrappers.  Nothing under tristage_rag_b200/ includes this header
+// unless TS_CUDASIM is defined by tests/cudasim/Makefile.
 #pragma once
 #include <math.h>
 #include <stdint.h>
