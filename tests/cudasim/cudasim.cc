@@ -1,7 +1,9 @@
 // TEST INFRASTRUCTURE ONLY -- scheduler of the SIMT emulator (see cudasim.h).
 #include "cudasim.h"
 
+#include <algorithm>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 // Context switch.  x86-64: a 12-instruction stack switch (callee-saved registers only);
@@ -93,6 +95,13 @@ struct Block {
   std::unordered_map<uint32_t, MBar> mbars;
   NamedBar named[16];
   std::vector<uint32_t> tmem;
+  // asynchronous engines (CUDASIM_ASYNC=<seed>): operations issued by TMA / tensor-core wrappers are queued and
+  // completed some scheduler rounds later -- TMA operations independently of each other, tensor-core operations
+  // (MMAs and the commits that follow them) strictly in issue order
+  struct Deferred { unsigned long long due; std::function<void()> fn; };
+  std::vector<Deferred> tma_q;
+  std::vector<Deferred> mma_q;
+  size_t mma_head = 0;
   // thread-block cluster (launch_cluster): rank inside the cluster and the cluster's blocks
   int cluster_rank = 0, cluster_size = 1;
   Block** cluster = nullptr;
@@ -100,6 +109,14 @@ struct Block {
   unsigned cl_gen = 0;
 };
 constexpr size_t kSmemMax = 232448;
+
+// CUDASIM_ASYNC=<seed != 0>: adversarial timing -- deferred completion of asynchronous operations and a shuffled
+// thread order every scheduler round.  Off (0 / unset): everything completes at issue time, round-robin order.
+unsigned long long g_async_seed = 0, g_rng = 0, g_round = 0;
+inline unsigned long long rnd() {
+  g_rng ^= g_rng << 13; g_rng ^= g_rng >> 7; g_rng ^= g_rng << 17;
+  return g_rng;
+}
 
 std::vector<Block*> g_blocks;     // blocks alive at the same time: 1, or the whole grid of a cooperative launch
 Block* g_blk = nullptr;           // block of the running simulated thread
@@ -183,6 +200,16 @@ unsigned char* smem_base() { return g_blk->smem; }
 uint32_t* tmem() { return g_blk->tmem.data(); }
 
 void yield_spin() { yield(); }
+
+// asynchronous engines: run now (default) or queue for a later scheduler round (CUDASIM_ASYNC)
+void defer_tma(std::function<void()> fn) {
+  if (!g_async_seed) { fn(); return; }
+  g_blk->tma_q.push_back({g_round + 1 + rnd() % 4, std::move(fn)});
+}
+void defer_mma(std::function<void()> fn) {
+  if (!g_async_seed) { fn(); return; }
+  g_blk->mma_q.push_back({g_round + rnd() % 3, std::move(fn)});
+}
 
 int cluster_rank() { return g_blk->cluster_rank; }
 static Block& block_of(int cta) {
@@ -293,8 +320,36 @@ uint64_t warp_collective(Collective kind, unsigned mask, uint64_t value, int aux
   return f.result;
 }
 
+// run the deferred operations of one block that are due (all of them when `drain`)
+static bool run_deferred(Block& B, bool drain) {
+  bool did = false;
+  Block* saved = g_blk;
+  g_blk = &B;
+  for (size_t i = 0; i < B.tma_q.size();) {
+    if (drain || B.tma_q[i].due <= g_round) {
+      auto fn = std::move(B.tma_q[i].fn);
+      B.tma_q.erase(B.tma_q.begin() + (long)i);
+      fn();
+      did = true;
+    } else {
+      ++i;
+    }
+  }
+  while (B.mma_head < B.mma_q.size() && (drain || B.mma_q[B.mma_head].due <= g_round)) {
+    auto fn = std::move(B.mma_q[B.mma_head].fn);
+    ++B.mma_head;
+    fn();
+    did = true;
+  }
+  if (B.mma_head == B.mma_q.size()) { B.mma_q.clear(); B.mma_head = 0; }
+  if (did) ++B.progress;
+  g_blk = saved;
+  return did;
+}
+
 static void setup_block(Block& B, int n, dim3 grid, dim3 block, unsigned bx, unsigned by, unsigned bz, size_t dyn_smem_bytes,
                         const std::function<void()>* body, size_t stack0) {
+  B.tma_q.clear(); B.mma_q.clear(); B.mma_head = 0;
   B.n = B.live = n;
   B.bar_arrived = 0; B.bar_gen = 0; B.progress = 0;
   B.body = body;
@@ -319,37 +374,58 @@ static void setup_block(Block& B, int n, dim3 grid, dim3 block, unsigned bx, uns
   }
 }
 
-// run the given blocks until every simulated thread has exited (round-robin over all of them)
+// run the given blocks until every simulated thread has exited (round-robin over all of them; with
+// CUDASIM_ASYNC the visiting order is reshuffled every round and some runnable threads sit a round out)
 static void run_blocks(Block** blocks, int nb) {
   unsigned long long last_progress = ~0ull;
   int idle_rounds = 0;
+  bool skipped_any = false;      // a runnable thread sat the previous round out: that round proves nothing
+  std::vector<std::pair<int, int>> order;
   for (;;) {
+    ++g_round;
     unsigned long long progress = 0;
     int live = 0;
-    for (int i = 0; i < nb; ++i) { progress += blocks[i]->progress; live += blocks[i]->live; }
-    if (live == 0) break;
-    idle_rounds = (progress == last_progress) ? idle_rounds + 1 : 0;
+    size_t pending = 0;
+    for (int i = 0; i < nb; ++i) {
+      run_deferred(*blocks[i], false);
+      progress += blocks[i]->progress; live += blocks[i]->live;
+      pending += blocks[i]->tma_q.size() + (blocks[i]->mma_q.size() - blocks[i]->mma_head);
+    }
+    if (live == 0) { for (int i = 0; i < nb; ++i) run_deferred(*blocks[i], true); break; }
+    idle_rounds = (progress == last_progress && pending == 0 && !skipped_any) ? idle_rounds + 1 : 0;
+    skipped_any = false;
     g_blk = blocks[0];
     if (idle_rounds > 3) die("deadlock: no simulated thread can make progress");
     last_progress = progress;
-    for (int i = 0; i < nb; ++i) {
+    order.clear();
+    for (int i = 0; i < nb; ++i)
+      for (int t = 0; t < blocks[i]->n; ++t) order.emplace_back(i, t);
+    if (g_async_seed)
+      for (size_t i = order.size(); i > 1; --i) std::swap(order[i - 1], order[rnd() % i]);
+    for (auto [i, t] : order) {
       Block& B = *blocks[i];
-      for (int t = 0; t < B.n; ++t) {
-        Fiber& f = B.fibers[t];
-        if (f.state == kDone) continue;
-        if (f.state == kWaitBarrier && B.bar_gen == f.wait_gen) continue;
-        if (f.state == kWaitCollective && !f.result_ready) continue;
-        g_blk = &B;
-        B.cur = t;
-        g_cur = &f.tc;
-        ++g_switches;
-        ctx_switch(&B.sched, &f.ctx);
-      }
+      Fiber& f = B.fibers[t];
+      if (f.state == kDone) continue;
+      if (f.state == kWaitBarrier && B.bar_gen == f.wait_gen) continue;
+      if (f.state == kWaitCollective && !f.result_ready) continue;
+      if (g_async_seed && (rnd() & 7) == 0) { skipped_any = true; continue; }   // a slow warp: skips this round
+      g_blk = &B;
+      B.cur = t;
+      g_cur = &f.tc;
+      ++g_switches;
+      ctx_switch(&B.sched, &f.ctx);
     }
   }
 }
 
+static void read_async_env() {
+  const char* e = getenv("CUDASIM_ASYNC");
+  const unsigned long long seed = e ? strtoull(e, nullptr, 10) : 0;
+  if (seed != g_async_seed) { g_async_seed = seed; g_rng = seed * 0x9E3779B97F4A7C15ull + 1; }
+}
+
 static void launch_impl(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body, bool cooperative) {
+  read_async_env();
   if (g_in_launch) { fprintf(stderr, "[cudasim] nested launch\n"); abort(); }
   const int n = (int)(block.x * block.y * block.z);
   if (n <= 0 || n > 1024) { fprintf(stderr, "[cudasim] bad block size %d\n", n); abort(); }
@@ -385,6 +461,7 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<vo
 // clusters of `csize` consecutive blocks (1-D grid) run together: distributed shared memory, remote
 // mbarrier arrives and the cluster barrier work inside a cluster; clusters run one after another
 void launch_cluster(dim3 grid, dim3 block, size_t dyn_smem_bytes, int csize, const std::function<void()>& body) {
+  read_async_env();
   if (g_in_launch) { fprintf(stderr, "[cudasim] nested launch\n"); abort(); }
   const int n = (int)(block.x * block.y * block.z);
   if (grid.y != 1 || grid.z != 1 || csize < 1 || csize > 8 || grid.x % (unsigned)csize) {

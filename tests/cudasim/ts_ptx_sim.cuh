@@ -20,6 +20,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <functional>
+
 #include "cudasim.h"
 
 struct alignas(64) CUtensorMap {
@@ -46,6 +48,10 @@ uint32_t* tmem_of(int cta);
 void mbar_arrive_at(int cta, uint32_t addr, uint32_t expect_tx_bytes);
 void mbar_complete_tx_at(int cta, uint32_t addr, uint32_t bytes);
 void yield_spin();                       // give the other simulated threads a turn (no progress made)
+// asynchronous engines: executed at once, or -- under CUDASIM_ASYNC -- some scheduler rounds later (TMA operations
+// independently, tensor-core operations in issue order), so a kernel that touches data before its barrier fails
+void defer_tma(std::function<void()> fn);
+void defer_mma(std::function<void()> fn);
 }  // namespace cudasim
 
 namespace ts {
@@ -92,9 +98,12 @@ inline int sim_make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64
   return 0;
 }
 
-inline void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint64_t) {
-  const uint32_t dst = smem_u32(smem_dst);
+inline void tma_load_2d(void* smem_dst, const CUtensorMap* mp, uint64_t* bar, int c0, int c1, uint64_t) {
+  const uint32_t dst = smem_u32(smem_dst), bar_addr = smem_u32(bar);
   if (dst & 1023u) { fprintf(stderr, "[cudasim] TMA destination %u is not 1024-byte aligned (swizzle atom)\n", dst); abort(); }
+  const CUtensorMap map = *mp;
+  cudasim::defer_tma([=]() {
+  const CUtensorMap* m = &map;
   unsigned char* sm = cudasim::smem_base();
   const uint16_t* g = static_cast<const uint16_t*>(m->base);
   for (int r = 0; r < m->box_rows; ++r) {
@@ -106,7 +115,8 @@ inline void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int
       memcpy(sm + sw128(dst + (uint32_t)r * 128u + (uint32_t)c * 2u), &v, 2);
     }
   }
-  cudasim::mbar_complete_tx(smem_u32(bar), (uint32_t)m->box_rows * 128u);   // the whole box counts, also past the end
+  cudasim::mbar_complete_tx(bar_addr, (uint32_t)m->box_rows * 128u);   // the whole box counts, also past the end
+  });
 }
 
 // -------------------------------------------------------------- tcgen05 ----
@@ -139,6 +149,7 @@ inline void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_
   const uint32_t a_sbo = (uint32_t)((adesc >> 32) & 0x3FFF) << 4, b_sbo = (uint32_t)((bdesc >> 32) & 0x3FFF) << 4;
   const uint32_t col0 = tmem_d & 0xFFFFu, lane0 = tmem_d >> 16;
   if (lane0 != 0 || col0 + (uint32_t)N > 512) { fprintf(stderr, "[cudasim] accumulator outside TMEM\n"); abort(); }
+  cudasim::defer_mma([=]() {
   uint32_t* T = cudasim::tmem();
   float a[128][16];
   for (int m = 0; m < 128; ++m)
@@ -156,8 +167,12 @@ inline void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_
       memcpy(cell, &out, 4);
     }
   }
+  });
 }
-inline void umma_commit(uint64_t* bar) { cudasim::mbar_arrive(smem_u32(bar), 0); }
+inline void umma_commit(uint64_t* bar) {
+  const uint32_t addr = smem_u32(bar);
+  cudasim::defer_mma([=]() { cudasim::mbar_arrive(addr, 0); });   // after every MMA issued before it
+}
 
 inline void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   const uint32_t lane = (taddr >> 16) + (threadIdx.x & 31u), col = taddr & 0xFFFFu;
@@ -178,9 +193,12 @@ inline void cluster_sync() { cudasim::cluster_barrier(); }
 inline void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) { cudasim::mbar_arrive_at((int)cta, smem_u32(bar), 0); }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 
-inline void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint64_t) {
-  const uint32_t dst = smem_u32(smem_dst);
+inline void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* mp, uint64_t* bar, int c0, int c1, uint64_t) {
+  const uint32_t dst = smem_u32(smem_dst), bar_addr = smem_u32(bar);
   if (dst & 1023u) { fprintf(stderr, "[cudasim] TMA destination %u is not 1024-byte aligned\n", dst); abort(); }
+  const CUtensorMap map = *mp;
+  cudasim::defer_tma([=]() {
+  const CUtensorMap* m = &map;
   unsigned char* sm = cudasim::smem_base();               // data lands in the ISSUER's shared memory
   const uint16_t* g = static_cast<const uint16_t*>(m->base);
   for (int r = 0; r < m->box_rows; ++r) {
@@ -192,7 +210,8 @@ inline void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
       memcpy(sm + sw128(dst + (uint32_t)r * 128u + (uint32_t)c * 2u), &v, 2);
     }
   }
-  cudasim::mbar_complete_tx_at(0, smem_u32(bar), (uint32_t)m->box_rows * 128u);   // ... the bytes count on the LEADER's barrier
+  cudasim::mbar_complete_tx_at(0, bar_addr, (uint32_t)m->box_rows * 128u);   // ... the bytes count on the LEADER's barrier
+  });
 }
 inline void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) { tmem_alloc(smem_dst, ncols); }
 inline void tmem_relinquish_2sm() {}
@@ -212,6 +231,7 @@ inline void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uin
   const uint32_t a0 = (uint32_t)(adesc & 0x3FFF) << 4, b0 = (uint32_t)(bdesc & 0x3FFF) << 4;
   const uint32_t a_sbo = (uint32_t)((adesc >> 32) & 0x3FFF) << 4, b_sbo = (uint32_t)((bdesc >> 32) & 0x3FFF) << 4;
   const uint32_t col0 = tmem_d & 0xFFFFu;
+  cudasim::defer_mma([=]() {
   for (int cta = 0; cta < 2; ++cta) {
     uint32_t* T = cudasim::tmem_of(cta);
     float a[128][16];
@@ -232,10 +252,14 @@ inline void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uin
       }
     }
   }
+  });
 }
 inline void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
-  for (int cta = 0; cta < 2; ++cta)
-    if (cta_mask & (1u << cta)) cudasim::mbar_arrive_at(cta, smem_u32(bar), 0);
+  const uint32_t addr = smem_u32(bar);
+  cudasim::defer_mma([=]() {
+    for (int cta = 0; cta < 2; ++cta)
+      if (cta_mask & (1u << cta)) cudasim::mbar_arrive_at(cta, addr, 0);
+  });
 }
 
 inline uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {

@@ -713,3 +713,43 @@ def test_peer_memory_exchange_equals_gather_and_merge(sim):
     # argument checks
     assert sim.ts_exchange_push(0, p(blobs[0]), nbytes, p(bases), G, G, slot, flags_off, 0, 1, None) == -1       # rank out of range
     assert sim.ts_exchange_wait_merge(0, p(bufs[0]), G, B, k, slot + 8, ids_off, flags_off, 0, 1, p(out_s), p(out_i), None) == -1
+
+
+# ------------------------------------------- long pipelines: few SMs, many tiles per CTA ---
+@pytest.mark.parametrize("sms,async_seed", [(2, 0), (6, 0), (3, 7)])
+def test_few_sms_many_tiles_per_cta_wrap_every_ring(sim, monkeypatch, sms, async_seed):
+    """On a 148-SM "GPU" a small corpus gives every CTA one or two tiles, so the shared-memory rings,
+    the TMEM double buffer and the mbarrier phase bits hardly ever wrap.  Shrinking the emulated GPU to
+    a few SMs makes each CTA walk dozens of tiles: every ring wraps many times, in all scan variants
+    and in the Stage-2 kernel, with the results still equal to the oracle / to each other.
+    async_seed != 0 adds adversarial timing (CUDASIM_ASYNC): TMA loads and tensor-core operations complete a
+    random number of scheduler rounds after issue, the thread order is reshuffled every round and random
+    threads stall -- a kernel that reads data before its barrier, or reuses a stage too early, fails
+    (checked by removing single waits from the kernels: both the emulator's diagnostics and these
+    comparisons catch it)."""
+    monkeypatch.setenv("HOSTSIM_SM_COUNT", str(sms))
+    monkeypatch.setenv("CUDASIM_ASYNC", str(async_seed))
+    N, d, k = 9000, 200, 100
+    for B in (7, 200):
+        X, Q = make(N, d, B, seed=B, planted=10)
+        idx = _lib.Index(d, "bf16", "ip", 0)
+        idx.add(X)
+        D, I = idx.search_host(Q, k, path="umma")
+        rD, rI, sc = oracle_search(X, Q, k, "bf16")
+        assert not flat_ip.check_topk(D, I, sc, rD, rI, rel=REL)
+        for var in ("TS_FUSE", "TS_PAIR", "TS_DUAL", "TS_DBG_NOSHARE"):
+            monkeypatch.setenv(var, "1")
+            D2, I2 = idx.search_host(Q, k, path="umma")
+            monkeypatch.delenv(var)
+            assert (I2 == I).all() and (D2 == D).all(), (var, B)
+    rng = np.random.default_rng(sms)
+    lens = rng.integers(1, 200, size=300)
+    st, docs = _make_store(lens, 128, "bf16", seed=sms)
+    for Lq in (32, 80):
+        q = rng.standard_normal((4, Lq, 128)).astype(np.float32)
+        cand = rng.integers(0, 300, size=(4, 160)).astype(np.int64)
+        got = st.maxsim_host(q, cand)
+        np.testing.assert_allclose(got, _oracle_scores(q, docs, cand, 0, "bf16"), rtol=1e-3, atol=2e-4)
+        monkeypatch.setenv("TS_S2_V2", "1")
+        assert np.array_equal(st.maxsim_host(q, cand), got)
+        monkeypatch.delenv("TS_S2_V2")
