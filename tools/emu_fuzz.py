@@ -27,7 +27,17 @@ def load():
     _lib._stream_ptr = lambda d: None
 
 
+def machine(rng):
+    """Random emulated GPU: number of SMs (few SMs = many tiles per CTA) and timing mode."""
+    sms = int(rng.choice([148, 148, 16, 4, 2]))
+    seed = int(rng.integers(1, 1 << 30)) if rng.random() < 0.5 else 0
+    os.environ["HOSTSIM_SM_COUNT"] = str(sms)
+    os.environ["CUDASIM_ASYNC"] = str(seed)
+    return f"sms={sms} async={seed}"
+
+
 def stage1_case(rng):
+    hw = machine(rng)
     dtype = rng.choice(["bf16", "fp16", "fp32"], p=[0.6, 0.25, 0.15])
     N = int(rng.choice([1, 3, 50, 255, 256, 257, 1000, 4000, 12000]))
     N += int(rng.integers(0, 7))
@@ -58,7 +68,7 @@ def stage1_case(rng):
             idx.add(part)
     base = int(rng.choice([0, 0, 12345, 5_000_000_000]))
     idx.set_id_base(base)
-    variant = str(rng.choice(["", "", "TS_PAIR", "TS_DUAL", "TS_DBG_NOSHARE", "TS_SELECT_V1"]))
+    variant = str(rng.choice(["", "", "TS_PAIR", "TS_DUAL", "TS_DBG_NOSHARE", "TS_SELECT_V1", "TS_FUSE"]))
     if variant:
         os.environ[variant] = "1"
     try:
@@ -82,10 +92,11 @@ def stage1_case(rng):
                 continue
         keep.append(msg)
     bad = keep
-    return f"S1 N={N} d={d} B={B} k={k} {dtype} {metric} {path} {flavour} base={base} variant={variant}", bad
+    return f"S1 N={N} d={d} B={B} k={k} {dtype} {metric} {path} {flavour} base={base} variant={variant} {hw}", bad
 
 
 def stage2_case(rng):
+    hw = machine(rng)
     dtype = rng.choice(["bf16", "fp16", "fp32"], p=[0.7, 0.2, 0.1])
     dim = int(rng.choice([8, 24, 64, 96, 128, 136, 256]))
     Lq = int(rng.choice([1, 2, 7, 31, 32, 33, 64, 65, 128]))
@@ -119,7 +130,7 @@ def stage2_case(rng):
             if 0 <= c < ndocs:
                 ref[b, j] = maxsim.score(nr(q[b, :lq]), nr(tok[off[c]:off[c + 1]]), mode, normalize=False)
     ok = np.allclose(got, ref, rtol=1e-3, atol=3e-4)
-    return (f"S2 dim={dim} Lq={Lq} ndocs={ndocs} {style} B={B} C={Cn} {dtype} mode={mode} v2={v2} simt={simt} "
+    return (f"S2 {hw} dim={dim} Lq={Lq} ndocs={ndocs} {style} B={B} C={Cn} {dtype} mode={mode} v2={v2} simt={simt} "
             f"q_len={None if q_len is None else q_len.tolist()} n_cand={None if n_cand is None else n_cand.tolist()}"), \
         ([] if ok else [f"max abs err {np.abs(got - ref).max()}"])
 
