@@ -27,9 +27,9 @@ def load():
     _lib._stream_ptr = lambda d: None
 
 
-def machine(rng):
+def machine(rng, max_sms=148):
     """Random emulated GPU: number of SMs (few SMs = many tiles per CTA) and timing mode."""
-    sms = int(rng.choice([148, 148, 16, 4, 2]))
+    sms = min(int(rng.choice([148, 148, 16, 4, 2])), max_sms)
     seed = int(rng.integers(1, 1 << 30)) if rng.random() < 0.5 else 0
     os.environ["HOSTSIM_SM_COUNT"] = str(sms)
     os.environ["CUDASIM_ASYNC"] = str(seed)
@@ -37,7 +37,8 @@ def machine(rng):
 
 
 def stage1_case(rng):
-    hw = machine(rng)
+    variant = str(rng.choice(["", "", "TS_PAIR", "TS_DUAL", "TS_DBG_NOSHARE", "TS_SELECT_V1", "TS_FUSE"]))
+    hw = machine(rng, 16 if variant == "TS_FUSE" else 148)      # a cooperative grid keeps every CTA alive at once
     dtype = rng.choice(["bf16", "fp16", "fp32"], p=[0.6, 0.25, 0.15])
     N = int(rng.choice([1, 3, 50, 255, 256, 257, 1000, 4000, 12000]))
     N += int(rng.integers(0, 7))
@@ -68,7 +69,6 @@ def stage1_case(rng):
             idx.add(part)
     base = int(rng.choice([0, 0, 12345, 5_000_000_000]))
     idx.set_id_base(base)
-    variant = str(rng.choice(["", "", "TS_PAIR", "TS_DUAL", "TS_DBG_NOSHARE", "TS_SELECT_V1", "TS_FUSE"]))
     if variant:
         os.environ[variant] = "1"
     try:
