@@ -555,6 +555,7 @@ def test_stage1_search_batch_hybrid_on_device_equals_host_path(sim, tmp_path, mo
                 # when a query has no lexical hit (or, after a stale refit, only negative ones)
                 qs = queries if fusion == "rrf" else (["w3 w3 w40", "w2 w7"] if refit else ["w0 w1", "w3 w3 w40", "w2 w7"])
                 out[(refit, on_device, fusion)] = r.search_batch(qs, 20)
+                assert r.search(qs[0], 20) == out[(refit, on_device, fusion)][0]      # the single-query call takes the same route
                 if on_device:
                     assert (getattr(r, "_device_bm25", None) is not None) == (not refit)
     for refit in (False, True):

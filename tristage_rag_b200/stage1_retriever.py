@@ -406,6 +406,8 @@ class Stage1Retriever:
         if self.faiss_index is None:
             raise ValueError("No documents indexed. Call add_documents() first.")
         top_k = top_k or self.config.top_k_candidates
+        if self.config.hybrid_on_device and self.config.enable_bm25 and self.bm25_index is not None:
+            return self.search_batch([query], top_k)[0]      # device BM25 + fusion; identical results
         q = self._normalize_embeddings(self._encode_batch([query]))
         D, I = self.faiss_index.search(q, top_k)
         dense = [(int(i), float(s)) for i, s in zip(I[0], D[0]) if i >= 0]
