@@ -19,7 +19,8 @@
 //                     caller falls back to the host otherwise) appends it to the query's
 //                     "touched" list.  Bound: HBM/L2 latency of the scattered fp64 updates;
 //                     bytes = postings touched * (4 + 8 + 16).
-// bm25_topk_kernel    one CTA per query: stable descending top-k of the touched documents
+// (each (query, range) CTA also selects its own best top_k and hands only those on)
+// bm25_topk_kernel    one CTA per query: stable descending top-k of the ranges' candidates
 //                     (score desc, doc index asc == CPython's stable sort with reverse=True over
 //                     enumerate(scores)), then zero-score documents in ascending index order
 //                     until k entries are filled, exactly what ranking all N scores gives.
@@ -85,6 +86,9 @@ __device__ __forceinline__ void block_sort_pairs(double* s, int* k, int n) {
   }
 }
 
+constexpr double kWorst = -1.7976931348623157e308;   // pads the sort buffer: ranks after everything
+constexpr int kWorstKey = 0x7fffffff;
+
 // exclusive rank of this thread's flag among the block's flags (block-wide scan over one chunk
 // of blockDim.x flags); *total = flags set in the chunk.  Ends with a barrier (s_wsum reusable).
 __device__ __forceinline__ int block_rank_of_flag(int z, int* s_wsum, int* total) {
@@ -107,8 +111,23 @@ __device__ __forceinline__ int block_rank_of_flag(int z, int* s_wsum, int* total
   return before_me + incl - z;
 }
 
-constexpr double kWorst = -1.7976931348623157e308;   // pads the sort buffer: ranks after everything
-constexpr int kWorstKey = 0x7fffffff;
+// Chunked block-wide selection: best `keep` of the T documents listed in tl[] (scores looked up in sc[]) end up in
+// s_sc / s_doc [0, keep), best first.  Buffer = [best so far | next chunk], sort, repeat.  All threads call it.
+__device__ __forceinline__ void block_select_docs(const double* __restrict__ sc, const int32_t* __restrict__ tl, int T, int keep,
+                                                  double* s_sc, int* s_doc) {
+  const int room = kBmBuf - keep;
+  for (int i = threadIdx.x; i < keep; i += blockDim.x) { s_sc[i] = kWorst; s_doc[i] = kWorstKey; }
+  __syncthreads();
+  for (int off = 0; off < T; off += room) {
+    const int take = min(room, T - off);
+    for (int i = threadIdx.x; i < room; i += blockDim.x) {
+      if (i < take) { const int d = tl[off + i]; s_doc[keep + i] = d; s_sc[keep + i] = sc[d]; }
+      else { s_doc[keep + i] = kWorstKey; s_sc[keep + i] = kWorst; }
+    }
+    __syncthreads();
+    block_sort_pairs(s_sc, s_doc, kBmBuf);
+  }
+}
 
 // first index in post_doc[lo, hi) whose document is >= d (postings of a term are ascending in document)
 __device__ __forceinline__ int64_t lower_bound_doc(const int32_t* __restrict__ post_doc, int64_t lo, int64_t hi, int64_t d) {
@@ -122,16 +141,25 @@ __device__ __forceinline__ int64_t lower_bound_doc(const int32_t* __restrict__ p
 // grid (B, R): CTA (b, r) owns the documents [r*span, (r+1)*span) of query b.  A document belongs to
 // exactly one CTA, so walking the query tokens in order with a block barrier in between keeps every
 // document's fp64 sum in the reference's accumulation order without any cross-CTA synchronisation.
+// The CTA lists the documents it touched in its own segment of `touched`, selects its best top_k of them
+// (anything outside a range's best top_k cannot be in the query's best top_k) and appends those to the
+// query's candidate list; touched_cnt[b] accumulates the TRUE number of touched documents.
 __global__ void __launch_bounds__(kBmThreads)
     bm25_score_kernel(const int64_t* __restrict__ term_off, const int32_t* __restrict__ post_doc,
                       const double* __restrict__ post_w, const int32_t* __restrict__ q_terms,
-                      const int64_t* __restrict__ q_off, int64_t n_docs, int64_t span, double* __restrict__ scores,
-                      int32_t* __restrict__ touched, int64_t touched_cap, int32_t* __restrict__ touched_cnt) {
+                      const int64_t* __restrict__ q_off, int64_t n_docs, int64_t span, int64_t seg_cap, int top_k,
+                      double* __restrict__ scores, int32_t* __restrict__ touched, int32_t* __restrict__ touched_cnt,
+                      int32_t* __restrict__ cand, int64_t cand_cap, int32_t* __restrict__ cand_cnt) {
+  __shared__ double s_sc[kBmBuf];
+  __shared__ int s_doc[kBmBuf];
+  __shared__ int s_n, s_at;
   const int b = blockIdx.x;
   const int64_t d_lo = (int64_t)blockIdx.y * span;
   const int64_t d_hi = (d_lo + span < n_docs) ? d_lo + span : n_docs;
   double* sc = scores + (size_t)b * n_docs;
-  int32_t* tl = touched + (size_t)b * touched_cap;
+  int32_t* tl = touched + ((size_t)b * gridDim.y + blockIdx.y) * seg_cap;     // this CTA's segment
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
   for (int64_t ti = q_off[b]; ti < q_off[b + 1]; ++ti) {
     const int t = q_terms[ti];
     int64_t p0 = term_off[t], p1 = term_off[t + 1];
@@ -144,40 +172,40 @@ __global__ void __launch_bounds__(kBmThreads)
       const double old = sc[d];
       sc[d] = dadd(old, post_w[p]);
       if (old == 0.0) {                               // first query token that hits this document
-        const int at = atomicAdd(touched_cnt + b, 1);
-        if (at < touched_cap) tl[at] = d;
+        const int at = atomicAdd(&s_n, 1);
+        if (at < seg_cap) tl[at] = d;
       }
     }
     __syncthreads();                                  // the next token may hit the same documents
     __threadfence_block();
   }
+  const int T = min(s_n, (int)min((int64_t)0x7fffffff, seg_cap));
+  const int keep = min(top_k, kBmBuf / 2);
+  block_select_docs(sc, tl, T, keep, s_sc, s_doc);
+  const int n_out = min(T, keep);
+  if (threadIdx.x == 0) {
+    s_at = atomicAdd(cand_cnt + b, n_out);
+    atomicAdd(touched_cnt + b, T);
+  }
+  __syncthreads();
+  int32_t* cl = cand + (size_t)b * cand_cap + s_at;
+  for (int i = threadIdx.x; i < n_out; i += blockDim.x) cl[i] = s_doc[i];
 }
 
 __global__ void __launch_bounds__(kBmThreads)
-    bm25_topk_kernel(const double* __restrict__ scores, int64_t n_docs, const int32_t* __restrict__ touched,
-                     int64_t touched_cap, const int32_t* __restrict__ touched_cnt, int top_k,
+    bm25_topk_kernel(const double* __restrict__ scores, int64_t n_docs, const int32_t* __restrict__ cand, int64_t cand_cap,
+                     const int32_t* __restrict__ cand_cnt, const int32_t* __restrict__ touched_cnt, int top_k,
                      double* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
   __shared__ double s_sc[kBmBuf];
   __shared__ int s_doc[kBmBuf];
   __shared__ int s_wsum[kBmThreads / 32];
   const int b = blockIdx.x;
   const double* sc = scores + (size_t)b * n_docs;
-  const int32_t* tl = touched + (size_t)b * touched_cap;
-  const int T = min(touched_cnt[b], (int)min((int64_t)0x7fffffff, touched_cap));
-  const int keep = min(top_k, kBmBuf / 2);            // best-so-far prefix of the buffer
-  const int room = kBmBuf - keep;
-  for (int i = threadIdx.x; i < keep; i += blockDim.x) { s_sc[i] = kWorst; s_doc[i] = kWorstKey; }
-  __syncthreads();
-  // chunked selection: buffer = [best `keep` so far | next `room` touched documents], sort, repeat
-  for (int off = 0; off < T; off += room) {
-    const int take = min(room, T - off);
-    for (int i = threadIdx.x; i < room; i += blockDim.x) {
-      if (i < take) { const int d = tl[off + i]; s_doc[keep + i] = d; s_sc[keep + i] = sc[d]; }
-      else { s_doc[keep + i] = kWorstKey; s_sc[keep + i] = kWorst; }
-    }
-    __syncthreads();
-    block_sort_pairs(s_sc, s_doc, kBmBuf);
-  }
+  const int32_t* tl = cand + (size_t)b * cand_cap;
+  const int n_cand = min(cand_cnt[b], (int)min((int64_t)0x7fffffff, cand_cap));
+  const int T = touched_cnt[b];                        // documents with a non-zero score (all ranges)
+  const int keep = min(top_k, kBmBuf / 2);
+  block_select_docs(sc, tl, n_cand, keep, s_sc, s_doc);
   const int n_hit = min(T, top_k);
   double* os = out_scores + (size_t)b * top_k;
   int64_t* oi = out_ids + (size_t)b * top_k;
@@ -363,24 +391,6 @@ int ts_bm25_search_host(ts_bm25* h, const int32_t* q_terms_host, const int64_t* 
     if (sum > h->n_docs) sum = h->n_docs;
     if (sum > cap) cap = sum;
   }
-  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
-  const size_t b_scores = up((size_t)B * h->n_docs * 8), b_touched = up((size_t)B * cap * 4), b_cnt = up((size_t)B * 4);
-  const size_t b_qt = up((size_t)(nq > 0 ? nq : 1) * 4), b_qo = up((size_t)(B + 1) * 8);
-  const size_t b_os = up((size_t)B * top_k * 8), b_oi = up((size_t)B * top_k * 8);
-  int rc = ensure_bytes(&h->scratch, &h->scratch_b, b_scores + b_touched + b_cnt + b_qt + b_qo + b_os + b_oi);
-  if (rc) return rc;
-  char* base = (char*)h->scratch;
-  double* d_scores = (double*)base; base += b_scores;
-  int32_t* d_touched = (int32_t*)base; base += b_touched;
-  int32_t* d_cnt = (int32_t*)base; base += b_cnt;
-  int32_t* d_qt = (int32_t*)base; base += b_qt;
-  int64_t* d_qo = (int64_t*)base; base += b_qo;
-  double* d_os = (double*)base; base += b_os;
-  int64_t* d_oi = (int64_t*)base;
-  TS_CUDA_OK(cudaMemsetAsync(d_scores, 0, (size_t)B * h->n_docs * 8, st));
-  TS_CUDA_OK(cudaMemsetAsync(d_cnt, 0, (size_t)B * 4, st));
-  if (nq > 0) TS_CUDA_OK(cudaMemcpyAsync(d_qt, q_terms_host, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
-  TS_CUDA_OK(cudaMemcpyAsync(d_qo, q_off_host, (size_t)(B + 1) * 8, cudaMemcpyHostToDevice, st));
   // enough CTAs to fill the GPU: split every query's documents into R contiguous ranges
   int R = (4 * h->sm_count + B - 1) / B;
   if (R > 64) R = 64;
@@ -388,10 +398,32 @@ int ts_bm25_search_host(ts_bm25* h, const int32_t* q_terms_host, const int64_t* 
   if (const char* e = getenv("TS_BM25_SPLIT")) { if (atoi(e) > 0) R = atoi(e); }      // tests force a split on tiny corpora
   if (R < 1) R = 1;
   const int64_t span = (h->n_docs + R - 1) / R;
+  const int64_t seg_cap = cap < span ? cap : span;     // a range cannot touch more documents than it holds
+  const int64_t cand_cap = (int64_t)R * (top_k < kBmBuf / 2 ? top_k : kBmBuf / 2);
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t b_scores = up((size_t)B * h->n_docs * 8), b_touched = up((size_t)B * R * seg_cap * 4), b_cnt = up((size_t)B * 8);
+  const size_t b_cand = up((size_t)B * cand_cap * 4);
+  const size_t b_qt = up((size_t)(nq > 0 ? nq : 1) * 4), b_qo = up((size_t)(B + 1) * 8);
+  const size_t b_os = up((size_t)B * top_k * 8), b_oi = up((size_t)B * top_k * 8);
+  int rc = ensure_bytes(&h->scratch, &h->scratch_b, b_scores + b_touched + b_cnt + b_cand + b_qt + b_qo + b_os + b_oi);
+  if (rc) return rc;
+  char* base = (char*)h->scratch;
+  double* d_scores = (double*)base; base += b_scores;
+  int32_t* d_touched = (int32_t*)base; base += b_touched;
+  int32_t* d_cnt = (int32_t*)base; base += b_cnt;        // [B] touched totals, then [B] candidate counts
+  int32_t* d_cand = (int32_t*)base; base += b_cand;
+  int32_t* d_qt = (int32_t*)base; base += b_qt;
+  int64_t* d_qo = (int64_t*)base; base += b_qo;
+  double* d_os = (double*)base; base += b_os;
+  int64_t* d_oi = (int64_t*)base;
+  TS_CUDA_OK(cudaMemsetAsync(d_scores, 0, (size_t)B * h->n_docs * 8, st));
+  TS_CUDA_OK(cudaMemsetAsync(d_cnt, 0, (size_t)B * 8, st));
+  if (nq > 0) TS_CUDA_OK(cudaMemcpyAsync(d_qt, q_terms_host, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
+  TS_CUDA_OK(cudaMemcpyAsync(d_qo, q_off_host, (size_t)(B + 1) * 8, cudaMemcpyHostToDevice, st));
   TS_LAUNCH(bm25_score_kernel, dim3(B, R), kBmThreads, 0, st, h->term_off, h->post_doc, h->post_w, d_qt, d_qo, h->n_docs, span,
-            d_scores, d_touched, cap, d_cnt);
+            seg_cap, top_k, d_scores, d_touched, d_cnt, d_cand, cand_cap, d_cnt + B);
   TS_CUDA_OK(cudaGetLastError());
-  TS_LAUNCH(bm25_topk_kernel, B, kBmThreads, 0, st, d_scores, h->n_docs, d_touched, cap, d_cnt, top_k, d_os, d_oi);
+  TS_LAUNCH(bm25_topk_kernel, B, kBmThreads, 0, st, d_scores, h->n_docs, d_cand, cand_cap, d_cnt + B, d_cnt, top_k, d_os, d_oi);
   TS_CUDA_OK(cudaGetLastError());
   h->launches += 2;
   TS_CUDA_OK(cudaMemcpyAsync(out_scores_host, d_os, (size_t)B * top_k * 8, cudaMemcpyDeviceToHost, st));
