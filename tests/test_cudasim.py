@@ -757,3 +757,35 @@ def test_few_sms_many_tiles_per_cta_wrap_every_ring(sim, monkeypatch, sms, async
         monkeypatch.setenv("TS_S2_V2", "1")
         assert np.array_equal(st.maxsim_host(q, cand), got)
         monkeypatch.delenv("TS_S2_V2")
+
+
+def test_load_index_imports_a_reference_written_faiss_file(sim, tmp_path):
+    """Migration: index_dir holds what the REFERENCE saved (pickle side-car + a flat FAISS index file, layout as in
+    tristage_rag_b200/faiss_io.py); load_index imports the vectors into a ts_index and search works on them."""
+    import pickle
+    import struct
+
+    from oracle import fakes
+    from tristage_rag_b200 import stage1_retriever as s1
+
+    docs = [f"document {i} about topic {i % 5}" for i in range(40)]
+    enc = fakes.FakeSentenceEncoder(48)
+    emb = flat_ip.normalize_rows(np.asarray(enc.encode(docs), np.float32)).astype(np.float32)
+    idir = tmp_path / "i"
+    idir.mkdir()
+    with open(idir / "stage1_faiss.index", "wb") as f:
+        f.write(b"IxFI" + struct.pack("<iqqqBi", 48, 40, 1 << 20, 1 << 20, 1, 0) + struct.pack("<Q", 40 * 48) + emb.tobytes())
+    with open(idir / "stage1_index.pkl", "wb") as f:
+        pickle.dump({"documents": docs, "doc_metadata": [{} for _ in docs], "config": {}, "bm25_index": None}, f)
+    cfg = s1.Stage1Config(device="cpu", cache_dir=str(tmp_path / "m"), index_dir=str(idir), enable_bm25=False,
+                          top_k_candidates=5, storage_dtype="fp32")
+    r = s1.Stage1Retriever(cfg, model=enc)
+    r.load_index()
+    assert r.faiss_index.ntotal == 40 and len(r.documents) == 40
+    res = r.search(docs[7])
+    assert res[0]["doc_id"] == 7 and res[0]["score"] == pytest.approx(1.0, abs=1e-5)
+    r.save_index()                                      # ... and is written back as a tristage shard file
+    assert _lib.file_probe(str(idir / "stage1_faiss.index"))["n"] == 40
+    r2 = s1.Stage1Retriever(cfg, model=enc)
+    r2.load_index()
+    assert [x["doc_id"] for x in r2.search(docs[7])] == [x["doc_id"] for x in res]

@@ -150,3 +150,34 @@ def test_stage2_empty_and_encode_failure_semantics():
     assert sc.rescore_candidates("q", cands) is cands       # reference :260-263: returned unchanged
     info = sc.get_model_info()
     assert info["embedding_dim"] == 32 and info["scoring_method"] == "maxsim"
+
+
+def test_faiss_flat_reader_accepts_only_self_consistent_files(tmp_path):
+    """tristage_rag_b200/faiss_io.py: the layout is restated from FAISS's public writer (FAISS is not installable
+    here, so the file below is produced by this test, not by FAISS); the reader must refuse anything whose
+    fields do not add up instead of guessing."""
+    import struct
+
+    from tristage_rag_b200.faiss_io import FaissFormatError, read_faiss_flat
+
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((57, 24)).astype(np.float32)
+
+    def blob(fourcc=b"IxFI", d=24, n=57, metric=0, n_floats=None, data=None):
+        data = x.tobytes() if data is None else data
+        return (fourcc + struct.pack("<iqqqBi", d, n, 1 << 20, 1 << 20, 1, metric) +
+                struct.pack("<Q", n * d if n_floats is None else n_floats) + data)
+
+    def write(name, b):
+        p = str(tmp_path / name)
+        open(p, "wb").write(b)
+        return p
+
+    got, metric = read_faiss_flat(write("ok", blob()))
+    assert metric == "ip" and got.dtype == np.float32 and (got == x).all()
+    assert read_faiss_flat(write("l2", blob(b"IxF2", metric=1)))[1] == "l2"
+    for name, b in (("ivf", blob(b"IwFl")), ("other", blob(b"IxPQ")), ("short", blob()[:-4]), ("long", blob() + b"\\0"),
+                    ("count", blob(n_floats=57 * 24 - 1)), ("dim", blob(d=25)), ("mix", blob(b"IxFI", metric=1)),
+                    ("tiny", b"IxFI")):
+        with pytest.raises(FaissFormatError):
+            read_faiss_flat(write(name, b))

@@ -460,7 +460,20 @@ class Stage1Retriever:
         self.bm25_index = data.get("bm25_index")
         faiss_path = os.path.join(self.config.index_dir, "stage1_faiss.index")
         if os.path.exists(faiss_path):
-            self.faiss_index = IndexFlatIP.load(faiss_path, self.config.storage_dtype, self.config.gpu_index)
+            with open(faiss_path, "rb") as f:
+                magic = f.read(8)
+            if magic == b"TSSHARD2":
+                self.faiss_index = IndexFlatIP.load(faiss_path, self.config.storage_dtype, self.config.gpu_index)
+            else:
+                # a file the reference itself wrote with faiss.write_index (:436): import the vectors
+                from .faiss_io import read_faiss_flat
+
+                x, metric = read_faiss_flat(faiss_path)
+                if metric != "ip":
+                    raise ValueError(f"{faiss_path}: the reference uses inner-product indexes, this one is {metric}")
+                self.faiss_index = None
+                self._create_faiss_index(np.ascontiguousarray(x, np.float32))     # already normalised at ingest (:307)
+        self._device_bm25 = None
         self.logger.info(f"Stage 1 index loaded from {index_path}")
 
     def get_stats(self) -> Dict[str, Any]:
