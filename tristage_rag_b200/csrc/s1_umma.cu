@@ -634,7 +634,7 @@ UmmaPlan umma_plan(const ScanArgs& a) {
   // single-tile layout is faster (19.2 vs 21.5 ms at B=1024, 10M x 1024), so it is opt-in.
   pl.dual = (pl.n_mt >= 2 && env_on("TS_DUAL")) ? 1 : 0;
   // CTA pairs (cta_group::2): two query tiles per cluster; an odd tile count is padded with an idle tile
-  pl.pair = (pl.n_mt >= 2 && !pl.dual && a.sm_count >= 2 && env_on("TS_PAIR")) ? 1 : 0;
+  pl.pair = (pl.n_mt >= 2 && !pl.dual && a.sm_count >= 2 && env_flag("TS_PAIR", kDefaultPair)) ? 1 : 0;
   if (pl.pair) pl.n_mt = (pl.n_mt + 1) & ~1;
   pl.n_mg = pl.dual ? (pl.n_mt + 1) / 2 : pl.n_mt;
   pl.n_tiles = (int)((a.n + kTileN - 1) / kTileN);
@@ -667,7 +667,7 @@ int s1_umma_plan(const ScanArgs& a, UmmaLayout* lay) {
   lay->jrank = (j <= 8 && !env_on("TS_DBG_NOSHARE")) ? j : 0;
   // One cooperative launch (pre-pass + grid barrier + scan) instead of two launches.  Written
   // after this round's GPU budget was spent: NOT yet validated on hardware, so it is opt-in.
-  lay->fused = (lay->jrank > 0 && !pl.dual && !pl.pair && env_on("TS_FUSE")) ? 1 : 0;
+  lay->fused = (lay->jrank > 0 && !pl.dual && !pl.pair && env_flag("TS_FUSE", kDefaultFuse)) ? 1 : 0;
   return TS_OK;
 }
 

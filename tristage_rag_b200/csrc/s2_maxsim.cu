@@ -574,7 +574,7 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
   p.out = a.out;
   { const char* e = getenv("TS_S2_STAGES"); p.n_stages = (e && atoi(e) == 4) ? 4 : 3; }
   int grid = a.sm_count < p.n_items ? a.sm_count : p.n_items;
-  const bool v2 = env_on("TS_S2_V2");   // opt-in until validated on hardware
+  const bool v2 = env_flag("TS_S2_V2", kDefaultS2V2);   // opt-in until validated on hardware
   auto launch = [&](auto kern) -> int {
     TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     TS_LAUNCH(kern, grid, kThreads, kSmemBytes, st, tq8, tq32, tq128, t8, t16, t32, t64, t128, p);

@@ -20,10 +20,20 @@ const char* get_error();
     }                                                                                      \
   } while (0)
 
-// experiment switches (TS_FUSE, TS_S2_V2, TS_DBG_*): on when set to anything but "" or "0"
+// experiment switches (TS_DBG_*, TS_DUAL, TS_SELECT_V1): on when set to anything but "" or "0"
 inline bool env_on(const char* name) {
   const char* e = getenv(name);
   return e && e[0] && !(e[0] == '0' && !e[1]);
+}
+// kernel variants with a build-time default that the environment can override in both directions
+// (NAME=1 / NAME=0).  Flip a default here once the variant has been validated and timed on hardware.
+constexpr bool kDefaultFuse = false;   // TS_FUSE : threshold pre-pass + scan in one cooperative launch
+constexpr bool kDefaultS2V2 = false;   // TS_S2_V2: second Stage-2 epilogue
+constexpr bool kDefaultPair = false;   // TS_PAIR : cta_group::2 CTA pairs for B >= 129
+inline bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  if (!e || !e[0]) return dflt;
+  return !(e[0] == '0' && !e[1]);
 }
 
 inline int dtype_size(int dt) { return dt == TS_F32 ? 4 : 2; }
