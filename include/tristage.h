@@ -161,6 +161,12 @@ int ts_exchange_wait_merge(int device, const void* local_base_dev, int n_ranks, 
                            int64_t ids_offset, int64_t flags_offset, int parity, uint32_t seq,
                            float* out_scores_dev, int64_t* out_ids_dev, void* stream);
 
+/* The same exchange for the Stage-2 score matrices (replaces the all-reduce(SUM) of the per-rank
+ * ts_maxsim outputs): every rank pushes its [B, C] fp32 matrix with ts_exchange_push (nbytes = B*C*4),
+ * ts_exchange_wait_sum waits for all n_ranks slots of the step and writes their element-wise sum.   */
+int ts_exchange_wait_sum(int device, const void* local_base_dev, int n_ranks, int64_t n_floats, int64_t slot_bytes,
+                         int64_t flags_offset, int parity, uint32_t seq, float* out_dev, void* stream);
+
 /* faiss.write_index / read_index  (stage1_retriever.py:436,463): one shard
  * file per handle (layout: see "shard files" below).  save synchronises the
  * device; load verifies the file's checksums.                                */

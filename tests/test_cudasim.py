@@ -789,3 +789,40 @@ def test_load_index_imports_a_reference_written_faiss_file(sim, tmp_path):
     r2 = s1.Stage1Retriever(cfg, model=enc)
     r2.load_index()
     assert [x["doc_id"] for x in r2.search(docs[7])] == [x["doc_id"] for x in res]
+
+
+def test_peer_memory_sum_of_stage2_scores(sim):
+    """ts_exchange_push + ts_exchange_wait_sum with three in-process ranks: the element-wise sum of the
+    ownership-filtered per-rank MaxSim outputs, i.e. what all-reduce(SUM) delivers, over several steps."""
+    G, B, Cn = 3, 4, 37                                        # 148 floats: not a multiple of 4 -> padded slot
+    n = B * Cn
+    slot = (n * 4 + 15) // 16 * 16
+    flags_off = 2 * G * slot
+    bufs = [np.zeros(flags_off + 2 * G * 4 + 16, np.uint8) for _ in range(G)]
+    bases = np.array([b.ctypes.data for b in bufs], np.int64)
+    rng = np.random.default_rng(1)
+    lens = rng.integers(2, 60, size=90)
+    tok = rng.standard_normal((int(lens.sum()), 32)).astype(np.float32)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    stores = []
+    for r in range(G):
+        lo, hi = r * 30, (r + 1) * 30
+        st = _lib.TokStore(32, "bf16", 0)
+        st.add(tok[off[lo]:off[hi]], lens[lo:hi], normalize=True)
+        st.set_id_base(lo)
+        stores.append(st)
+    whole = _lib.TokStore(32, "bf16", 0)
+    whole.add(tok, lens, normalize=True)
+    for step in range(3):
+        q = rng.standard_normal((B, 8, 32)).astype(np.float32)
+        cand = rng.integers(0, 90, size=(B, Cn)).astype(np.int64)
+        parity, seq = step & 1, step + 1
+        for r in range(G):
+            part = np.zeros(slot // 4, np.float32)
+            part[:n] = stores[r].maxsim_host(q, cand).ravel()
+            _lib.check(sim.ts_exchange_push(0, p(part), slot, p(bases), G, r, slot, flags_off, parity, seq, None))
+        ref = whole.maxsim_host(q, cand)
+        for r in range(G):
+            out = np.empty((B, Cn), np.float32)
+            _lib.check(sim.ts_exchange_wait_sum(0, p(bufs[r]), G, n, slot, flags_off, parity, seq, p(out), None))
+            assert np.array_equal(out, ref), (step, r)

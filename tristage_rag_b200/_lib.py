@@ -70,6 +70,7 @@ SYMBOLS = {
     "ts_topk_merge_packed": (_i, [_i, _vp, _i64, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "ts_exchange_push": (_i, [_i, _vp, _i64, _vp, _i, _i, _i64, _i64, _i, _u, _vp]),
     "ts_exchange_wait_merge": (_i, [_i, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _u, _vp, _vp, _vp]),
+    "ts_exchange_wait_sum": (_i, [_i, _vp, _i, _i64, _i64, _i64, _i, _u, _vp, _vp]),
     "ts_index_save": (_i, [_vp, C.c_char_p]),
     "ts_index_load": (_i, [C.POINTER(_vp), _i, C.c_char_p]),
     "ts_index_append_file": (_i, [_vp, C.c_char_p, _i64, _i64, _vp]),

@@ -354,6 +354,18 @@ int ts_exchange_wait_merge(int device, const void* local_base_dev, int n_ranks, 
                                  k, flags, seq, out_scores, out_ids, (cudaStream_t)stream);
 }
 
+int ts_exchange_wait_sum(int device, const void* local_base_dev, int n_ranks, int64_t n_floats, int64_t slot_bytes,
+                         int64_t flags_offset, int parity, uint32_t seq, float* out_dev, void* stream) {
+  if (!local_base_dev || !out_dev || n_ranks < 1 || (parity != 0 && parity != 1) || (slot_bytes % 16) || n_floats * 4 > slot_bytes) {
+    set_error("ts_exchange_wait_sum: bad layout");
+    return TS_ERR_INVALID;
+  }
+  TS_CUDA_OK(cudaSetDevice(device));
+  const char* slots = (const char*)local_base_dev + (size_t)parity * n_ranks * slot_bytes;
+  const unsigned int* flags = (const unsigned int*)((const char*)local_base_dev + flags_offset) + (size_t)parity * n_ranks;
+  return launch_exchange_wait_sum(slots, slot_bytes, flags, n_ranks, seq, n_floats, out_dev, (cudaStream_t)stream);
+}
+
 int ts_index_get_rows(const ts_index* h, int64_t start, int64_t n, float* out_host) {
   if (!h || start < 0 || n < 0 || start + n > h->n || (n > 0 && !out_host)) { set_error("ts_index_get_rows: bad range"); return TS_ERR_INVALID; }
   if (n == 0) return TS_OK;

@@ -86,6 +86,31 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x == 0) st_release_sys(reinterpret_cast<unsigned int*>(base + flag_off), seq);
 }
 
+// Exchange, consumer side for the Stage-2 score matrices: wait until all n_ranks slots of this step are
+// published, then out[i] = sum over ranks of slot_r[i] (every candidate is owned by exactly one rank, the
+// others contribute 0.0 -- the sum is what an all-reduce(SUM) of the per-rank outputs would deliver).
+__global__ void __launch_bounds__(256)
+    exchange_wait_sum_kernel(const char* __restrict__ slots, long long slot_bytes, const unsigned int* __restrict__ flags,
+                             int n_ranks, unsigned int seq, long long n, float* __restrict__ out) {
+  if ((int)threadIdx.x < n_ranks) {
+    const unsigned int* f = flags + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) != seq) {
+      TS_SPIN_YIELD();
+      if (clock64() - t0 > kExchangeTimeoutCycles) {
+        printf("[tristage] exchange timeout: rank %d never published step %u\n", (int)threadIdx.x, seq);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < n_ranks; ++r) acc += *reinterpret_cast<const float*>(slots + (size_t)r * slot_bytes + (size_t)i * 4);
+    out[i] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
   TS_DYN_SMEM(uint64_t, sbuf);
   __shared__ int pre[kMaxLists + 1];
@@ -330,6 +355,16 @@ int launch_exchange_push(const void* blob, long long nbytes, const long long* pe
     return TS_ERR_INVALID;
   }
   TS_LAUNCH(exchange_push_kernel, n_ranks, 256, 0, st, (const uint4*)blob, (int)(nbytes / 16), peer_bases_dev, slot_off, flag_off, seq);
+  TS_CUDA_OK(cudaGetLastError());
+  return TS_OK;
+}
+
+int launch_exchange_wait_sum(const void* slots, long long slot_bytes, const unsigned int* flags, int n_ranks, unsigned int seq,
+                             long long n, float* out, cudaStream_t st) {
+  if (!slots || !flags || !out || n_ranks < 1 || n_ranks > 256 || n <= 0 || n * 4 > slot_bytes) { set_error("exchange_wait_sum: bad arguments"); return TS_ERR_INVALID; }
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  TS_LAUNCH(exchange_wait_sum_kernel, (unsigned)blocks, 256, 0, st, (const char*)slots, slot_bytes, flags, n_ranks, seq, n, out);
   TS_CUDA_OK(cudaGetLastError());
   return TS_OK;
 }

@@ -100,6 +100,8 @@ int launch_merge_pairs(const float* scores, const int64_t* ids, long long stride
 // peer-memory exchange (multi-GPU merge without a collective library call)
 int launch_exchange_push(const void* blob, long long nbytes, const long long* peer_bases_dev, int n_ranks, long long slot_off,
                          long long flag_off, unsigned int seq, cudaStream_t st);
+int launch_exchange_wait_sum(const void* slots, long long slot_bytes, const unsigned int* flags, int n_ranks, unsigned int seq,
+                             long long n, float* out, cudaStream_t st);
 int launch_merge_pairs_wait(const float* scores, const int64_t* ids, long long stride_scores, long long stride_ids, int L, int B,
                             int k, const unsigned int* wait_flags, unsigned int wait_seq, float* out_scores, int64_t* out_ids,
                             cudaStream_t st);

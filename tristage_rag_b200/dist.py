@@ -303,8 +303,57 @@ class ShardedTokStore:
             local.append_file(os.path.join(directory, fname), first, n)
         return cls(local, man["n_total"], group=group)
 
+    def _p2p_setup(self, n_floats: int, device: torch.device):
+        import torch.distributed._symmetric_memory as symm
+
+        slot = (n_floats * 4 + 15) // 16 * 16
+        flags_off = 2 * self.world * slot
+        total = (flags_off + 2 * self.world * 4 + 15) // 16 * 16
+        buf = symm.empty(total, dtype=torch.uint8, device=device)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+        bases = torch.tensor([int(x) for x in hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        torch.cuda.current_stream(device).synchronize()
+        hdl.barrier()
+        return {"key": n_floats, "buf": buf, "hdl": hdl, "bases": bases, "slot": slot, "flags_off": flags_off}
+
+    def _maxsim_p2p(self, out: torch.Tensor) -> torch.Tensor:
+        """Sum of the per-rank score matrices over peer memory: push + wait-sum kernels, no collective call."""
+        import ctypes as C
+
+        from . import _lib
+
+        n = out.numel()
+        st = getattr(self, "_p2p_state", None)
+        if st is None or st["key"] != n:
+            st = self._p2p_state = self._p2p_setup(n, out.device)
+            self._step = 0
+        dev = out.device.index
+        parity, seq = self._step & 1, (self._step % 0x7FFFFFFF) + 1
+        self._step += 1
+        stream = _lib._stream_ptr(dev)
+        if st["slot"] != n * 4:                       # the push copies whole 16-byte units: give it a padded source
+            src = torch.zeros(st["slot"] // 4, dtype=torch.float32, device=out.device)
+            src[:n] = out.reshape(-1)
+        else:
+            src = out.contiguous()
+        _lib.check(_lib.lib().ts_exchange_push(dev, C.c_void_p(src.data_ptr()), st["slot"], C.c_void_p(st["bases"].data_ptr()),
+                                               self.world, self.rank, st["slot"], st["flags_off"], parity, seq, stream))
+        res = torch.empty_like(out)
+        _lib.check(_lib.lib().ts_exchange_wait_sum(dev, C.c_void_p(st["buf"].data_ptr()), self.world, n, st["slot"],
+                                                   st["flags_off"], parity, seq, C.c_void_p(res.data_ptr()), stream))
+        return res
+
     def maxsim(self, q_tok: torch.Tensor, cand: torch.Tensor, **kw) -> torch.Tensor:
         out = self.local.maxsim(q_tok, cand, **kw)        # 0.0 for ids this shard does not own
         if self.world > 1:
+            if out.is_cuda and os.environ.get("TS_P2P", "0") not in ("", "0") and not getattr(self, "_p2p_off", False):
+                try:
+                    return self._maxsim_p2p(out)
+                except (ImportError, RuntimeError, AttributeError) as e:
+                    import logging
+
+                    logging.getLogger(__name__).warning(f"peer-memory exchange unavailable ({e}); using all-reduce")
+                    self._p2p_off = True
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
         return out
