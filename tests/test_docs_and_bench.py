@@ -90,3 +90,13 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["config"]["rows"] == 200000 and line["config"]["batch"] == 4
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present")
+def test_unmodified_reference_orchestrator_runs_over_the_drop_in_stages():
+    """INTEGRATION.md way A end to end: /root/reference/src/retrieval_pipeline.py, unmodified, with the two stage
+    modules aliased to this package, reproduces the output of the unmodified reference classes
+    (tools/dropin_check.py; the kernels run on the CPU emulator build here)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dropin_check.py"), "--emulate"], capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0 and "drop-in ok" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
