@@ -292,6 +292,52 @@ int ts_hybrid_fuse_host(int device, int method, int rrf_k, double w_dense, doubl
                         int top_k, int64_t* out_ids_host, double* out_scores_host, int32_t* out_n_host,
                         void* stream);
 
+/* ------------------------------------------- approximate mode (inverted lists) -- */
+/* faiss.IndexIVFFlat(IndexFlatIP(d), d, nlist, METRIC_INNER_PRODUCT), the index
+ * the reference builds when its first batch has more than 1000 rows
+ * (stage1_retriever.py:262-273), as a view over the rows of an existing
+ * ts_index: the corpus is NOT copied, the lists hold row numbers (SURVEY.md
+ * section 8f-4).  `base` must outlive the ts_ivf.  Scores are those of the
+ * exact scan restricted to the probed lists; nprobe == nlist gives the exact
+ * result.  Ties: score descending, then id ascending.                        */
+#define TS_IVF_MAX_NLIST 4096
+typedef struct ts_ivf ts_ivf;
+int ts_ivf_create(ts_ivf** out, ts_index* base, int nlist);
+int ts_ivf_destroy(ts_ivf* h);
+int ts_ivf_nlist(const ts_ivf* h);
+int ts_ivf_is_trained(const ts_ivf* h);
+/* rows of `base` that are in a list (ts_ivf_sync brings it up to ntotal)     */
+int64_t ts_ivf_nassigned(const ts_ivf* h);
+int64_t ts_ivf_launch_count(const ts_ivf* h);
+/* index.train(x) (:267): installs the coarse centroids [nlist, dim] fp32 (host).
+ * The k-means itself runs in the binding (tristage_rag_b200/ivf.py), as FAISS
+ * runs it on the host for the reference.  Drops all lists.                   */
+int ts_ivf_set_centroids(ts_ivf* h, const float* centroids_host, void* stream);
+int ts_ivf_get_centroids(const ts_ivf* h, float* out_host);
+/* index.add(x) (:270,313), list part: every row of `base` not yet in a list
+ * goes to the list of the centroid with the largest inner product (fp32, ties
+ * to the lowest list); the lists are rebuilt.  Called by ts_ivf_search when
+ * rows were added since the last call.  Synchronises `stream`.               */
+int ts_ivf_sync(ts_ivf* h, void* stream);
+/* install the list of every row directly (n == ntotal of base): lists saved
+ * by ts_ivf_get_assignments, or taken from an index file written by the
+ * reference (tristage_rag_b200/faiss_io.py)                                  */
+int ts_ivf_set_assignments(ts_ivf* h, const int32_t* assign_host, int64_t n, void* stream);
+int ts_ivf_get_assignments(const ts_ivf* h, int32_t* out_host, int64_t n);
+int ts_ivf_list_sizes(const ts_ivf* h, int64_t* out_host /* [nlist] */);
+/* quantizer.search(q, nprobe): the nprobe lists with the largest <q, centroid>
+ * (fp32 queries on the host), best first: out_lists [B, nprobe] int32,
+ * out_scores [B, nprobe] fp32.                                               */
+int ts_ivf_coarse_host(ts_ivf* h, const void* q_host, int B, int nprobe, unsigned flags,
+                       int32_t* out_lists_host, float* out_scores_host, void* stream);
+/* index.nprobe = nprobe; index.search(q, k)  (:273,380).  Arguments and
+ * results as ts_index_search; slots beyond the rows of the probed lists hold
+ * id -1 and the lowest float.  nprobe is clamped to 1..nlist.                */
+int ts_ivf_search(ts_ivf* h, const void* q_dev, int q_dtype, int B, int k, int nprobe, unsigned flags,
+                  float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+int ts_ivf_search_host(ts_ivf* h, const void* q_host, int q_dtype, int B, int k, int nprobe,
+                       unsigned flags, float* out_scores_host, int64_t* out_ids_host, void* stream);
+
 /* ------------------------------------------------------------ shard files -- */
 /* On-disk form of one shard, little endian, sections
  * 4096-byte aligned so the payload can be mmap'ed:

@@ -80,3 +80,36 @@ def cuda_device(request):
 
     assert _lib.lib().ts_device_count() >= 1, "libtristage sees no sm_100 device"
     return 0
+
+
+@pytest.fixture(scope="session")
+def sim_lib():
+    """The kernels' own sources compiled for the CPU emulator (tests/cudasim): test infrastructure, loaded
+    explicitly by the emulator tests and never by the package."""
+    import ctypes as C
+    import subprocess
+
+    from tristage_rag_b200 import _lib
+
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    out = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cudasim"), "-j", "8"], env=env,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0, out.stdout[-4000:]
+    L = C.CDLL(os.path.join(ROOT, "build", "cudasim", "libtristage_cudasim.so"))
+    assert L.hostsim_is_simulation() == 2
+    for name, (res, args) in _lib.SYMBOLS.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    for name in ("cudasim_launches", "cudasim_blocks", "cudasim_switches"):
+        getattr(L, name).restype = C.c_ulonglong
+    return L
+
+
+@pytest.fixture()
+def sim(sim_lib, monkeypatch):
+    from tristage_rag_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", sim_lib)
+    monkeypatch.setattr(_lib, "_stream_ptr", lambda device: None)
+    return sim_lib

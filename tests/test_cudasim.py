@@ -22,30 +22,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REL = 1e-3
 
 
-@pytest.fixture(scope="module")
-def sim_lib():
-    env = dict(os.environ)
-    env.pop("CXX", None)
-    out = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cudasim"), "-j", "8"], env=env,
-                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    assert out.returncode == 0, out.stdout[-4000:]
-    L = C.CDLL(os.path.join(ROOT, "build", "cudasim", "libtristage_cudasim.so"))
-    assert L.hostsim_is_simulation() == 2
-    for name, (res, args) in _lib.SYMBOLS.items():
-        fn = getattr(L, name)
-        fn.restype, fn.argtypes = res, args
-    for name in ("cudasim_launches", "cudasim_blocks", "cudasim_switches"):
-        getattr(L, name).restype = C.c_ulonglong
-    return L
-
-
-@pytest.fixture()
-def sim(sim_lib, monkeypatch):
-    monkeypatch.setattr(_lib, "_lib", sim_lib)
-    monkeypatch.setattr(_lib, "_stream_ptr", lambda device: None)
-    return sim_lib
-
-
 def make(N, d, B, seed=0, planted=0):
     rng = np.random.default_rng(seed)
     X = flat_ip.normalize_rows(rng.standard_normal((N, d)).astype(np.float32)).astype(np.float32)

@@ -105,6 +105,21 @@ SYMBOLS = {
     "ts_bm25_search_host": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "ts_hybrid_fuse_host": (_i, [_i, _i, _i, C.c_double, C.c_double, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i,
                                  _vp, _vp, _vp, _vp]),
+    "ts_ivf_create": (_i, [C.POINTER(_vp), _vp, _i]),
+    "ts_ivf_destroy": (_i, [_vp]),
+    "ts_ivf_nlist": (_i, [_vp]),
+    "ts_ivf_is_trained": (_i, [_vp]),
+    "ts_ivf_nassigned": (_i64, [_vp]),
+    "ts_ivf_launch_count": (_i64, [_vp]),
+    "ts_ivf_set_centroids": (_i, [_vp, _vp, _vp]),
+    "ts_ivf_get_centroids": (_i, [_vp, _vp]),
+    "ts_ivf_sync": (_i, [_vp, _vp]),
+    "ts_ivf_set_assignments": (_i, [_vp, _vp, _i64, _vp]),
+    "ts_ivf_get_assignments": (_i, [_vp, _vp, _i64]),
+    "ts_ivf_list_sizes": (_i, [_vp, _vp]),
+    "ts_ivf_coarse_host": (_i, [_vp, _vp, _i, _i, _u, _vp, _vp, _vp]),
+    "ts_ivf_search": (_i, [_vp, _vp, _i, _i, _i, _i, _u, _vp, _vp, _vp]),
+    "ts_ivf_search_host": (_i, [_vp, _vp, _i, _i, _i, _i, _u, _vp, _vp, _vp]),
     "ts_file_probe": (_i, [C.c_char_p, C.POINTER(FileInfo)]),
     "ts_file_verify": (_i, [C.c_char_p]),
     "ts_file_write_index_host": (_i, [C.c_char_p, _i, _i, _i, _i64, _i64, _vp, _vp]),
@@ -339,6 +354,124 @@ class Index:
         obj.dtype, obj.metric = int(lib().ts_index_dtype(h)), int(lib().ts_index_metric(h))
         obj._lock = threading.RLock()
         return obj
+
+
+class IVF:
+    """Inverted lists over the rows of an ``Index`` (``ts_ivf``): the approximate mode that stands in for the
+    reference's ``faiss.IndexIVFFlat`` branch (``/root/reference/src/stage1_retriever.py:262-273``).  The
+    corpus is not copied; the lists hold row numbers.  Training (k-means) is ``tristage_rag_b200/ivf.py``."""
+
+    def __init__(self, base: Index, nlist: int):
+        self.base, self.nlist, self.device = base, int(nlist), base.device     # keeps `base` alive
+        self._lock = base._lock            # the two handles share rows and are used one call at a time
+        h = C.c_void_p()
+        check(lib().ts_ivf_create(C.byref(h), base._h, self.nlist))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and _lib is not None:
+            _lib.ts_ivf_destroy(h)
+
+    @property
+    def is_trained(self) -> bool:
+        return bool(lib().ts_ivf_is_trained(self._h))
+
+    @property
+    def nassigned(self) -> int:
+        return int(lib().ts_ivf_nassigned(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(lib().ts_ivf_launch_count(self._h))
+
+    @_locked
+    def set_centroids(self, centroids) -> None:
+        import numpy as np
+
+        c = np.ascontiguousarray(centroids, np.float32)
+        assert c.shape == (self.nlist, self.base.dim), (c.shape, self.nlist, self.base.dim)
+        check(lib().ts_ivf_set_centroids(self._h, C.c_void_p(c.ctypes.data), _stream_ptr(self.device)))
+
+    @_locked
+    def centroids(self):
+        import numpy as np
+
+        out = np.empty((self.nlist, self.base.dim), np.float32)
+        check(lib().ts_ivf_get_centroids(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    @_locked
+    def sync(self) -> None:
+        """Put every row added to the base index since the last call into its list."""
+        check(lib().ts_ivf_sync(self._h, _stream_ptr(self.device)))
+
+    @_locked
+    def set_assignments(self, assign) -> None:
+        import numpy as np
+
+        a = np.ascontiguousarray(assign, np.int32)
+        check(lib().ts_ivf_set_assignments(self._h, C.c_void_p(a.ctypes.data) if a.size else None, a.size,
+                                           _stream_ptr(self.device)))
+
+    @_locked
+    def assignments(self):
+        import numpy as np
+
+        out = np.empty(self.nassigned, np.int32)
+        check(lib().ts_ivf_get_assignments(self._h, C.c_void_p(out.ctypes.data) if out.size else None, out.size))
+        return out
+
+    def list_sizes(self):
+        import numpy as np
+
+        out = np.empty(self.nlist, np.int64)
+        check(lib().ts_ivf_list_sizes(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    @_locked
+    def coarse_host(self, q, nprobe: int, normalize_q: bool = False):
+        """quantizer.search(q, nprobe): ([B, nprobe] int32 lists, [B, nprobe] fp32 scores), best first."""
+        import numpy as np
+
+        q = np.ascontiguousarray(q, np.float32)
+        assert q.ndim == 2 and q.shape[1] == self.base.dim, (q.shape, self.base.dim)
+        B = q.shape[0]
+        lists, scores = np.empty((B, nprobe), np.int32), np.empty((B, nprobe), np.float32)
+        check(lib().ts_ivf_coarse_host(self._h, C.c_void_p(q.ctypes.data), B, int(nprobe),
+                                       TS_FLAG_NORMALIZE_Q if normalize_q else 0, C.c_void_p(lists.ctypes.data),
+                                       C.c_void_p(scores.ctypes.data), _stream_ptr(self.device)))
+        return lists, scores
+
+    @_locked
+    def search(self, q, k: int, nprobe: int, normalize_q: bool = False):
+        """q: cuda tensor [B, dim] -> (scores [B,k] f32, ids [B,k] i64) on the device, asynchronous."""
+        import torch
+
+        assert q.is_cuda and q.dim() == 2 and q.shape[1] == self.base.dim, (q.shape, self.base.dim)
+        q = q.contiguous()
+        B = q.shape[0]
+        dev = torch.device("cuda", self.device)
+        scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+        ids = torch.empty((B, k), dtype=torch.int64, device=dev)
+        check(lib().ts_ivf_search(self._h, C.c_void_p(q.data_ptr()), _code_of_torch(q.dtype), B, int(k), int(nprobe),
+                                  TS_FLAG_NORMALIZE_Q if normalize_q else 0, C.c_void_p(scores.data_ptr()),
+                                  C.c_void_p(ids.data_ptr()), _stream_ptr(self.device)))
+        return scores, ids
+
+    @_locked
+    def search_host(self, q, k: int, nprobe: int, normalize_q: bool = False):
+        """numpy in / numpy out -- the faiss call shape (``index.nprobe = nprobe; index.search(q, k)``)."""
+        import numpy as np
+
+        q = np.ascontiguousarray(q, np.float32)
+        assert q.ndim == 2 and q.shape[1] == self.base.dim, (q.shape, self.base.dim)
+        B = q.shape[0]
+        D, I = np.empty((B, k), np.float32), np.empty((B, k), np.int64)
+        check(lib().ts_ivf_search_host(self._h, C.c_void_p(q.ctypes.data), TS_F32, B, int(k), int(nprobe),
+                                       TS_FLAG_NORMALIZE_Q if normalize_q else 0, C.c_void_p(D.ctypes.data),
+                                       C.c_void_p(I.ctypes.data), _stream_ptr(self.device)))
+        return D, I
 
 
 def file_probe(path: str) -> dict:

@@ -10,10 +10,12 @@ reference class that ``src/retrieval_pipeline.py:244-256,316,358`` and
   corpus resident in HBM as bf16 (``storage_dtype``), fp32 accumulate, exact
   top-k fused into the scan.  No CPU fallback: without the library or a B200
   the constructor's first device call raises.
-* search is ALWAYS exact.  The reference silently switches to an approximate
+* search is exact by default.  The reference silently switches to an approximate
   ``IndexIVFFlat(nlist=100, nprobe=10)`` when the first batch has more than
-  1000 rows (:262-273); BASELINE.json pins exact search, so that switch is not
-  reproduced (``get_stats()['faiss_index_type']`` is always ``IndexFlatIP``).
+  1000 rows (:262-273); BASELINE.json pins exact search, so that switch is
+  opt-in here: ``Stage1Config.approximate=True`` reproduces the reference's rule
+  with inverted lists over the same resident rows (``IndexIVFFlat`` below,
+  ``csrc/ivf.cu``); ``get_stats()['faiss_index_type']`` names the index in use.
 * the encoder (SentenceTransformer, :137-254) stays the reference's PyTorch
   model and is outside the hot path; pass ``model=`` to inject one (tests use
   ``oracle/fakes.py``), otherwise it is loaded like the reference does.
@@ -67,6 +69,7 @@ class Stage1Config:
     storage_dtype: str = "bf16"   # HBM corpus dtype: bf16 | fp16 | fp32
     gpu_index: int = 0
     hybrid_on_device: bool = False   # search_batch: BM25 search + RRF/weighted fusion as GPU kernels (ts_bm25_*)
+    approximate: bool = False        # the reference's index rule: IVF (nlist, nprobe) when the first batch has > 1000 rows
 
 
 class BM25Index:
@@ -234,6 +237,8 @@ class IndexFlatIP:
 
     def save(self, path: str) -> None:
         self._index.save(path)
+        if os.path.exists(path + ".ivf.npz"):      # lists of an earlier approximate index at the same place
+            os.remove(path + ".ivf.npz")
 
     @classmethod
     def load(cls, path: str, storage_dtype: str = "bf16", device: int = 0) -> "IndexFlatIP":
@@ -241,6 +246,69 @@ class IndexFlatIP:
         obj._index = _lib.Index.load(path, device)
         obj.d, obj.storage_dtype, obj.device, obj.is_trained = obj._index.dim, storage_dtype, device, True
         return obj
+
+
+class IndexIVFFlat:
+    """The ``faiss.IndexIVFFlat`` surface the reference touches (``train``, ``add``, ``nprobe``, ``search``,
+    ``ntotal``; reference :263-273,313,380), backed by one ``ts_index`` shard plus inverted lists of row numbers
+    over it (``ts_ivf``).  The rows are stored once; ``exact_search`` scans all of them."""
+
+    def __init__(self, d: int, nlist: int, storage_dtype: str = "bf16", device: int = 0, nprobe: int = 1):
+        self.d, self.nlist, self.nprobe = int(d), int(nlist), int(nprobe)      # faiss default nprobe = 1
+        self.storage_dtype, self.device = storage_dtype, device
+        self._index = _lib.Index(self.d, storage_dtype, "ip", device)
+        self._ivf = _lib.IVF(self._index, self.nlist)
+
+    @property
+    def is_trained(self) -> bool:
+        return self._ivf.is_trained
+
+    @property
+    def ntotal(self) -> int:
+        return self._index.ntotal
+
+    def train(self, x: np.ndarray) -> None:
+        from .ivf import train_centroids
+
+        self._ivf.set_centroids(train_centroids(np.ascontiguousarray(x, dtype=np.float32), self.nlist))
+
+    def add(self, x: np.ndarray) -> None:
+        if not self.is_trained:
+            raise RuntimeError("IndexIVFFlat.add before train")      # faiss asserts is_trained
+        self._index.add(np.ascontiguousarray(x, dtype=np.float32), normalize=False)
+        self._ivf.sync()
+
+    def search(self, q: np.ndarray, k: int, path: str = "auto"):
+        if k > _lib.TS_MAX_K:
+            raise ValueError(f"top_k={k} exceeds the fused top-k limit {_lib.TS_MAX_K}")
+        return self._ivf.search_host(q, k, self.nprobe, normalize_q=False)
+
+    def exact_search(self, q: np.ndarray, k: int, path: str = "auto"):
+        return self._index.search_host(q, k, normalize_q=False, path=path)
+
+    def save(self, path: str) -> None:
+        self._index.save(path)
+        tmp = path + ".ivf.tmp.npz"
+        np.savez(tmp, centroids=self._ivf.centroids(), assign=self._ivf.assignments(),
+                 nlist=np.int64(self.nlist), nprobe=np.int64(self.nprobe))
+        os.replace(tmp, path + ".ivf.npz")
+
+    @classmethod
+    def from_parts(cls, index: "_lib.Index", centroids: np.ndarray, assign: np.ndarray, nprobe: int,
+                   storage_dtype: str, device: int) -> "IndexIVFFlat":
+        obj = cls.__new__(cls)
+        obj.d, obj.nlist, obj.nprobe = index.dim, int(centroids.shape[0]), int(nprobe)
+        obj.storage_dtype, obj.device, obj._index = storage_dtype, device, index
+        obj._ivf = _lib.IVF(index, obj.nlist)
+        obj._ivf.set_centroids(centroids)
+        obj._ivf.set_assignments(assign)
+        return obj
+
+    @classmethod
+    def load(cls, path: str, storage_dtype: str = "bf16", device: int = 0) -> "IndexIVFFlat":
+        with np.load(path + ".ivf.npz") as z:
+            return cls.from_parts(_lib.Index.load(path, device), z["centroids"], z["assign"], int(z["nprobe"]),
+                                  storage_dtype, device)
 
 
 class Stage1Retriever:
@@ -292,6 +360,17 @@ class Stage1Retriever:
         return embeddings / (norms + 1e-8)
 
     def _create_faiss_index(self, embeddings: np.ndarray):
+        from .ivf import MIN_ROWS_FOR_IVF
+
+        if self.config.approximate and len(embeddings) > MIN_ROWS_FOR_IVF:
+            # the reference's rule (:262-273): IVF trained on the first batch, nprobe from the config
+            self.faiss_index = IndexIVFFlat(embeddings.shape[1], self.config.nlist, self.config.storage_dtype,
+                                            self.config.gpu_index)
+            self.faiss_index.train(embeddings)
+            self.faiss_index.add(embeddings)
+            self.faiss_index.nprobe = self.config.nprobe
+            self.logger.info(f"GPU IVF index created with {len(embeddings)} vectors")
+            return
         self.faiss_index = IndexFlatIP(embeddings.shape[1], self.config.storage_dtype, self.config.gpu_index)
         self.faiss_index.add(embeddings)
         self.logger.info(f"GPU flat index created with {len(embeddings)} vectors")
@@ -463,7 +542,24 @@ class Stage1Retriever:
             with open(faiss_path, "rb") as f:
                 magic = f.read(8)
             if magic == b"TSSHARD2":
-                self.faiss_index = IndexFlatIP.load(faiss_path, self.config.storage_dtype, self.config.gpu_index)
+                kind = IndexIVFFlat if os.path.exists(faiss_path + ".ivf.npz") else IndexFlatIP
+                self.faiss_index = kind.load(faiss_path, self.config.storage_dtype, self.config.gpu_index)
+            elif magic[:4] == b"IwFl":
+                # the reference's approximate index (:264): import vectors, centroids and lists.  With
+                # approximate=False only the vectors are kept and every search is exact.
+                from .faiss_io import read_faiss_ivf
+
+                parts = read_faiss_ivf(faiss_path)
+                self.faiss_index = None
+                if self.config.approximate:
+                    base = _lib.Index(parts["vectors"].shape[1], self.config.storage_dtype, "ip", self.config.gpu_index)
+                    base.add(parts["vectors"], normalize=False)
+                    self.faiss_index = IndexIVFFlat.from_parts(base, parts["centroids"], parts["assign"], parts["nprobe"],
+                                                               self.config.storage_dtype, self.config.gpu_index)
+                else:
+                    self.faiss_index = IndexFlatIP(parts["vectors"].shape[1], self.config.storage_dtype,
+                                                   self.config.gpu_index)
+                    self.faiss_index.add(parts["vectors"])
             else:
                 # a file the reference itself wrote with faiss.write_index (:436): import the vectors
                 from .faiss_io import read_faiss_flat
