@@ -45,6 +45,17 @@ def test_integration_md_binding_stub_runs_against_the_abi(monkeypatch):
     assert not flat_ip.check_topk(D, I, lambda b, ids: Xr[ids].astype(np.float64) @ Qr[b].astype(np.float64), rD, rI)
     with pytest.raises(RuntimeError):
         idx.search(Q, 10_000)                             # k beyond TS_MAX_K
+    # the IVF half of the stub, driven the way the reference's _create_faiss_index does (:263-273)
+    ivf = mod.IndexIVFFlat(mod.IndexFlatIP(48), 48, 6, mod.METRIC_INNER_PRODUCT)
+    ivf.train(X)
+    ivf.add(X)
+    ivf.nprobe = 6                                        # every list probed: the exact result
+    D2, I2 = ivf.search(Q, 10)
+    assert ivf.is_trained and ivf.ntotal == 700
+    assert not flat_ip.check_topk(D2, I2, lambda b, ids: Xr[ids].astype(np.float64) @ Qr[b].astype(np.float64), rD, rI)
+    ivf.nprobe = 2
+    D3, I3 = ivf.search(Q, 10)
+    assert (D3[:, 0] <= D2[:, 0] + 1e-6).all() and (I3 >= -1).all()
 
 
 def test_bench_contract_helpers():

@@ -35,7 +35,7 @@ def sim(sim_built, monkeypatch):
     L = C.CDLL(os.path.join(sim_built, "libtristage_hostsim.so"))
     assert L.hostsim_is_simulation() == 1
     for name, (res, args) in _lib.SYMBOLS.items():
-        if name.startswith(("ts_bm25_", "ts_hybrid_")):
+        if name.startswith(("ts_bm25_", "ts_hybrid_", "ts_ivf_")):
             continue                 # kernels + their host code live in one file: covered by tests/cudasim instead
         fn = getattr(L, name)
         fn.restype, fn.argtypes = res, args

@@ -10,6 +10,7 @@ run s2 tests/test_gpu_stage2.py
 run zfull tests/test_gpu_z_fullsize.py
 run zhybrid tests/test_gpu_z_hybrid.py
 run zshards tests/test_gpu_z_shards.py
+run zzivf tests/test_gpu_zz_ivf.py
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$? $(tail -1 gpurun_out/smoke.log)"
 timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; tail -c 600 gpurun_out/bench_n1.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"

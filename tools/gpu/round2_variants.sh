@@ -42,3 +42,13 @@ import json
 for l in open('gpurun_out/pair_probe.jsonl'):
     r=json.loads(l); print(f"{r['tag']:8s} B={r['B']:5d} scan={r['scan_ms_per_launch']:.3f} ms  {r['TFLOPs']:.0f} TFLOP/s  ({r['tensor_frac_sustained']:.2f} of sustained)")
 PY
+# approximate mode (inverted lists over the resident rows): list scan vs the exact scan of the same shard
+timeout 600 python tools/ivf_probe.py --rows 10000000 --dim 1024 --batches 1,8,32 --tag ivf_10M > gpurun_out/ivf_probe.jsonl 2> gpurun_out/ivf_probe.err
+timeout 300 python tools/ivf_probe.py --rows 1000000 --dim 768 --batches 1,32 --tag ivf_1M >> gpurun_out/ivf_probe.jsonl 2>> gpurun_out/ivf_probe.err
+python - <<'PY'
+import json
+for l in open('gpurun_out/ivf_probe.jsonl'):
+    r=json.loads(l)
+    if r['what'] in ('ivf','exact'): print(f"{r['tag']:8s} {r['what']:6s} B={r['B']:3d} step={r['step_ms']:.3f} ms scan={r['scan_ms']:.3f} ms {r['GBps']:.0f} GB/s ({r['hbm_frac']:.2f})")
+    else: print(r)
+PY
