@@ -41,6 +41,32 @@ def main():
         ref = [torch.empty_like(i) for _ in range(world)]
         dist.all_gather(ref, i)
         assert all((r == ref[0]).all() for r in ref)
+    # approximate mode: the same centroids on every rank, lists over the local rows -> the merged result is what
+    # one GPU holding all rows returns for the same probes (oracle/ivf.py on the full data)
+    from oracle import ivf as oivf
+    from tristage_rag_b200.dist import IVFShard
+    from tristage_rag_b200.ivf import train_centroids
+
+    nlist, nprobe = 50, 5
+    cent = train_centroids(X[:20000], nlist)
+    iv = _lib.IVF(idx, nlist)
+    iv.set_centroids(cent)
+    iv.sync()
+    shi = ShardedIndex(IVFShard(iv, nprobe), N)
+    parts = [None] * world                       # the lists the kernels built (near-tied rows may differ from fp64)
+    dist.all_gather_object(parts, iv.assignments())
+    assign = np.concatenate(parts)
+    assert assign.shape == (N,) and (assign != oivf.assign_lists(Xr, cent)).mean() < 1e-3
+    Q = flat_ip.normalize_rows(X[rng.integers(0, N, size=16)] + 0.05 * rng.standard_normal((16, d)).astype(np.float32))
+    Q = Q.astype(np.float32)
+    Qr = flat_ip.round_to(Q, "bf16")
+    s, i = shi.search(torch.from_numpy(Q).to(dev), k)
+    torch.cuda.synchronize()
+    lists, _ = iv.coarse_host(Q, nprobe)
+    rD, rI = oivf.ivf_search(Xr, Qr, assign, lists, k)
+    bad = flat_ip.check_topk(s.cpu().numpy(), i.cpu().numpy(),
+                             lambda b, ids: Xr[ids].astype(np.float64) @ Qr[b].astype(np.float64), rD, rI)
+    assert not bad, (rank, "ivf", bad[:3])
     # Stage 2
     ndocs, dim = 3000, 128
     lens = rng.integers(16, 181, size=ndocs)

@@ -460,6 +460,19 @@ class IVF:
         return scores, ids
 
     @_locked
+    def search_packed(self, q, k: int, nprobe: int, blob, normalize_q: bool = False):
+        """Like search(), but scores and ids land in one uint8 cuda buffer (packed_layout): the shape the
+        multi-GPU all-gather / peer-memory exchange moves (dist.ShardedIndex over dist.IVFShard)."""
+        q = q.contiguous()
+        B = q.shape[0]
+        ids_off, nbytes = packed_layout(B, k)
+        assert blob.is_cuda and blob.numel() >= nbytes and blob.data_ptr() % 8 == 0
+        check(lib().ts_ivf_search(self._h, C.c_void_p(q.data_ptr()), _code_of_torch(q.dtype), B, int(k), int(nprobe),
+                                  TS_FLAG_NORMALIZE_Q if normalize_q else 0, C.c_void_p(blob.data_ptr()),
+                                  C.c_void_p(blob.data_ptr() + ids_off), _stream_ptr(self.device)))
+        return blob
+
+    @_locked
     def search_host(self, q, k: int, nprobe: int, normalize_q: bool = False):
         """numpy in / numpy out -- the faiss call shape (``index.nprobe = nprobe; index.search(q, k)``)."""
         import numpy as np

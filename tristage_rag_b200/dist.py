@@ -125,6 +125,28 @@ def gather_topk(scores: torch.Tensor, ids: torch.Tensor, group=None) -> Tuple[to
     return all_s.view(world, B, k), all_i.view(world, B, k)
 
 
+class IVFShard:
+    """Local index of a ``ShardedIndex`` in the approximate mode: this rank's rows behind inverted lists
+    (``_lib.IVF``) with the SAME centroids on every rank.  A global list is then the union of the ranks' local
+    lists, every rank probes the same ``nprobe`` lists, and the merged result equals what one GPU holding all
+    rows returns -- the exchange step is unchanged (all-gather or peer-memory push of the [B, k] lists)."""
+
+    def __init__(self, ivf, nprobe: int):
+        self.ivf, self.nprobe = ivf, int(nprobe)
+
+    def set_id_base(self, base: int) -> None:
+        self.ivf.base.set_id_base(base)
+
+    def search(self, q, k: int, **kw):
+        return self.ivf.search(q, k, self.nprobe, **kw)
+
+    def search_packed(self, q, k: int, blob, **kw):
+        return self.ivf.search_packed(q, k, self.nprobe, blob, **kw)
+
+    def save(self, path: str) -> None:
+        self.ivf.base.save(path)
+
+
 class ShardedIndex:
     """Stage-1 index whose rows are split across the ranks of a process group."""
 
