@@ -63,7 +63,9 @@ typedef enum ts_metric { TS_METRIC_IP = 0, TS_METRIC_COSINE = 1 } ts_metric;
 typedef enum ts_path {
   TS_PATH_AUTO = 0,   /* umma for bf16/fp16 storage (faster at every B on B200), stream for fp32 */
   TS_PATH_STREAM = 1, /* CUDA-core 128-bit streaming scan (bandwidth path)   */
-  TS_PATH_UMMA = 2    /* TMA -> smem -> tcgen05.mma -> TMEM (tensor path)    */
+  TS_PATH_UMMA = 2    /* TMA -> smem -> tcgen05.mma -> TMEM (tensor path); on fp32
+                         storage the operands are read as tf32 (10-bit mantissa,
+                         fp32 accumulate)                                     */
 } ts_path;
 
 /* search / maxsim flags */
@@ -93,7 +95,8 @@ int ts_device_count(void);
 /* ---------------------------------------------------------------- Stage 1 -- */
 
 /* faiss.IndexFlatIP(d)   (stage1_retriever.py:263,276).
- * storage: TS_BF16 / TS_F16 (both scan kernels) or TS_F32 (stream kernel only).
+ * storage: TS_BF16 / TS_F16 / TS_F32 (both scan kernels; fp32 rows are read
+ * as tf32 on the tensor path).
  * reserve_rows: rows to pre-allocate (grows by doubling beyond that).        */
 int ts_index_create(ts_index** out, int device, int dim, int storage_dtype, int metric,
                     int64_t reserve_rows);

@@ -123,6 +123,11 @@ def round_to(x: np.ndarray, dtype: str) -> np.ndarray:
         return t.to(torch.float16).to(torch.float32).numpy()
     if dtype in ("fp32", "f32", "float32"):
         return t.numpy().copy()
+    if dtype == "tf32":
+        # what the tensor path sees of fp32 storage (kind::tf32): 10 mantissa bits, round to nearest even
+        u = t.numpy().view(np.uint32).astype(np.uint64)
+        r = ((u + 0xFFF + ((u >> 13) & 1)) & 0xFFFFE000).astype(np.uint32)
+        return r.view(np.float32).copy()
     raise ValueError(dtype)
 
 

@@ -91,11 +91,18 @@ inline void prefetch_tmap(const CUtensorMap*) {}
 inline int sim_make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, int dim, int ld, int box_cols, int box_rows) {
   memset(out, 0, sizeof(*out));
   out->base = base; out->rows = rows; out->dim = dim; out->ld = ld; out->box_cols = box_cols; out->box_rows = box_rows; out->dtype = dtype;
-  if (box_cols * 2 != 128 || box_rows < 1 || box_rows > 256 || (reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16) {
+  const int esz = (dtype == 0 /* TS_F32, mapped as TFLOAT32 */) ? 4 : 2;
+  if (box_cols * esz != 128 || box_rows < 1 || box_rows > 256 || (reinterpret_cast<uintptr_t>(base) & 15) || (ld * esz) % 16) {
     fprintf(stderr, "[cudasim] tensor map violates the SWIZZLE_128B / alignment rules\n");
     abort();
   }
   return 0;
+}
+
+// fp32 -> tf32 as a TFLOAT32 tensor map delivers it: round to nearest (even) on the 13 dropped mantissa bits
+inline uint32_t sim_round_tf32(uint32_t u) {
+  if ((u & 0x7F800000u) == 0x7F800000u) return u;      // inf / nan
+  return (u + 0xFFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;
 }
 
 inline void tma_load_2d(void* smem_dst, const CUtensorMap* mp, uint64_t* bar, int c0, int c1, uint64_t) {
@@ -105,6 +112,20 @@ inline void tma_load_2d(void* smem_dst, const CUtensorMap* mp, uint64_t* bar, in
   cudasim::defer_tma([=]() {
   const CUtensorMap* m = &map;
   unsigned char* sm = cudasim::smem_base();
+  if (m->dtype == 0) {                                  // fp32 rows through a TFLOAT32 map: 32 elements per 128-byte row
+    const uint32_t* g32 = static_cast<const uint32_t*>(m->base);
+    for (int r = 0; r < m->box_rows; ++r) {
+      const int64_t row = (int64_t)c1 + r;
+      for (int c = 0; c < m->box_cols; ++c) {
+        const int col = c0 + c;
+        uint32_t v = 0;
+        if (row >= 0 && row < m->rows && col >= 0 && col < m->dim) v = sim_round_tf32(g32[row * m->ld + col]);
+        memcpy(sm + sw128(dst + (uint32_t)r * 128u + (uint32_t)c * 4u), &v, 4);
+      }
+    }
+    cudasim::mbar_complete_tx(bar_addr, (uint32_t)m->box_rows * 128u);
+    return;
+  }
   const uint16_t* g = static_cast<const uint16_t*>(m->base);
   for (int r = 0; r < m->box_rows; ++r) {
     const int64_t row = (int64_t)c1 + r;
@@ -160,6 +181,39 @@ inline void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_
     for (int m = 0; m < 128; ++m) {
       float acc = 0.f;
       for (int k = 0; k < 16; ++k) acc += a[m][k] * b[k];
+      uint32_t* cell = T + (size_t)m * 512 + col0 + (uint32_t)n;
+      float prev;
+      memcpy(&prev, cell, 4);
+      const float out = accumulate ? prev + acc : acc;
+      memcpy(cell, &out, 4);
+    }
+  }
+  });
+}
+// kind::tf32: 8 fp32 elements (32 bytes) of K per instruction; the tensor core ignores the 13 low mantissa bits
+inline void umma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
+  if (M != 128 || N < 8 || N > 256 || (N & 15) || ((idesc >> 4) & 3) != 1 || ((idesc >> 7) & 7) != 2 || ((idesc >> 10) & 7) != 2) {
+    fprintf(stderr, "[cudasim] unsupported tf32 instruction descriptor %08x (M %d N %d)\n", idesc, M, N); abort();
+  }
+  for (uint64_t d : {adesc, bdesc})
+    if ((d >> 61) != 2 || ((d >> 46) & 3) != 1) { fprintf(stderr, "[cudasim] shared-memory descriptor is not K-major SWIZZLE_128B\n"); abort(); }
+  const uint32_t a0 = (uint32_t)(adesc & 0x3FFF) << 4, b0 = (uint32_t)(bdesc & 0x3FFF) << 4;
+  const uint32_t a_sbo = (uint32_t)((adesc >> 32) & 0x3FFF) << 4, b_sbo = (uint32_t)((bdesc >> 32) & 0x3FFF) << 4;
+  const uint32_t col0 = tmem_d & 0xFFFFu, lane0 = tmem_d >> 16;
+  if (lane0 != 0 || col0 + (uint32_t)N > 512) { fprintf(stderr, "[cudasim] accumulator outside TMEM\n"); abort(); }
+  cudasim::defer_mma([=]() {
+  uint32_t* T = cudasim::tmem();
+  auto elem = [](uint32_t addr) { uint32_t u; memcpy(&u, cudasim::smem_base() + addr, 4); u &= 0xFFFFE000u; float f; memcpy(&f, &u, 4); return f; };
+  float a[128][8];
+  for (int m = 0; m < 128; ++m)
+    for (int k = 0; k < 8; ++k) a[m][k] = elem(sw128(a0 + (uint32_t)(m >> 3) * a_sbo + (uint32_t)(m & 7) * 128u + (uint32_t)k * 4u));
+  for (int n = 0; n < N; ++n) {
+    float b[8];
+    for (int k = 0; k < 8; ++k) b[k] = elem(sw128(b0 + (uint32_t)(n >> 3) * b_sbo + (uint32_t)(n & 7) * 128u + (uint32_t)k * 4u));
+    for (int m = 0; m < 128; ++m) {
+      float acc = 0.f;
+      for (int k = 0; k < 8; ++k) acc += a[m][k] * b[k];
       uint32_t* cell = T + (size_t)m * 512 + col0 + (uint32_t)n;
       float prev;
       memcpy(&prev, cell, 4);
@@ -275,6 +329,9 @@ constexpr uint64_t kDescKStep = 2;
 constexpr uint32_t make_idesc_f16(int M, int N, bool bf16) {
   return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
+}
+constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -171,6 +171,41 @@ def test_tensor_scan_matches_the_oracle(sim, N, d, B, k, dtype):
     assert (Ia == I).all() and (Da == D).all()
 
 
+@pytest.mark.parametrize("N,d,B,k", [(5, 768, 1, 50), (3000, 100, 17, 7), (1500, 768, 65, 100), (2500, 36, 130, 20),
+                                     (5000, 64, 8, 500)])
+def test_tensor_scan_over_fp32_storage_reads_tf32(sim, monkeypatch, N, d, B, k):
+    """fp32 storage on the tensor path (kind::tf32, TFLOAT32 tensor maps, 32-element K chunks): scores are those of
+    the tf32-rounded operands with fp32 accumulation; ids / scores within the Stage-1 tolerance of the fp32 oracle
+    as well.  TS_PATH_AUTO keeps the CUDA-core scan for fp32 storage unless TS_TF32=1 and B > 4."""
+    X, Q = make(N, d, B, seed=N + B, planted=10 if N > 10 * B else 0)
+    idx = _lib.Index(d, "fp32", "ip", 0)
+    for part in np.array_split(X, 2):
+        idx.add(part)
+    D, I = idx.search_host(Q, k, path="umma")
+    rD, rI, sc = oracle_search(X, Q, k, "tf32")
+    assert not flat_ip.check_topk(D, I, sc, rD, rI, rel=REL)           # against the tf32-rounded operands
+    # against the fp32 reference (what FAISS computes): tf32 operands cost ~1e-5 ABSOLUTE on unit vectors, so the
+    # relative rule only makes sense for scores well above that; ids may differ only inside that absolute band
+    fD, fI, fsc = oracle_search(X, Q, k, "fp32")
+    for b in range(B):
+        ok = I[b] >= 0
+        assert (ok == (fI[b] >= 0)).all()
+        ref = fsc(b, I[b][ok])
+        assert (np.abs(D[b][ok] - ref) <= REL * np.maximum(np.abs(ref), 0.05)).all()
+        extra = np.setdiff1d(I[b][ok], fI[b][ok])
+        if extra.size:
+            kth = float(fD[b][ok].min())
+            assert (fsc(b, extra) >= kth - 2 * REL * max(abs(kth), 0.05)).all()
+    sD, sI = idx.search_host(Q, k)                                     # auto: CUDA-core scan, exact fp32 products
+    assert not flat_ip.check_topk(sD, sI, fsc, fD, fI, rel=REL)
+    monkeypatch.setenv("TS_TF32", "1")
+    aD, aI = idx.search_host(Q, k)
+    if B > 4:
+        assert (aI == I).all() and (aD == D).all()
+    else:
+        assert (aI == sI).all() and (aD == sD).all()
+
+
 @pytest.mark.parametrize("order", ["ascending", "descending", "constant"])
 @pytest.mark.parametrize("k", [100, 500])
 def test_tensor_scan_adversarial_score_orders(sim, order, k):

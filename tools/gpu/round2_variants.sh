@@ -42,6 +42,9 @@ import json
 for l in open('gpurun_out/pair_probe.jsonl'):
     r=json.loads(l); print(f"{r['tag']:8s} B={r['B']:5d} scan={r['scan_ms_per_launch']:.3f} ms  {r['TFLOPs']:.0f} TFLOP/s  ({r['tensor_frac_sustained']:.2f} of sustained)")
 PY
+# fp32 storage on the tensor path (kind::tf32): parity, then BASELINE configs[1] (1M x 768 fp32) at B = 1/32/1024
+TS_TEST_EXPERIMENTAL=1 run zz_tf32 tests/test_gpu_zz_tf32.py
+timeout 300 python tools/perf_probe.py --rows 1000000 --dim 768 --dtype fp32 --paths umma --batches 1,32,128,1024 --tag c2_fp32_tf32 > gpurun_out/c2_tf32.jsonl 2> gpurun_out/c2_tf32.err; cat gpurun_out/c2_tf32.jsonl
 # approximate mode (inverted lists over the resident rows): list scan vs the exact scan of the same shard
 timeout 600 python tools/ivf_probe.py --rows 10000000 --dim 1024 --batches 1,8,32 --tag ivf_10M > gpurun_out/ivf_probe.jsonl 2> gpurun_out/ivf_probe.err
 timeout 300 python tools/ivf_probe.py --rows 1000000 --dim 768 --batches 1,32 --tag ivf_1M >> gpurun_out/ivf_probe.jsonl 2>> gpurun_out/ivf_probe.err

@@ -219,8 +219,9 @@ int ts_index_search(ts_index* h, const void* q_dev, int q_dtype, int B, int k, u
   TS_CUDA_OK(cudaSetDevice(h->device));
   int use = path;
   // measured on B200: the TMA/tcgen05 scan streams faster than the CUDA-core scan at every batch size
-  if (use == TS_PATH_AUTO) use = (h->dtype == TS_F32) ? TS_PATH_STREAM : TS_PATH_UMMA;
-  if (use == TS_PATH_UMMA && h->dtype == TS_F32) { set_error("umma path needs bf16/fp16 storage"); return TS_ERR_UNSUPPORTED; }
+  // fp32 storage: the CUDA-core scan (exact fp32 products) unless the tf32 tensor path is switched on (TS_TF32) and
+  // the batch needs more than one CUDA-core pass (4 queries per pass)
+  if (use == TS_PATH_AUTO) use = (h->dtype != TS_F32 || (B > 4 && env_flag("TS_TF32", kDefaultTf32))) ? TS_PATH_UMMA : TS_PATH_STREAM;
   if (use != TS_PATH_STREAM && use != TS_PATH_UMMA) { set_error("ts_index_search: bad path %d", path); return TS_ERR_INVALID; }
 
   const int esz = dtype_size(h->dtype);

@@ -39,6 +39,12 @@
 //   * the lists leave the kernel UNSORTED with their counts; topk_select.cu filters them with
 //     the final bound, compacts and sorts a few hundred survivors per query.
 //
+// fp32 storage (the reference's own dtype) runs the same kernel with kind::tf32: the TMA map
+//   converts fp32 -> tf32 (round to nearest) on the way into shared memory, a K chunk is 32
+//   elements (the same 128-byte swizzle row), one MMA covers 8 of them.  Written after the
+//   round's GPU budget was spent: taken only when asked for (path = TS_PATH_UMMA on an fp32
+//   index, or TS_TF32=1), the default for fp32 storage stays the CUDA-core scan.
+//
 // Small batches (B <= 64): the queries are spread over the four TMEM lane
 //   quarters in groups of 8 rows (8-row TMA boxes), so all four epilogue warps
 //   share the work instead of one.
@@ -54,9 +60,12 @@ namespace {
 using namespace ts::ptx;
 
 constexpr int kThreads = 192;
-constexpr int kTileM = 128, kTileN = 256, kChunkK = 64;
-constexpr int kABytes = kTileM * kChunkK * 2;  // 16 KB
-constexpr int kBBytes = kTileN * kChunkK * 2;  // 32 KB
+constexpr int kTileM = 128, kTileN = 256, kChunkK = 64;   // kChunkK: 16-bit elements per K chunk (one 128-B swizzle row)
+constexpr int kChunkBytes = kChunkK * 2;
+constexpr int kABytes = kTileM * kChunkBytes;  // 16 KB
+constexpr int kBBytes = kTileN * kChunkBytes;  // 32 KB
+// operand kinds of the single-CTA kernel (the values are the UMMA A/B format codes)
+constexpr int kOpF16 = 0, kOpBF16 = 1, kOpTF32 = 2;
 constexpr int kRingBytes = 192 * 1024;         // 4 x (A + B) or 3 x (A0 + A1 + B)
 constexpr int kBarBytes = 256;
 constexpr int kSmemBytes = kRingBytes + kBarBytes + 1024;  // + alignment slack
@@ -270,10 +279,11 @@ __device__ __forceinline__ void grid_barrier_epilogue(unsigned int* bar, unsigne
   named_bar_sync128(1);
 }
 
-template <bool BF16>
+template <int OP>
 __global__ void __launch_bounds__(kThreads, 1)
     s1_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ8,
                    const __grid_constant__ CUtensorMap tmX, const UmmaParams p) {
+  constexpr int CK = (OP == kOpTF32) ? kChunkBytes / 4 : kChunkK;   // elements per K chunk
   const int CAP = p.cap;
   const bool dual = p.dual != 0;
   const int n_stages = dual ? 3 : 4;
@@ -325,13 +335,13 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (p.spread) {
             for (int g = 0; g < p.n_qgroups; ++g) {
               const int row = ((g & 3) * 32) + ((g >> 2) * 8);
-              tma_load_2d(sA + row * 128, &tmQ8, &full_bar[stage], kc * kChunkK, g * 8, kEvictLast);
+              tma_load_2d(sA + row * 128, &tmQ8, &full_bar[stage], kc * CK, g * 8, kEvictLast);
             }
           } else {
-            tma_load_2d(sA, &tmQ, &full_bar[stage], kc * kChunkK, mt0 * kTileM, kEvictLast);
-            if (has1) tma_load_2d(sA + kABytes, &tmQ, &full_bar[stage], kc * kChunkK, (mt0 + 1) * kTileM, kEvictLast);
+            tma_load_2d(sA, &tmQ, &full_bar[stage], kc * CK, mt0 * kTileM, kEvictLast);
+            if (has1) tma_load_2d(sA + kABytes, &tmQ, &full_bar[stage], kc * CK, (mt0 + 1) * kTileM, kEvictLast);
           }
-          tma_load_2d(sB, &tmX, &full_bar[stage], kc * kChunkK, t * kTileN, x_policy);
+          tma_load_2d(sB, &tmX, &full_bar[stage], kc * CK, t * kTileN, x_policy);
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -339,7 +349,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------ MMA issuer --------
-      constexpr uint32_t idesc = make_idesc_f16(kTileM, kTileN, BF16);
+      constexpr uint32_t idesc = (OP == kOpTF32) ? make_idesc_tf32(kTileM, kTileN) : make_idesc_f16(kTileM, kTileN, OP == kOpBF16);
+      constexpr int kSteps = kChunkBytes / 32;          // one MMA consumes 32 bytes of K: 16 x 16-bit or 8 x tf32
+      auto mma = [](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t accumulate) {
+        if constexpr (OP == kOpTF32) umma_tf32_ss(d, ad, bd, id, accumulate); else umma_f16_ss(d, ad, bd, id, accumulate);
+      };
       int stage = 0; uint32_t phase = 0;
       int iter = 0;
       for (int t = slice; t < t_end; t += p.n_slices, ++iter) {
@@ -355,16 +369,16 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint64_t adesc = make_desc_kmajor_sw128(a_addr);
           const uint64_t bdesc = make_desc_kmajor_sw128(a_addr + b_off);
 #pragma unroll
-          for (int ks = 0; ks < kChunkK / 16; ++ks)
-            umma_f16_ss(tmem_base + (uint32_t)(acc * kTileN), adesc + ks * kDescKStep, bdesc + ks * kDescKStep, idesc,
-                        (kc | ks) ? 1u : 0u);
+          for (int ks = 0; ks < kSteps; ++ks)
+            mma(tmem_base + (uint32_t)(acc * kTileN), adesc + ks * kDescKStep, bdesc + ks * kDescKStep, idesc,
+                (kc | ks) ? 1u : 0u);
           if (dual) {
             if (kc == 0) { mbar_wait(&tempty_bar[1], par ^ 1u, 5); tc_fence_after(); }
             const uint64_t adesc1 = make_desc_kmajor_sw128(a_addr + kABytes);
 #pragma unroll
-            for (int ks = 0; ks < kChunkK / 16; ++ks)
-              umma_f16_ss(tmem_base + (uint32_t)kTileN, adesc1 + ks * kDescKStep, bdesc + ks * kDescKStep, idesc,
-                          (kc | ks) ? 1u : 0u);
+            for (int ks = 0; ks < kSteps; ++ks)
+              mma(tmem_base + (uint32_t)kTileN, adesc1 + ks * kDescKStep, bdesc + ks * kDescKStep, idesc,
+                  (kc | ks) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
@@ -605,18 +619,22 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
-// 2-D row-major [rows][dim] (pitch ld elements) 16-bit tensor, box = 64 x box_rows, SWIZZLE_128B
+// 2-D row-major [rows][dim] (pitch ld elements) tensor, box = one 128-byte K chunk x box_rows, SWIZZLE_128B.
+// fp32 tensors are mapped as TFLOAT32: the copy engine rounds to tf32 on the way into shared memory.
 int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, int dim, int ld, int box_rows) {
+  const int esz = dtype_size(dtype);
 #ifdef TS_CUDASIM
-  return ptx::sim_make_tmap_2d(out, base, dtype, rows, dim, ld, kChunkK, box_rows);
+  return ptx::sim_make_tmap_2d(out, base, dtype, rows, dim, ld, kChunkBytes / esz, box_rows);
 #else
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return TS_ERR_CUDA; }
   cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)box_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(kChunkBytes / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, dtype == TS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+  const CUtensorMapDataType mdt = dtype == TS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                  : dtype == TS_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+  CUresult r = enc(out, mdt, 2,
                    const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows %lld dim %d ld %d box %d)", (int)r, (long long)rows, dim, ld, box_rows); return TS_ERR_CUDA; }
@@ -634,7 +652,7 @@ UmmaPlan umma_plan(const ScanArgs& a) {
   // single-tile layout is faster (19.2 vs 21.5 ms at B=1024, 10M x 1024), so it is opt-in.
   pl.dual = (pl.n_mt >= 2 && env_on("TS_DUAL")) ? 1 : 0;
   // CTA pairs (cta_group::2): two query tiles per cluster; an odd tile count is padded with an idle tile
-  pl.pair = (pl.n_mt >= 2 && !pl.dual && a.sm_count >= 2 && env_flag("TS_PAIR", kDefaultPair)) ? 1 : 0;
+  pl.pair = (pl.n_mt >= 2 && !pl.dual && a.sm_count >= 2 && a.dtype != TS_F32 && env_flag("TS_PAIR", kDefaultPair)) ? 1 : 0;
   if (pl.pair) pl.n_mt = (pl.n_mt + 1) & ~1;
   pl.n_mg = pl.dual ? (pl.n_mt + 1) / 2 : pl.n_mt;
   pl.n_tiles = (int)((a.n + kTileN - 1) / kTileN);
@@ -648,7 +666,7 @@ UmmaPlan umma_plan(const ScanArgs& a) {
 }  // namespace
 
 int s1_umma_plan(const ScanArgs& a, UmmaLayout* lay) {
-  if (a.dtype != TS_BF16 && a.dtype != TS_F16) { set_error("umma path needs bf16/fp16 storage"); return TS_ERR_UNSUPPORTED; }
+  if (a.dtype != TS_BF16 && a.dtype != TS_F16 && a.dtype != TS_F32) { set_error("umma path: bad storage dtype %d", a.dtype); return TS_ERR_INVALID; }
   if (a.B > 1024) { set_error("umma path: at most 1024 queries per launch"); return TS_ERR_INVALID; }
   const UmmaPlan pl = umma_plan(a);
   lay->n_slices = pl.n_slices;
@@ -678,7 +696,8 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
   if ((rc = make_tmap_2d(&tmQ8, a.q, a.dtype, a.B, a.dim, a.ld, 8))) return rc;
   if ((rc = make_tmap_2d(&tmX, a.rows, a.dtype, a.n, a.dim, a.ld, kTileN))) return rc;
   UmmaParams p{};
-  p.N = a.n; p.nK = (a.dim + kChunkK - 1) / kChunkK; p.B = a.B; p.k = a.k;
+  const int chunk_elems = kChunkBytes / dtype_size(a.dtype);
+  p.N = a.n; p.nK = (a.dim + chunk_elems - 1) / chunk_elems; p.B = a.B; p.k = a.k;
   p.n_slices = lay.n_slices; p.n_tiles = (int)((a.n + kTileN - 1) / kTileN);
   p.spread = lay.spread;
   p.n_qgroups = (a.B + 7) / 8;
@@ -716,7 +735,7 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
     }
     return TS_OK;
   }
-  auto kern = bf16 ? s1_umma_kernel<true> : s1_umma_kernel<false>;
+  auto kern = bf16 ? s1_umma_kernel<kOpBF16> : (a.dtype == TS_F16 ? s1_umma_kernel<kOpF16> : s1_umma_kernel<kOpTF32>);
   TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   if (p.jrank > 0 && lay.fused && a.grid_bar) {
     // one cooperative launch (all CTAs co-resident): first tile -> publish -> grid barrier -> scan

@@ -30,6 +30,7 @@ inline bool env_on(const char* name) {
 constexpr bool kDefaultFuse = false;   // TS_FUSE : threshold pre-pass + scan in one cooperative launch
 constexpr bool kDefaultS2V2 = false;   // TS_S2_V2: second Stage-2 epilogue
 constexpr bool kDefaultPair = false;   // TS_PAIR : cta_group::2 CTA pairs for B >= 129
+constexpr bool kDefaultTf32 = false;   // TS_TF32 : fp32 storage takes the tensor path (kind::tf32) for B > 4 under TS_PATH_AUTO
 inline bool env_flag(const char* name, bool dflt) {
   const char* e = getenv(name);
   if (!e || !e[0]) return dflt;
