@@ -184,18 +184,18 @@ def test_tensor_scan_over_fp32_storage_reads_tf32(sim, monkeypatch, N, d, B, k):
     D, I = idx.search_host(Q, k, path="umma")
     rD, rI, sc = oracle_search(X, Q, k, "tf32")
     assert not flat_ip.check_topk(D, I, sc, rD, rI, rel=REL)           # against the tf32-rounded operands
-    # against the fp32 reference (what FAISS computes): tf32 operands cost ~1e-5 ABSOLUTE on unit vectors, so the
-    # relative rule only makes sense for scores well above that; ids may differ only inside that absolute band
+    # against the fp32 reference (what FAISS computes): two 10-bit-mantissa operands cost ~2^-11 / sqrt(d) ABSOLUTE on
+    # unit vectors (6e-5 at d = 64, 2e-5 at d = 768) on top of the relative rule; ids may differ only inside that band
     fD, fI, fsc = oracle_search(X, Q, k, "fp32")
     for b in range(B):
         ok = I[b] >= 0
         assert (ok == (fI[b] >= 0)).all()
         ref = fsc(b, I[b][ok])
-        assert (np.abs(D[b][ok] - ref) <= REL * np.maximum(np.abs(ref), 0.05)).all()
+        assert (np.abs(D[b][ok] - ref) <= REL * np.abs(ref) + 1e-3 / np.sqrt(d)).all()
         extra = np.setdiff1d(I[b][ok], fI[b][ok])
         if extra.size:
             kth = float(fD[b][ok].min())
-            assert (fsc(b, extra) >= kth - 2 * REL * max(abs(kth), 0.05)).all()
+            assert (fsc(b, extra) >= kth - 2 * (REL * abs(kth) + 1e-3 / np.sqrt(d))).all()
     sD, sI = idx.search_host(Q[:4], k)                                 # auto: CUDA-core scan, exact fp32 products
     assert not flat_ip.check_topk(sD, sI, fsc, fD[:4], fI[:4], rel=REL)
     monkeypatch.setenv("TS_TF32", "1")

@@ -5,8 +5,8 @@ TS_TEST_EXPERIMENTAL=1 (tools/gpu/round2_variants.sh).  The same cases run on th
 tests/test_cudasim.py::test_tensor_scan_over_fp32_storage_reads_tf32.
 
 Tolerance: against the oracle on tf32-rounded operands the Stage-1 rule (1e-3 relative); against the fp32
-oracle (what FAISS computes) 1e-3 relative for scores above 0.05 and 5e-5 absolute below (tf32 keeps 10 mantissa
-bits), ids equal outside that band."""
+oracle (what FAISS computes) 1e-3 relative + 1e-3 / sqrt(d) absolute (tf32 keeps 10 mantissa bits: ~2^-11 / sqrt(d)
+on unit vectors), ids equal outside that band."""
 import os
 
 import numpy as np
@@ -35,10 +35,10 @@ def test_fp32_storage_on_the_tensor_path(cuda_device, N, d, B, k):
     fD, fI, fsc = oracle_search(X, Q, k, "fp32")
     for b in range(B):
         ref = fsc(b, I[b])
-        assert (np.abs(D[b] - ref) <= REL * np.maximum(np.abs(ref), 0.05)).all()
+        assert (np.abs(D[b] - ref) <= REL * np.abs(ref) + 1e-3 / np.sqrt(d)).all()
         extra = np.setdiff1d(I[b], fI[b])
         if extra.size:
             kth = float(fD[b].min())
-            assert (fsc(b, extra) >= kth - 2 * REL * max(abs(kth), 0.05)).all()
+            assert (fsc(b, extra) >= kth - 2 * (REL * abs(kth) + 1e-3 / np.sqrt(d))).all()
     sD, sI = idx.search_host(Q[:4], k, path="stream")           # the CUDA-core scan of the same index: exact fp32 products
     assert not flat_ip.check_topk(sD, sI, fsc, fD[:4], fI[:4], rel=REL)
