@@ -154,6 +154,13 @@ def test_incremental_add_autosync_reset_and_id_base(sim):
     idx.add(X[:50])
     D5, I5 = iv.search_host(Q, 5, 6)                     # lists rebuilt for the new contents
     assert iv.nassigned == 50 and I5.max() < 50 and (I5 >= 0).all()
+    idx.reset()
+    idx.add(X[100:400])                                  # MORE rows than before the reset: still nothing stale
+    D6, I6 = iv.search_host(Q, 5, 6)
+    assert iv.nassigned == 300
+    Xs = flat_ip.round_to(X[100:400], "bf16")
+    rD6, rI6 = flat_ip.topk_desc(Qr @ Xs.T, 5)
+    assert not flat_ip.check_topk(D6, I6, lambda b, ids: Xs[ids].astype(np.float64) @ Qr[b].astype(np.float64), rD6, rI6, rel=REL)
     with pytest.raises(_lib.TristageError):
         _lib.IVF(idx, 0)
     with pytest.raises(_lib.TristageError):

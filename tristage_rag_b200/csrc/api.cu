@@ -205,7 +205,7 @@ int64_t ts_index_ntotal(const ts_index* h) { return h ? h->n : -1; }
 int ts_index_dim(const ts_index* h) { return h ? h->dim : -1; }
 int ts_index_dtype(const ts_index* h) { return h ? h->dtype : -1; }
 int ts_index_metric(const ts_index* h) { return h ? h->metric : -1; }
-int ts_index_reset(ts_index* h) { if (!h) return TS_ERR_INVALID; h->n = 0; return TS_OK; }
+int ts_index_reset(ts_index* h) { if (!h) return TS_ERR_INVALID; h->n = 0; ++h->reset_gen; return TS_OK; }
 int ts_index_set_id_base(ts_index* h, int64_t b) { if (!h) return TS_ERR_INVALID; h->id_base = b; return TS_OK; }
 int64_t ts_index_launch_count(const ts_index* h) { return h ? h->launches : -1; }
 

@@ -41,6 +41,7 @@ struct ts_ivf {
   ts_index* base;
   int nlist, ldc, trained;
   int64_t n_assigned;
+  int64_t base_gen;                 // base->reset_gen the lists were built under
   float* cent;                      // device [nlist][ldc]
   int64_t* off;                     // device [nlist + 1]
   int32_t* order; int64_t order_cap;
@@ -352,7 +353,7 @@ int ts_ivf_create(ts_ivf** out, ts_index* base, int nlist) {
   TS_CUDA_OK(cudaSetDevice(base->device));
   ts_ivf* h = new ts_ivf();
   memset(h, 0, sizeof(*h));
-  h->base = base; h->nlist = nlist; h->ldc = (base->dim + 7) / 8 * 8;
+  h->base = base; h->nlist = nlist; h->ldc = (base->dim + 7) / 8 * 8; h->base_gen = base->reset_gen;
   h->assign_host = new std::vector<int32_t>();
   h->off_host = new std::vector<int64_t>((size_t)nlist + 1, 0);
   if (cudaMalloc((void**)&h->cent, (size_t)nlist * h->ldc * 4) != cudaSuccess || cudaMalloc((void**)&h->off, ((size_t)nlist + 1) * 8) != cudaSuccess) {
@@ -412,7 +413,9 @@ int ts_ivf_sync(ts_ivf* h, void* stream) {
   const ts_index* base = h->base;
   cudaStream_t st = (cudaStream_t)stream;
   TS_CUDA_OK(cudaSetDevice(base->device));
-  if (base->n < h->n_assigned) { h->assign_host->clear(); h->n_assigned = 0; }   // the index was reset
+  if (base->reset_gen != h->base_gen || base->n < h->n_assigned) {   // the index was reset: every list is stale
+    h->assign_host->clear(); h->n_assigned = 0; h->base_gen = base->reset_gen;
+  }
   const int64_t lo = h->n_assigned, hi = base->n;
   if (lo == hi && (int64_t)h->assign_host->size() == hi) return TS_OK;
   if (hi > 0x7fffffffll) { set_error("ivf: shard limited to 2^31 rows"); return TS_ERR_UNSUPPORTED; }
@@ -441,6 +444,7 @@ int ts_ivf_set_assignments(ts_ivf* h, const int32_t* assign_host, int64_t n, voi
     if (assign_host[i] < 0 || assign_host[i] >= h->nlist) { set_error("ts_ivf_set_assignments: row %lld names list %d of %d", (long long)i, assign_host[i], h->nlist); return TS_ERR_INVALID; }
   TS_CUDA_OK(cudaSetDevice(h->base->device));
   h->assign_host->assign(assign_host, assign_host + n);
+  h->base_gen = h->base->reset_gen;
   return rebuild_lists(h, (cudaStream_t)stream);
 }
 
@@ -485,7 +489,7 @@ static int ivf_check_search(ts_ivf* h, const void* q, int q_dtype, int B, int k,
   if (h->base->n == 0) { set_error("No documents indexed. Call add_documents() first."); return TS_ERR_EMPTY; }
   if (*nprobe < 1) *nprobe = 1;
   if (*nprobe > h->nlist) *nprobe = h->nlist;
-  if (h->n_assigned != h->base->n) return ts_ivf_sync(h, stream);   // rows added since the last sync
+  if (h->n_assigned != h->base->n || h->base_gen != h->base->reset_gen) return ts_ivf_sync(h, stream);   // rows added (or index reset) since the last sync
   return TS_OK;
 }
 

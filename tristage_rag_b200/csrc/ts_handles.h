@@ -63,6 +63,7 @@ struct ts_index {
   void* stage; size_t stage_b;       // staging for host inputs (add / search_host)
   void* hout; size_t hout_b;         // device result buffers for search_host
   ts::ScanTimer* timer;
+  int64_t reset_gen;                 // bumped by ts_index_reset: views over the rows (ts_ivf) drop their state
 };
 
 struct ts_tokstore {
