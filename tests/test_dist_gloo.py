@@ -36,6 +36,28 @@ class _OracleLocalIndex:
         return torch.from_numpy(D), torch.from_numpy(I)
 
 
+class _OracleLocalIVF:
+    """What _lib.IVF offers dist.IVFShard (base.set_id_base, search(q, k, nprobe)), over oracle/ivf.py."""
+
+    class _Base:
+        def __init__(self):
+            self.id_base = 0
+
+        def set_id_base(self, b):
+            self.id_base = b
+
+    def __init__(self, X, cent):
+        from oracle import ivf as oivf
+
+        self.X, self.cent, self.base, self.oivf = X, cent, self._Base(), oivf
+        self.assign = oivf.assign_lists(X, cent)
+
+    def search(self, q, k, nprobe):
+        lists, _ = self.oivf.coarse_probe(q.numpy(), self.cent, nprobe)
+        D, I = self.oivf.ivf_search(self.X, q.numpy(), self.assign, lists, k)
+        return torch.from_numpy(D), torch.from_numpy(np.where(I >= 0, I + self.base.id_base, -1))
+
+
 def _numpy_merge(all_s, all_i):
     G, B, k = all_s.shape
     s = all_s.permute(1, 0, 2).reshape(B, G * k).numpy()
@@ -81,6 +103,15 @@ def _worker(rank, world, port, n_total, ret):
             D, I = idx.search(torch.from_numpy(Q), k)
             rD, rI = flat_ip.topk_desc(Q @ X.T, k)
             assert (I.numpy() == rI).all() and np.allclose(D.numpy(), rD)
+        # approximate mode: same centroids on every rank, lists over the local rows -> merged result == one index
+        from oracle import ivf as oivf
+
+        cent = X[:5].copy()
+        shard = tdist.ShardedIndex(tdist.IVFShard(_OracleLocalIVF(X[lo:hi], cent), nprobe=2), n_total, merge_fn=_numpy_merge)
+        D, I = shard.search(torch.from_numpy(Q), 7)
+        lists, _ = oivf.coarse_probe(Q, cent, 2)
+        rD, rI = oivf.ivf_search(X, Q, oivf.assign_lists(X, cent), lists, 7)
+        assert (I.numpy() == rI).all() and np.allclose(D.numpy(), rD)
         # Stage 2: ownership-filtered scores, summed across ranks
         lens = rng.integers(2, 9, size=n_total)
         docs = [rng.standard_normal((int(L), 8)).astype(np.float32) for L in lens]
