@@ -26,4 +26,9 @@ for v in 0 1; do
   TS_S2_V2=$v timeout 900 $NCU -k regex:maxsim_umma -s 2 -c 1 -o gpurun_out/prof_s2_v$v $CMD > gpurun_out/ncu_s2_v$v.log 2>&1
   echo "s2 v2=$v rc=$?"
 done
+# 5. approximate mode: the list scan at the reference's batch 1 (gathered rows; is it HBM-bound?)
+CMD="python tools/ivf_probe.py --rows 10000000 --dim 1024 --batches 1 --steps 2"
+timeout 600 $CMD > gpurun_out/plain_ivf.log 2>&1 && \
+timeout 900 $NCU -k regex:ivf_scan -s 2 -c 1 -o gpurun_out/prof_ivf_scan $CMD > gpurun_out/ncu_ivf.log 2>&1
+echo "ivf rc=$?"
 ls -la gpurun_out/*.ncu-rep
