@@ -378,3 +378,24 @@ def test_lists_shard_by_rows_like_the_exact_index(sim):
     p = lambda a: C.c_void_p(a.ctypes.data)      # noqa: E731
     _lib.check(sim.ts_topk_merge(0, p(S), p(Id), G, 4, k, p(out_s), p(out_i), None))
     assert np.array_equal(out_i, I) and np.array_equal(out_s, D)
+
+
+def test_batches_scan_list_by_list_with_identical_results(sim, monkeypatch):
+    """Batches: the (query, probe) pairs are sorted by list so the CTAs of one list are neighbours in launch
+    order (L2 reuse on the device); the result must not depend on that order, nor on falling back to the
+    (segment, probe, query) grid when there are more pairs than the order kernel sorts."""
+    X, centers = clustered(1400, 24, 7, seed=31)
+    idx, iv, cent = build(X, 7, "bf16")
+    rng = np.random.default_rng(1)
+    Q = flat_ip.normalize_rows(centers[rng.integers(0, 7, size=40)]
+                               + 0.4 * rng.standard_normal((40, 24)).astype(np.float32) / np.sqrt(24)).astype(np.float32)
+    D, I = iv.search_host(Q, 10, 3)                       # 120 pairs: ordered by list
+    monkeypatch.setenv("TS_IVF_NOORDER", "1")
+    D0, I0 = iv.search_host(Q, 10, 3)
+    monkeypatch.delenv("TS_IVF_NOORDER")
+    assert np.array_equal(I, I0) and np.array_equal(D, D0)
+    one = [iv.search_host(Q[b:b + 1], 10, 3) for b in range(5)]          # batch 1 never builds a work list
+    assert all(np.array_equal(one[b][1][0], I[b]) and np.array_equal(one[b][0][0], D[b]) for b in range(5))
+    monkeypatch.setenv("TS_IVF_MAXPAIRS", "100")          # more pairs than the order kernel takes (4096 in production):
+    D1, I1 = iv.search_host(Q, 10, 3)                     # the (segment, probe, query) grid, unordered
+    assert np.array_equal(I1, I) and np.array_equal(D1, D)

@@ -52,6 +52,7 @@ struct ts_ivf {
   void* q32; size_t q32_b;          // [B][ldc] fp32 queries for the coarse step
   void* qst; size_t qst_b;          // [B][ld] queries in the storage dtype for the scan
   void* probe; size_t probe_b;      // [B][nprobe] int32 lists + [B][nprobe] fp32 scores
+  void* work; size_t work_b;        // [B * nprobe] (query, probe) pairs ordered by list (batches)
   void* partial; size_t partial_b;
   void* tmp0; size_t tmp0_b;
   void* tmp1; size_t tmp1_b;
@@ -69,6 +70,7 @@ constexpr int kIvfR = 4;            // rows per warp step
 constexpr int kIvfJ = 4;            // centroids per assign step
 constexpr int kIvfMergeCap = 4096;  // keys of the CTA merge buffer
 constexpr int kIvfMaxSeg = 64;      // segments per probed list
+constexpr int kIvfMaxPairs = 4096;  // (query, probe) pairs the order kernel sorts (32 KB of keys)
 
 // shared-memory twin of warp_prune_list (ts_common.cuh): the warp sorts list[0..cnt) and keeps the
 // best k in list[0..k), descending, zero padded; returns the k-th key
@@ -211,19 +213,37 @@ __global__ void __launch_bounds__(kIvfThreads)
   }
 }
 
+// ---- search(), batches: co-schedule the probes of one list ---------------------------------------
+// B queries x nprobe probes touch each list B*nprobe/nlist times on average.  Sorting the (query, probe)
+// pairs by list makes the CTAs that scan the same list neighbours in launch order, so the list comes from
+// HBM once and from the 126 MB L2 for the other queries.  One CTA, one bitonic sort of <= kIvfMaxPairs keys.
+__global__ void __launch_bounds__(1024)
+    ivf_order_kernel(const int32_t* __restrict__ probe, int n_pairs, int npow2, int32_t* __restrict__ work) {
+  TS_DYN_SMEM(uint64_t, keys);
+  for (int i = threadIdx.x; i < npow2; i += blockDim.x)
+    keys[i] = (i < n_pairs) ? (((uint64_t)(uint32_t)(__ldg(probe + i) + 1) << 32) | (uint32_t)(n_pairs - 1 - i) | (1ull << 63)) : 0ull;
+  __syncthreads();
+  block_sort_desc(keys, npow2);
+  for (int i = threadIdx.x; i < n_pairs; i += blockDim.x) work[i] = n_pairs - 1 - (int32_t)(uint32_t)keys[i];
+}
+
 // ---- search(), step 2: scan the probed lists --------------------------------------------------
-// grid (S, nprobe, B): CTA (s, j, b) scans segment s of the j-th probed list of query b.
+// grid (S, nprobe, B): CTA (s, j, b) scans segment s of the j-th probed list of query b; with a work
+// list (batches) the grid is (S, B * nprobe) and CTA (s, w) takes pair work[w] = b * nprobe + j.
 template <typename T>
 __global__ void __launch_bounds__(kIvfThreads, 3)
     ivf_scan_kernel(const T* __restrict__ X, int ld, const float* __restrict__ inv_norm, const T* __restrict__ Q,
                     const int32_t* __restrict__ probe, int nprobe, const int64_t* __restrict__ off,
-                    const int32_t* __restrict__ order, int k, int CAP, uint64_t* __restrict__ partial, int B) {
+                    const int32_t* __restrict__ order, int k, int CAP, uint64_t* __restrict__ partial, int B,
+                    const int32_t* __restrict__ work) {
   constexpr int R = kIvfR, EPC = Elem<T>::kPerChunk;
   TS_DYN_SMEM(unsigned char, smem_raw);
   uint64_t* sbuf = reinterpret_cast<uint64_t*>(smem_raw);            // [kIvfMergeCap] CTA merge buffer
   uint64_t* wl = sbuf + kIvfMergeCap;                                // [warps][CAP] per-warp candidate lists
   float* Qs = reinterpret_cast<float*>(wl + (size_t)kIvfWarps * CAP);  // [ld]
-  const int s = blockIdx.x, S = gridDim.x, j = blockIdx.y, b = blockIdx.z;
+  const int s = blockIdx.x, S = gridDim.x;
+  int j = blockIdx.y, b = blockIdx.z;
+  if (work) { const int pair = __ldg(work + blockIdx.y); b = pair / nprobe; j = pair % nprobe; }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < ld; i += blockDim.x) Qs[i] = Elem<T>::to_f32(Q[(size_t)b * ld + i]);
   __syncthreads();
@@ -305,16 +325,17 @@ int launch_assign_t(const ts_index* base, int64_t lo, int64_t hi, const float* c
 }
 
 template <typename T>
-int launch_scan_t(const ts_ivf* h, int B, int k, int nprobe, int S, cudaStream_t st) {
+int launch_scan_t(const ts_ivf* h, int B, int k, int nprobe, int S, const int32_t* work, cudaStream_t st) {
   const ts_index* base = h->base;
   const int CAP = cap_for_k(k);
   const size_t smem = (size_t)kIvfMergeCap * 8 + (size_t)kIvfWarps * CAP * 8 + (size_t)base->ld * sizeof(float);
   auto kern = ivf_scan_kernel<T>;
   if (smem > 48 * 1024) TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(S, nprobe, B);
+  const dim3 grid = work ? dim3(S, B * nprobe, 1) : dim3(S, nprobe, B);
   TS_LAUNCH(kern, grid, kIvfThreads, smem, st, reinterpret_cast<const T*>(base->rows), base->ld,
             (base->metric == TS_METRIC_COSINE) ? base->inv_norm : nullptr, reinterpret_cast<const T*>(h->qst),
-            reinterpret_cast<const int32_t*>(h->probe), nprobe, h->off, h->order, k, CAP, reinterpret_cast<uint64_t*>(h->partial), B);
+            reinterpret_cast<const int32_t*>(h->probe), nprobe, h->off, h->order, k, CAP, reinterpret_cast<uint64_t*>(h->partial), B,
+            work);
   TS_CUDA_OK(cudaGetLastError());
   return TS_OK;
 }
@@ -370,7 +391,7 @@ int ts_ivf_create(ts_ivf** out, ts_index* base, int nlist) {
 int ts_ivf_destroy(ts_ivf* h) {
   if (!h) return TS_OK;
   cudaSetDevice(h->base->device);
-  void* ptrs[] = {h->cent, h->off, h->order, h->q32, h->qst, h->probe, h->partial, h->tmp0, h->tmp1, h->atmp, h->stage, h->hout};
+  void* ptrs[] = {h->cent, h->off, h->order, h->q32, h->qst, h->probe, h->work, h->partial, h->tmp0, h->tmp1, h->atmp, h->stage, h->hout};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h->assign_host;
   delete h->off_host;
@@ -533,15 +554,28 @@ int ts_ivf_search(ts_ivf* h, const void* q_dev, int q_dtype, int B, int k, int n
       if ((rc = ensure_bytes(&h->tmp0, &h->tmp0_b, tmpk * 8))) return rc;
       if ((rc = ensure_bytes(&h->tmp1, &h->tmp1_b, tmpk * 8))) return rc;
     }
+    // batches: order the (query, probe) pairs by list so the CTAs of one list run together (L2 reuse)
+    const int n_pairs = Bc * nprobe;
+    const int32_t* work = nullptr;
+    int launches = 1;
+    int max_pairs = kIvfMaxPairs;
+    if (const char* e = getenv("TS_IVF_MAXPAIRS")) { const int v = atoi(e); if (v >= 0 && v < max_pairs) max_pairs = v; }   // test knob
+    if (Bc > 1 && n_pairs <= max_pairs && !env_on("TS_IVF_NOORDER")) {
+      if ((rc = ensure_bytes(&h->work, &h->work_b, (size_t)n_pairs * 4))) return rc;
+      const int np2 = next_pow2(n_pairs < 2 ? 2 : n_pairs);
+      TS_LAUNCH(ivf_order_kernel, 1, 1024, (size_t)np2 * 8, st, (const int32_t*)h->probe, n_pairs, np2, (int32_t*)h->work);
+      TS_CUDA_OK(cudaGetLastError());
+      work = (const int32_t*)h->work;
+      ++launches;
+    }
     base->timer->begin(st);
     switch (base->dtype) {
-      case TS_BF16: rc = launch_scan_t<__nv_bfloat16>(h, Bc, k, nprobe, S, st); break;
-      case TS_F16: rc = launch_scan_t<__half>(h, Bc, k, nprobe, S, st); break;
-      default: rc = launch_scan_t<float>(h, Bc, k, nprobe, S, st); break;
+      case TS_BF16: rc = launch_scan_t<__nv_bfloat16>(h, Bc, k, nprobe, S, work, st); break;
+      case TS_F16: rc = launch_scan_t<__half>(h, Bc, k, nprobe, S, work, st); break;
+      default: rc = launch_scan_t<float>(h, Bc, k, nprobe, S, work, st); break;
     }
     base->timer->end(st);
     if (rc) return rc;
-    int launches = 1;
     if ((rc = launch_merge_keys((const uint64_t*)h->partial, L, Bc, k, base->id_base, (uint64_t*)h->tmp0, (uint64_t*)h->tmp1,
                                 out_scores + (size_t)b0 * k, out_ids + (size_t)b0 * k, st, &launches))) return rc;
     h->launches += launches;
