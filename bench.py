@@ -198,11 +198,18 @@ def finish(code: int = 0):
     os._exit(code)
 
 
+_PENDING = {"line": None}      # the result line once the headline is measured: the watchdog prints it rather than nothing
+
+
 def arm_watchdog(seconds: int):
     """Hard wall-clock limit for the whole run; a wedged collective must not hold the box."""
     import threading
 
     def _kill():
+        if _PENDING["line"] is not None:
+            print(f"[bench] watchdog after {seconds}s: printing the measured line without the side measurements", file=sys.stderr, flush=True)
+            print(json.dumps(_PENDING["line"]), flush=True)
+            os._exit(0)
         print(f"[bench] watchdog: no result after {seconds}s, aborting", file=sys.stderr, flush=True)
         os._exit(3)
 
@@ -385,9 +392,50 @@ def main():
         line["cpu_baseline"] = cb
     if dist_on:
         dist.barrier()
+    _PENDING["line"] = line
+    if rank == 0 and world == 1 and not args.no_extra:
+        line["extra"]["unvalidated_variants"] = variant_probes()
     if rank == 0:
         print(json.dumps(line), flush=True)
     finish(0)
+
+
+def variant_probes():
+    """First hardware numbers of what was written after the round-1 GPU budget ended (approximate mode, tf32
+    tensor path for fp32 storage): each runs in its OWN process with a short timeout, after the headline is
+    measured, so a fault in unvalidated code cannot touch this process's CUDA context or the result line.
+    BASELINE configs[1] shape (1 M x 768); device-vs-device self-checks only (no oracle here)."""
+    jobs = {
+        "approximate_mode_1Mx768_bf16": [sys.executable, os.path.join(ROOT, "tools", "ivf_probe.py"), "--rows", "1000000", "--dim", "768",
+                                         "--batches", "1,32", "--steps", "20", "--selfcheck"],
+        "fp32_storage_tf32_tensor_path_1Mx768": [sys.executable, os.path.join(ROOT, "tools", "perf_probe.py"), "--rows", "1000000",
+                                                 "--dim", "768", "--dtype", "fp32", "--paths", "umma", "--batches", "32,1024",
+                                                 "--steps", "10", "--selfcheck"],
+    }
+    out = {}
+    for name, cmd in jobs.items():
+        rec = {"status": "not run"}
+        try:
+            p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
+            try:
+                so, se = p.communicate(timeout=120)
+                rows = []
+                for ln in so.splitlines():
+                    if ln.startswith("{"):
+                        try:
+                            rows.append(json.loads(ln))
+                        except ValueError:
+                            pass
+                rec = {"status": "ok" if p.returncode == 0 else f"exit {p.returncode}", "lines": rows}
+                if p.returncode != 0:
+                    rec["stderr_tail"] = se[-400:]
+            except subprocess.TimeoutExpired:
+                p.kill()
+                rec = {"status": "timeout (120 s), killed"}
+        except Exception as e:                               # noqa: BLE001
+            rec = {"status": f"{type(e).__name__}: {e}"}
+        out[name] = rec
+    return out
 
 
 def extras(idx, d, k, dev, pk, ld, n_local, sm):

@@ -25,7 +25,11 @@ def main():
     ap.add_argument("--batches", default="1,8,32")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--selfcheck", action="store_true",
+                    help="device-vs-device consistency: all lists probed must equal the exact scan; probed rows must "
+                         "belong to the probed lists")
     args = ap.parse_args()
+    bench.arm_watchdog(300)
     dev = torch.device("cuda", 0)
     pk = bench.peaks()
     idx = _lib.Index(args.dim, "bf16", "ip", 0, reserve_rows=args.rows)
@@ -42,6 +46,22 @@ def main():
     print(json.dumps({"tag": args.tag, "what": "assign+lists", "rows": args.rows, "ms": t0.elapsed_time(t1),
                       "list_min": int(sizes.min()), "list_max": int(sizes.max())}), flush=True)
     ld = (args.dim + 7) // 8 * 8
+    if args.selfcheck:
+        _, q = bench.make_queries(8, args.dim, dev, seed=3)
+        es, ei = idx.search(q, args.k)
+        fs, fi = iv.search(q, args.k, args.nlist)                     # every list probed == the exact search
+        ps, pi = iv.search(q, args.k, args.nprobe)
+        torch.cuda.synchronize()
+        a = torch.from_numpy(iv.assignments().astype("int64")).to(dev)
+        lists, _ = iv.coarse_host(q.cpu().numpy(), args.nprobe)
+        lists = torch.from_numpy(lists.astype("int64")).to(dev)
+        ok = pi >= 0
+        member = (a[pi.clamp(min=0)][:, :, None] == lists[:, None, :]).any(dim=2) | ~ok
+        subset_best = bool((ps[:, 0] <= es[:, 0] + 1e-6).all())
+        print(json.dumps({"tag": args.tag, "what": "selfcheck", "all_lists_ids_equal_exact": float((fi == ei).float().mean()),
+                          "all_lists_max_score_diff": float((fs - es).abs().max()),
+                          "probed_rows_in_probed_lists": float(member.float().mean()), "probe_best_le_exact_best": subset_best,
+                          "scores_descending": bool((ps[:, 1:] <= ps[:, :-1]).all())}), flush=True)
     for B in [int(b) for b in args.batches.split(",")]:
         qh, q = bench.make_queries(B, args.dim, dev, seed=B)
         lists, _ = iv.coarse_host(qh.numpy(), args.nprobe)

@@ -24,13 +24,25 @@ def main():
     ap.add_argument("--tag", default="")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"],
                     help="corpus storage dtype (fp32 = the reference's; its umma path reads tf32)")
+    ap.add_argument("--selfcheck", action="store_true",
+                    help="device-vs-device consistency of the two scan kernels on the same index (4 queries)")
     args = ap.parse_args()
+    bench.arm_watchdog(300)
     dev = torch.device("cuda", 0)
     pk = bench.peaks()
     idx = _lib.Index(args.dim, args.dtype, "ip", 0, reserve_rows=args.rows)
     bench.build_shard(idx, 0, args.rows, args.dim, dev, 1234, dtype=args.dtype)
     esz = 4 if args.dtype == "fp32" else 2
     ld = (args.dim + 3) // 4 * 4 if args.dtype == "fp32" else (args.dim + 7) // 8 * 8
+    if args.selfcheck:
+        _, q = bench.make_queries(4, args.dim, dev, seed=7)
+        us, ui = idx.search(q, args.k, path="umma")
+        ss, si = idx.search(q, args.k, path="stream")
+        torch.cuda.synchronize()
+        overlap = sum(len(set(ui[b].tolist()) & set(si[b].tolist())) for b in range(4)) / (4.0 * args.k)
+        print(json.dumps({"tag": args.tag, "what": "selfcheck", "dtype": args.dtype, "topk_overlap_umma_vs_stream": overlap,
+                          "max_abs_score_diff_rankwise": float((us - ss).abs().max()),
+                          "best_id_equal": bool((ui[:, 0] == si[:, 0]).all())}), flush=True)
     for B in [int(b) for b in args.batches.split(",")]:
         for path in args.paths.split(","):
             if path == "stream" and B > 8:

@@ -41,8 +41,10 @@ def train_centroids(x: np.ndarray, nlist: int, niter: int = NITER, seed: int = 1
         a = np.argmax(x64 @ cent.astype(np.float64).T, axis=1)
         cnt = np.bincount(a, minlength=nlist).astype(np.float64)
         new = np.zeros((nlist, d), np.float64)
-        np.add.at(new, a, x64)
+        order = np.argsort(a, kind="stable")                       # members of a cluster in row order, clusters back to back
         nz = cnt > 0
+        starts = np.concatenate([[0], np.cumsum(cnt.astype(np.int64))])[:-1][nz]
+        new[nz] = np.add.reduceat(x64[order], starts, axis=0)      # row-by-row sums, the order of the obvious loop
         new[nz] /= cnt[nz, None]
         for c in np.nonzero(~nz)[0]:
             big = int(np.argmax(cnt))
