@@ -402,9 +402,10 @@ def main():
 
 def variant_probes():
     """First hardware numbers of what was written after the round-1 GPU budget ended (approximate mode, tf32
-    tensor path for fp32 storage): each runs in its OWN process with a short timeout, after the headline is
-    measured, so a fault in unvalidated code cannot touch this process's CUDA context or the result line.
-    BASELINE configs[1] shape (1 M x 768); device-vs-device self-checks only (no oracle here)."""
+    tensor path for fp32 storage, the TS_FUSE / TS_S2_V2 variants, the select-kernel rewrite): each job runs in
+    its OWN process with a short timeout, after the headline is measured, so a fault in unvalidated code cannot
+    touch this process's CUDA context or the result line.  Device-vs-device self-checks only (no oracle here).
+    The cta_group::2 pair kernel (TS_PAIR) and the peer-memory exchange (TS_P2P) are left to dedicated GPU calls."""
     jobs = {
         "approximate_mode_1Mx768_bf16": [sys.executable, os.path.join(ROOT, "tools", "ivf_probe.py"), "--rows", "1000000", "--dim", "768",
                                          "--batches", "1,32", "--steps", "20", "--selfcheck"],
@@ -412,13 +413,21 @@ def variant_probes():
                                                  "--dim", "768", "--dtype", "fp32", "--paths", "umma", "--batches", "32,1024",
                                                  "--steps", "10", "--selfcheck"],
     }
+    ab = os.path.join(ROOT, "tools", "variant_ab.py")
+    # opt-in variants against the validated default, same process, results compared bit for bit on the device
+    jobs["stage1_TS_FUSE_and_select_rewrite_AB_1.25Mx1024"] = [sys.executable, ab, "--what", "s1"]
+    jobs["stage2_TS_S2_V2_AB_config4"] = [sys.executable, ab, "--what", "s2"]
     out = {}
+    t_start = time.perf_counter()
     for name, cmd in jobs.items():
         rec = {"status": "not run"}
+        if time.perf_counter() - t_start > 300:              # overall budget of the side jobs
+            out[name] = {"status": "skipped: side-measurement budget (300 s) used up"}
+            continue
         try:
             p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
             try:
-                so, se = p.communicate(timeout=120)
+                so, se = p.communicate(timeout=100)
                 rows = []
                 for ln in so.splitlines():
                     if ln.startswith("{"):
@@ -431,7 +440,7 @@ def variant_probes():
                     rec["stderr_tail"] = se[-400:]
             except subprocess.TimeoutExpired:
                 p.kill()
-                rec = {"status": "timeout (120 s), killed"}
+                rec = {"status": "timeout (100 s), killed"}
         except Exception as e:                               # noqa: BLE001
             rec = {"status": f"{type(e).__name__}: {e}"}
         out[name] = rec
