@@ -421,13 +421,13 @@ def variant_probes():
     t_start = time.perf_counter()
     for name, cmd in jobs.items():
         rec = {"status": "not run"}
-        if time.perf_counter() - t_start > 300:              # overall budget of the side jobs
-            out[name] = {"status": "skipped: side-measurement budget (300 s) used up"}
+        if time.perf_counter() - t_start > 240:              # overall budget of the side jobs
+            out[name] = {"status": "skipped: side-measurement budget (240 s) used up"}
             continue
         try:
             p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
             try:
-                so, se = p.communicate(timeout=100)
+                so, se = p.communicate(timeout=90)
                 rows = []
                 for ln in so.splitlines():
                     if ln.startswith("{"):
@@ -440,7 +440,7 @@ def variant_probes():
                     rec["stderr_tail"] = se[-400:]
             except subprocess.TimeoutExpired:
                 p.kill()
-                rec = {"status": "timeout (100 s), killed"}
+                rec = {"status": "timeout (90 s), killed"}
         except Exception as e:                               # noqa: BLE001
             rec = {"status": f"{type(e).__name__}: {e}"}
         out[name] = rec
