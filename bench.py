@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--path", default="auto")
     ap.add_argument("--no-extra", action="store_true", help="skip the B=1 / B=1024 / Stage-2 side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-variants", action="store_true",
+                    help="skip the child-process side jobs on unvalidated variants (use under a profiler)")
     ap.add_argument("--graph", action="store_true",
                     help="also time the step replayed from a CUDA graph and report the faster launch mode "
                          "(off by default: measured within 1%% of eager launches on B200)")
@@ -393,7 +395,7 @@ def main():
     if dist_on:
         dist.barrier()
     _PENDING["line"] = line
-    if rank == 0 and world == 1 and not args.no_extra:
+    if rank == 0 and world == 1 and not args.no_extra and not args.no_variants:
         line["extra"]["unvalidated_variants"] = variant_probes()
     if rank == 0:
         print(json.dumps(line), flush=True)

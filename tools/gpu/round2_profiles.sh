@@ -5,7 +5,7 @@
 mkdir -p gpurun_out
 NCU="ncu --set full --clock-control none --import-source on"
 # 1. launch list of the bench command (kernel SHARES of the step)
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-variants"
 timeout 600 $CMD > gpurun_out/plain_bench.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 echo "launch list rc=$?"
