@@ -332,6 +332,14 @@ def test_retriever_follows_the_reference_index_rule_when_approximate(sim, tmp_pa
     assert r3.get_stats()["faiss_index_type"] == "IndexFlatIP"
 
 
+def test_environment_switch_for_unmodified_callers(monkeypatch):
+    from tristage_rag_b200.stage1_retriever import Stage1Config
+
+    assert Stage1Config().approximate is False
+    monkeypatch.setenv("TS_APPROXIMATE", "1")
+    assert Stage1Config(top_k_candidates=5).approximate is True and Stage1Config(approximate=False).approximate is False
+
+
 def test_load_index_imports_the_reference_ivf_file(sim, tmp_path):
     import pickle
 

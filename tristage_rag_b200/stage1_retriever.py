@@ -38,7 +38,7 @@ import os
 import pickle
 import re
 from collections import defaultdict
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -69,7 +69,10 @@ class Stage1Config:
     storage_dtype: str = "bf16"   # HBM corpus dtype: bf16 | fp16 | fp32
     gpu_index: int = 0
     hybrid_on_device: bool = False   # search_batch: BM25 search + RRF/weighted fusion as GPU kernels (ts_bm25_*)
-    approximate: bool = False        # the reference's index rule: IVF (nlist, nprobe) when the first batch has > 1000 rows
+    # the reference's index rule: IVF (nlist, nprobe) when the first batch has > 1000 rows.  The reference's callers
+    # build this config with explicit keywords (src/retrieval_pipeline.py:244-255) and cannot pass new fields, so
+    # the default can also be flipped from the environment of an unmodified deployment: TS_APPROXIMATE=1
+    approximate: bool = field(default_factory=lambda: os.environ.get("TS_APPROXIMATE", "0") not in ("", "0"))
 
 
 class BM25Index:
