@@ -411,8 +411,8 @@ def variant_probes():
     jobs = {
         "approximate_mode_1Mx768_bf16": [sys.executable, os.path.join(ROOT, "tools", "ivf_probe.py"), "--rows", "1000000", "--dim", "768",
                                          "--batches", "1,32", "--steps", "20", "--selfcheck"],
-        "fp32_storage_tf32_tensor_path_1Mx768": [sys.executable, os.path.join(ROOT, "tools", "perf_probe.py"), "--rows", "1000000",
-                                                 "--dim", "768", "--dtype", "fp32", "--paths", "umma", "--batches", "32,1024",
+        "fp32_storage_1Mx768_cuda_core_scan_and_tf32_tensor_path": [sys.executable, os.path.join(ROOT, "tools", "perf_probe.py"), "--rows", "1000000",
+                                                 "--dim", "768", "--dtype", "fp32", "--paths", "stream,umma", "--batches", "1,4,32,1024",
                                                  "--steps", "10", "--selfcheck"],
     }
     ab = os.path.join(ROOT, "tools", "variant_ab.py")
