@@ -34,17 +34,8 @@ def main():
     bench.build_shard(idx, 0, args.rows, args.dim, dev, 1234, dtype=args.dtype)
     esz = 4 if args.dtype == "fp32" else 2
     ld = (args.dim + 3) // 4 * 4 if args.dtype == "fp32" else (args.dim + 7) // 8 * 8
-    if args.selfcheck:
-        _, q = bench.make_queries(4, args.dim, dev, seed=7)
-        us, ui = idx.search(q, args.k, path="umma")
-        ss, si = idx.search(q, args.k, path="stream")
-        torch.cuda.synchronize()
-        overlap = sum(len(set(ui[b].tolist()) & set(si[b].tolist())) for b in range(4)) / (4.0 * args.k)
-        print(json.dumps({"tag": args.tag, "what": "selfcheck", "dtype": args.dtype, "topk_overlap_umma_vs_stream": overlap,
-                          "max_abs_score_diff_rankwise": float((us - ss).abs().max()),
-                          "best_id_equal": bool((ui[:, 0] == si[:, 0]).all())}), flush=True)
-    for B in [int(b) for b in args.batches.split(",")]:
-        for path in args.paths.split(","):
+    for path in args.paths.split(","):          # all of one path first: a fault in an unvalidated path cannot hide the other's lines
+        for B in [int(b) for b in args.batches.split(",")]:
             if path == "stream" and B > 8:
                 continue
             _, q = bench.make_queries(B, args.dim, dev, seed=B)
@@ -62,6 +53,16 @@ def main():
                               "qps": B * args.steps / (ms / 1e3), "corpus_GBps_per_scan": gb,
                               "hbm_frac": gb / pk["hbm_gbs"], "TFLOPs": tf,
                               "tensor_frac_sustained": tf / pk["bf16_tflops_sustained"]}), flush=True)
+
+    if args.selfcheck:
+        _, q = bench.make_queries(4, args.dim, dev, seed=7)
+        us, ui = idx.search(q, args.k, path="umma")
+        ss, si = idx.search(q, args.k, path="stream")
+        torch.cuda.synchronize()
+        overlap = sum(len(set(ui[b].tolist()) & set(si[b].tolist())) for b in range(4)) / (4.0 * args.k)
+        print(json.dumps({"tag": args.tag, "what": "selfcheck", "dtype": args.dtype, "topk_overlap_umma_vs_stream": overlap,
+                          "max_abs_score_diff_rankwise": float((us - ss).abs().max()),
+                          "best_id_equal": bool((ui[:, 0] == si[:, 0]).all())}), flush=True)
 
 
 if __name__ == "__main__":
