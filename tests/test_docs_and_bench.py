@@ -111,3 +111,13 @@ def test_unmodified_reference_orchestrator_runs_over_the_drop_in_stages():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dropin_check.py"), "--emulate"], capture_output=True,
                          text=True, timeout=900)
     assert out.returncode == 0 and "drop-in ok" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present")
+def test_unmodified_reference_stage1_runs_over_the_faiss_shaped_module():
+    """INTEGRATION.md way C: the reference's own src/stage1_retriever.py with sys.modules["faiss"] set to
+    tristage_rag_b200.faiss_compat reproduces the reference's Stage-1 output (flat branch, persistence) and its
+    IVF branch agrees with oracle/ivf.py (tools/faiss_shim_check.py; kernels on the CPU emulator build here)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "faiss_shim_check.py"), "--emulate"], capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0 and "faiss shim ok" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
