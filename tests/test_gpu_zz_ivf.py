@@ -98,3 +98,38 @@ def test_device_pointer_api(corpus, request):
     D, I = iv.search_host(Q, 100, nprobe)
     s, i = iv.search(torch.from_numpy(Q).cuda(), 100, nprobe)
     assert np.array_equal(i.cpu().numpy(), I) and np.array_equal(s.cpu().numpy(), D)
+
+
+def test_faiss_shaped_module_drives_both_index_kinds(cuda_device, tmp_path, monkeypatch):
+    """tristage_rag_b200/faiss_compat.py (INTEGRATION.md way C) called the way the reference's _create_faiss_index /
+    search / save_index / load_index call faiss (src/stage1_retriever.py:262-277,380,436,463)."""
+    from tristage_rag_b200 import faiss_compat as faiss
+
+    monkeypatch.setenv("TS_STORAGE_DTYPE", "bf16")
+    monkeypatch.setenv("TS_GPU_INDEX", str(cuda_device))
+    X, centers = clustered(5000, 64, 10, seed=23)
+    Q = _queries(centers, 4, 64, seed=2)
+    Xr, Qr = flat_ip.round_to(X, "bf16"), flat_ip.round_to(Q, "bf16")
+    sc = lambda b, ids: Xr[ids].astype(np.float64) @ Qr[b].astype(np.float64)   # noqa: E731
+    flat = faiss.IndexFlatIP(64)
+    flat.add(X)
+    D, I = flat.search(Q, 10)
+    rD, rI = flat_ip.topk_desc(Qr @ Xr.T, 10)
+    assert flat.ntotal == 5000 and not flat_ip.check_topk(D, I, sc, rD, rI, rel=REL)
+    ivf = faiss.IndexIVFFlat(faiss.IndexFlatIP(64), 64, 10, faiss.METRIC_INNER_PRODUCT)
+    ivf.train(X)
+    ivf.add(X)
+    ivf.nprobe = 10
+    D2, I2 = ivf.search(Q, 10)
+    assert ivf.is_trained and ivf.ntotal == 5000 and not flat_ip.check_topk(D2, I2, sc, rD, rI, rel=REL)
+    ivf.nprobe = 2
+    D3, I3 = ivf.search(Q, 10)
+    for kind, index in (("flat", flat), ("ivf", ivf)):
+        path = str(tmp_path / f"{kind}.index")
+        faiss.write_index(index, path)
+        back = faiss.read_index(path)
+        assert type(back).__name__ == type(index).__mro__[1].__name__ and back.ntotal == 5000
+        bD, bI = back.search(Q, 10)
+        assert np.array_equal(bI, I if kind == "flat" else I3) and np.array_equal(bD, D if kind == "flat" else D3)
+    with pytest.raises(ValueError):
+        faiss.IndexIVFFlat(faiss.IndexFlatIP(32), 64, 10)
