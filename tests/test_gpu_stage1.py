@@ -194,8 +194,8 @@ def test_argument_errors(cuda_device):
             idx.search_host(q, k)
     f32 = _lib.Index(32, "fp32", "ip", cuda_device)
     f32.add(np.ones((4, 32), np.float32))
-    with pytest.raises(_lib.TristageError):
-        f32.search_host(q, 2, path="umma")           # tensor path needs 16-bit storage
+    with pytest.raises(KeyError):
+        f32.search_host(q, 2, path="nonsense")        # (path="umma" on fp32 storage = the opt-in tf32 scan, tests/test_gpu_zz_tf32.py)
     D, I = f32.search_host(np.ones((9, 32), np.float32), 2)   # fp32 + B > 4: stream passes of 4
     assert I.shape == (9, 2) and (I >= 0).all()
 
