@@ -209,7 +209,7 @@ def test_tensor_scan_over_fp32_storage_reads_tf32(sim, monkeypatch, N, d, B, k):
 @pytest.mark.parametrize("order", ["ascending", "descending", "constant"])
 @pytest.mark.parametrize("k", [100, 500])
 def test_tensor_scan_adversarial_score_orders(sim, order, k):
-    """The cases of tests/test_gpu_z_fullsize.py::test_adversarial_score_orders_on_device: ascending
+    """The cases of tests/test_gpu_zzz_fullsize.py::test_adversarial_score_orders_on_device: ascending
     scores overflow every list (in-scan warp prune under a stale shared bound), constant scores tie
     everywhere (the k smallest ids must win through scan, prune and select)."""
     N, d = 60_000, 64
@@ -230,7 +230,7 @@ def test_tensor_scan_adversarial_score_orders(sim, order, k):
 
 
 def test_tensor_scan_variants_agree_bit_for_bit(sim, monkeypatch):
-    """tests/test_gpu_z_fullsize.py::test_scan_variants_agree_bit_for_bit on the emulator: without
+    """tests/test_gpu_zzz_fullsize.py::test_scan_variants_agree_bit_for_bit on the emulator: without
     threshold sharing, with two query tiles per CTA (TS_DUAL), without the small-batch spread, and
     with the first select kernel -- identical ids and scores."""
     N, d, B, k = 20000, 128, 48, 100

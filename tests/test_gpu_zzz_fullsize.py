@@ -1,4 +1,6 @@
-"""GPU: BASELINE.json's full sizes through size-independent properties
+"""(Named zzz so that it runs LAST under `pytest -x`: it is the longest file and the only one whose logic cannot be
+rehearsed on the CPU emulator, because it builds its corpora with torch CUDA tensors.)
+GPU: BASELINE.json's full sizes through size-independent properties
 (planted known answers, sortedness, idempotence, shard-merge == full search,
 agreement of the two scan kernels) plus oracle checks on a few queries."""
 import os

@@ -7,7 +7,7 @@ run() { name=$1; shift; timeout 900 python -m pytest "$@" -q -m gpu -p no:cachep
 run pipe tests/test_gpu_pipeline.py
 run s1 tests/test_gpu_stage1.py
 run s2 tests/test_gpu_stage2.py
-run zfull tests/test_gpu_z_fullsize.py
+run zfull tests/test_gpu_zzz_fullsize.py
 run zhybrid tests/test_gpu_z_hybrid.py
 run zshards tests/test_gpu_z_shards.py
 run zzivf tests/test_gpu_zz_ivf.py

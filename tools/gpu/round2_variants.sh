@@ -3,7 +3,7 @@
 # Usage: gpurun --timeout 1500 -- tools/gpu/round2_variants.sh   (after round2_first.sh is green)
 mkdir -p gpurun_out
 run() { name=$1; shift; timeout 900 python -m pytest "$@" -q -m gpu -p no:cacheprovider > gpurun_out/$name.log 2>&1; echo "$name rc=$? $(tail -1 gpurun_out/$name.log)"; }
-TS_TEST_EXPERIMENTAL=1 run zvariants tests/test_gpu_z_fullsize.py -k scan_variants
+TS_TEST_EXPERIMENTAL=1 run zvariants tests/test_gpu_zzz_fullsize.py -k scan_variants
 # select kernel: parallel count prefix (default since the emulator-validated rewrite) vs the first version
 P8="timeout 300 python tools/perf_probe.py --paths umma --rows 1250000 --dim 1024 --batches 1,32 --steps 50"
 $P8 --tag select_v2 > gpurun_out/select_probe.jsonl 2> gpurun_out/select_probe.err
