@@ -428,21 +428,26 @@ def variant_probes():
             continue
         try:
             p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
+            status = None
             try:
                 so, se = p.communicate(timeout=90)
-                rows = []
-                for ln in so.splitlines():
-                    if ln.startswith("{"):
-                        try:
-                            rows.append(json.loads(ln))
-                        except ValueError:
-                            pass
-                rec = {"status": "ok" if p.returncode == 0 else f"exit {p.returncode}", "lines": rows}
-                if p.returncode != 0:
-                    rec["stderr_tail"] = se[-400:]
             except subprocess.TimeoutExpired:
                 p.kill()
-                rec = {"status": "timeout (90 s), killed"}
+                status = "timeout (90 s), killed"
+                try:
+                    so, se = p.communicate(timeout=10)       # whatever it printed before the limit
+                except subprocess.TimeoutExpired:
+                    so, se = "", ""
+            rows = []
+            for ln in so.splitlines():
+                if ln.startswith("{"):
+                    try:
+                        rows.append(json.loads(ln))
+                    except ValueError:
+                        pass
+            rec = {"status": status or ("ok" if p.returncode == 0 else f"exit {p.returncode}"), "lines": rows}
+            if rec["status"] != "ok":
+                rec["stderr_tail"] = se[-400:]
         except Exception as e:                               # noqa: BLE001
             rec = {"status": f"{type(e).__name__}: {e}"}
         out[name] = rec
