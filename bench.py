@@ -418,7 +418,7 @@ def variant_probes():
     ab = os.path.join(ROOT, "tools", "variant_ab.py")
     # opt-in variants against the validated default, same process, results compared bit for bit on the device
     jobs["stage1_TS_FUSE_and_select_rewrite_AB_1.25Mx1024"] = [sys.executable, ab, "--what", "s1"]
-    jobs["stage2_TS_S2_V2_AB_config4"] = [sys.executable, ab, "--what", "s2"]
+    jobs["stage2_TS_S2_V2_and_TS_S2_EPI2_AB_config4"] = [sys.executable, ab, "--what", "s2"]
     out = {}
     t_start = time.perf_counter()
     for name, cmd in jobs.items():

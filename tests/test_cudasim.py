@@ -640,12 +640,23 @@ def test_tensor_maxsim_matches_the_oracle_both_epilogues(sim, monkeypatch, dim, 
     assert np.array_equal(st.maxsim_host(q, cand, mode=mode), got)
     monkeypatch.delenv("TS_S2_V2")
     assert np.array_equal(st.maxsim_host(q, cand, mode=mode), got)
+    # two epilogue warpgroups (TS_S2_EPI2: 320 threads, one group per accumulator), with either epilogue
+    monkeypatch.setenv("TS_S2_EPI2", "1")
+    assert np.array_equal(st.maxsim_host(q, cand, mode=mode), got)
+    monkeypatch.setenv("TS_S2_V2", "1")
+    assert np.array_equal(st.maxsim_host(q, cand, mode=mode), got)
+    for sms in ("1", "3"):                                           # few SMs: many tiles per CTA, odd and even counts
+        monkeypatch.setenv("HOSTSIM_SM_COUNT", sms)
+        st2, _ = _make_store(lens, dim, dtype, seed=dim)
+        assert np.array_equal(st2.maxsim_host(q, cand, mode=mode), got)
 
 
-@pytest.mark.parametrize("v2", [False, True])
-def test_tensor_maxsim_n_cand_q_len_unowned_and_length_mixes(sim, monkeypatch, v2):
+@pytest.mark.parametrize("v2,epi2", [(False, False), (True, False), (False, True), (True, True)])
+def test_tensor_maxsim_n_cand_q_len_unowned_and_length_mixes(sim, monkeypatch, v2, epi2):
     if v2:
         monkeypatch.setenv("TS_S2_V2", "1")
+    if epi2:
+        monkeypatch.setenv("TS_S2_EPI2", "1")
     rng = np.random.default_rng(2)
     dim, ndocs, B, Cn, Lq = 128, 200, 6, 64, 32
     lens = rng.integers(16, 181, size=ndocs)

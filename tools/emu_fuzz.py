@@ -215,6 +215,8 @@ def stage2_case(rng):
     v2 = bool(rng.random() < 0.5)
     simt = bool(rng.random() < 0.2)
     os.environ["TS_S2_V2"] = "1" if v2 else "0"
+    epi2 = bool(rng.random() < 0.5)
+    os.environ["TS_S2_EPI2"] = "1" if epi2 else "0"
     got = st.maxsim_host(q, np.where((cand >= 0) & (cand < ndocs), cand + base, cand if base == 0 else -1), q_len=q_len,
                          n_cand=n_cand, mode=mode | (_lib.TS_S2_FORCE_SIMT if simt else 0))
     off = np.concatenate([[0], np.cumsum(lens)])
@@ -227,7 +229,7 @@ def stage2_case(rng):
             if 0 <= c < ndocs:
                 ref[b, j] = maxsim.score(nr(q[b, :lq]), nr(tok[off[c]:off[c + 1]]), mode, normalize=False)
     ok = np.allclose(got, ref, rtol=1e-3, atol=3e-4)
-    return (f"S2 {hw} dim={dim} Lq={Lq} ndocs={ndocs} {style} B={B} C={Cn} {dtype} mode={mode} v2={v2} simt={simt} "
+    return (f"S2 {hw} dim={dim} Lq={Lq} ndocs={ndocs} {style} B={B} C={Cn} {dtype} mode={mode} v2={v2} epi2={epi2} simt={simt} "
             f"q_len={None if q_len is None else q_len.tolist()} n_cand={None if n_cand is None else n_cand.tolist()}"), \
         ([] if ok else [f"max abs err {np.abs(got - ref).max()}"])
 

@@ -30,6 +30,11 @@ import json
 for l in open('gpurun_out/s2_v2_probe.jsonl'):
     r=json.loads(l); print(f"{r['tag']:45s} kernel={r['kernel_ms']:.3f} ms  {r['cand_per_s']/1e6:.1f} Mcand/s  hbm={r['hbm_frac']:.2f}")
 PY
+# two epilogue warpgroups (TS_S2_EPI2), alone and with V2: parity, then bit-equality + timing against the default
+TS_S2_EPI2=1 run s2_epi2 tests/test_gpu_stage2.py
+TS_S2_EPI2=1 TS_S2_V2=1 run s2_epi2_v2 tests/test_gpu_stage2.py
+timeout 300 python tools/variant_ab.py --what s2 > gpurun_out/s2_ab.jsonl 2> gpurun_out/s2_ab.err; cat gpurun_out/s2_ab.jsonl
+timeout 300 python tools/variant_ab.py --what s1 > gpurun_out/s1_ab.jsonl 2> gpurun_out/s1_ab.err; cat gpurun_out/s1_ab.jsonl
 # BASELINE configs[1] with the reference's own storage dtype (fp32 corpus, CUDA-core stream scan): not timed in round 1
 timeout 300 python tools/perf_probe.py --rows 1000000 --dim 768 --dtype fp32 --paths stream --batches 1,2,4 --tag c2_fp32 > gpurun_out/c2_fp32.jsonl 2> gpurun_out/c2_fp32.err; cat gpurun_out/c2_fp32.jsonl
 # CTA pairs (cta_group::2) for B >= 129: parity, then A/B at the tensor-bound batch sizes

@@ -4,7 +4,7 @@ at every launch): same inputs, results compared bit for bit on the device, CUDA-
 line per comparison.  Used by `bench.py` (child process, after the headline) and by the round-2 GPU scripts.
 
   python tools/variant_ab.py --what s1      # TS_FUSE (one cooperative launch) and TS_SELECT_V1 (first select kernel)
-  python tools/variant_ab.py --what s2      # TS_S2_V2 (second Stage-2 epilogue)
+  python tools/variant_ab.py --what s2      # TS_S2_V2 (second Stage-2 epilogue), TS_S2_EPI2 (two epilogue warpgroups), both
 """
 import argparse
 import json
@@ -20,14 +20,17 @@ from tristage_rag_b200 import _lib  # noqa: E402
 
 
 def ab(name, switch, fn, steps, dev, extra=None):
-    """fn() -> tuple of cuda tensors.  Default first (validated), then with `switch`=1."""
-    os.environ[switch] = "0"
+    """fn() -> tuple of cuda tensors.  Default first (validated), then with `switch`=1 (several switches: "A+B")."""
+    switches = switch.split("+")
+    for sw in switches:
+        os.environ[sw] = "0"
     ref = fn()
     torch.cuda.synchronize()
     t0 = bench.timed(fn, steps, 3, dev, False) / steps
     rec = {"what": name, "switch": switch, "default_ms": t0}
     try:
-        os.environ[switch] = "1"
+        for sw in switches:
+            os.environ[sw] = "1"
         got = fn()
         torch.cuda.synchronize()
         rec["bit_equal"] = bool(all(torch.equal(a, b) for a, b in zip(got, ref)))
@@ -38,7 +41,8 @@ def ab(name, switch, fn, steps, dev, extra=None):
     except Exception as e:                                   # noqa: BLE001 -- recorded, the next comparison still runs
         rec["error"] = f"{type(e).__name__}: {e}"[:300]
     finally:
-        os.environ[switch] = "0"
+        for sw in switches:
+            os.environ[sw] = "0"
     if extra:
         rec.update(extra)
     print(json.dumps(rec), flush=True)
@@ -76,8 +80,12 @@ def main():
         cand = torch.stack([torch.randperm(ndocs, generator=g, device=dev)[:C] for _ in range(B)])
         for mode, name in ((_lib.TS_S2_MAXSIM, "maxsim"), (_lib.TS_S2_COLBERT, "colbert")):
             fn = lambda: (st.maxsim(q, cand, mode=mode, normalize_q=False),)      # noqa: E731,B023
-            ab(f"stage2 {name} 64 q x 1000 cand (config #4 shapes): second epilogue", "TS_S2_V2", fn, args.steps, dev,
-               {"ndocs": ndocs, "dim": dim})
+            for sw, what in (("TS_S2_V2", "second epilogue"), ("TS_S2_EPI2", "two epilogue warpgroups"),
+                             ("TS_S2_V2+TS_S2_EPI2", "second epilogue in two warpgroups")):
+                if mode == _lib.TS_S2_COLBERT and sw != "TS_S2_V2+TS_S2_EPI2":
+                    continue                          # the softmax-sum mode only differs in the finalize step
+                ab(f"stage2 {name} 64 q x 1000 cand (config #4 shapes): {what}", sw, fn, args.steps, dev,
+                   {"ndocs": ndocs, "dim": dim})
 
 
 if __name__ == "__main__":

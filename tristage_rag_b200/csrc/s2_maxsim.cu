@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(128)
 
 // ========================================================== tensor path ====
 constexpr int kThreads = 192;
+constexpr int kThreadsEpi2 = 320;   // producer + MMA + two epilogue warpgroups (TS_S2_EPI2)
 constexpr int kMaxStages = 4;   // 3 stages + double-buffered maxima, or 4 stages + single buffer (p.n_stages)
 constexpr int kTileM = 128, kTileN = 256, kChunkK = 64;
 constexpr int kABytes = kTileM * kChunkK * 2;
@@ -153,8 +154,13 @@ struct MaxSimParams {
 //     doc really overlaps,
 //   * the drain keeps two tcgen05.ld in flight and reduces each 8-column unit with a max tree
 //     (unmasked when the unit lies inside a doc) instead of a 32-long dependent FMNMX chain.
-template <bool BF16, bool V2>
-__global__ void __launch_bounds__(kThreads, 1)
+// EPI2 (opt-in, TS_S2_EPI2=1; written without a GPU): TWO epilogue warpgroups (320 threads).  Group g
+// (warps 2+4g .. 5+4g) owns the tiles of accumulator g -- the tiles with seq % 2 == g -- so the drain +
+// finalize of one tile overlaps the drain + finalize of the next instead of following it; the round-1
+// profile showed the MMA warp waiting for a free accumulator on 99 % of the tiles.  Each group has its
+// own maxima buffer and named barriers; the producer ends the work with one sentinel per group.
+template <bool BF16, bool V2, bool EPI2>
+__global__ void __launch_bounds__(EPI2 ? kThreadsEpi2 : kThreads, 1)
     maxsim_umma_kernel(const __grid_constant__ CUtensorMap tmQ8, const __grid_constant__ CUtensorMap tmQ32,
                        const __grid_constant__ CUtensorMap tmQ128,
                        const __grid_constant__ CUtensorMap tmT8, const __grid_constant__ CUtensorMap tmT16,
@@ -324,12 +330,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       emit_tile(m);
       cur = nxt;
     }
-    // end-of-work sentinel
-    {
+    // end-of-work sentinel (EPI2: one per epilogue group -- consecutive seq numbers belong to different groups)
+    for (int rep = 0; rep < (EPI2 ? 2 : 1); ++rep) {
       TileMeta* m = begin_tile();
       if (lane == 0) { m->used = 0; m->ndocs = 0; }
       __syncwarp();
       if (lane == 0) mbar_arrive(&mfull_bar[seq % kMetaSlots]);
+      ++seq;
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -370,10 +377,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     // all columns of its 32 tokens.  Per-doc partial maxima meet in mvals
     // (double buffered: one named barrier per tile).
     const int quarter = warp & 3;
-    const int ew = warp - 2;  // 0..3: finalize docs d with d % 4 == ew
+    const int grp = EPI2 ? ((warp - 2) >> 2) : 0;          // epilogue warpgroup
+    const int ew = EPI2 ? ((warp - 2) & 3) : (warp - 2);   // 0..3: finalize docs d with d % 4 == ew
+    const int bar_a = EPI2 ? 1 + 2 * grp : 1, bar_b = EPI2 ? 2 + 2 * grp : 2;   // named barriers of this group
     const int lane_row = quarter * 32 + lane;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (uint32_t seq = 0;; ++seq) {
+    int acc = EPI2 ? grp : 0; uint32_t acc_phase = 0;
+    for (uint32_t seq = EPI2 ? (uint32_t)grp : 0u;; seq += EPI2 ? 2u : 1u) {
       const uint32_t slot = seq % kMetaSlots;
       mbar_wait(&mfull_bar[slot], (seq / kMetaSlots) & 1u, 31);
       const TileMeta* m = &metas[slot];
@@ -472,8 +481,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
-      named_bar_sync(1, 128);   // all per-doc maxima of this tile are in mvals
+      if constexpr (EPI2) { acc_phase ^= 1u; }             // the group keeps its accumulator: one use per own tile
+      else { acc ^= 1; if (acc == 0) acc_phase ^= 1u; }
+      named_bar_sync(bar_a, 128);   // all per-doc maxima of this tile are in mvals
       for (int d = ew; d < nd; d += 4) {
         // m_i = max over doc tokens for query token i (lane i, i + 32, ...)
         float res;
@@ -518,7 +528,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (lane == 0) mbar_arrive(&mempty_bar[slot]);   // meta slot reusable
       // two buffers: mvals[(seq & 1)] is rewritten at tile seq + 2, after the barrier of tile
       // seq + 1, which every warp reaches only after this finalize.  one buffer: wait here.
-      if (mvals_bufs == 1) named_bar_sync(2, 128);
+      // EPI2: buffer (seq & 1) belongs to this group alone and is rewritten by its NEXT tile: wait as well.
+      if (EPI2 || mvals_bufs == 1) named_bar_sync(bar_b, 128);
     }
   }
 
@@ -575,13 +586,21 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
   { const char* e = getenv("TS_S2_STAGES"); p.n_stages = (e && atoi(e) == 4) ? 4 : 3; }
   int grid = a.sm_count < p.n_items ? a.sm_count : p.n_items;
   const bool v2 = env_flag("TS_S2_V2", kDefaultS2V2);   // opt-in until validated on hardware
+  const bool epi2 = env_flag("TS_S2_EPI2", kDefaultS2Epi2);   // two epilogue warpgroups; opt-in until validated on hardware
+  if (epi2) p.n_stages = 3;                               // one maxima buffer per group
+  const int threads = epi2 ? kThreadsEpi2 : kThreads;
   auto launch = [&](auto kern) -> int {
     TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    TS_LAUNCH(kern, grid, kThreads, kSmemBytes, st, tq8, tq32, tq128, t8, t16, t32, t64, t128, p);
+    TS_LAUNCH(kern, grid, threads, kSmemBytes, st, tq8, tq32, tq128, t8, t16, t32, t64, t128, p);
     return TS_OK;
   };
-  if (a.dtype == TS_BF16) rc = v2 ? launch(maxsim_umma_kernel<true, true>) : launch(maxsim_umma_kernel<true, false>);
-  else rc = v2 ? launch(maxsim_umma_kernel<false, true>) : launch(maxsim_umma_kernel<false, false>);
+  if (a.dtype == TS_BF16) {
+    if (epi2) rc = v2 ? launch(maxsim_umma_kernel<true, true, true>) : launch(maxsim_umma_kernel<true, false, true>);
+    else rc = v2 ? launch(maxsim_umma_kernel<true, true, false>) : launch(maxsim_umma_kernel<true, false, false>);
+  } else {
+    if (epi2) rc = v2 ? launch(maxsim_umma_kernel<false, true, true>) : launch(maxsim_umma_kernel<false, false, true>);
+    else rc = v2 ? launch(maxsim_umma_kernel<false, true, false>) : launch(maxsim_umma_kernel<false, false, false>);
+  }
   if (rc) return rc;
   TS_CUDA_OK(cudaGetLastError());
   if (launches) ++*launches;
