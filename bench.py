@@ -407,7 +407,8 @@ def variant_probes():
     tensor path for fp32 storage, the TS_FUSE / TS_S2_V2 variants, the select-kernel rewrite): each job runs in
     its OWN process with a short timeout, after the headline is measured, so a fault in unvalidated code cannot
     touch this process's CUDA context or the result line.  Device-vs-device self-checks only (no oracle here).
-    The cta_group::2 pair kernel (TS_PAIR) and the peer-memory exchange (TS_P2P) are left to dedicated GPU calls."""
+    Every mbarrier wait in the kernels is bounded (a protocol error traps after ~4 s instead of hanging) and a
+    fault is confined to the child's context.  The peer-memory exchange (TS_P2P) needs several GPUs and is not here."""
     jobs = {
         "approximate_mode_1Mx768_bf16": [sys.executable, os.path.join(ROOT, "tools", "ivf_probe.py"), "--rows", "1000000", "--dim", "768",
                                          "--batches", "1,32", "--steps", "20", "--selfcheck"],
@@ -419,6 +420,7 @@ def variant_probes():
     # opt-in variants against the validated default, same process, results compared bit for bit on the device
     jobs["stage1_TS_FUSE_and_select_rewrite_AB_1.25Mx1024"] = [sys.executable, ab, "--what", "s1"]
     jobs["stage2_TS_S2_V2_and_TS_S2_EPI2_AB_config4"] = [sys.executable, ab, "--what", "s2"]
+    jobs["stage1_TS_PAIR_AB_4Mx1024"] = [sys.executable, ab, "--what", "pair"]      # last: the least rehearsed protocol
     out = {}
     t_start = time.perf_counter()
     for name, cmd in jobs.items():

@@ -4,6 +4,7 @@ at every launch): same inputs, results compared bit for bit on the device, CUDA-
 line per comparison.  Used by `bench.py` (child process, after the headline) and by the round-2 GPU scripts.
 
   python tools/variant_ab.py --what s1      # TS_FUSE (one cooperative launch) and TS_SELECT_V1 (first select kernel)
+  python tools/variant_ab.py --what pair    # TS_PAIR (cta_group::2 CTA pairs, B >= 129)
   python tools/variant_ab.py --what s2      # TS_S2_V2 (second Stage-2 epilogue), TS_S2_EPI2 (two epilogue warpgroups), both
 """
 import argparse
@@ -50,7 +51,7 @@ def ab(name, switch, fn, steps, dev, extra=None):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="s1", choices=["s1", "s2"])
+    ap.add_argument("--what", default="s1", choices=["s1", "s2", "pair"])
     ap.add_argument("--steps", type=int, default=30)
     args = ap.parse_args()
     bench.arm_watchdog(300)
@@ -66,6 +67,15 @@ def main():
                {"rows": rows, "dim": dim})
             ab(f"stage1 search B={B}: FIRST select kernel (the default is its rewrite)", "TS_SELECT_V1", fn, args.steps, dev,
                {"rows": rows, "dim": dim})
+    elif args.what == "pair":
+        rows, dim, k = 4_000_000, 1024, 100          # the tensor-bound regime: two query tiles of one slice on a CTA pair
+        idx = _lib.Index(dim, "bf16", "ip", 0, reserve_rows=rows)
+        bench.build_shard(idx, 0, rows, dim, dev, 1234)
+        for B in (256, 1024):
+            _, q = bench.make_queries(B, dim, dev, seed=B)
+            fn = lambda: idx.search(q, k)            # noqa: E731
+            ab(f"stage1 search B={B}: cta_group::2 CTA pairs", "TS_PAIR", fn, min(args.steps, 10), dev,
+               {"rows": rows, "dim": dim, "TFLOP_per_search": 2.0 * B * rows * dim / 1e12})
     else:
         ndocs, dim, B, C, Lq = 200_000, 128, 64, 1000, 32
         g = torch.Generator(device=dev).manual_seed(77)
