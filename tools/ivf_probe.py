@@ -62,6 +62,19 @@ def main():
                           "all_lists_max_score_diff": float((fs - es).abs().max()),
                           "probed_rows_in_probed_lists": float(member.float().mean()), "probe_best_le_exact_best": subset_best,
                           "scores_descending": bool((ps[:, 1:] <= ps[:, :-1]).all())}), flush=True)
+    if args.selfcheck:                                   # grid granularity of the list scan at the reference's batch 1
+        _, q1 = bench.make_queries(1, args.dim, dev, seed=1)
+        for per_sm in (2, 4, 8, 16):
+            os.environ["TS_IVF_CTAS_PER_SM"] = str(per_sm)
+            fn = lambda: iv.search(q1, args.k, args.nprobe)          # noqa: E731
+            bench.timed(fn, 1, 2, dev, False)
+            idx.set_profiling(True)
+            ms = bench.timed(fn, args.steps, 0, dev, False)
+            kms, _n = idx.scan_time_ms()
+            idx.set_profiling(False)
+            print(json.dumps({"tag": args.tag, "what": "grid sweep B=1", "ctas_per_sm": per_sm, "step_ms": ms / args.steps,
+                              "scan_ms": kms}), flush=True)
+        os.environ.pop("TS_IVF_CTAS_PER_SM", None)
     for B in [int(b) for b in args.batches.split(",")]:
         qh, q = bench.make_queries(B, args.dim, dev, seed=B)
         lists, _ = iv.coarse_host(qh.numpy(), args.nprobe)

@@ -69,7 +69,8 @@ constexpr int kIvfWarps = kIvfThreads / 32;
 constexpr int kIvfR = 4;            // rows per warp step
 constexpr int kIvfJ = 4;            // centroids per assign step
 constexpr int kIvfMergeCap = 4096;  // keys of the CTA merge buffer
-constexpr int kIvfMaxSeg = 64;      // segments per probed list
+constexpr int kIvfMaxSeg = 256;     // segments per probed list
+constexpr int kIvfCtasPerSm = 4;    // grid target: CTAs per SM (TS_IVF_CTAS_PER_SM overrides, 1..32 -- tuning knob)
 constexpr int kIvfMaxPairs = 4096;  // (query, probe) pairs the order kernel sorts (32 KB of keys)
 
 // shared-memory twin of warp_prune_list (ts_common.cuh): the warp sorts list[0..cnt) and keeps the
@@ -543,8 +544,10 @@ int ts_ivf_search(ts_ivf* h, const void* q_dev, int q_dtype, int B, int k, int n
   for (int b0 = 0; b0 < B; b0 += chunkB) {
     const int Bc = (B - b0) < chunkB ? (B - b0) : chunkB;
     if ((rc = ivf_probe(h, (const char*)q_dev + (size_t)b0 * base->dim * dtype_size(q_dtype), q_dtype, Bc, nprobe, flags, st))) return rc;
-    // enough CTAs for ~4 per SM; a probed list is cut into at most kIvfMaxSeg segments
-    int S = (4 * base->info.sm_count + Bc * nprobe - 1) / (Bc * nprobe);
+    // enough CTAs for ~kIvfCtasPerSm per SM; a probed list is cut into at most kIvfMaxSeg segments
+    int per_sm = kIvfCtasPerSm;
+    if (const char* e = getenv("TS_IVF_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 32) per_sm = v; }
+    int S = (per_sm * base->info.sm_count + Bc * nprobe - 1) / (Bc * nprobe);
     if (S < 1) S = 1;
     if (S > kIvfMaxSeg) S = kIvfMaxSeg;
     const int L = nprobe * S;
