@@ -645,7 +645,7 @@ def test_tensor_maxsim_matches_the_oracle_both_epilogues(sim, monkeypatch, dim, 
     assert np.array_equal(st.maxsim_host(q, cand, mode=mode), got)
     monkeypatch.setenv("TS_S2_V2", "1")
     assert np.array_equal(st.maxsim_host(q, cand, mode=mode), got)
-    for sms in ("1", "3"):                                           # few SMs: many tiles per CTA, odd and even counts
+    for sms in (("1", "3") if (dim, Lq, dtype) == (128, 32, "bf16") else ()):   # few SMs: many tiles per CTA, odd and even counts
         monkeypatch.setenv("HOSTSIM_SM_COUNT", sms)
         st2, _ = _make_store(lens, dim, dtype, seed=dim)
         assert np.array_equal(st2.maxsim_host(q, cand, mode=mode), got)
