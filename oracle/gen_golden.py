@@ -260,6 +260,31 @@ def gen_flat_ip():
     print("stage1_flat_ip.json")
 
 
+def gen_ivf():
+    """Oracle-generated regression vectors for the restated IndexIVFFlat (FAISS is absent: these pin
+    oracle/ivf.py against itself and document the semantics -- assignment, probe order, -1 padding)."""
+    from oracle import ivf as oivf
+
+    rng = np.random.default_rng(7)
+    centers = flat_ip.normalize_rows(rng.standard_normal((4, 12)).astype(np.float32))
+    x = flat_ip.normalize_rows(centers[rng.integers(0, 4, size=60)] + 0.25 * rng.standard_normal((60, 12)).astype(np.float32))
+    x = x.astype(np.float32)
+    q = flat_ip.normalize_rows(centers[:2] + 0.05).astype(np.float32)
+    cent = oivf.kmeans_ip(x, 5, niter=10, seed=1234)
+    assign = oivf.assign_lists(x, cent)
+    lists, lscores = oivf.coarse_probe(q, cent, 2)
+    D, I = oivf.ivf_search(x, q, assign, lists, 8)
+    Dp, Ip = oivf.ivf_search(x, q, assign, lists[:, :1], 40)          # one list, k larger than the list
+    with open(os.path.join(GOLD, "stage1_ivf.json"), "w") as f:
+        json.dump(dict(source="oracle/ivf.py (restated faiss.IndexIVFFlat over IndexFlatIP; FAISS not installable)",
+                       seed=7, n=60, d=12, nlist=5, nprobe=2, x=x.tolist(), q=q.tolist(),
+                       centroids=cent.tolist(), assign=assign.tolist(), lists=lists.tolist(),
+                       lscores=lscores.tolist(), k8=dict(D=D.tolist(), I=I.tolist()),
+                       one_list_k40_valid=[int((Ip[b] >= 0).sum()) for b in range(2)], one_list_k40_I0=Ip[0].tolist()),
+                  f, indent=1)
+    print("stage1_ivf.json")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     s1, s2 = import_reference()
@@ -273,6 +298,7 @@ def main():
     finally:
         os.chdir(cwd)
     gen_flat_ip()
+    gen_ivf()
 
 
 if __name__ == "__main__":

@@ -136,3 +136,36 @@ def test_maxsim_batch_matches_loop():
         got = c_oracle.maxsim_batch(q, tok, off, mode)
         ref = maxsim.score_candidates(q, [tok[off[i]:off[i + 1]] for i in range(len(lens))], mode)
         np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-6)
+
+
+def test_ivf_golden_and_semantics(golden_dir):
+    """oracle/ivf.py against its committed vectors (FAISS is absent: this pins the restated IndexIVFFlat against
+    itself) and the properties the kernels are tested for: every row in exactly one list, probes best first,
+    results only from probed lists, -1 padding past the probed rows, all lists probed == the flat index."""
+    import json
+
+    from oracle import ivf as oivf
+
+    with open(os.path.join(golden_dir, "stage1_ivf.json")) as f:
+        g = json.load(f)
+    x, q = np.asarray(g["x"], np.float32), np.asarray(g["q"], np.float32)
+    cent = oivf.kmeans_ip(x, g["nlist"], niter=10, seed=1234)
+    assert np.allclose(cent, np.asarray(g["centroids"], np.float32), atol=1e-6)
+    assign = oivf.assign_lists(x, cent)
+    assert assign.tolist() == g["assign"] and assign.min() >= 0 and assign.max() < g["nlist"]
+    lists, lscores = oivf.coarse_probe(q, cent, g["nprobe"])
+    assert lists.tolist() == g["lists"] and np.allclose(lscores, g["lscores"], atol=1e-6)
+    assert (np.diff(lscores, axis=1) <= 0).all()
+    D, I = oivf.ivf_search(x, q, assign, lists, 8)
+    assert I.tolist() == g["k8"]["I"] and np.allclose(D, g["k8"]["D"], atol=1e-6)
+    for b in range(2):
+        ok = I[b] >= 0
+        assert np.isin(assign[I[b][ok]], lists[b]).all() and (np.diff(D[b][ok]) <= 0).all()
+    Dp, Ip = oivf.ivf_search(x, q, assign, lists[:, :1], 40)
+    assert [int((Ip[b] >= 0).sum()) for b in range(2)] == g["one_list_k40_valid"] and Ip[0].tolist() == g["one_list_k40_I0"]
+    n0 = g["one_list_k40_valid"][0]
+    assert n0 == int((assign == lists[0, 0]).sum()) and (Ip[0, n0:] == -1).all() and (Dp[0, n0:] == flat_ip.LOWEST_F32).all()
+    all_lists = np.tile(np.arange(g["nlist"], dtype=np.int32), (2, 1))
+    De, Ie = oivf.ivf_search(x, q, assign, all_lists, 8)
+    rD, rI = flat_ip.topk_desc(q @ x.T, 8)
+    assert (Ie == rI).all() and np.allclose(De, rD, atol=1e-6)
