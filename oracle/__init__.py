@@ -15,6 +15,8 @@ What it restates (reference paths are relative to /root/reference):
   in ``flat_ip.py``: fp32 inner product, k results per query in descending
   score order, int64 labels, ``-1`` labels (score = lowest float) when
   ``k > ntotal``.
+* Stage 1, approximate mode (``src/stage1_retriever.py:262-273``): ``faiss.IndexIVFFlat`` over an
+  ``IndexFlatIP`` quantizer, restated in ``ivf.py`` (k-means training, list assignment, probing, list scan).
 * Stage 2 (``src/stage2_rescorer.py``): ``_maxsim_score`` (:167-183) and
   ``_colbert_score`` (:185-201), plus the stable descending sort + truncate of
   ``rescore_candidates`` (:294-297).
