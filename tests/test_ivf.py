@@ -416,3 +416,39 @@ def test_batches_scan_list_by_list_with_identical_results(sim, monkeypatch):
     monkeypatch.setenv("TS_IVF_MAXPAIRS", "100")          # more pairs than the order kernel takes (4096 in production):
     D1, I1 = iv.search_host(Q, 10, 3)                     # the (segment, probe, query) grid, unordered
     assert np.array_equal(I1, I) and np.array_equal(D1, D)
+
+
+def test_faiss_readers_never_crash_on_damaged_files(tmp_path):
+    """Seeded random truncations, byte flips and length-field edits of valid flat / IVF index files: the readers
+    either return a self-consistent result or raise FaissFormatError -- never another exception."""
+    import struct
+
+    from tristage_rag_b200.faiss_io import FaissFormatError, read_faiss_flat, read_faiss_ivf
+
+    X, _ = clustered(120, 8, 3, seed=4)
+    cent = ivf_train.train_centroids(X, 4)
+    a = oivf.assign_lists(X, cent)
+    ivf_blob = write_faiss_ivf(str(tmp_path / "v.index"), X, cent, a, nprobe=2)
+    flat_blob = b"IxFI" + struct.pack("<iqqqBi", 8, 120, 1 << 20, 1 << 20, 1, 0) + struct.pack("<Q", 960) + X.tobytes()
+    rng = np.random.default_rng(0)
+    outcomes = {"ok": 0, "refused": 0}
+    for blob, reader in ((ivf_blob, read_faiss_ivf), (flat_blob, read_faiss_flat)):
+        for trial in range(150):
+            b = bytearray(blob)
+            kind = trial % 3
+            if kind == 0:
+                b = b[: int(rng.integers(0, len(b)))]
+            elif kind == 1:
+                for _ in range(int(rng.integers(1, 4))):
+                    b[int(rng.integers(0, min(len(b), 200)))] ^= 1 << int(rng.integers(0, 8))     # header area
+            else:
+                at = int(rng.integers(0, max(1, min(len(b), 220) - 8)))
+                b[at:at + 8] = struct.pack("<Q", [0, 1, 2 ** 31, 2 ** 63 - 1, 2 ** 64 - 1, 121, 7][int(rng.integers(0, 7))])
+            p = str(tmp_path / "damaged")
+            open(p, "wb").write(bytes(b))
+            try:
+                reader(p)
+                outcomes["ok"] += 1
+            except FaissFormatError:
+                outcomes["refused"] += 1
+    assert outcomes["refused"] > 100 and outcomes["ok"] > 0, outcomes      # flips inside float payloads and ignored fields are legitimate
