@@ -270,7 +270,7 @@ def test_tensor_scan_variants_agree_bit_for_bit(sim, monkeypatch):
 
 
 @pytest.mark.parametrize("N,d,B,k,dtype", [(3000, 64, 200, 10, "bf16"), (5000, 128, 300, 100, "bf16"), (600, 100, 129, 7, "fp16"),
-                                           (9000, 64, 1024, 100, "bf16"), (4000, 256, 256, 500, "bf16"), (5, 72, 130, 50, "bf16")])
+                                           (6000, 64, 1024, 100, "bf16"), (4000, 256, 256, 500, "bf16"), (5, 72, 130, 50, "bf16")])
 def test_cta_pair_scan_equals_the_single_cta_scan(sim, monkeypatch, N, d, B, k, dtype):
     """s1_pair_kernel (TS_PAIR=1: tcgen05.mma cta_group::2 over a 2-CTA cluster, each CTA loading half of
     every corpus chunk, remote mbarrier arrives, multicast commits) on the emulator's cluster model:
@@ -755,7 +755,7 @@ def test_few_sms_many_tiles_per_cta_wrap_every_ring(sim, monkeypatch, sms, async
     comparisons catch it)."""
     monkeypatch.setenv("HOSTSIM_SM_COUNT", str(sms))
     monkeypatch.setenv("CUDASIM_ASYNC", str(async_seed))
-    N, d, k = 9000, 200, 100
+    N, d, k = 6500, 200, 100
     for B in (7, 200):
         X, Q = make(N, d, B, seed=B, planted=10)
         idx = _lib.Index(d, "bf16", "ip", 0)
