@@ -99,6 +99,7 @@ def main():
     r.add_documents(docs[1100:])
     assert type(r.faiss_index) is faiss_compat.IndexIVFFlat and r.faiss_index.nprobe == 3 and r.faiss_index.ntotal == 1300
     X = r._normalize_embeddings(r._encode_batch(docs)).astype(np.float32)
+    r.faiss_index._ivf.sync()                                  # (a search does this by itself; the check reads the lists first)
     a = r.faiss_index._ivf.assignments()
     cent = r.faiss_index._ivf.centroids()
     for query in ("w1 w2 w3", "w10 w399 w7 w7", docs[5]):

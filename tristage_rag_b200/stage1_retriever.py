@@ -278,8 +278,9 @@ class IndexIVFFlat:
     def add(self, x: np.ndarray) -> None:
         if not self.is_trained:
             raise RuntimeError("IndexIVFFlat.add before train")      # faiss asserts is_trained
+        # the rows are appended now and put into their lists by the next search / save (ts_ivf_search syncs by itself):
+        # ingest in many small batches does not rebuild the lists once per batch
         self._index.add(np.ascontiguousarray(x, dtype=np.float32), normalize=False)
-        self._ivf.sync()
 
     def search(self, q: np.ndarray, k: int, path: str = "auto"):
         if k > _lib.TS_MAX_K:
@@ -290,6 +291,7 @@ class IndexIVFFlat:
         return self._index.search_host(q, k, normalize_q=False, path=path)
 
     def save(self, path: str) -> None:
+        self._ivf.sync()
         self._index.save(path)
         tmp = path + ".ivf.tmp.npz"
         np.savez(tmp, centroids=self._ivf.centroids(), assign=self._ivf.assignments(),
