@@ -5,6 +5,8 @@ The same kernels run at small sizes on the SIMT emulator in tests/test_ivf.py.
 
 Tolerance: ids exact except near-ties within 1e-3 relative score, scores within 1e-3 relative
 (bf16 storage, fp32 accumulation) -- the Stage-1 rule of BASELINE.json."""
+import os
+
 import numpy as np
 import pytest
 
@@ -23,6 +25,8 @@ REL = 1e-3
 def corpus(request, cuda_device):
     small = request.config.getoption("--emulate")
     N, d, nlist = (3000, 64, 12) if small else (200_000, 256, 100)
+    if os.environ.get("TS_TEST_IVF_SIZE"):                     # "N,d,nlist": rehearse other sizes (e.g. on the emulator)
+        N, d, nlist = (int(v) for v in os.environ["TS_TEST_IVF_SIZE"].split(","))
     X, centers = clustered(N, d, nlist, seed=17)
     idx = _lib.Index(d, "bf16", "ip", cuda_device)
     idx.add(X[: N // 2])
