@@ -200,6 +200,7 @@ def finish(code: int = 0):
     os._exit(code)
 
 
+_T0 = time.perf_counter()       # process start: the side jobs stop being launched once the whole run is 7 min old
 _PENDING = {"line": None}      # the result line once the headline is measured: the watchdog prints it rather than nothing
 
 
@@ -425,17 +426,18 @@ def variant_probes():
     t_start = time.perf_counter()
     for name, cmd in jobs.items():
         rec = {"status": "not run"}
-        if time.perf_counter() - t_start > 240:              # overall budget of the side jobs
-            out[name] = {"status": "skipped: side-measurement budget (240 s) used up"}
+        now = time.perf_counter()
+        if now - t_start > 200 or now - _T0 > 420:           # budget of the side jobs / age of the whole run
+            out[name] = {"status": "skipped: side-measurement budget used up"}
             continue
         try:
             p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
             status = None
             try:
-                so, se = p.communicate(timeout=90)
+                so, se = p.communicate(timeout=75)
             except subprocess.TimeoutExpired:
                 p.kill()
-                status = "timeout (90 s), killed"
+                status = "timeout (75 s), killed"
                 try:
                     so, se = p.communicate(timeout=10)       # whatever it printed before the limit
                 except subprocess.TimeoutExpired:
