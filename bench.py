@@ -397,7 +397,10 @@ def main():
         dist.barrier()
     _PENDING["line"] = line
     if rank == 0 and world == 1 and not args.no_extra and not args.no_variants:
-        line["extra"]["unvalidated_variants"] = variant_probes()
+        try:
+            line["extra"]["unvalidated_variants"] = variant_probes()
+        except Exception as e:                               # noqa: BLE001 -- never at the expense of the result line
+            line["extra"]["unvalidated_variants"] = {"status": f"{type(e).__name__}: {e}"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     finish(0)
