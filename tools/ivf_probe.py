@@ -85,6 +85,7 @@ def main():
             ms = bench.timed(fn, args.steps, 0, dev, False)
             kms, n = idx.scan_time_ms()
             idx.set_profiling(False)
+            kms = max(kms, 1e-9)
             rows_read = probed_rows if name == "ivf" else args.rows
             gb = rows_read * ld * 2 / (kms / 1e3) / 1e9
             print(json.dumps({"tag": args.tag, "what": name, "rows": args.rows, "dim": args.dim, "B": B, "nlist": args.nlist,

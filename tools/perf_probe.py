@@ -45,7 +45,8 @@ def main():
             ms = bench.timed(fn, args.steps, 0, dev, False)
             kms, n = idx.scan_time_ms()
             idx.set_profiling(False)
-            n_scans = n / args.steps
+            kms = max(kms, 1e-9)
+            n_scans = max(n, 1) / args.steps
             gb = args.rows * ld * esz * n_scans / (kms * n_scans / 1e3) / 1e9
             tf = 2.0 * B * args.rows * ld / (kms * n_scans / 1e3) / 1e12
             print(json.dumps({"tag": args.tag, "rows": args.rows, "dim": args.dim, "dtype": args.dtype, "B": B, "path": path, "step_ms": ms / args.steps,

@@ -53,11 +53,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--what", default="s1", choices=["s1", "s2", "pair"])
     ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--rows", type=int, default=0, help="corpus rows (default: 1.25 M for s1, 4 M for pair)")
+    ap.add_argument("--dim", type=int, default=1024)
+    ap.add_argument("--ndocs", type=int, default=200_000, help="token-store documents (s2)")
+    ap.add_argument("--cands", type=int, default=1000, help="candidates per query (s2)")
+    ap.add_argument("--queries", type=int, default=64, help="query batch (s2)")
+    ap.add_argument("--pair-batches", default="256,1024", help="query batches of the pair comparison (>= 129)")
     args = ap.parse_args()
     bench.arm_watchdog(300)
     dev = torch.device("cuda", 0)
     if args.what == "s1":
-        rows, dim, k = 1_250_000, 1024, 100          # the per-GPU shard of the 8-GPU headline run: fixed costs show
+        rows, dim, k = args.rows or 1_250_000, args.dim, 100   # the per-GPU shard of the 8-GPU headline run: fixed costs show
         idx = _lib.Index(dim, "bf16", "ip", 0, reserve_rows=rows)
         bench.build_shard(idx, 0, rows, dim, dev, 1234)
         for B in (1, 32):
@@ -68,16 +74,16 @@ def main():
             ab(f"stage1 search B={B}: FIRST select kernel (the default is its rewrite)", "TS_SELECT_V1", fn, args.steps, dev,
                {"rows": rows, "dim": dim})
     elif args.what == "pair":
-        rows, dim, k = 4_000_000, 1024, 100          # the tensor-bound regime: two query tiles of one slice on a CTA pair
+        rows, dim, k = args.rows or 4_000_000, args.dim, 100   # the tensor-bound regime: two query tiles of one slice on a CTA pair
         idx = _lib.Index(dim, "bf16", "ip", 0, reserve_rows=rows)
         bench.build_shard(idx, 0, rows, dim, dev, 1234)
-        for B in (256, 1024):
+        for B in [int(b) for b in args.pair_batches.split(",")]:
             _, q = bench.make_queries(B, dim, dev, seed=B)
             fn = lambda: idx.search(q, k)            # noqa: E731
             ab(f"stage1 search B={B}: cta_group::2 CTA pairs", "TS_PAIR", fn, min(args.steps, 10), dev,
                {"rows": rows, "dim": dim, "TFLOP_per_search": 2.0 * B * rows * dim / 1e12})
     else:
-        ndocs, dim, B, C, Lq = 200_000, 128, 64, 1000, 32
+        ndocs, dim, B, C, Lq = args.ndocs, 128, args.queries, args.cands, 32
         g = torch.Generator(device=dev).manual_seed(77)
         rng = np.random.default_rng(77)
         lens = rng.integers(16, 181, size=ndocs).astype(np.int32)
@@ -87,14 +93,15 @@ def main():
             t = torch.nn.functional.normalize(torch.randn((int(ln.sum()), dim), generator=g, device=dev), dim=-1)
             st.add(t.to(torch.bfloat16), ln, normalize=False)
         q = torch.nn.functional.normalize(torch.randn((B, Lq, dim), generator=g, device=dev), dim=-1).to(torch.bfloat16)
-        cand = torch.stack([torch.randperm(ndocs, generator=g, device=dev)[:C] for _ in range(B)])
+        cand = torch.stack([torch.randperm(ndocs, generator=g, device=dev)[:C] if C <= ndocs
+                            else torch.randint(0, ndocs, (C,), generator=g, device=dev) for _ in range(B)])
         for mode, name in ((_lib.TS_S2_MAXSIM, "maxsim"), (_lib.TS_S2_COLBERT, "colbert")):
             fn = lambda: (st.maxsim(q, cand, mode=mode, normalize_q=False),)      # noqa: E731,B023
             for sw, what in (("TS_S2_V2", "second epilogue"), ("TS_S2_EPI2", "two epilogue warpgroups"),
                              ("TS_S2_V2+TS_S2_EPI2", "second epilogue in two warpgroups")):
                 if mode == _lib.TS_S2_COLBERT and sw != "TS_S2_V2+TS_S2_EPI2":
                     continue                          # the softmax-sum mode only differs in the finalize step
-                ab(f"stage2 {name} 64 q x 1000 cand (config #4 shapes): {what}", sw, fn, args.steps, dev,
+                ab(f"stage2 {name} {B} q x {C} cand (config #4 shapes): {what}", sw, fn, args.steps, dev,
                    {"ndocs": ndocs, "dim": dim})
 
 
