@@ -96,6 +96,7 @@ def test_ivf_probe_runs_end_to_end(fake_cuda, monkeypatch):
                                   "--steps", "1", "--selfcheck"], monkeypatch)
     kinds = [r["what"] for r in rows]
     assert kinds.count("ivf") == 2 and kinds.count("exact") == 2 and kinds.count("grid sweep B=1") == 4
+    assert kinds.count("batch order B=32") == 2 and "TS_IVF_NOORDER" not in os.environ
     chk = next(r for r in rows if r["what"] == "selfcheck")
     assert chk["all_lists_ids_equal_exact"] > 0.95 and chk["probed_rows_in_probed_lists"] == 1.0
     assert chk["probe_best_le_exact_best"] and chk["scores_descending"]

@@ -75,6 +75,18 @@ def main():
             print(json.dumps({"tag": args.tag, "what": "grid sweep B=1", "ctas_per_sm": per_sm, "step_ms": ms / args.steps,
                               "scan_ms": kms}), flush=True)
         os.environ.pop("TS_IVF_CTAS_PER_SM", None)
+        _, q32 = bench.make_queries(32, args.dim, dev, seed=32)       # batches: pairs ordered by list (L2 reuse) vs grid order
+        for noorder in ("0", "1"):
+            os.environ["TS_IVF_NOORDER"] = noorder
+            fn = lambda: iv.search(q32, args.k, args.nprobe)           # noqa: E731
+            bench.timed(fn, 1, 2, dev, False)
+            idx.set_profiling(True)
+            ms = bench.timed(fn, args.steps, 0, dev, False)
+            kms, _n = idx.scan_time_ms()
+            idx.set_profiling(False)
+            print(json.dumps({"tag": args.tag, "what": "batch order B=32", "pairs_ordered_by_list": noorder == "0",
+                              "step_ms": ms / args.steps, "scan_ms": kms}), flush=True)
+        os.environ.pop("TS_IVF_NOORDER", None)
     for B in [int(b) for b in args.batches.split(",")]:
         qh, q = bench.make_queries(B, args.dim, dev, seed=B)
         lists, _ = iv.coarse_host(qh.numpy(), args.nprobe)
