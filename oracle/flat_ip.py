@@ -90,25 +90,34 @@ class IndexFlatIP:
         if self.ntotal <= block:
             return topk_desc(q @ x.T, k)
         # blocked scan so a [B, N] score matrix is never materialised
-        bestD = np.full((B, 0), LOWEST_F32, np.float32)
-        bestI = np.full((B, 0), -1, np.int64)
-        for s in range(0, self.ntotal, block):
-            e = min(s + block, self.ntotal)
-            D, I = topk_desc(q @ x[s:e].T, min(k, e - s))
-            I = I + s
-            catD = np.concatenate([bestD, D], axis=1)
-            catI = np.concatenate([bestI, I], axis=1)
-            newD = np.empty((B, min(k, catD.shape[1])), np.float32)
-            newI = np.empty_like(newD, dtype=np.int64)
-            for b in range(B):
-                o = np.lexsort((catI[b], -catD[b].astype(np.float64)))[: newD.shape[1]]
-                newD[b], newI[b] = catD[b][o], catI[b][o]
-            bestD, bestI = newD, newI
-        D = np.full((B, k), LOWEST_F32, np.float32)
-        I = np.full((B, k), -1, np.int64)
-        D[:, : bestD.shape[1]] = bestD
-        I[:, : bestI.shape[1]] = bestI
-        return D, I
+        return search_streamed(((s, x[s:min(s + block, self.ntotal)]) for s in range(0, self.ntotal, block)), q, k)
+
+
+def search_streamed(blocks, q: np.ndarray, k: int):
+    """The same exact search over a corpus that arrives as ``(first_row, rows[n, d])`` blocks (a corpus too
+    large for host memory is fetched back from the device shard by shard): per-block exact top-k, merged
+    with the deterministic order (score desc, id asc).  Returns (D[B,k], I[B,k]) padded like FAISS."""
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    B = q.shape[0]
+    bestD = np.full((B, 0), LOWEST_F32, np.float32)
+    bestI = np.full((B, 0), -1, np.int64)
+    for s, xb in blocks:
+        xb = np.asarray(xb, dtype=np.float32)
+        D, I = topk_desc(q @ xb.T, min(k, xb.shape[0]))
+        I = I + s
+        catD = np.concatenate([bestD, D], axis=1)
+        catI = np.concatenate([bestI, I], axis=1)
+        newD = np.empty((B, min(k, catD.shape[1])), np.float32)
+        newI = np.empty_like(newD, dtype=np.int64)
+        for b in range(B):
+            o = np.lexsort((catI[b], -catD[b].astype(np.float64)))[: newD.shape[1]]
+            newD[b], newI[b] = catD[b][o], catI[b][o]
+        bestD, bestI = newD, newI
+    D = np.full((B, k), LOWEST_F32, np.float32)
+    I = np.full((B, k), -1, np.int64)
+    D[:, : bestD.shape[1]] = bestD
+    I[:, : bestI.shape[1]] = bestI
+    return D, I
 
 
 def round_to(x: np.ndarray, dtype: str) -> np.ndarray:

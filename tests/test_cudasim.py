@@ -631,8 +631,12 @@ def test_tensor_maxsim_matches_the_oracle_both_epilogues(sim, monkeypatch, dim, 
     cand = rng.integers(0, ndocs, size=(B, Cn)).astype(np.int64)
     cand[0, :6] = np.arange(6)
     ref = _oracle_scores(q, docs, cand, mode, dtype)
+    got_flow = st.maxsim_host(q, cand, mode=mode)                   # default: maxsim_flow_kernel (s2_flow.cu)
+    np.testing.assert_allclose(got_flow, ref, rtol=1e-3, atol=2e-4)
+    monkeypatch.setenv("TS_S2_FLOW", "0")                            # the first kernel and its variants
     got = st.maxsim_host(q, cand, mode=mode)
     np.testing.assert_allclose(got, ref, rtol=1e-3, atol=2e-4)
+    assert np.array_equal(got_flow, got)                              # same products, same order: bit-equal
     monkeypatch.setenv("TS_S2_V2", "1")
     got2 = st.maxsim_host(q, cand, mode=mode)
     assert np.array_equal(got2, got)
@@ -653,6 +657,7 @@ def test_tensor_maxsim_matches_the_oracle_both_epilogues(sim, monkeypatch, dim, 
 
 @pytest.mark.parametrize("v2,epi2", [(False, False), (True, False), (False, True), (True, True)])
 def test_tensor_maxsim_n_cand_q_len_unowned_and_length_mixes(sim, monkeypatch, v2, epi2):
+    monkeypatch.setenv("TS_S2_FLOW", "0")
     if v2:
         monkeypatch.setenv("TS_S2_V2", "1")
     if epi2:
@@ -684,6 +689,55 @@ def test_tensor_maxsim_n_cand_q_len_unowned_and_length_mixes(sim, monkeypatch, v
         c2 = np.stack([rng.permutation(len(ln))[: min(len(ln), 40)] for _ in range(2)]).astype(np.int64)
         np.testing.assert_allclose(st2.maxsim_host(q2, c2), _oracle_scores(q2, docs2, c2, 0, "bf16"), rtol=1e-3, atol=2e-4,
                                    err_msg=name)
+
+
+@pytest.mark.parametrize("stages,a_bufs,sms,async_seed", [(0, 0, 0, 0), (2, 1, 2, 0), (3, 2, 3, 5), (5, 1, 1, 9), (4, 2, 5, 0)])
+def test_flow_maxsim_splits_docs_across_tiles_and_keeps_the_query_resident(sim, monkeypatch, stages, a_bufs, sms, async_seed):
+    """maxsim_flow_kernel (s2_flow.cu): docs split across tile boundaries (carry of the running maxima), the
+    16-segment cap, query changes inside a CTA with one and two query-tile buffers, n_cand / q_len / un-owned
+    ids, every ring depth, few SMs (long pipelines) and adversarial timing -- against the oracle, and bit for
+    bit against the first kernel."""
+    if stages:
+        monkeypatch.setenv("TS_S2_STAGES", str(stages))
+    if a_bufs:
+        monkeypatch.setenv("TS_S2_ABUFS", str(a_bufs))
+    if sms:
+        monkeypatch.setenv("HOSTSIM_SM_COUNT", str(sms))
+    monkeypatch.setenv("CUDASIM_ASYNC", str(async_seed))
+    rng = np.random.default_rng(11 + stages)
+    dim, ndocs = 128, 220
+    lens = rng.integers(1, 257, size=ndocs)
+    lens[:12] = [256, 255, 249, 248, 1, 8, 9, 7, 200, 56, 256, 64]
+    st, docs = _make_store(lens, dim, "bf16", seed=3)
+    for B, Cn, Lq in ((5, 37, 32), (3, 90, 70), (2, 130, 128), (9, 9, 20)):
+        q = rng.standard_normal((B, Lq, dim)).astype(np.float32)
+        cand = rng.integers(0, ndocs, size=(B, Cn)).astype(np.int64)
+        cand[0, : min(Cn, 12)] = np.arange(min(Cn, 12))
+        cand[1, 3] = -1
+        cand[1, 4] = ndocs + 3
+        n_cand = rng.integers(0, Cn + 1, size=B).astype(np.int32)
+        n_cand[0] = Cn
+        q_len = rng.integers(1, Lq + 1, size=B).astype(np.int32)
+        q_len[0] = Lq
+        for mode in (0, 1):
+            got = st.maxsim_host(q, cand, q_len=q_len, n_cand=n_cand, mode=mode)
+            ref = _oracle_scores(q, docs, cand, mode, "bf16", n_cand=n_cand, q_len=q_len)
+            np.testing.assert_allclose(got, ref, rtol=1e-3, atol=2e-4, err_msg=f"{B}x{Cn} Lq={Lq} mode={mode}")
+            assert got[1, 3] == 0.0 and got[1, 4] == 0.0
+            monkeypatch.setenv("TS_S2_FLOW", "0")
+            assert np.array_equal(st.maxsim_host(q, cand, q_len=q_len, n_cand=n_cand, mode=mode), got)
+            monkeypatch.delenv("TS_S2_FLOW")
+    # length mixes: only tiny docs (the 16-segment cap closes tiles early), only 256-token docs (every doc but
+    # the first is split), exact multiples of the tile, quarter straddlers
+    for name, ln in (("tiny", np.full(90, 3)), ("max", np.full(12, 256)), ("eights", np.full(70, 8)), ("128s", np.full(20, 128)),
+                     ("248", np.full(15, 248)),
+                     ("straddle", np.array([60, 10, 120, 7, 59, 130, 3, 3, 3, 250, 5, 1, 63, 1, 64, 1, 127, 129] * 3))):
+        st2, docs2 = _make_store(ln, 64, "bf16", seed=len(ln))
+        q2 = rng.standard_normal((2, 20, 64)).astype(np.float32)
+        c2 = np.stack([rng.permutation(len(ln))[: min(len(ln), 40)] for _ in range(2)]).astype(np.int64)
+        for mode in (0, 1):
+            np.testing.assert_allclose(st2.maxsim_host(q2, c2, mode=mode), _oracle_scores(q2, docs2, c2, mode, "bf16"), rtol=1e-3,
+                                       atol=2e-4, err_msg=name)
 
 
 # ------------------------------------------- multi-GPU exchange over peer memory ---
@@ -776,9 +830,12 @@ def test_few_sms_many_tiles_per_cta_wrap_every_ring(sim, monkeypatch, sms, async
         cand = rng.integers(0, 300, size=(4, 160)).astype(np.int64)
         got = st.maxsim_host(q, cand)
         np.testing.assert_allclose(got, _oracle_scores(q, docs, cand, 0, "bf16"), rtol=1e-3, atol=2e-4)
+        monkeypatch.setenv("TS_S2_FLOW", "0")
+        assert np.array_equal(st.maxsim_host(q, cand), got)
         monkeypatch.setenv("TS_S2_V2", "1")
         assert np.array_equal(st.maxsim_host(q, cand), got)
         monkeypatch.delenv("TS_S2_V2")
+        monkeypatch.delenv("TS_S2_FLOW")
 
 
 def test_load_index_imports_a_reference_written_faiss_file(sim, tmp_path):

@@ -91,6 +91,109 @@ def test_config2_1Mx768_properties(cuda_device, B):
     assert not bad, bad[:3]
 
 
+def _oracle_over_the_whole_shard(idx, N, q, k, chunk):
+    """exact fp32 top-k of the STORED rows, fetched back shard by shard (oracle/flat_ip.search_streamed)"""
+    Qr = flat_ip.round_to(q.cpu().numpy(), "bf16")
+    rD, rI = flat_ip.search_streamed(((s, idx.get_rows(s, min(chunk, N - s))) for s in range(0, N, chunk)), Qr, k)
+
+    def scores_of(b, ids):
+        return np.array([idx.get_rows(int(i), 1)[0].astype(np.float64) @ Qr[b].astype(np.float64) for i in ids])
+    return rD, rI, scores_of
+
+
+def test_config2_1Mx768_whole_corpus_against_the_oracle(cuda_device):
+    """BASELINE configs[1] at its full size: 8 queries of a batch of 32 checked against the oracle's exact
+    search over ALL 1 M stored rows (not a sub-index), B = 32 on the tensor path and B = 1 on both paths."""
+    N, d, k, B = 1_000_000, 768, 100, 32
+    idx, qp, pos = build_planted(cuda_device, N, d, 2, 100, seed=12)
+    dev = qp.device
+    g = torch.Generator(device=dev).manual_seed(15)
+    q = torch.randn((B, d), generator=g, device=dev)
+    q /= q.norm(dim=1, keepdim=True) + 1e-8
+    q[:2] = qp
+    s, i = idx.search(q, k)
+    torch.cuda.synchronize()
+    rD, rI, scores_of = _oracle_over_the_whole_shard(idx, N, q[:8], k, 250_000)
+    bad = flat_ip.check_topk(s[:8].cpu().numpy(), i[:8].cpu().numpy(), scores_of, rD, rI)
+    assert not bad, bad[:3]
+    for path in ("umma", "stream"):
+        s1, i1 = idx.search(q[2:3].contiguous(), k, path=path)
+        bad = flat_ip.check_topk(s1.cpu().numpy(), i1.cpu().numpy(), lambda b, ids: scores_of(2, ids), rD[2:3], rI[2:3])
+        assert not bad, (path, bad[:3])
+
+
+def test_config3_10Mx1024_two_queries_against_the_oracle(cuda_device):
+    """BASELINE configs[2] at its full size on one GPU: 2 queries of the batch of 32 (one planted, one not)
+    against the oracle's exact search over all 10 M stored rows, fetched back in 1 M-row shards."""
+    free, _ = torch.cuda.mem_get_info(cuda_device)
+    if free < 60 * 2 ** 30:
+        pytest.skip("needs ~45 GB of free HBM")
+    N, d, k, B = 10_000_000, 1024, 100, 32
+    idx, qp, pos = build_planted(cuda_device, N, d, 1, 100, seed=13, chunk=1_000_000)
+    dev = qp.device
+    g = torch.Generator(device=dev).manual_seed(19)
+    q = torch.randn((B, d), generator=g, device=dev)
+    q /= q.norm(dim=1, keepdim=True) + 1e-8
+    q[0] = qp[0]
+    s, i = idx.search(q, k)
+    torch.cuda.synchronize()
+    sel = q[[0, 31]].contiguous()
+    rD, rI, scores_of = _oracle_over_the_whole_shard(idx, N, sel, k, 1_000_000)
+    got_s, got_i = s[[0, 31]].cpu().numpy(), i[[0, 31]].cpu().numpy()
+    bad = flat_ip.check_topk(got_s, got_i, scores_of, rD, rI)
+    assert not bad, bad[:3]
+    assert set(got_i[0].tolist()) == set(pos[0].tolist())
+
+
+def test_config4_full_store_all_queries_against_the_c_oracle(cuda_device, monkeypatch):
+    """BASELINE configs[3] at its full size: 64 queries x 1000 candidates drawn from a 1 M-doc token store
+    (Ld ~ U[16,180], dim 128, Lq 32); EVERY score is checked against oracle/c/oracle.c (maxsim_batch over the
+    stored bf16 values in fp32), both scoring modes, and the two tensor kernels must agree bit for bit."""
+    from oracle import c_oracle
+    free, _ = torch.cuda.mem_get_info(cuda_device)
+    if free < 70 * 2 ** 30:
+        pytest.skip("needs ~55 GB of free HBM")
+    rng = np.random.default_rng(77)
+    dim, ndocs, B, C, Lq = 128, 1_000_000, 64, 1000, 32
+    lens = rng.integers(16, 181, size=ndocs).astype(np.int32)
+    dev = torch.device("cuda", cuda_device)
+    g = torch.Generator(device=dev).manual_seed(77)
+    st = _lib.TokStore(dim, "bf16", cuda_device, reserve_docs=ndocs, reserve_tokens=int(lens.sum()))
+    toks = []
+    for s0 in range(0, ndocs, 100_000):
+        ln = lens[s0:s0 + 100_000]
+        t = torch.nn.functional.normalize(torch.randn((int(ln.sum()), dim), generator=g, device=dev), dim=-1).to(torch.bfloat16)
+        st.add(t, ln, normalize=False)
+        toks.append(t)
+    tok = torch.cat(toks)
+    del toks
+    off = torch.from_numpy(np.concatenate([[0], np.cumsum(lens.astype(np.int64))])).to(dev)
+    q = torch.nn.functional.normalize(torch.randn((B, Lq, dim), generator=g, device=dev), dim=-1).to(torch.bfloat16)
+    cand = torch.stack([torch.randperm(ndocs, generator=g, device=dev)[:C] for _ in range(B)])
+    lens_t = torch.from_numpy(lens.astype(np.int64)).to(dev)
+    for mode in (0, 1):
+        scores = st.maxsim(q, cand, normalize_q=False, mode=mode)
+        torch.cuda.synchronize()
+        monkeypatch.setenv("TS_S2_FLOW", "0")
+        first = st.maxsim(q, cand, normalize_q=False, mode=mode)
+        torch.cuda.synchronize()
+        monkeypatch.delenv("TS_S2_FLOW")
+        assert torch.equal(first, scores), "the two tensor kernels disagree"
+        sh = scores.cpu().numpy()
+        qh = q.float().cpu().numpy()
+        worst = 0.0
+        for b in range(B):
+            ln = lens_t[cand[b]]
+            o = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(ln, 0)])
+            # rows of the query's 1000 candidates, in candidate order
+            ridx = torch.repeat_interleave(off[cand[b]] - o[:-1], ln) + torch.arange(int(o[-1]), device=dev)
+            rows = tok[ridx].float().cpu().numpy()
+            ref = c_oracle.maxsim_batch(qh[b], rows, o.cpu().numpy(), mode=mode)
+            np.testing.assert_allclose(sh[b], ref, rtol=1e-3, atol=2e-4, err_msg=f"query {b} mode {mode}")
+            worst = max(worst, float(np.abs(sh[b] - ref).max()))
+        assert worst < 1e-3
+
+
 def test_config3_10Mx1024_properties(cuda_device):
     free, _ = torch.cuda.mem_get_info(cuda_device)
     if free < 60 * 2 ** 30:

@@ -565,6 +565,11 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
     if (launches) ++*launches;
     return TS_OK;
   }
+  if (env_flag("TS_S2_FLOW", kDefaultS2Flow) && maxsim_flow_takes(a)) {
+    MaxSimArgs a2 = a;
+    a2.mode = mode;
+    return launch_maxsim_flow(a2, st, launches);
+  }
   CUtensorMap tq8, tq32, tq128, t8, t16, t32, t64, t128;
   int rc;
   const int64_t qrows = (int64_t)a.B * a.lq_stride;

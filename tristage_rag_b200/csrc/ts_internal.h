@@ -29,6 +29,7 @@ inline bool env_on(const char* name) {
 // (NAME=1 / NAME=0).  Flip a default here once the variant has been validated and timed on hardware.
 constexpr bool kDefaultFuse = false;   // TS_FUSE : threshold pre-pass + scan in one cooperative launch
 constexpr bool kDefaultS2V2 = false;   // TS_S2_V2: second Stage-2 epilogue
+constexpr bool kDefaultS2Flow = true;   // TS_S2_FLOW: Stage-2 tensor kernel with the resident query tile (s2_flow.cu); 0 = first kernel
 constexpr bool kDefaultS2Epi2 = false; // TS_S2_EPI2: two Stage-2 epilogue warpgroups (320 threads), one per accumulator
 constexpr bool kDefaultPair = false;   // TS_PAIR : cta_group::2 CTA pairs for B >= 129
 constexpr bool kDefaultTf32 = false;   // TS_TF32 : fp32 storage takes the tensor path (kind::tf32) for B > 4 under TS_PATH_AUTO
@@ -128,5 +129,8 @@ struct MaxSimArgs {
   int sm_count;
 };
 int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches);
+// s2_flow.cu: resident query tile, docs split across full tiles (dim <= 256); launch_maxsim dispatches to it
+bool maxsim_flow_takes(const MaxSimArgs& a);
+int launch_maxsim_flow(const MaxSimArgs& a, cudaStream_t st, int* launches);
 
 }  // namespace ts
