@@ -227,6 +227,11 @@ int ts_tokstore_load(ts_tokstore** out, int device, const char* path);
 int ts_tokstore_append_file(ts_tokstore* h, const char* path, int64_t doc_lo, int64_t n_docs, void* stream);
 int ts_tokstore_dim(const ts_tokstore* h);
 int ts_tokstore_dtype(const ts_tokstore* h);
+/* HBM layout of the shard, fixed at creation: 0 = row-major rows with zero pad rows; 1 = tile layout
+ * (tok[row/8][dim/8][row%8][8], pad rows repeat the doc's last token) -- the tcgen05 operand image the
+ * Stage-2 tensor kernel copies with one cp.async.bulk per doc; chosen for 2-byte dtypes with dim % 16 == 0,
+ * dim <= 256.  Shard FILES always hold the row-major image (save / load / append_file convert).          */
+int ts_tokstore_layout(const ts_tokstore* h);
 /* same measurement aid for the MaxSim kernel                                 */
 int ts_tokstore_set_profiling(ts_tokstore* h, int enable);
 int ts_tokstore_scan_time(ts_tokstore* h, float* mean_ms_out, int* n_out);

@@ -268,6 +268,12 @@ void mbar_arrive(uint32_t addr, uint32_t expect_tx_bytes) {
   mbar_check_complete(b);
   ++g_blk->progress;
 }
+void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
+  Block::MBar& b = mbar_at(addr);
+  b.tx += bytes;
+  mbar_check_complete(b);
+  ++g_blk->progress;
+}
 void mbar_complete_tx(uint32_t addr, uint32_t bytes) {
   Block::MBar& b = mbar_at(addr);
   b.tx -= bytes;

@@ -38,6 +38,7 @@ uint32_t* tmem();                        // [128][512]
 void mbar_init(uint32_t addr, uint32_t count);
 void mbar_arrive(uint32_t addr, uint32_t expect_tx_bytes);
 void mbar_complete_tx(uint32_t addr, uint32_t bytes);
+void mbar_expect_tx(uint32_t addr, uint32_t bytes);   // more pending bytes, no arrival
 bool mbar_phase_done(uint32_t addr, uint32_t parity);
 void named_barrier(int id, int nthreads);
 // thread-block clusters (launch_cluster)
@@ -140,6 +141,23 @@ inline void tma_load_2d(void* smem_dst, const CUtensorMap* mp, uint64_t* bar, in
   });
 }
 
+// cp.async.bulk global -> shared: contiguous bytes, the size is credited to the mbarrier on completion
+inline void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t) {
+  const uint32_t dst = smem_u32(smem_dst), bar_addr = smem_u32(bar);
+  if ((dst & 15u) || (reinterpret_cast<uintptr_t>(gsrc) & 15u) || (bytes & 15u) || bytes == 0) {
+    fprintf(stderr, "[cudasim] cp.async.bulk needs 16-byte aligned addresses and size (dst %u bytes %u)\n", dst, bytes); abort();
+  }
+  cudasim::defer_tma([=]() {
+    memcpy(cudasim::smem_base() + dst, gsrc, bytes);
+    cudasim::mbar_complete_tx(bar_addr, bytes);
+  });
+}
+inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { cudasim::mbar_expect_tx(smem_u32(bar), bytes); }
+inline uint32_t warp_or(uint32_t v) {
+  for (int o = 16; o >= 1; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // -------------------------------------------------------------- tcgen05 ----
 inline void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   if (ncols != 512) { fprintf(stderr, "[cudasim] tmem_alloc(%u): the model has 512 columns\n", ncols); abort(); }
@@ -157,6 +175,17 @@ inline float sim_elem(uint32_t addr, bool bf16) {
   _Float16 x; memcpy(&x, &h, 2); return (float)x;
 }
 
+// address of element (row m, K index k of this instruction) of a K-major operand: SWIZZLE_128B (layout type 2:
+// 128-byte rows, 8-row atoms SBO apart, XOR swizzle) or no swizzle (type 0: core matrices of 8 rows x 16 bytes,
+// LBO apart along K, SBO apart along the rows) -- the fields csrc/ts_ptx.cuh documents
+inline uint32_t sim_operand_addr(uint64_t desc, int m, int k, int esz) {
+  const uint32_t base = (uint32_t)(desc & 0x3FFF) << 4;
+  const uint32_t lbo = (uint32_t)((desc >> 16) & 0x3FFF) << 4, sbo = (uint32_t)((desc >> 32) & 0x3FFF) << 4;
+  if ((desc >> 61) == 2) return sw128(base + (uint32_t)(m >> 3) * sbo + (uint32_t)(m & 7) * 128u + (uint32_t)k * (uint32_t)esz);
+  const int per = 16 / esz;                                  // elements per 16-byte core-matrix row
+  return base + (uint32_t)(m >> 3) * sbo + (uint32_t)(m & 7) * 16u + (uint32_t)(k / per) * lbo + (uint32_t)(k % per) * (uint32_t)esz;
+}
+
 // descriptor fields as documented in csrc/ts_ptx.cuh
 inline void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
@@ -165,19 +194,17 @@ inline void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_
     fprintf(stderr, "[cudasim] unsupported instruction descriptor %08x (M %d N %d)\n", idesc, M, N); abort();
   }
   for (uint64_t d : {adesc, bdesc})
-    if ((d >> 61) != 2 || ((d >> 46) & 3) != 1) { fprintf(stderr, "[cudasim] shared-memory descriptor is not K-major SWIZZLE_128B\n"); abort(); }
-  const uint32_t a0 = (uint32_t)(adesc & 0x3FFF) << 4, b0 = (uint32_t)(bdesc & 0x3FFF) << 4;
-  const uint32_t a_sbo = (uint32_t)((adesc >> 32) & 0x3FFF) << 4, b_sbo = (uint32_t)((bdesc >> 32) & 0x3FFF) << 4;
+    if (((d >> 61) != 2 && (d >> 61) != 0) || ((d >> 46) & 3) != 1) { fprintf(stderr, "[cudasim] shared-memory descriptor is neither K-major SWIZZLE_128B nor un-swizzled\n"); abort(); }
   const uint32_t col0 = tmem_d & 0xFFFFu, lane0 = tmem_d >> 16;
   if (lane0 != 0 || col0 + (uint32_t)N > 512) { fprintf(stderr, "[cudasim] accumulator outside TMEM\n"); abort(); }
   cudasim::defer_mma([=]() {
   uint32_t* T = cudasim::tmem();
   float a[128][16];
   for (int m = 0; m < 128; ++m)
-    for (int k = 0; k < 16; ++k) a[m][k] = sim_elem(sw128(a0 + (uint32_t)(m >> 3) * a_sbo + (uint32_t)(m & 7) * 128u + (uint32_t)k * 2u), bf16);
+    for (int k = 0; k < 16; ++k) a[m][k] = sim_elem(sim_operand_addr(adesc, m, k, 2), bf16);
   for (int n = 0; n < N; ++n) {
     float b[16];
-    for (int k = 0; k < 16; ++k) b[k] = sim_elem(sw128(b0 + (uint32_t)(n >> 3) * b_sbo + (uint32_t)(n & 7) * 128u + (uint32_t)k * 2u), bf16);
+    for (int k = 0; k < 16; ++k) b[k] = sim_elem(sim_operand_addr(bdesc, n, k, 2), bf16);
     for (int m = 0; m < 128; ++m) {
       float acc = 0.f;
       for (int k = 0; k < 16; ++k) acc += a[m][k] * b[k];
@@ -323,6 +350,14 @@ inline uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1024 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+inline uint64_t make_desc_kmajor_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
   return d;
 }
 constexpr uint64_t kDescKStep = 2;

@@ -58,21 +58,48 @@ int launch_convert_rows(const void* src, int sdt, int64_t src_ld, void* dst, int
   return TS_OK;
 }
 
+static size_t tok_elem(int layout, long long row, int c, int dim) {
+  if (layout == kTokRowMajor) return (size_t)row * dim + c;
+  return (size_t)(row >> 3) * 8 * dim + (size_t)(c >> 3) * 64 + (size_t)(row & 7) * 8 + (c & 7);
+}
+
 int launch_tok_ingest(const void* src, int sdt, const int64_t* so, const int64_t* dof, const int32_t* len, int n_docs,
-                      void* dst, int ddt, int dim, int normalize, cudaStream_t) {
+                      void* dst, int ddt, int dim, int normalize, int layout, cudaStream_t) {
   for (int d = 0; d < n_docs; ++d) {
     const int L = len[d], Lp = (L + 7) & ~7;
     for (int r = 0; r < Lp; ++r) {
-      const size_t o = (size_t)(dof[d] + r) * dim;
-      if (r >= L) { for (int c = 0; c < dim; ++c) store(dst, ddt, o + c, 0.f); continue; }
-      const size_t s = (size_t)(so[d] + r) * dim;
+      if (r >= L && layout == kTokRowMajor) { for (int c = 0; c < dim; ++c) store(dst, ddt, tok_elem(layout, dof[d] + r, c, dim), 0.f); continue; }
+      const size_t s = (size_t)(so[d] + (r < L ? r : L - 1)) * dim;   // tile layout: pad rows repeat the last token
       float denom = 1.f;
       if (normalize) {
         float ss = 0.f;
         for (int c = 0; c < dim; ++c) { const float v = load(src, sdt, s + c); ss += v * v; }
         denom = fmaxf(sqrtf(ss), 1e-12f);
       }
-      for (int c = 0; c < dim; ++c) { float v = load(src, sdt, s + c); if (normalize) v /= denom; store(dst, ddt, o + c, v); }
+      for (int c = 0; c < dim; ++c) { float v = load(src, sdt, s + c); if (normalize) v /= denom; store(dst, ddt, tok_elem(layout, dof[d] + r, c, dim), v); }
+    }
+  }
+  return TS_OK;
+}
+
+int launch_tok_relayout(void* tok, int dtype, const int64_t* doc_off, const int32_t* doc_len, int64_t doc_lo, int64_t n_docs,
+                        int dim, int to_layout, cudaStream_t) {
+  if (dtype == TS_F32 || dim % 8) return TS_ERR_UNSUPPORTED;
+  uint16_t* t = (uint16_t*)tok;
+  std::vector<uint16_t> g((size_t)8 * dim);
+  const int from = to_layout == kTokTile ? kTokRowMajor : kTokTile;
+  for (int64_t d = doc_lo; d < doc_lo + n_docs; ++d) {
+    const int L = doc_len[d];
+    for (int r0 = 0; r0 < L; r0 += 8) {
+      const long long row0 = doc_off[d] + r0;
+      const int valid = L - r0 < 8 ? L - r0 : 8;
+      for (int r = 0; r < 8; ++r) for (int c = 0; c < dim; ++c) g[(size_t)r * dim + c] = t[tok_elem(from, row0 + r, c, dim)];
+      for (int r = 0; r < 8; ++r) for (int c = 0; c < dim; ++c) {
+        uint16_t v = 0;
+        if (r < valid) v = g[(size_t)r * dim + c];
+        else if (to_layout == kTokTile) v = g[(size_t)(valid - 1) * dim + c];
+        t[tok_elem(to_layout, row0 + r, c, dim)] = v;
+      }
     }
   }
   return TS_OK;

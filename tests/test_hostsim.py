@@ -91,6 +91,15 @@ def test_index_ingest_bookkeeping_matches_the_oracle_rounding(sim, tmp_path):
     part.append_file(p, 4000, 1000)
     part.append_file(p, 0, 10)
     assert (part.get_rows(0, 1010) == np.concatenate([got[4000:], got[:10]])).all()
+    # a damaged file must not load through a PARTIAL range either (the re-sharding path): one flipped payload
+    # byte far from the requested rows is found before anything is appended
+    raw = bytearray(open(p, "rb").read())
+    raw[fi["payload_offset"] + 104 * 2 * 2500 + 11] ^= 0x40
+    bad = str(tmp_path / "damaged.tsshard")
+    open(bad, "wb").write(bytes(raw))
+    with pytest.raises(_lib.TristageError, match="checksum"):
+        part.append_file(bad, 4000, 1000)
+    assert part.ntotal == 1010
     idx.reset()
     assert idx.ntotal == 0
     with pytest.raises(_lib.TristageError):

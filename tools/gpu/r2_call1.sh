@@ -1,5 +1,6 @@
 #!/bin/bash
-# Round 2, GPU call 1 (1 GPU, ~10 min): Stage-2 flow kernel -- parity, A/B against the first kernel, role trace, ncu.
+# Round 2, Stage-2 call (1 GPU, ~6 min): flow kernel on tile-layout shards -- parity, A/B against the first kernel
+# (TS_S2_FLOW=0: row-major shards), role trace, ncu.
 # Usage: gpurun --timeout 1500 -- tools/gpu/r2_call1.sh
 mkdir -p gpurun_out
 run() { name=$1; shift; timeout 900 python -m pytest "$@" -q -m gpu -p no:cacheprovider > gpurun_out/$name.log 2>&1; echo "$name rc=$? $(tail -1 gpurun_out/$name.log)"; }
@@ -9,7 +10,9 @@ P="timeout 300 python tools/s2_probe.py"
 O=gpurun_out/s2_probe.jsonl; E=gpurun_out/s2_probe.err; : > $O; : > $E
 $P --ndocs 1000000 --tag "flow c4_1M" >> $O 2>> $E
 TS_S2_FLOW=0 $P --ndocs 1000000 --tag "first c4_1M" >> $O 2>> $E
-for st in 2 3 4; do TS_S2_STAGES=$st $P --tag "flow stages=$st" >> $O 2>> $E; done
+for st in 1 2; do TS_S2_STAGES=$st $P --tag "flow stages=$st" >> $O 2>> $E; done
+TS_S2_TILE=128 $P --tag "flow tile=128" >> $O 2>> $E
+TS_S2_TILE=128 TS_S2_STAGES=3 $P --tag "flow tile=128 stages=3" >> $O 2>> $E
 TS_S2_ABUFS=2 $P --tag "flow abufs=2" >> $O 2>> $E
 for cfg in "--lo 16 --hi 180" "--lo 180 --hi 180" "--lo 16 --hi 40" "--Lq 128" "--dim 64" "--dim 256 --ndocs 100000" "--B 2000 --C 32" "--B 1 --C 1000" "--B 8 --C 500"; do
   $P $cfg --tag "flow $cfg" >> $O 2>> $E
@@ -25,8 +28,8 @@ PY
 # role trace (cycle counters per warp role, mean/max over CTAs)
 TS_S2_TRACE=1 $P --steps 2 --tag trace > gpurun_out/s2_trace.out 2> gpurun_out/s2_trace.err; grep "s2 trace" gpurun_out/s2_trace.err | tail -1
 TS_S2_TRACE=1 $P --steps 2 --lo 180 --hi 180 --tag trace180 > /dev/null 2> gpurun_out/s2_trace180.err; grep "s2 trace" gpurun_out/s2_trace180.err | tail -1
-run s1 tests/test_gpu_stage1.py
 run pipe tests/test_gpu_pipeline.py
+run zshards tests/test_gpu_z_shards.py
 # ncu: flow kernel and the first kernel on config #4
 NCU="ncu --set full --clock-control none --import-source on"
 CMD="python tools/s2_probe.py --steps 2"

@@ -93,6 +93,7 @@ SYMBOLS = {
     "ts_tokstore_append_file": (_i, [_vp, C.c_char_p, _i64, _i64, _vp]),
     "ts_tokstore_dim": (_i, [_vp]),
     "ts_tokstore_dtype": (_i, [_vp]),
+    "ts_tokstore_layout": (_i, [_vp]),
     "ts_tokstore_set_profiling": (_i, [_vp, _i]),
     "ts_tokstore_scan_time": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(_i)]),
     "ts_maxsim": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _u, _vp, _vp]),
@@ -598,6 +599,8 @@ class BM25:
     """Device-resident BM25 postings (``ts_bm25``): CSR term offsets, document ids and one fp64
     weight per posting, as built by ``stage1_retriever.BM25Index._build_postings``."""
 
+    SCRATCH_BYTES = 2 << 30      # budget of the dense per-query score accumulator; ``search`` slices the batch to fit
+
     def __init__(self, n_docs: int, term_off, post_doc, post_w, device: int = 0):
         import numpy as np
 
@@ -630,15 +633,25 @@ class BM25:
         import numpy as np
 
         B = len(query_terms)
-        off = np.zeros(B + 1, np.int64)
-        off[1:] = np.cumsum([len(q) for q in query_terms])
-        flat = np.ascontiguousarray(np.concatenate([np.asarray(q, np.int32) for q in query_terms])
-                                    if int(off[-1]) else np.zeros(0, np.int32), np.int32)
         scores = np.empty((B, top_k), np.float64)
         ids = np.empty((B, top_k), np.int64)
-        check(lib().ts_bm25_search_host(self._h, C.c_void_p(flat.ctypes.data) if len(flat) else None,
-                                        C.c_void_p(off.ctypes.data), B, int(top_k), C.c_void_p(scores.ctypes.data),
-                                        C.c_void_p(ids.ctypes.data), _stream_ptr(self.device)))
+        # the kernels keep a dense [B, n_docs] fp64 accumulator: walk the batch in slices that keep it under
+        # BM25_SCRATCH_BYTES (2 GiB) instead of asking for B * n_docs * 8 bytes at once
+        per_query = max(1, int(self.n_docs)) * 8
+        step = max(1, min(B, self.SCRATCH_BYTES // per_query))
+        for b0 in range(0, B, step):
+            qs = query_terms[b0:b0 + step]
+            nb = len(qs)
+            off = np.zeros(nb + 1, np.int64)
+            off[1:] = np.cumsum([len(q) for q in qs])
+            flat = np.ascontiguousarray(np.concatenate([np.asarray(q, np.int32) for q in qs])
+                                        if int(off[-1]) else np.zeros(0, np.int32), np.int32)
+            sc = np.empty((nb, top_k), np.float64)
+            ii = np.empty((nb, top_k), np.int64)
+            check(lib().ts_bm25_search_host(self._h, C.c_void_p(flat.ctypes.data) if len(flat) else None,
+                                            C.c_void_p(off.ctypes.data), nb, int(top_k), C.c_void_p(sc.ctypes.data),
+                                            C.c_void_p(ii.ctypes.data), _stream_ptr(self.device)))
+            scores[b0:b0 + nb], ids[b0:b0 + nb] = sc, ii
         return scores, ids
 
 
@@ -712,6 +725,11 @@ class TokStore:
     @property
     def ndocs(self) -> int:
         return int(lib().ts_tokstore_ndocs(self._h))
+
+    @property
+    def layout(self) -> int:
+        """0 = row-major shard, 1 = tile layout (the Stage-2 tensor kernel's operand image)."""
+        return int(lib().ts_tokstore_layout(self._h))
 
     @property
     def ntokens(self) -> int:

@@ -397,6 +397,9 @@ int ts_tokstore_create(ts_tokstore** out, int device, int dim, int storage_dtype
   ts_tokstore* h = new ts_tokstore();
   memset(h, 0, sizeof(*h));
   h->device = device; h->dim = dim; h->dtype = storage_dtype; h->info = info;
+  // tile layout (the Stage-2 flow kernel's operand image) whenever the shape allows it; TS_S2_FLOW=0 keeps
+  // the row-major shard of the first tensor kernel (A/B timing, debugging)
+  h->layout = (tok_tile_layout_ok(dim, storage_dtype) && env_flag("TS_S2_FLOW", kDefaultS2Flow)) ? kTokTile : kTokRowMajor;
   h->timer = new ScanTimer();
   h->hint_docs = reserve_docs;
   h->hint_rows = reserve_tokens + 8 * reserve_docs;  // every doc is padded to 8 rows
@@ -464,10 +467,6 @@ int tok_reserve(ts_tokstore* h, int64_t docs, int64_t rows, cudaStream_t st) {
 }
 
 
-// scatter ragged docs into the 8-row padded store (defined in tok_ingest.cu)
-int launch_tok_ingest(const void* src, int src_dtype, const int64_t* src_off_dev, const int64_t* dst_off_dev,
-                      const int32_t* len_dev, int n_docs, void* dst, int dst_dtype, int dim, int normalize,
-                      cudaStream_t st);
 }
 
 extern "C" {
@@ -503,7 +502,7 @@ int ts_tokstore_add(ts_tokstore* h, const void* tok, int src_dtype, int src_on_d
     dsrc = h->stage;
   }
   rc = launch_tok_ingest(dsrc, src_dtype, (const int64_t*)h->meta, h->doc_off + h->ndocs, h->doc_len + h->ndocs, n_docs,
-                         h->tok, h->dtype, h->dim, normalize, st);
+                         h->tok, h->dtype, h->dim, normalize, h->layout, st);
   if (rc) return rc;
   ++h->launches;
   TS_CUDA_OK(cudaStreamSynchronize(st));  // host vectors / staging are reused
@@ -515,6 +514,7 @@ int64_t ts_tokstore_ndocs(const ts_tokstore* h) { return h ? h->ndocs : -1; }
 int64_t ts_tokstore_ntokens(const ts_tokstore* h) { return h ? h->ntokens : -1; }
 int ts_tokstore_dim(const ts_tokstore* h) { return h ? h->dim : -1; }
 int ts_tokstore_dtype(const ts_tokstore* h) { return h ? h->dtype : -1; }
+int ts_tokstore_layout(const ts_tokstore* h) { return h ? h->layout : -1; }
 int ts_tokstore_reset(ts_tokstore* h) { if (!h) return TS_ERR_INVALID; h->ndocs = 0; h->nrows = 0; h->ntokens = 0; return TS_OK; }
 int ts_tokstore_set_id_base(ts_tokstore* h, int64_t b) { if (!h) return TS_ERR_INVALID; h->id_base = b; return TS_OK; }
 int64_t ts_tokstore_launch_count(const ts_tokstore* h) { return h ? h->launches : -1; }
@@ -536,6 +536,7 @@ int ts_maxsim(ts_tokstore* h, const void* q_tok, int q_dtype, const int32_t* q_l
   if (rc) return rc;
   ++h->launches;
   MaxSimArgs a{};
+  a.layout = h->layout;
   a.tok = h->tok; a.doc_off = h->doc_off; a.doc_len = h->doc_len; a.ndocs = h->ndocs; a.id_base = h->id_base;
   a.ntok_rows = h->nrows; a.dim = h->dim; a.dtype = h->dtype; a.q = h->qbuf; a.q_len = q_len; a.B = B;
   a.lq_stride = lq_stride; a.cand = cand; a.n_cand = n_cand; a.C = C; a.mode = mode; a.out = out;

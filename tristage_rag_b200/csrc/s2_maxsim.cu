@@ -54,16 +54,16 @@ __global__ void __launch_bounds__(128)
                        const int32_t* __restrict__ doc_len, int64_t ndocs, int64_t id_base, int dim,
                        const T* __restrict__ q, const int32_t* __restrict__ q_len, int lq_stride,
                        const int64_t* __restrict__ cand, const int32_t* __restrict__ n_cand, int C, int mode,
-                       float* __restrict__ out) {
+                       float* __restrict__ out, int layout) {
   TS_DYN_SMEM(float, sm);  // m[lq_stride]
   const int b = blockIdx.y, j = blockIdx.x;
   const int nc = n_cand ? n_cand[b] : C;
   if (j >= nc) return;
   const int64_t id = cand[(size_t)b * C + j] - id_base;
   if (id < 0 || id >= ndocs) return;
-  const int Lq = q_len ? q_len[b] : lq_stride;
+  const int Lq = q_len ? min(max(q_len[b], 1), lq_stride) : lq_stride;   // as the tensor path clamps it
   const int Ld = doc_len[id];
-  const T* d = tok + doc_off[id] * dim;
+  const long long row0 = doc_off[id];
   const T* qb = q + (size_t)b * lq_stride * dim;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int i = warp; i < Lq; i += nw) {
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128)
     for (int t = 0; t < Ld; ++t) {
       float acc = 0.f;
       for (int c = lane; c < dim; c += 32)
-        acc = fmaf(Elem<T>::to_f32(qb[(size_t)i * dim + c]), Elem<T>::to_f32(d[(size_t)t * dim + c]), acc);
+        acc = fmaf(Elem<T>::to_f32(qb[(size_t)i * dim + c]), Elem<T>::to_f32(tok[tok_elem(layout, row0 + t, c, dim)]), acc);
       acc = warp_sum(acc);
       best = fmaxf(best, acc);
     }
@@ -544,8 +544,11 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
   if (a.B <= 0 || a.C <= 0) { set_error("maxsim: empty batch"); return TS_ERR_INVALID; }
   TS_CUDA_OK(cudaMemsetAsync(a.out, 0, (size_t)a.B * a.C * sizeof(float), st));
   if (a.ndocs == 0) return TS_OK;
-  const bool tensor_ok = (a.dtype == TS_BF16 || a.dtype == TS_F16) && (a.dim % 8 == 0) && a.lq_stride >= 1 &&
-                         a.lq_stride <= TS_S2_MAX_LQ && !(a.mode & 0x100);
+  // tensor kernels: the flow kernel reads tile-layout shards, the first kernel row-major ones; everything
+  // else (fp32, odd dims, Lq > 128, the test switch) takes the CUDA-core kernel, which reads either layout
+  bool tensor_ok = (a.dtype == TS_BF16 || a.dtype == TS_F16) && (a.dim % 8 == 0) && a.lq_stride >= 1 &&
+                   a.lq_stride <= TS_S2_MAX_LQ && !(a.mode & 0x100);
+  if (tensor_ok && a.layout == kTokTile && !maxsim_flow_takes(a)) tensor_ok = false;
   const int mode = a.mode & 0xff;
   if (!tensor_ok) {
     if (a.lq_stride > 4096) { set_error("maxsim: lq_stride too large"); return TS_ERR_UNSUPPORTED; }
@@ -555,7 +558,7 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
   do {                                                                                                \
     auto kern = maxsim_simt_kernel<T>;                                                                \
     TS_LAUNCH(kern, grid, 128, smem, st, (const T*)a.tok, a.doc_off, a.doc_len, a.ndocs, a.id_base,   \
-              a.dim, (const T*)a.q, a.q_len, a.lq_stride, a.cand, a.n_cand, a.C, mode, a.out);        \
+              a.dim, (const T*)a.q, a.q_len, a.lq_stride, a.cand, a.n_cand, a.C, mode, a.out, a.layout); \
   } while (0)
     if (a.dtype == TS_BF16) TS_SIMT(__nv_bfloat16);
     else if (a.dtype == TS_F16) TS_SIMT(__half);
@@ -565,7 +568,7 @@ int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
     if (launches) ++*launches;
     return TS_OK;
   }
-  if (env_flag("TS_S2_FLOW", kDefaultS2Flow) && maxsim_flow_takes(a)) {
+  if (a.layout == kTokTile) {
     MaxSimArgs a2 = a;
     a2.mode = mode;
     return launch_maxsim_flow(a2, st, launches);

@@ -211,9 +211,16 @@ struct ShardWriter {
   int finish(const ShardHeader& hd) {
     if (fseek(f, 0, SEEK_SET) != 0 || fwrite(&hd, sizeof(hd), 1, f) != 1) return fail();
     if (fflush(f) != 0) return fail();
+    // the data must be durable BEFORE the name appears: fsync the file, rename, fsync the directory --
+    // otherwise a crash can leave a renamed file whose pages never reached the disk
+    if (fsync(fileno(f)) != 0) return fail();
     if (fclose(f) != 0) { f = nullptr; remove(tmp.c_str()); set_error("closing %s failed", tmp.c_str()); return TS_ERR_IO; }
     f = nullptr;
     if (rename(tmp.c_str(), path.c_str()) != 0) { set_error("rename %s -> %s failed: %s", tmp.c_str(), path.c_str(), strerror(errno)); remove(tmp.c_str()); return TS_ERR_IO; }
+    const size_t slash = path.find_last_of('/');
+    const std::string dir = slash == std::string::npos ? std::string(".") : (slash == 0 ? std::string("/") : path.substr(0, slash));
+    const int dfd = open(dir.c_str(), O_RDONLY | O_DIRECTORY);
+    if (dfd >= 0) { (void)fsync(dfd); close(dfd); }   // best effort: some filesystems refuse fsync on a directory
     return TS_OK;
   }
   ~ShardWriter() { abort_(); }
@@ -465,6 +472,12 @@ int ts_index_append_file(ts_index* h, const char* path, int64_t row_lo, int64_t 
   if ((rc = sg.init())) return rc;
   const size_t row_b = (size_t)h->ld * dtype_size(h->dtype);
   const bool whole = (row_lo == 0 && n_rows == hd.n);
+  // a partial range (re-sharded load) cannot be checked while it streams: check the whole file first, so a
+  // corrupt or torn shard never loads silently on the path this format exists for
+  if (!whole) {
+    if ((rc = verify_section(path, "table", mf.table(), hd.table_bytes, hd.table_hash))) return rc;
+    if ((rc = verify_section(path, "payload", mf.payload(), hd.payload_bytes, hd.payload_hash))) return rc;
+  }
   XXH64 hash;
   if ((rc = copy_in(sg, (char*)h->rows + (size_t)h->n * row_b, mf.payload() + (size_t)row_lo * row_b, (size_t)n_rows * row_b, st,
                     whole ? &hash : nullptr))) return rc;
@@ -511,7 +524,18 @@ int ts_tokstore_save(const ts_tokstore* h, const char* path) {
   if ((rc = w.pad())) return rc;
   hd.payload_offset = w.pos;
   w.start_section();
-  if ((rc = copy_out(sg, w, h->tok, (size_t)h->nrows * h->dim * dtype_size(h->dtype), 0))) return rc;
+  // shard files hold ONE image whatever the HBM layout is: row-major rows, zero pad rows.  A tile-layout
+  // shard is converted in place for the duration of the copy (two extra HBM passes; saving is rare and disk-bound)
+  const bool tile = (h->layout == kTokTile);
+  if (tile && (rc = launch_tok_relayout(h->tok, h->dtype, h->doc_off, h->doc_len, 0, h->ndocs, h->dim, kTokRowMajor, 0))) return rc;
+  if (tile) TS_CUDA_OK(cudaDeviceSynchronize());
+  rc = copy_out(sg, w, h->tok, (size_t)h->nrows * h->dim * dtype_size(h->dtype), 0);
+  if (tile) {
+    const int rc2 = launch_tok_relayout(h->tok, h->dtype, h->doc_off, h->doc_len, 0, h->ndocs, h->dim, kTokTile, 0);
+    if (rc2 == TS_OK) { TS_CUDA_OK(cudaDeviceSynchronize()); }
+    if (!rc) rc = rc2;
+  }
+  if (rc) return rc;
   hd.payload_bytes = w.pos - hd.payload_offset; hd.payload_hash = w.hash.digest();
   return w.finish(hd);
 }
@@ -526,6 +550,10 @@ int ts_tokstore_append_file(ts_tokstore* h, const char* path, int64_t doc_lo, in
   if (hd.dim != h->dim || hd.dtype != h->dtype) { set_error("%s: dim/dtype (%d/%d) do not match the store (%d/%d)", path, hd.dim, hd.dtype, h->dim, h->dtype); return TS_ERR_INVALID; }
   if (doc_lo + n_docs > hd.n) { set_error("%s: docs [%lld, %lld) outside the file's %lld docs", path, (long long)doc_lo, (long long)(doc_lo + n_docs), (long long)hd.n); return TS_ERR_INVALID; }
   if (n_docs == 0) return TS_OK;
+  if (!(doc_lo == 0 && n_docs == hd.n)) {    // partial range: check the whole file before trusting any of it
+    if ((rc = verify_section(path, "table", mf.table(), hd.table_bytes, hd.table_hash))) return rc;
+    if ((rc = verify_section(path, "payload", mf.payload(), hd.payload_bytes, hd.payload_hash))) return rc;
+  }
   const int64_t* off = reinterpret_cast<const int64_t*>(mf.table());
   const int32_t* len = reinterpret_cast<const int32_t*>(mf.table() + (size_t)hd.n * 8);
   // the doc table is trusted for addressing: validate the slice before using it
@@ -559,6 +587,10 @@ int ts_tokstore_append_file(ts_tokstore* h, const char* path, int64_t doc_lo, in
                     whole ? &hash : nullptr))) return rc;
   TS_CUDA_OK(cudaStreamSynchronize(st));   // dst_off (host vector) was read asynchronously
   if (whole && hash.digest() != hd.payload_hash) { set_error("%s: payload checksum mismatch (file is corrupt)", path); return TS_ERR_IO; }
+  if (h->layout == kTokTile) {             // the file image is row-major: bring the appended docs into the shard's layout
+    if ((rc = launch_tok_relayout(h->tok, h->dtype, h->doc_off, h->doc_len, h->ndocs, n_docs, h->dim, kTokTile, st))) return rc;
+    TS_CUDA_OK(cudaStreamSynchronize(st));
+  }
   h->ndocs += n_docs; h->nrows += n_rows; h->ntokens += tokens;
   return TS_OK;
 }

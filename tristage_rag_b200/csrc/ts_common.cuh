@@ -208,6 +208,12 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
 #endif
 }
 
+// element index of (store row, column) in a token shard (TokLayout in ts_internal.h: 0 row-major, 1 tile)
+__host__ __device__ __forceinline__ size_t tok_elem(int layout, long long row, int c, int dim) {
+  if (layout == 0) return (size_t)row * dim + c;
+  return (size_t)(row >> 3) * 8 * dim + (size_t)(c >> 3) * 64 + (size_t)(row & 7) * 8 + (c & 7);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

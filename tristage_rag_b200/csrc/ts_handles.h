@@ -68,6 +68,7 @@ struct ts_index {
 
 struct ts_tokstore {
   int device, dim, dtype;
+  int layout;                       // ts::TokLayout of tok (fixed at creation)
   int64_t ndocs, nrows, cap_docs, cap_rows, id_base, ntokens;
   int64_t hint_docs, hint_rows;     // reservation hints honoured by the first add
   void* tok;

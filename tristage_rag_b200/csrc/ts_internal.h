@@ -112,7 +112,26 @@ int launch_rank_desc(const float* scores, const int32_t* n_cand, int B, int C, i
                      int32_t* out_pos, cudaStream_t st);
 
 // ---- Stage-2 ---------------------------------------------------------------
+// Layout of a token shard in HBM.  Both keep every doc on an 8-row boundary and use the same doc tables; they
+// differ in the byte order INSIDE each 8-row group (8 * dim elements) and in what the pad rows hold:
+//   kTokRowMajor : tok[row][dim], pad rows zero                      (first tensor kernel, fp32 / odd dims)
+//   kTokTile     : tok[row / 8][dim / 8][row % 8][8], pad rows repeat the doc's last token
+// kTokTile is the shared-memory image tcgen05.mma reads for a K-major operand without swizzle (core matrices of
+// 8 rows x 16 bytes, LBO = 128 B along K, SBO = 16 * dim B between 8-row groups): a doc -- or any 8-row-aligned
+// part of it -- moves from HBM into its columns of a tile with ONE contiguous cp.async.bulk, and the repeated
+// last token makes the pad columns harmless for a row maximum, so the epilogue never masks.
+enum TokLayout { kTokRowMajor = 0, kTokTile = 1 };
+inline bool tok_tile_layout_ok(int dim, int dtype) { return dtype != TS_F32 && dim >= 16 && dim % 16 == 0 && dim <= 256; }
+// scatter ragged docs into the 8-row padded store (tok_ingest.cu)
+int launch_tok_ingest(const void* src, int src_dtype, const int64_t* src_off_dev, const int64_t* dst_off_dev,
+                      const int32_t* len_dev, int n_docs, void* dst, int dst_dtype, int dim, int normalize, int layout,
+                      cudaStream_t st);
+// in-place conversion of docs [doc_lo, doc_lo + n_docs) between the two layouts (2-byte dtypes, dim % 8 == 0)
+int launch_tok_relayout(void* tok, int dtype, const int64_t* doc_off_dev, const int32_t* doc_len_dev, int64_t doc_lo,
+                        int64_t n_docs, int dim, int to_layout, cudaStream_t st);
+
 struct MaxSimArgs {
+  int layout;              // TokLayout of tok
   const void* tok;         // [ntok_pad][dim] storage dtype, docs padded to 8 rows
   const int64_t* doc_off;  // [ndocs] first row of each doc (multiple of 8)
   const int32_t* doc_len;  // [ndocs]

@@ -113,6 +113,26 @@ def _barrier(group) -> None:
         dist.barrier(group=group)
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """Raised on EVERY rank when any rank could not set the peer-memory exchange up."""
+
+
+def _agree_on_setup(setup: Callable, device: torch.device, group):
+    """Run ``setup()`` (symmetric-memory allocation + rendezvous) and let the group decide together whether the
+    peer-memory exchange is usable: a rank that fell back to the collective on its own would leave its peers
+    spinning on flags it never writes.  Every rank either gets its state or raises PeerExchangeUnavailable."""
+    state, err = None, None
+    try:
+        state = setup()
+    except (ImportError, RuntimeError, AttributeError) as e:       # no symmetric memory on this system
+        err = e
+    ok = torch.tensor([0 if state is None else 1], dtype=torch.int32, device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 0:
+        raise PeerExchangeUnavailable(str(err) if err is not None else "another rank could not set it up")
+    return state
+
+
 def gather_topk(scores: torch.Tensor, ids: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """all-gather per-rank [B, k] results into [G, B, k] (rank-major = ascending id ranges)."""
     world = dist.get_world_size(group)
@@ -245,7 +265,7 @@ class ShardedIndex:
         B = q.shape[0]
         st = self._p2p_state
         if st is None or st["key"] != (B, k):
-            st = self._p2p_state = self._p2p_setup(B, k, q.device)
+            st = self._p2p_state = _agree_on_setup(lambda: self._p2p_setup(B, k, q.device), q.device, self.group)
             self._step = 0
         dev = q.device.index
         self.local.search_packed(q, k, st["mine"], **kw)
@@ -269,7 +289,7 @@ class ShardedIndex:
         if self._p2p:
             try:
                 return self._search_p2p(q, k, **kw)
-            except (ImportError, RuntimeError, AttributeError) as e:      # no symmetric memory on this system: NCCL path
+            except PeerExchangeUnavailable as e:      # decided by ALL ranks together (see _agree_on_setup): NCCL path
                 import logging
 
                 logging.getLogger(__name__).warning(f"peer-memory exchange unavailable ({e}); using all-gather")
@@ -348,7 +368,7 @@ class ShardedTokStore:
         n = out.numel()
         st = getattr(self, "_p2p_state", None)
         if st is None or st["key"] != n:
-            st = self._p2p_state = self._p2p_setup(n, out.device)
+            st = self._p2p_state = _agree_on_setup(lambda: self._p2p_setup(n, out.device), out.device, self.group)
             self._step = 0
         dev = out.device.index
         parity, seq = self._step & 1, (self._step % 0x7FFFFFFF) + 1
@@ -372,7 +392,7 @@ class ShardedTokStore:
             if out.is_cuda and os.environ.get("TS_P2P", "0") not in ("", "0") and not getattr(self, "_p2p_off", False):
                 try:
                     return self._maxsim_p2p(out)
-                except (ImportError, RuntimeError, AttributeError) as e:
+                except PeerExchangeUnavailable as e:
                     import logging
 
                     logging.getLogger(__name__).warning(f"peer-memory exchange unavailable ({e}); using all-reduce")

@@ -434,7 +434,13 @@ class Stage1Retriever:
                 if e.code != -4:                        # TS_ERR_UNSUPPORTED: weights <= 0
                     raise
                 return None
-        bs, bi = self._device_bm25.search_arrays(texts, k2)
+        try:
+            bs, bi = self._device_bm25.search_arrays(texts, k2)
+        except _lib.TristageError as e:
+            if e.code != -3:                            # TS_ERR_NOMEM: no room for the score accumulator -> host path
+                raise
+            self.logger.warning(f"device BM25 out of memory ({e}); this batch takes the host path")
+            return None
         if cfg.fusion_method != "rrf":
             if (D[:, 0] == 0).any() or (bs[:, 0] == 0).any() or (D.max(axis=1) == 0).any():
                 return None

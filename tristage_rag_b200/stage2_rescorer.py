@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import logging
 import os
+import threading
 from dataclasses import dataclass
 from typing import Any, Dict, Hashable, List, Optional
 
@@ -66,6 +67,15 @@ class ColBERTScorer:
         _lib.lib()                        # fail loudly if the CUDA library is missing
         self._store: Optional[_lib.TokStore] = None
         self._slot: Dict[Hashable, int] = {}      # doc key -> position in the token store
+        # "which keys are missing -> encode -> append to the store -> remember the slots" must be one step: two
+        # threads (the reference's Flask UI is threaded) that both read the same ``store.ndocs`` would map
+        # their keys onto each other's documents, and the wrong slots would stay cached
+        self._index_lock = threading.RLock()
+        self._truncation_warned = False
+        if self.config.max_seq_length > _lib.TS_S2_MAX_LD:
+            self.logger.warning(f"max_seq_length={self.config.max_seq_length} exceeds the token store's limit of "
+                                f"{_lib.TS_S2_MAX_LD} tokens per document: longer documents are cut to "
+                                f"{_lib.TS_S2_MAX_LD} tokens (the reference scores all of them)")
         self._load_model()
 
     # -- encoder side: outside the hot path -----------------------------------
@@ -140,19 +150,35 @@ class ColBERTScorer:
                 .reshape(-1, np.shape(t)[-1]) for t in token_embeddings]
         if not mats:
             return
+        n_long = sum(1 for m in mats if m.shape[0] > _lib.TS_S2_MAX_LD)
+        if n_long and not self._truncation_warned:
+            self._truncation_warned = True
+            self.logger.warning(f"{n_long} document(s) longer than {_lib.TS_S2_MAX_LD} tokens were cut to that length "
+                                "(token-store limit); their scores differ from the reference's")
         mats = [m[: _lib.TS_S2_MAX_LD] for m in mats]
-        store = self._ensure_store(mats[0].shape[1])
-        base = store.ndocs
-        store.add(np.concatenate(mats, axis=0), [m.shape[0] for m in mats], normalize=True)
-        for i, key in enumerate(keys):
-            self._slot[key] = base + i
+        with self._index_lock:
+            store = self._ensure_store(mats[0].shape[1])
+            base = store.ndocs
+            store.add(np.concatenate(mats, axis=0), [m.shape[0] for m in mats], normalize=True)
+            for i, key in enumerate(keys):
+                self._slot[key] = base + i
+
+    def _ensure_indexed(self, pairs) -> None:
+        """``pairs`` = (key, text) of the documents a request needs: the ones the store does not hold yet are
+        encoded and appended, atomically with respect to other threads doing the same."""
+        with self._index_lock:
+            seen, todo = set(), []
+            for k, d in pairs:
+                if k not in self._slot and k not in seen:
+                    seen.add(k)
+                    todo.append((k, d))
+            if todo:
+                self.add_token_embeddings([k for k, _ in todo], self.encode_documents_batch([d for _, d in todo]))
 
     def index_documents(self, documents: List[str], doc_ids: Optional[List[Hashable]] = None) -> None:
         """Encode documents once and keep their token embeddings on the GPU."""
         keys = [(i, d) for i, d in zip(doc_ids, documents)] if doc_ids is not None else [("text", d) for d in documents]
-        todo = [(k, d) for k, d in zip(keys, documents) if k not in self._slot]
-        if todo:
-            self.add_token_embeddings([k for k, _ in todo], self.encode_documents_batch([d for _, d in todo]))
+        self._ensure_indexed(zip(keys, documents))
 
     @staticmethod
     def _key(candidate: Dict[str, Any]) -> Hashable:
@@ -190,14 +216,7 @@ class ColBERTScorer:
         query_embeddings = self.encode_query(query)
         try:
             keys = [self._key(c) for c in candidates]
-            missing = [(k, c["document"]) for k, c in zip(keys, candidates) if k not in self._slot]
-            if missing:
-                seen, uniq = set(), []
-                for k, d in missing:
-                    if k not in seen:
-                        seen.add(k)
-                        uniq.append((k, d))
-                self.add_token_embeddings([k for k, _ in uniq], self.encode_documents_batch([d for _, d in uniq]))
+            self._ensure_indexed((k, c["document"]) for k, c in zip(keys, candidates))
         except Exception as e:                         # reference :260-263
             self.logger.error(f"Error encoding documents: {e}")
             return candidates
@@ -232,15 +251,7 @@ class ColBERTScorer:
             return out
         q_embs = [self.encode_query(queries[b]) for b in live]
         try:
-            missing, seen = [], set()
-            for b in live:
-                for c in candidates[b]:
-                    k = self._key(c)
-                    if k not in self._slot and k not in seen:
-                        seen.add(k)
-                        missing.append((k, c["document"]))
-            if missing:
-                self.add_token_embeddings([k for k, _ in missing], self.encode_documents_batch([d for _, d in missing]))
+            self._ensure_indexed((self._key(c), c["document"]) for b in live for c in candidates[b])
         except Exception as e:                         # reference :260-263, per batch
             self.logger.error(f"Error encoding documents: {e}")
             return [list(c) for c in candidates]
@@ -297,6 +308,9 @@ class ColBERTScorer:
             "scoring_method": self.config.scoring_method,
             "batch_size": self.config.batch_size,
             "embedding_dim": self.model.config.hidden_size if self.model else None,
+            # limits of the GPU token store / kernels the reference does not have
+            "max_doc_tokens": _lib.TS_S2_MAX_LD,
+            "max_top_k_on_device": _lib.TS_MAX_K,
         }
 
     def clear_gpu_memory(self):
