@@ -112,4 +112,8 @@ def sim(sim_lib, monkeypatch):
 
     monkeypatch.setattr(_lib, "_lib", sim_lib)
     monkeypatch.setattr(_lib, "_stream_ptr", lambda device: None)
+    # the emulator tests compare each scan variant with the plain single-CTA two-launch scan: start from that,
+    # whatever the product's build-time defaults are (csrc/ts_internal.h); a test enables a variant with "1"
+    for var in ("TS_PAIR", "TS_FUSE", "TS_TF32"):
+        monkeypatch.setenv(var, "0")
     return sim_lib

@@ -63,11 +63,54 @@ def test_bench_contract_helpers():
     import bench
 
     cfg = bench.workload_config(10_000_000, 1024, 100, 32, 8)
-    assert cfg["rows"] == 10_000_000 and cfg["batch"] == 32 and "row-sharded over 8 GPU" in cfg["workload"]
+    assert cfg["rows"] == 10_000_000 and cfg["batch"] == 32 and cfg["n_gpus"] == 8 and "10000000x1024" in cfg["workload"]
+    # both arms print the SAME config for the same arguments (the driver compares them)
+    assert cfg == bench.workload_config(10_000_000, 1024, 100, 32, 8)
+    pos = bench.plant_positions(10_000_000)
+    assert pos.shape == (bench.PLANT_QUERIES, bench.PLANT_ROWS) and len(set(pos.ravel().tolist())) == pos.size
+    assert (pos == bench.plant_positions(10_000_000)).all()
     # algorithmic bytes of one search per GPU: shard once + queries + candidate lists
     assert bench.stage1_alg_bytes(1_250_000, 1024, 32, 100, 148) == 1_250_000 * 2048 + 32 * 2048 + 148 * 32 * 100 * 8
     pk = bench.peaks()
     assert pk["hbm_gbs"] > 1000 and pk["bf16_tflops"] >= pk["bf16_tflops_sustained"] > 100
+
+
+def test_bench_parity_check_accepts_the_oracle_and_rejects_a_wrong_result():
+    """bench.check_stage1 (the oracle check of the TIMED index) on a CPU stand-in for the index: the oracle's own
+    answer passes, a result with one id swapped for a low-scoring row or one score off by 1 % fails."""
+    sys.path.insert(0, ROOT)
+    import torch
+
+    import bench
+
+    rng = np.random.default_rng(3)
+    N, d, B, k = 5000, 64, 4, 20
+    q = flat_ip.normalize_rows(rng.standard_normal((B, d)).astype(np.float32)).astype(np.float32)
+    X = flat_ip.normalize_rows(rng.standard_normal((N, d)).astype(np.float32)).astype(np.float32)
+    pos = rng.choice(N, bench.PLANT_QUERIES * bench.PLANT_ROWS, replace=False).reshape(bench.PLANT_QUERIES, bench.PLANT_ROWS)
+    k = bench.PLANT_ROWS
+    for b in range(bench.PLANT_QUERIES):
+        X[pos[b]] = flat_ip.normalize_rows(q[b][None, :] + 0.7 * rng.standard_normal((bench.PLANT_ROWS, d)).astype(np.float32) / d ** 0.5)
+    Xr, Qr = flat_ip.round_to(X, "bf16"), flat_ip.round_to(q, "bf16")
+
+    class FakeIndex:
+        def get_rows(self, start, n):
+            return Xr[start:start + n]
+
+    D, I = flat_ip.topk_desc(Qr @ Xr.T, k)
+    qd = torch.from_numpy(q).to(torch.bfloat16)
+    good = bench.check_stage1(FakeIndex(), 0, N, qd, torch.from_numpy(D), torch.from_numpy(I), pos, k, rank=0)
+    assert good["planted_ok"] and good["oracle_ok"] and good["oracle_rows"] == N
+    I2 = I.copy()
+    I2[2, 5] = int(np.argmin(Qr[2] @ Xr.T))                     # a clearly wrong row among query 2's results
+    bad = bench.check_stage1(FakeIndex(), 0, N, qd, torch.from_numpy(D), torch.from_numpy(I2), pos, k, rank=0)
+    assert not bad["oracle_ok"]
+    D2 = D.copy()
+    D2[3, 0] *= 1.01
+    assert not bench.check_stage1(FakeIndex(), 0, N, qd, torch.from_numpy(D2), torch.from_numpy(I), pos, k, rank=0)["oracle_ok"]
+    I3 = I.copy()
+    I3[0, -1] = int(np.setdiff1d(np.arange(N), pos[0])[0])      # a planted row lost
+    assert not bench.check_stage1(FakeIndex(), 0, N, qd, torch.from_numpy(D), torch.from_numpy(I3), pos, k, rank=0)["planted_ok"]
 
 
 def test_clock_sampler_parses_nvidia_smi_rows(tmp_path, monkeypatch):

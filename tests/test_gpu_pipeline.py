@@ -143,3 +143,33 @@ def test_batched_pipeline_matches_reference_batch_search(cuda_device, golden_dir
                 seq = fakes.FakeReranker(cfg["stage3_top_k"]).rerank(q, seq)[: cfg["stage3_top_k"]]
                 assert [x["doc_id"] for x in got["results"]] == [x["doc_id"] for x in seq]
             assert s1_launches < r1.faiss_index._index.launches - l1
+
+
+@pytest.mark.parametrize("method", ["maxsim", "colbert"])
+def test_compute_similarity_matrix_equals_the_per_pair_scores(cuda_device, method):
+    """ColBERTScorer.compute_similarity_matrix (src/stage2_rescorer.py:307-320): the reference returns
+    np.array([_maxsim_score / _colbert_score(query, doc) for doc in documents]) without sorting.  Here it is one
+    launch over the resident token store; every entry must equal the oracle's score of the SAME encoder outputs,
+    the per-pair functions of the class, and what rescore_candidates attaches to the documents."""
+    from oracle import flat_ip, maxsim
+
+    docs = [f"document number {i} talks about topic {i % 7} and item {i * 3 % 11} in some detail" for i in range(40)]
+    docs += ["", "short", "a much longer text " * 30]
+    tok = fakes.FakeTokenizer()
+    sc = ColBERTScorer(Stage2Config(device="cpu", top_k_candidates=len(docs), scoring_method=method, gpu_index=cuda_device),
+                       tokenizer=tok, model=fakes.FakeTokenModel(tok, 128))
+    query = "topic 3 item 5 in detail"
+    got = sc.compute_similarity_matrix(query, docs)
+    assert isinstance(got, np.ndarray) and got.shape == (len(docs),)
+    q = sc.encode_query(query)[0].float().numpy()
+    mode = 0 if method == "maxsim" else 1
+    nr = lambda x: flat_ip.round_to(maxsim.l2_normalize_tokens(x), "bf16")   # noqa: E731
+    ref = np.array([maxsim.score(nr(q), nr(sc.encode_single_document(d)[0].float().numpy()), mode, normalize=False) for d in docs])
+    np.testing.assert_allclose(got, ref, rtol=1e-3, atol=2e-4)
+    pair = sc._maxsim_score if method == "maxsim" else sc._colbert_score
+    for i in (0, 17, len(docs) - 1):
+        assert float(pair(sc.encode_query(query), sc.encode_single_document(docs[i]))) == pytest.approx(got[i], rel=1e-5, abs=1e-6)
+    res = sc.rescore_candidates(query, [{"doc_id": i, "document": d, "score": 0.0} for i, d in enumerate(docs)])
+    by_id = {r["doc_id"]: r["stage2_score"] for r in res}
+    assert len(by_id) == len(docs) and all(by_id[i] == pytest.approx(got[i], rel=1e-6, abs=1e-7) for i in range(len(docs)))
+    assert [r["doc_id"] for r in res] == sorted(range(len(docs)), key=lambda i: -got[i])     # stable descending

@@ -262,10 +262,7 @@ def test_config5_shapes_stage1_k500_into_stage2(cuda_device):
 
 def test_scan_variants_agree_bit_for_bit(cuda_device, monkeypatch):
     """The scan with and without cross-CTA threshold sharing must return identical results: the
-    shared bound only prunes rows that cannot be in the top-k.  Experimental layouts that lost
-    on hardware (TS_DUAL, two query tiles per CTA) and the not-yet-validated single-launch scan
-    (TS_FUSE) and CTA-pair scan (TS_PAIR) are compared too when TS_TEST_EXPERIMENTAL=1
-    (tools/gpu/round2_variants.sh)."""
+    shared bound only prunes rows that cannot be in the top-k; so must the scan layouts."""
     N, d, B, k = 60000, 256, 48, 100
     X, Q = make(N, d, B, seed=77, planted=20)
     idx = _lib.Index(d, "bf16", "ip", cuda_device)
@@ -275,11 +272,11 @@ def test_scan_variants_agree_bit_for_bit(cuda_device, monkeypatch):
     assert not flat_ip.check_topk(base[0], base[1], sc, rD, rI, rel=REL)
     Q2 = make(10, d, 300, seed=78)[1]                 # 300 queries: three query tiles
     base2 = idx.search_host(Q2, k, path="umma")
-    variants = ["TS_DBG_NOSHARE"]
-    if os.environ.get("TS_TEST_EXPERIMENTAL"):
-        variants += ["TS_DUAL", "TS_FUSE", "TS_PAIR"]
-    for var in variants:
-        monkeypatch.setenv(var, "1")
+    # defaults: one cooperative launch (TS_FUSE) and CTA pairs for B >= 129 (TS_PAIR); the alternatives -- two
+    # launches, single-CTA tiles, no threshold sharing, two query tiles per CTA -- must give the same bits
+    variants = [("TS_DBG_NOSHARE", "1"), ("TS_FUSE", "0"), ("TS_PAIR", "0"), ("TS_DUAL", "1")]
+    for var, val in variants:
+        monkeypatch.setenv(var, val)
         D, I = idx.search_host(Q, k, path="umma")
         D2, I2 = idx.search_host(Q2, k, path="umma")
         monkeypatch.delenv(var)

@@ -683,8 +683,8 @@ int s1_umma_plan(const ScanArgs& a, UmmaLayout* lay) {
   lay->pub_n = (size_t)(pl.n_slices + 1) * lay->bpad;   // + one row for tau_g
   const int j = (a.k + pl.n_slices - 1) / pl.n_slices;
   lay->jrank = (j <= 8 && !env_on("TS_DBG_NOSHARE")) ? j : 0;
-  // One cooperative launch (pre-pass + grid barrier + scan) instead of two launches.  Written
-  // after this round's GPU budget was spent: NOT yet validated on hardware, so it is opt-in.
+  // One cooperative launch (pre-pass + grid barrier + scan) instead of two launches: bit-equal to the
+  // two-launch sequence on a B200 and x1.02-1.03 on 1.25 M-row shards (profiles/README.md); TS_FUSE=0 for A/B.
   lay->fused = (lay->jrank > 0 && !pl.dual && !pl.pair && env_flag("TS_FUSE", kDefaultFuse)) ? 1 : 0;
   return TS_OK;
 }

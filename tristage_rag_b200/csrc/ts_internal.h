@@ -27,12 +27,18 @@ inline bool env_on(const char* name) {
 }
 // kernel variants with a build-time default that the environment can override in both directions
 // (NAME=1 / NAME=0).  Flip a default here once the variant has been validated and timed on hardware.
-constexpr bool kDefaultFuse = false;   // TS_FUSE : threshold pre-pass + scan in one cooperative launch
+// Validated on a B200 (bit-equal to the two-launch single-CTA scan; profiles/README.md): TS_FUSE x1.02-1.03 on
+// 1.25 M-row shards, TS_PAIR x1.12 at B = 256, tf32 for fp32 storage replaces B/4 CUDA-core passes by one.
+#ifdef TS_CUDASIM
+constexpr bool kDefaultFuse = false;   // the emulator would need all 148 x 192 fibers of a cooperative grid alive at once
+#else
+constexpr bool kDefaultFuse = true;    // TS_FUSE : threshold pre-pass + scan in one cooperative launch
+#endif
 constexpr bool kDefaultS2V2 = false;   // TS_S2_V2: second Stage-2 epilogue
 constexpr bool kDefaultS2Flow = true;   // TS_S2_FLOW: Stage-2 tensor kernel with the resident query tile (s2_flow.cu); 0 = first kernel
 constexpr bool kDefaultS2Epi2 = false; // TS_S2_EPI2: two Stage-2 epilogue warpgroups (320 threads), one per accumulator
-constexpr bool kDefaultPair = false;   // TS_PAIR : cta_group::2 CTA pairs for B >= 129
-constexpr bool kDefaultTf32 = false;   // TS_TF32 : fp32 storage takes the tensor path (kind::tf32) for B > 4 under TS_PATH_AUTO
+constexpr bool kDefaultPair = true;    // TS_PAIR : cta_group::2 CTA pairs for B >= 129
+constexpr bool kDefaultTf32 = true;    // TS_TF32 : fp32 storage takes the tensor path (kind::tf32) for B > 4 under TS_PATH_AUTO
 inline bool env_flag(const char* name, bool dflt) {
   const char* e = getenv(name);
   if (!e || !e[0]) return dflt;
