@@ -147,3 +147,65 @@ def test_shard_range_partitions_exactly():
     for r in range(4):
         lo, hi = tdist.shard_range(103, r, 4)
         assert (own[lo:hi] == r).all()
+
+
+# ------------------------------------------------- the drop-in classes, sharded (Stage1Config.sharded) ---
+def _dropin_worker(rank, world, port, ret):
+    """Every rank makes the SAME calls on the drop-in classes; the kernels run on the CPU emulator build here
+    (test infrastructure), the exchange over gloo.  Results must equal the un-sharded classes' on every rank."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import tempfile
+
+    import conftest
+    from oracle import fakes
+    from tristage_rag_b200 import ColBERTScorer, Stage1Config, Stage1Retriever, Stage2Config
+
+    conftest._enter_emulation()
+    for var in ("TS_PAIR", "TS_FUSE", "TS_TF32"):
+        os.environ[var] = "0"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        docs = [f"document number {i} talks about topic {i % 7} and item {i * 3 % 11} in some detail {i}" for i in range(23)]
+        queries = ["topic 3 item 5", "document number 12 in detail", "item 9"]
+        with tempfile.TemporaryDirectory() as tmp:
+            kw = dict(device="cpu", cache_dir=os.path.join(tmp, "m"), index_dir=os.path.join(tmp, "i"), top_k_candidates=12,
+                      enable_bm25=False, storage_dtype="fp32")
+            one = Stage1Retriever(Stage1Config(**kw), model=fakes.FakeSentenceEncoder(64))
+            many = Stage1Retriever(Stage1Config(sharded=True, **kw), model=fakes.FakeSentenceEncoder(64))
+            many._shard_merge_fn = _numpy_merge
+            for part in (docs[:1], docs[1:9], docs[9:]):          # a 1-doc batch leaves rank 1 without rows at first
+                one.add_documents(list(part))
+                many.add_documents(list(part))
+                assert many.faiss_index.ntotal == one.faiss_index.ntotal == len(one.documents)
+                a, b = one.search(queries[0], 5), many.search(queries[0], 5)
+                assert [x["doc_id"] for x in a] == [x["doc_id"] for x in b]
+            assert 0 < many.faiss_index.local.ntotal < len(docs)  # this rank keeps only its share
+            tok = fakes.FakeTokenizer()
+            s_one = ColBERTScorer(Stage2Config(device="cpu", top_k_candidates=6, storage_dtype="fp32"), tokenizer=tok,
+                                  model=fakes.FakeTokenModel(tok, 32))
+            s_many = ColBERTScorer(Stage2Config(device="cpu", top_k_candidates=6, storage_dtype="fp32", sharded=True),
+                                   tokenizer=tok, model=fakes.FakeTokenModel(tok, 32))
+            for q in queries:
+                a, b = one.search(q), many.search(q)
+                assert [x["doc_id"] for x in a] == [x["doc_id"] for x in b] and len(b) == 12
+                assert np.allclose([x["score"] for x in a], [x["score"] for x in b], rtol=1e-6)
+                ra, rb = s_one.rescore_candidates(q, a), s_many.rescore_candidates(q, b)
+                assert [x["doc_id"] for x in ra] == [x["doc_id"] for x in rb] and len(rb) == 6
+                assert np.allclose([x["stage2_score"] for x in ra], [x["stage2_score"] for x in rb], rtol=1e-6)
+            assert s_many._store.ndocs < s_one._store.ndocs      # token embeddings live on their owner only
+            ba = s_one.rescore_candidates_batch(queries, [one.search(q) for q in queries])
+            bb = s_many.rescore_candidates_batch(queries, [many.search(q) for q in queries])
+            assert [[x["doc_id"] for x in r] for r in ba] == [[x["doc_id"] for x in r] for r in bb]
+            m1 = s_one.compute_similarity_matrix(queries[1], docs[:10])
+            m2 = s_many.compute_similarity_matrix(queries[1], docs[:10])
+            assert np.allclose(m1, m2, rtol=1e-6)
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_drop_in_classes_sharded_world2_gloo():
+    world, port = 2, _free_port()
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_dropin_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world))

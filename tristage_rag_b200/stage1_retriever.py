@@ -73,6 +73,12 @@ class Stage1Config:
     # build this config with explicit keywords (src/retrieval_pipeline.py:244-255) and cannot pass new fields, so
     # the default can also be flipped from the environment of an unmodified deployment: TS_APPROXIMATE=1
     approximate: bool = field(default_factory=lambda: os.environ.get("TS_APPROXIMATE", "0") not in ("", "0"))
+    # one process per GPU (torchrun): stripe the corpus rows over the ranks of the default (or the given) process
+    # group.  Every rank makes the SAME add_documents / search calls; a rank encodes and keeps only its share of each
+    # added batch, searches it, and the [B, k] lists are all-gathered and merged (dist.gather_topk + ts_topk_merge),
+    # so every rank returns the identical, exact result.  TS_SHARDED=1 flips the default for an unmodified deployment.
+    sharded: bool = field(default_factory=lambda: os.environ.get("TS_SHARDED", "0") not in ("", "0"))
+    process_group: Any = None
 
 
 class BM25Index:
@@ -251,6 +257,52 @@ class IndexFlatIP:
         return obj
 
 
+class ShardedFlatIP:
+    """``IndexFlatIP`` whose rows are striped over the ranks of a ``torch.distributed`` group: ``add_local`` appends
+    this rank's share of a batch together with the GLOBAL row numbers of those rows, ``search`` runs the local exact
+    top-k, maps local rows to global ids, all-gathers the [B, k] lists and merges them on the device
+    (``ts_topk_merge``; tie rule score desc, id asc) -- the same result on every rank, equal to one flat index over
+    all rows because the global top-k is a subset of the union of the local top-k lists."""
+
+    def __init__(self, d: int, storage_dtype: str = "bf16", device: int = 0, group=None, merge_fn=None, local=None):
+        self.d, self.storage_dtype, self.device, self.group = int(d), storage_dtype, device, group
+        self.local = local if local is not None else IndexFlatIP(d, storage_dtype, device)
+        self.merge_fn = merge_fn
+        self._gids = np.zeros(0, np.int64)
+        self.ntotal = 0                    # GLOBAL row count (what faiss's ntotal means to the callers)
+        self.is_trained = True
+
+    def add_local(self, x_local: np.ndarray, gids: np.ndarray, ntotal_after: int) -> None:
+        if len(x_local):
+            self.local.add(x_local)
+            self._gids = np.concatenate([self._gids, np.asarray(gids, np.int64)])
+        self.ntotal = int(ntotal_after)
+
+    def search(self, q: np.ndarray, k: int, path: str = "auto"):
+        import torch
+        import torch.distributed as dist
+
+        from . import dist as tdist
+
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        B = q.shape[0]
+        if self.local.ntotal > 0:
+            D, I = self.local.search(q, k, path=path)
+            I = np.where(I >= 0, self._gids[np.maximum(I, 0)], -1)
+        else:                                   # this rank holds no rows (fewer rows than ranks)
+            D = np.full((B, k), np.float32(-3.4028234663852886e38), np.float32)
+            I = np.full((B, k), -1, np.int64)
+        on_gpu = dist.get_backend(self.group) == "nccl"
+        dev = torch.device("cuda", self.device) if on_gpu else torch.device("cpu")
+        all_s, all_i = tdist.gather_topk(torch.from_numpy(D).to(dev), torch.from_numpy(I).to(dev), self.group)
+        merge = self.merge_fn or (lambda s, i: _lib.topk_merge(s, i, device=self.device))
+        ms, mi = merge(all_s, all_i)
+        return ms.cpu().numpy(), mi.cpu().numpy()
+
+    def save(self, path: str) -> None:
+        raise NotImplementedError("a sharded Stage-1 index is saved per rank with dist.ShardedIndex.save")
+
+
 class IndexIVFFlat:
     """The ``faiss.IndexIVFFlat`` surface the reference touches (``train``, ``add``, ``nprobe``, ``search``,
     ``ntotal``; reference :263-273,313,380), backed by one ``ts_index`` shard plus inverted lists of row numbers
@@ -329,6 +381,7 @@ class Stage1Retriever:
         self.documents: List[str] = []
         self.doc_metadata: List[Dict[str, Any]] = []
         self._device_bm25 = None
+        self._shard_merge_fn = None       # tests on a CPU-only box inject the G*k -> k merge
         os.makedirs(self.config.cache_dir, exist_ok=True)
         os.makedirs(self.config.index_dir, exist_ok=True)
         _lib.lib()                       # fail loudly now if the CUDA library is missing
@@ -364,6 +417,33 @@ class Stage1Retriever:
         norms = np.linalg.norm(embeddings, axis=1, keepdims=True)
         return embeddings / (norms + 1e-8)
 
+    def _shard(self):
+        """(rank, world, group) when the corpus is striped over a process group, else None"""
+        if not self.config.sharded:
+            return None
+        import torch.distributed as dist
+
+        if not dist.is_initialized() or dist.get_world_size(self.config.process_group) < 2:
+            return None
+        g = self.config.process_group
+        return dist.get_rank(g), dist.get_world_size(g), g
+
+    def _add_sharded(self, texts: Optional[List[str]], embeddings: Optional[np.ndarray], n: int, base: int, shard):
+        """this rank's share of a batch of n rows whose global row numbers start at `base`"""
+        from .dist import shard_range
+
+        rank, world, group = shard
+        lo, hi = shard_range(n, rank, world)
+        if embeddings is None:
+            mine = self._normalize_embeddings(self._encode_batch(texts[lo:hi])).astype(np.float32) if hi > lo \
+                else np.zeros((0, self.embedding_dim), np.float32)
+        else:
+            mine = embeddings[lo:hi]
+        if self.faiss_index is None:
+            self.faiss_index = ShardedFlatIP(self.embedding_dim if embeddings is None else embeddings.shape[1],
+                                             self.config.storage_dtype, self.config.gpu_index, group, self._shard_merge_fn)
+        self.faiss_index.add_local(mine, np.arange(base + lo, base + hi, dtype=np.int64), base + n)
+
     def _create_faiss_index(self, embeddings: np.ndarray):
         from .ivf import MIN_ROWS_FOR_IVF
 
@@ -388,8 +468,12 @@ class Stage1Retriever:
         if metadata is None:
             metadata = [{}] * len(documents)   # one shared dict, like the reference (:302)
         self.doc_metadata.extend(metadata)
-        embeddings = self._normalize_embeddings(self._encode_batch(documents)).astype(np.float32)
-        self._add_normalized(embeddings)
+        shard = self._shard()
+        if shard is not None:                 # every rank encodes and keeps only its share of the batch
+            self._add_sharded(documents, None, len(documents), len(self.documents) - len(documents), shard)
+        else:
+            embeddings = self._normalize_embeddings(self._encode_batch(documents)).astype(np.float32)
+            self._add_normalized(embeddings)
         self._refit_bm25()
 
     def add_embeddings(self, embeddings: np.ndarray, documents: Optional[List[str]] = None,
@@ -401,7 +485,12 @@ class Stage1Retriever:
         self.documents.extend(docs)
         self.doc_metadata.extend(metadata if metadata is not None else [{}] * n)
         e = np.asarray(embeddings, dtype=np.float32)
-        self._add_normalized(self._normalize_embeddings(e).astype(np.float32) if normalize else e)
+        e = self._normalize_embeddings(e).astype(np.float32) if normalize else e
+        shard = self._shard()
+        if shard is not None:
+            self._add_sharded(None, e, n, len(self.documents) - n, shard)
+        else:
+            self._add_normalized(e)
         if documents is not None:
             self._refit_bm25()
 
@@ -531,6 +620,8 @@ class Stage1Retriever:
         data = {"documents": self.documents, "doc_metadata": self.doc_metadata,
                 "config": self.config.__dict__, "bm25_index": self.bm25_index}
         faiss_path = os.path.join(self.config.index_dir, "stage1_faiss.index")   # fixed location, like :434
+        if isinstance(self.faiss_index, ShardedFlatIP):
+            raise NotImplementedError("sharded Stage 1: save the shards with tristage_rag_b200.dist.ShardedIndex.save")
         if self.faiss_index is not None:
             self.faiss_index.save(faiss_path)
         with open(index_path, "wb") as f:

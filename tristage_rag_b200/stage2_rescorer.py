@@ -26,7 +26,7 @@ from __future__ import annotations
 import logging
 import os
 import threading
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import Any, Dict, Hashable, List, Optional
 
 import numpy as np
@@ -52,6 +52,11 @@ class Stage2Config:
     use_gpu_if_available: bool = True
     storage_dtype: str = "bf16"      # HBM token-store dtype: bf16 | fp16 | fp32
     gpu_index: int = 0
+    # one process per GPU (torchrun): every rank makes the same calls; a document's token embeddings live on ONE
+    # rank (doc_id % world, or a hash of the text), which encodes and scores it; the [B, C] score matrices are
+    # summed with one all-reduce, so every rank returns the identical result.  TS_SHARDED=1 flips the default.
+    sharded: bool = field(default_factory=lambda: os.environ.get("TS_SHARDED", "0") not in ("", "0"))
+    process_group: Any = None
 
 
 class ColBERTScorer:
@@ -163,9 +168,45 @@ class ColBERTScorer:
             for i, key in enumerate(keys):
                 self._slot[key] = base + i
 
+    def _shard(self):
+        if not self.config.sharded:
+            return None
+        import torch.distributed as dist
+
+        if not dist.is_initialized() or dist.get_world_size(self.config.process_group) < 2:
+            return None
+        g = self.config.process_group
+        return dist.get_rank(g), dist.get_world_size(g), g
+
+    @staticmethod
+    def _owner(key: Hashable, world: int) -> int:
+        """rank that keeps the token embeddings of a document: by doc id when it is an int, else by its text"""
+        import zlib
+
+        ident = key[0] if isinstance(key, tuple) else key
+        if isinstance(ident, (int, np.integer)) and not isinstance(ident, bool):
+            return int(ident) % world
+        text = key[1] if isinstance(key, tuple) and len(key) > 1 else str(key)
+        return zlib.crc32(str(text).encode("utf-8", "replace")) % world
+
+    def _sum_over_ranks(self, scores: np.ndarray, shard) -> np.ndarray:
+        """every candidate was scored by exactly one rank (0.0 elsewhere): one all-reduce assembles the matrix"""
+        import torch.distributed as dist
+
+        _, _, group = shard
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.from_numpy(np.ascontiguousarray(scores, np.float32))
+        t = t.to(torch.device("cuda", self.config.gpu_index)) if on_gpu else t
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t.cpu().numpy()
+
     def _ensure_indexed(self, pairs) -> None:
         """``pairs`` = (key, text) of the documents a request needs: the ones the store does not hold yet are
-        encoded and appended, atomically with respect to other threads doing the same."""
+        encoded and appended, atomically with respect to other threads doing the same.  Sharded: only the
+        documents this rank owns."""
+        shard = self._shard()
+        if shard is not None:
+            pairs = [(k, d) for k, d in pairs if self._owner(k, shard[1]) == shard[0]]
         with self._index_lock:
             seen, todo = set(), []
             for k, d in pairs:
@@ -189,9 +230,15 @@ class ColBERTScorer:
         return _lib.TS_S2_MAXSIM if self.config.scoring_method == "maxsim" else _lib.TS_S2_COLBERT
 
     def _score_slots(self, query_embeddings: torch.Tensor, slots: List[int]) -> np.ndarray:
+        """slots: position in THIS rank's token store, or -1 for a document another rank owns (scores 0.0 here)"""
         q = query_embeddings.detach().float().cpu().numpy().reshape(1, -1, query_embeddings.shape[-1])
         cand = np.asarray(slots, dtype=np.int64).reshape(1, -1)
-        return self._store.maxsim_host(q, cand, mode=self._mode(), normalize_q=True)[0]
+        if self._store is None:                       # this rank owns none of the documents seen so far
+            s = np.zeros(cand.shape[1], np.float32)
+        else:
+            s = self._store.maxsim_host(q, cand, mode=self._mode(), normalize_q=True)[0]
+        shard = self._shard()
+        return self._sum_over_ranks(s, shard) if shard is not None else s
 
     # -- the two scoring functions, one pair at a time (reference :167-201) ----
     def _pair_score(self, query_embeddings, doc_embeddings, mode: int) -> torch.Tensor:
@@ -220,7 +267,7 @@ class ColBERTScorer:
         except Exception as e:                         # reference :260-263
             self.logger.error(f"Error encoding documents: {e}")
             return candidates
-        scores = self._score_slots(query_embeddings, [self._slot[k] for k in keys])
+        scores = self._score_slots(query_embeddings, [self._slot.get(k, -1) for k in keys])
         scored = []
         for c, s in zip(candidates, scores):
             u = c.copy()
@@ -267,11 +314,17 @@ class ColBERTScorer:
         n_cand = np.zeros(len(live), np.int32)
         for r, b in enumerate(live):
             qbuf[r, : lq[r]] = q_embs[r].detach().float().cpu().numpy().reshape(-1, H)
-            slots = [self._slot[self._key(c)] for c in candidates[b]]
+            slots = [self._slot.get(self._key(c), -1) for c in candidates[b]]
             cand[r, : len(slots)] = slots
             n_cand[r] = len(slots)
-        scores = self._store.maxsim_host(qbuf, cand, q_len=np.asarray(lq, np.int32), n_cand=n_cand,
-                                         mode=self._mode(), normalize_q=True)
+        if self._store is None:
+            scores = np.zeros(cand.shape, np.float32)
+        else:
+            scores = self._store.maxsim_host(qbuf, cand, q_len=np.asarray(lq, np.int32), n_cand=n_cand,
+                                             mode=self._mode(), normalize_q=True)
+        shard = self._shard()
+        if shard is not None:
+            scores = self._sum_over_ranks(scores, shard)
         top_k = min(self.config.top_k_candidates, Cmax, _lib.TS_MAX_K)
         dev = torch.device("cuda", self.config.gpu_index)
         _, pos = _lib.rank_desc(torch.from_numpy(scores).to(dev), top_k,
@@ -295,7 +348,7 @@ class ColBERTScorer:
     def compute_similarity_matrix(self, query: str, documents: List[str]) -> np.ndarray:
         query_embeddings = self.encode_query(query)
         self.index_documents(documents)
-        slots = [self._slot[("text", d)] for d in documents]
+        slots = [self._slot.get(("text", d), -1) for d in documents]
         return np.array([float(s) for s in self._score_slots(query_embeddings, slots)])
 
     def get_model_info(self) -> Dict[str, Any]:
