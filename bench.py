@@ -563,6 +563,8 @@ def main():
     def e2e_step():
         if world == 1:
             idx.search_host(q_np, k, path=path, out=out_np)  # the C-ABI host call: H2D, search, D2H, sync
+        elif p2p:
+            sharded.search_host(q_np, k, out=out_np, path=path)   # one C call: H2D, scan, select+push, wait+merge, D2H, sync
         else:
             q_stage.copy_(q_pin, non_blocking=True)
             s, i = sharded.search(q_stage, k, path=path)

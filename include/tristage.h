@@ -164,6 +164,34 @@ int ts_exchange_wait_merge(int device, const void* local_base_dev, int n_ranks, 
                            int64_t ids_offset, int64_t flags_offset, int parity, uint32_t seq,
                            float* out_scores_dev, int64_t* out_ids_dev, void* stream);
 
+/* FUSED exchange (the default multi-GPU data plane when peer memory is available): no separate push kernel and
+ * no collective-library call in the step.  The final pass of the local top-k selection stores query b's k
+ * (score, id) pairs straight into slot `rank` of EVERY rank's receive buffer (NVLink stores; the own buffer is one
+ * of them) and publishes flag[parity][rank][b] = seq with a system-scope release; the merge kernel (one CTA per
+ * query) waits with system-scope acquires -- bounded: a missing peer traps after ~4 s -- until all n_ranks rows of
+ * ITS query have arrived and merges them.  A step is therefore: query prep, scan, select+push, wait+merge.
+ * Receive buffer of one rank (ts_exchange_buffer_bytes; allocate it zeroed as symmetric / peer-mapped memory):
+ *   [parity 2][rank n] slots of { scores f32[B_max*k_max] | ids i64[B_max*k_max] }, then flags u32 [parity 2][rank n][B_max].
+ * All ranks must make the same sequence of ts_index_search_push / ts_exchange_merge calls (SPMD); two parities
+ * suffice because a rank can be at most one step ahead of its slowest peer.
+ * peer_bases_host[n_ranks]: base address of every rank's buffer as seen from THIS device (own buffer at [rank]). */
+typedef struct ts_exchange ts_exchange;
+int64_t ts_exchange_buffer_bytes(int n_ranks, int B_max, int k_max);
+int ts_exchange_create(ts_exchange** out, int device, int rank, int n_ranks, const int64_t* peer_bases_host,
+                       int B_max, int k_max);
+int ts_exchange_destroy(ts_exchange* x);
+/* local search (as ts_index_search) whose result goes to every rank's buffer instead of a local output          */
+int ts_index_search_push(ts_index* h, ts_exchange* x, const void* q_dev, int q_dtype, int B, int k, unsigned flags,
+                         int path, void* stream);
+/* wait for all ranks' rows of this step and merge them: identical [B, k] result on every rank                    */
+int ts_exchange_merge(ts_exchange* x, int B, int k, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+/* both, back to back; the _host variant takes pinned or pageable HOST buffers (H2D, step, D2H, synchronise) --
+ * the sharded counterpart of ts_index_search_host                                                               */
+int ts_index_search_sharded(ts_index* h, ts_exchange* x, const void* q_dev, int q_dtype, int B, int k, unsigned flags,
+                            int path, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
+int ts_index_search_sharded_host(ts_index* h, ts_exchange* x, const void* q_host, int q_dtype, int B, int k,
+                                 unsigned flags, int path, float* out_scores_host, int64_t* out_ids_host, void* stream);
+
 /* The same exchange for the Stage-2 score matrices (replaces the all-reduce(SUM) of the per-rank
  * ts_maxsim outputs): every rank pushes its [B, C] fp32 matrix with ts_exchange_push (nbytes = B*C*4),
  * ts_exchange_wait_sum waits for all n_ranks slots of the step and writes their element-wise sum.   */

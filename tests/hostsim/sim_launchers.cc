@@ -113,14 +113,14 @@ int s1_stream_plan(const ScanArgs&, int*, size_t*) { return not_simulated("s1_st
 int s1_umma_plan(const ScanArgs&, UmmaLayout*) { return not_simulated("s1_umma"); }
 int launch_s1_stream(const ScanArgs&, cudaStream_t, int*) { return not_simulated("s1_stream"); }
 int launch_s1_umma(const ScanArgs&, const UmmaLayout&, cudaStream_t, int*) { return not_simulated("s1_umma"); }
-int launch_merge_keys(const uint64_t*, int, int, int, int64_t, uint64_t*, uint64_t*, float*, int64_t*, cudaStream_t, int*) { return not_simulated("merge_keys"); }
+int launch_merge_keys(const uint64_t*, int, int, int, int64_t, uint64_t*, uint64_t*, float*, int64_t*, cudaStream_t, int*, const PushTarget*) { return not_simulated("merge_keys"); }
 size_t merge_tmp_keys(int, int, int) { return 0; }
-int launch_merge_lists(const uint64_t*, const int*, const float*, const UmmaLayout&, int, int, int64_t, float*, int64_t*, cudaStream_t, int*) { return not_simulated("merge_lists"); }
+int launch_merge_lists(const uint64_t*, const int*, const float*, const UmmaLayout&, int, int, int64_t, float*, int64_t*, cudaStream_t, int*, const PushTarget*) { return not_simulated("merge_lists"); }
 int launch_merge_pairs(const float*, const int64_t*, long long, long long, int, int, int, float*, int64_t*, cudaStream_t) { return not_simulated("merge_pairs"); }
 int launch_rank_desc(const float*, const int32_t*, int, int, int, float*, int32_t*, cudaStream_t) { return not_simulated("rank_desc"); }
 int launch_exchange_push(const void*, long long, const long long*, int, long long, long long, unsigned int, cudaStream_t) { return not_simulated("exchange_push"); }
 int launch_exchange_wait_sum(const void*, long long, const unsigned int*, int, unsigned int, long long, float*, cudaStream_t) { return not_simulated("exchange_wait_sum"); }
-int launch_merge_pairs_wait(const float*, const int64_t*, long long, long long, int, int, int, const unsigned int*, unsigned int, float*, int64_t*, cudaStream_t) { return not_simulated("merge_pairs_wait"); }
+int launch_merge_pairs_wait(const float*, const int64_t*, long long, long long, int, int, int, const unsigned int*, unsigned int, float*, int64_t*, cudaStream_t, int) { return not_simulated("merge_pairs_wait"); }
 int launch_maxsim(const MaxSimArgs&, cudaStream_t, int*) { return not_simulated("maxsim"); }
 
 }  // namespace ts

@@ -802,6 +802,48 @@ def test_peer_memory_exchange_equals_gather_and_merge(sim):
     assert sim.ts_exchange_wait_merge(0, p(bufs[0]), G, B, k, slot + 8, ids_off, flags_off, 0, 1, p(out_s), p(out_i), None) == -1
 
 
+@pytest.mark.parametrize("path", ["stream", "umma"])
+def test_fused_exchange_select_pushes_rows_and_merge_waits_per_query(sim, path):
+    """The fused exchange (ts_exchange_*): the select kernel of every "rank" stores its rows into every rank's
+    receive buffer and publishes per-query flags, the merge kernel waits for its query's rows.  G ranks live in
+    one process here (buffers are host memory, "peer" pointers ordinary pointers; all pushes of a step run before
+    the merges, as separate launches cannot wait on each other in the emulator).  Result == the oracle over all
+    rows, on every rank, over several steps (both parities) and changing batch sizes."""
+    G, N, d, k = 3, 1800, 64, 40
+    X, _ = make(N, d, 1, seed=14)
+    X[900] = X[5]
+    X[1700] = X[5]                                             # exact ties across shards: ids must ascend
+    B_max, k_max = 16, 64
+    nbytes = _lib.Exchange.buffer_bytes(G, B_max, k_max)
+    bufs = [np.zeros(nbytes + 16, np.uint8) for _ in range(G)]
+    bases = [b.ctypes.data + (-b.ctypes.data % 16) for b in bufs]
+    shards, xs = [], []
+    for r in range(G):
+        lo, hi = r * N // G, (r + 1) * N // G
+        sh = _lib.Index(d, "bf16", "ip", 0)
+        sh.add(X[lo:hi])
+        sh.set_id_base(lo)
+        shards.append(sh)
+        xs.append(_lib.Exchange(0, r, G, bases, B_max, k_max))
+    rng = np.random.default_rng(19)
+    for step, B in enumerate((5, 16, 1, 7, 7)):
+        Q = flat_ip.normalize_rows(rng.standard_normal((B, d)).astype(np.float32)).astype(np.float32)
+        Q[0] = X[5]
+        for r in range(G):
+            _lib.check(sim.ts_index_search_push(shards[r]._h, xs[r]._h, p(Q), _lib.TS_F32, B, k, 0, _lib.PATHS[path], None))
+        rD, rI, sc = oracle_search(X, Q, k, "bf16")
+        for r in range(G):
+            out_s, out_i = np.empty((B, k), np.float32), np.empty((B, k), np.int64)
+            _lib.check(sim.ts_exchange_merge(xs[r]._h, B, k, p(out_s), p(out_i), None))
+            assert not flat_ip.check_topk(out_s, out_i, sc, rD, rI, rel=REL), (step, r)
+            assert out_i[0, :3].tolist() == [5, 900, 1700]
+            if r == 0:
+                first = (out_s.copy(), out_i.copy())
+            assert (out_i == first[1]).all() and (out_s == first[0]).all()      # identical on every rank
+    assert sim.ts_index_search_push(shards[0]._h, xs[0]._h, p(Q), _lib.TS_F32, B_max + 1, k, 0, 0, None) == -1   # over capacity
+    assert sim.ts_exchange_create(C.byref(C.c_void_p()), 0, G, G, p(np.array(bases, np.int64)), B_max, k_max) == -1   # rank out of range
+
+
 # ------------------------------------------- long pipelines: few SMs, many tiles per CTA ---
 @pytest.mark.parametrize("sms,async_seed", [(2, 0), (6, 0), (3, 7)])
 def test_few_sms_many_tiles_per_cta_wrap_every_ring(sim, monkeypatch, sms, async_seed):

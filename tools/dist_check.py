@@ -16,6 +16,9 @@ from tristage_rag_b200.dist import ShardedIndex, ShardedTokStore, shard_range  #
 
 
 def main():
+    import bench
+
+    bench.arm_watchdog(int(os.environ.get("TS_CHECK_TIMEOUT", "240")))     # a wedged exchange must not hold the box
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -41,6 +44,9 @@ def main():
         ref = [torch.empty_like(i) for _ in range(world)]
         dist.all_gather(ref, i)
         assert all((r == ref[0]).all() for r in ref)
+        # the host-buffer call (one C call per step on the peer-memory plane) returns the same
+        hD, hI = sh.search_host(Q, k)
+        assert (hI == i.cpu().numpy()).all() and (hD == s.cpu().numpy()).all(), (rank, B, "host call")
     # approximate mode: the same centroids on every rank, lists over the local rows -> the merged result is what
     # one GPU holding all rows returns for the same probes (oracle/ivf.py on the full data)
     from oracle import ivf as oivf
@@ -112,7 +118,7 @@ def main():
         assert torch.equal(i2, i0) and torch.equal(s2, s0)
     dist.barrier()
     if rank == 0:
-        mode = "peer-memory exchange" if os.environ.get("TS_P2P", "0") not in ("", "0") and sh._p2p else "nccl all-gather"
+        mode = "peer-memory exchange (fused select+push, wait+merge)" if sh._p2p else "nccl all-gather + merge kernel"
         print(f"dist_check ok: world={world} merge via {mode}; stage2 candidates per rank max/mean = {own.max() / own.mean():.3f}",
               flush=True)
     sys.stdout.flush()

@@ -92,6 +92,13 @@ SYMBOLS = {
     "ts_tokstore_load": (_i, [C.POINTER(_vp), _i, C.c_char_p]),
     "ts_tokstore_append_file": (_i, [_vp, C.c_char_p, _i64, _i64, _vp]),
     "ts_tokstore_dim": (_i, [_vp]),
+    "ts_exchange_buffer_bytes": (C.c_int64, [_i, _i, _i]),
+    "ts_exchange_create": (_i, [C.POINTER(_vp), _i, _i, _i, _vp, _i, _i]),
+    "ts_exchange_destroy": (_i, [_vp]),
+    "ts_index_search_push": (_i, [_vp, _vp, _vp, _i, _i, _i, C.c_uint, _i, _vp]),
+    "ts_exchange_merge": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "ts_index_search_sharded": (_i, [_vp, _vp, _vp, _i, _i, _i, C.c_uint, _i, _vp, _vp, _vp]),
+    "ts_index_search_sharded_host": (_i, [_vp, _vp, _vp, _i, _i, _i, C.c_uint, _i, _vp, _vp, _vp]),
     "ts_tokstore_dtype": (_i, [_vp]),
     "ts_tokstore_layout": (_i, [_vp]),
     "ts_tokstore_set_profiling": (_i, [_vp, _i]),
@@ -559,6 +566,62 @@ def topk_merge(scores, ids, device: int = 0):
     check(lib().ts_topk_merge(device, C.c_void_p(scores.data_ptr()), C.c_void_p(ids.data_ptr()), L, B, k,
                               C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()), _stream_ptr(device)))
     return out_s, out_i
+
+
+class Exchange:
+    """Fused multi-GPU exchange state (``ts_exchange``): this rank's receive buffer plus the peers' buffers as seen
+    from this device.  ``peer_bases``: int sequence [n_ranks] of buffer base addresses (own buffer at [rank]);
+    every buffer holds ``Exchange.buffer_bytes(n_ranks, B_max, k_max)`` ZEROED bytes of peer-mapped memory."""
+
+    def __init__(self, device: int, rank: int, n_ranks: int, peer_bases, B_max: int, k_max: int):
+        import numpy as np
+
+        self.device, self.rank, self.n_ranks, self.B_max, self.k_max = int(device), int(rank), int(n_ranks), int(B_max), int(k_max)
+        bases = np.ascontiguousarray(peer_bases, np.int64)
+        assert len(bases) == n_ranks
+        h = C.c_void_p()
+        check(lib().ts_exchange_create(C.byref(h), self.device, self.rank, self.n_ranks, C.c_void_p(bases.ctypes.data),
+                                       self.B_max, self.k_max))
+        self._h = h
+
+    @staticmethod
+    def buffer_bytes(n_ranks: int, B_max: int, k_max: int) -> int:
+        n = int(lib().ts_exchange_buffer_bytes(int(n_ranks), int(B_max), int(k_max)))
+        if n <= 0:
+            raise ValueError("bad exchange capacity")
+        return n
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and _lib is not None:
+            _lib.ts_exchange_destroy(h)
+
+    def search(self, index: "Index", q, k: int, normalize_q: bool = False, path: str = "auto"):
+        """q: cuda tensor [B, dim] replicated on every rank -> merged (scores, ids) [B, k], identical on every rank.
+        Four launches (query prep, scan, select+push, wait+merge), asynchronous on the current stream."""
+        import torch
+
+        q = q.contiguous()
+        B = q.shape[0]
+        dev = torch.device("cuda", self.device)
+        out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+        check(lib().ts_index_search_sharded(index._h, self._h, C.c_void_p(q.data_ptr()), _code_of_torch(q.dtype), B, int(k),
+                                            TS_FLAG_NORMALIZE_Q if normalize_q else 0, PATHS[path],
+                                            C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()), _stream_ptr(self.device)))
+        return out_s, out_i
+
+    def search_host(self, index: "Index", q, k: int, normalize_q: bool = False, path: str = "auto", out=None):
+        """numpy fp32 [B, dim] in, (D, I) numpy out: H2D, the four launches, D2H and the synchronise in ONE C call."""
+        import numpy as np
+
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        B = q.shape[0]
+        D, I = out if out is not None else (np.empty((B, k), np.float32), np.empty((B, k), np.int64))
+        check(lib().ts_index_search_sharded_host(index._h, self._h, C.c_void_p(q.ctypes.data), TS_F32, B, int(k),
+                                                 TS_FLAG_NORMALIZE_Q if normalize_q else 0, PATHS[path],
+                                                 C.c_void_p(D.ctypes.data), C.c_void_p(I.ctypes.data), _stream_ptr(self.device)))
+        return D, I
 
 
 def packed_layout(B: int, k: int):

@@ -209,9 +209,37 @@ int ts_index_reset(ts_index* h) { if (!h) return TS_ERR_INVALID; h->n = 0; ++h->
 int ts_index_set_id_base(ts_index* h, int64_t b) { if (!h) return TS_ERR_INVALID; h->id_base = b; return TS_OK; }
 int64_t ts_index_launch_count(const ts_index* h) { return h ? h->launches : -1; }
 
+}  // extern "C"
+
+// fused multi-GPU exchange state (ts_exchange_*): the receive buffers are allocated and mapped by the caller
+struct ts_exchange {
+  int device, rank, n_ranks, B_max, k_max;
+  long long* peer_bases_dev;     // [n_ranks]
+  char* local_base;              // this rank's own buffer
+  int64_t slot_bytes, ids_in_slot, flags_off;
+  uint64_t step;                 // calls made so far: parity = step & 1, seq = step + 1
+};
+
+namespace ts {
+static int index_search_impl(ts_index* h, const void* q_dev, int q_dtype, int B, int k, unsigned flags, int path,
+                             float* out_scores, int64_t* out_ids, void* stream, const PushTarget* push);
+}
+
+extern "C" {
+
 int ts_index_search(ts_index* h, const void* q_dev, int q_dtype, int B, int k, unsigned flags, int path,
                     float* out_scores, int64_t* out_ids, void* stream) {
-  if (!h || !q_dev || !out_scores || !out_ids || B <= 0) { set_error("ts_index_search: invalid argument"); return TS_ERR_INVALID; }
+  if (!out_scores || !out_ids) { set_error("ts_index_search: invalid argument"); return TS_ERR_INVALID; }
+  return ts::index_search_impl(h, q_dev, q_dtype, B, k, flags, path, out_scores, out_ids, stream, nullptr);
+}
+
+}  // extern "C"
+
+namespace ts {
+static int index_search_impl(ts_index* h, const void* q_dev, int q_dtype, int B, int k, unsigned flags, int path,
+                             float* out_scores, int64_t* out_ids, void* stream, const PushTarget* push) {
+  if (!h || !q_dev || B <= 0) { set_error("ts_index_search: invalid argument"); return TS_ERR_INVALID; }
+  if (push && B > 1024) { set_error("ts_index_search: the fused exchange takes at most 1024 queries per call"); return TS_ERR_UNSUPPORTED; }
   if (k <= 0 || k > TS_MAX_K) { set_error("ts_index_search: k=%d outside 1..%d", k, TS_MAX_K); return TS_ERR_INVALID; }
   if (q_dtype != TS_F32 && q_dtype != h->dtype) { set_error("ts_index_search: query dtype must be f32 or the storage dtype"); return TS_ERR_INVALID; }
   if (h->n == 0) { set_error("No documents indexed. Call add_documents() first."); return TS_ERR_EMPTY; }
@@ -258,7 +286,8 @@ int ts_index_search(ts_index* h, const void* q_dev, int q_dtype, int B, int k, u
       h->timer->end(st);
       if (rc) return rc;
       rc = launch_merge_keys((const uint64_t*)h->partial, L, Bc, k, h->id_base, (uint64_t*)h->tmp0, (uint64_t*)h->tmp1,
-                             out_scores + (size_t)b0 * k, out_ids + (size_t)b0 * k, st, &launches);
+                             out_scores ? out_scores + (size_t)b0 * k : nullptr, out_ids ? out_ids + (size_t)b0 * k : nullptr, st,
+                             &launches, push);
       if (rc) return rc;
     } else {
       UmmaLayout lay{};
@@ -273,11 +302,114 @@ int ts_index_search(ts_index* h, const void* q_dev, int q_dtype, int B, int k, u
       h->timer->end(st);
       if (rc) return rc;
       rc = launch_merge_lists((const uint64_t*)h->lists, (const int*)h->counts, (const float*)h->pub, lay, Bc, k, h->id_base,
-                              out_scores + (size_t)b0 * k, out_ids + (size_t)b0 * k, st, &launches);
+                              out_scores ? out_scores + (size_t)b0 * k : nullptr, out_ids ? out_ids + (size_t)b0 * k : nullptr, st,
+                              &launches, push);
       if (rc) return rc;
     }
     h->launches += launches;
   }
+  return TS_OK;
+}
+}  // namespace ts
+
+extern "C" {
+
+// ---- fused multi-GPU exchange -------------------------------------------------
+static int64_t xchg_slot_bytes(int B_max, int k_max, int64_t* ids_in_slot) {
+  const int64_t sc = ((int64_t)B_max * k_max * 4 + 15) / 16 * 16;
+  if (ids_in_slot) *ids_in_slot = sc;
+  return sc + (int64_t)B_max * k_max * 8;
+}
+
+int64_t ts_exchange_buffer_bytes(int n_ranks, int B_max, int k_max) {
+  if (n_ranks < 1 || B_max < 1 || k_max < 1 || k_max > TS_MAX_K) return -1;
+  const int64_t slot = xchg_slot_bytes(B_max, k_max, nullptr);
+  return 2 * n_ranks * slot + 2 * (int64_t)n_ranks * B_max * 4;
+}
+
+int ts_exchange_create(ts_exchange** out, int device, int rank, int n_ranks, const int64_t* peer_bases_host, int B_max, int k_max) {
+  if (!out || !peer_bases_host || n_ranks < 1 || n_ranks > 256 || rank < 0 || rank >= n_ranks || B_max < 1 || B_max > 1024 || k_max < 1 || k_max > TS_MAX_K) {
+    set_error("ts_exchange_create: invalid argument");
+    return TS_ERR_INVALID;
+  }
+  for (int r = 0; r < n_ranks; ++r)
+    if (!peer_bases_host[r] || (peer_bases_host[r] & 15)) { set_error("ts_exchange_create: buffer %d is null or not 16-byte aligned", r); return TS_ERR_INVALID; }
+  TS_CUDA_OK(cudaSetDevice(device));
+  ts_exchange* x = new ts_exchange();
+  memset(x, 0, sizeof(*x));
+  x->device = device; x->rank = rank; x->n_ranks = n_ranks; x->B_max = B_max; x->k_max = k_max;
+  x->slot_bytes = xchg_slot_bytes(B_max, k_max, &x->ids_in_slot);
+  x->flags_off = 2 * n_ranks * x->slot_bytes;
+  x->local_base = reinterpret_cast<char*>(peer_bases_host[rank]);
+  if (cudaMalloc((void**)&x->peer_bases_dev, (size_t)n_ranks * 8) != cudaSuccess) { cudaGetLastError(); delete x; set_error("ts_exchange_create: cudaMalloc failed"); return TS_ERR_NOMEM; }
+  if (cudaMemcpy(x->peer_bases_dev, peer_bases_host, (size_t)n_ranks * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError(); cudaFree(x->peer_bases_dev); delete x; set_error("ts_exchange_create: copy failed"); return TS_ERR_CUDA;
+  }
+  *out = x;
+  return TS_OK;
+}
+
+int ts_exchange_destroy(ts_exchange* x) {
+  if (!x) return TS_OK;
+  cudaSetDevice(x->device);
+  if (x->peer_bases_dev) cudaFree(x->peer_bases_dev);
+  delete x;
+  return TS_OK;
+}
+
+int ts_index_search_push(ts_index* h, ts_exchange* x, const void* q_dev, int q_dtype, int B, int k, unsigned flags, int path,
+                         void* stream) {
+  if (!h || !x || B < 1 || B > x->B_max || k < 1 || k > x->k_max) { set_error("ts_index_search_push: B / k outside the exchange's capacity"); return TS_ERR_INVALID; }
+  if (x->device != h->device) { set_error("ts_index_search_push: index and exchange live on different devices"); return TS_ERR_INVALID; }
+  const int parity = (int)(x->step & 1);
+  PushTarget pt{};
+  pt.peer_bases = x->peer_bases_dev; pt.n_ranks = x->n_ranks;
+  pt.scores_off = ((long long)parity * x->n_ranks + x->rank) * x->slot_bytes;
+  pt.ids_off = pt.scores_off + x->ids_in_slot;
+  pt.flags_off = x->flags_off + ((long long)parity * x->n_ranks + x->rank) * x->B_max * 4;
+  pt.seq = (unsigned int)((x->step % 0x7FFFFFFFull) + 1);
+  return ts::index_search_impl(h, q_dev, q_dtype, B, k, flags, path, nullptr, nullptr, stream, &pt);
+}
+
+int ts_exchange_merge(ts_exchange* x, int B, int k, float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
+  if (!x || !out_scores_dev || !out_ids_dev || B < 1 || B > x->B_max || k < 1 || k > x->k_max) { set_error("ts_exchange_merge: invalid argument"); return TS_ERR_INVALID; }
+  TS_CUDA_OK(cudaSetDevice(x->device));
+  const int parity = (int)(x->step & 1);
+  const unsigned int seq = (unsigned int)((x->step % 0x7FFFFFFFull) + 1);
+  ++x->step;                                       // the pair (push, merge) is one step
+  const char* slots = x->local_base + (size_t)parity * x->n_ranks * x->slot_bytes;
+  const unsigned int* fl = reinterpret_cast<const unsigned int*>(x->local_base + x->flags_off) + (size_t)parity * x->n_ranks * x->B_max;
+  return launch_merge_pairs_wait((const float*)slots, (const int64_t*)(slots + x->ids_in_slot), x->slot_bytes / 4, x->slot_bytes / 8,
+                                 x->n_ranks, B, k, fl, seq, out_scores_dev, out_ids_dev, (cudaStream_t)stream, x->B_max);
+}
+
+int ts_index_search_sharded(ts_index* h, ts_exchange* x, const void* q_dev, int q_dtype, int B, int k, unsigned flags, int path,
+                            float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
+  int rc = ts_index_search_push(h, x, q_dev, q_dtype, B, k, flags, path, stream);
+  if (rc) return rc;
+  return ts_exchange_merge(x, B, k, out_scores_dev, out_ids_dev, stream);
+}
+
+int ts_index_search_sharded_host(ts_index* h, ts_exchange* x, const void* q_host, int q_dtype, int B, int k, unsigned flags,
+                                 int path, float* out_scores_host, int64_t* out_ids_host, void* stream) {
+  if (!h || !x || !q_host || !out_scores_host || !out_ids_host || B <= 0 || k <= 0 || k > TS_MAX_K) {
+    set_error("ts_index_search_sharded_host: invalid argument");
+    return TS_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  TS_CUDA_OK(cudaSetDevice(h->device));
+  const size_t qb = (size_t)B * h->dim * dtype_size(q_dtype);
+  int rc = ensure_bytes(&h->stage, &h->stage_b, qb);
+  if (rc) return rc;
+  const size_t sb = (size_t)B * k * sizeof(float), ib = (size_t)B * k * sizeof(int64_t);
+  if ((rc = ensure_bytes(&h->hout, &h->hout_b, sb + ib + 256))) return rc;
+  float* ds = (float*)h->hout;
+  int64_t* di = (int64_t*)((char*)h->hout + ((sb + 255) / 256) * 256);
+  TS_CUDA_OK(cudaMemcpyAsync(h->stage, q_host, qb, cudaMemcpyHostToDevice, st));
+  if ((rc = ts_index_search_sharded(h, x, h->stage, q_dtype, B, k, flags, path, ds, di, stream))) return rc;
+  TS_CUDA_OK(cudaMemcpyAsync(out_scores_host, ds, sb, cudaMemcpyDeviceToHost, st));
+  TS_CUDA_OK(cudaMemcpyAsync(out_ids_host, di, ib, cudaMemcpyDeviceToHost, st));
+  TS_CUDA_OK(cudaStreamSynchronize(st));
   return TS_OK;
 }
 

@@ -51,6 +51,9 @@ struct SelectParams {
   // number of the step whose list l is complete (null = lists are already there, e.g. after an NCCL all-gather)
   const unsigned int* wait_flags;
   unsigned int wait_seq;
+  int wait_flag_stride;   // 0: flag l covers the whole list; > 0: flag of (list l, query b) at l * stride + b
+  // final pass of a local search in a multi-GPU step: push the rows into every rank's receive buffer (PushTarget)
+  PushTarget push;
 };
 
 // system-scope flag accesses for the peer-memory exchange (NVLink): the producer's data stores are made
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   if (p.wait_flags) {
     // one thread per list spins (system-scope acquire) until its producer GPU has published this step
     if ((int)threadIdx.x < p.L) {
-      const unsigned int* f = p.wait_flags + threadIdx.x;
+      const unsigned int* f = p.wait_flags + (p.wait_flag_stride ? (size_t)threadIdx.x * p.wait_flag_stride + b : (size_t)threadIdx.x);
       const long long t0 = clock64();
       while (ld_acquire_sys(f) != p.wait_seq) {
         TS_SPIN_YIELD();
@@ -257,20 +260,39 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
       continue;
     }
     const size_t o = (size_t)b * p.k_out + r;
-    if (key == 0ull) {
-      p.out_scores[o] = kLowestF32;
-      if (p.mode == kRank) p.out_pos[o] = -1; else p.out_ids[o] = -1;
-    } else {
-      p.out_scores[o] = key_score(key);
+    float sc = kLowestF32;
+    int64_t id = -1;
+    if (key != 0ull) {
+      sc = key_score(key);
       const uint32_t idx = key_idx(key);
       if (p.mode == kKeys || p.mode == kLists) {
-        p.out_ids[o] = p.id_base + (int64_t)idx;
+        id = p.id_base + (int64_t)idx;
       } else if (p.mode == kPairs) {
         const int l = idx / p.k_in, r2 = idx % p.k_in;
-        p.out_ids[o] = p.ids[(size_t)l * p.pair_stride_ids + (size_t)b * p.k_in + r2];
+        id = p.ids[(size_t)l * p.pair_stride_ids + (size_t)b * p.k_in + r2];
       } else {
-        p.out_pos[o] = (int32_t)idx;
+        id = (int64_t)idx;
       }
+    }
+    if (p.out_scores) {
+      p.out_scores[o] = sc;
+      if (p.mode == kRank) p.out_pos[o] = (int32_t)id; else p.out_ids[o] = id;
+    }
+    if (p.push.peer_bases) {
+      for (int d = 0; d < p.push.n_ranks; ++d) {
+        char* base = reinterpret_cast<char*>(p.push.peer_bases[d]);
+        reinterpret_cast<float*>(base + p.push.scores_off)[o] = sc;
+        reinterpret_cast<int64_t*>(base + p.push.ids_off)[o] = id;
+      }
+    }
+  }
+  if (p.final_pass && p.push.peer_bases) {
+    // publish: this query's row is complete in every rank's buffer
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < p.push.n_ranks) {
+      char* base = reinterpret_cast<char*>(p.push.peer_bases[threadIdx.x]);
+      st_release_sys(reinterpret_cast<unsigned int*>(base + p.push.flags_off) + b, p.push.seq);
     }
   }
 }
@@ -292,7 +314,7 @@ size_t merge_tmp_keys(int L, int B, int k) {
 }
 
 int launch_merge_keys(const uint64_t* keys, int L, int B, int k, int64_t id_base, uint64_t* tmp0, uint64_t* tmp1,
-                      float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches) {
+                      float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches, const PushTarget* push) {
   if (k <= 0 || k > TS_MAX_K || B <= 0 || L <= 0) { set_error("merge: bad L/B/k"); return TS_ERR_INVALID; }
   const int room = kSelCap - k;
   const uint64_t* cur = keys;
@@ -315,6 +337,7 @@ int launch_merge_keys(const uint64_t* keys, int L, int B, int k, int64_t id_base
   SelectParams p{};
   p.mode = kKeys; p.keys = cur; p.L = L; p.B = B; p.k_in = k; p.group = L; p.k_out = k;
   p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids; p.id_base = id_base;
+  if (push) p.push = *push;
   int rc = launch_select(p, 1, st);
   if (rc) return rc;
   if (launches) ++*launches;
@@ -322,7 +345,8 @@ int launch_merge_keys(const uint64_t* keys, int L, int B, int k, int64_t id_base
 }
 
 int launch_merge_lists(const uint64_t* lists, const int* counts, const float* pub, const UmmaLayout& lay, int B, int k,
-                       int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches) {
+                       int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches,
+                       const PushTarget* push) {
   if (k <= 0 || k > TS_MAX_K || B <= 0 || lay.n_slices > kMaxLists) { set_error("merge_lists: bad arguments"); return TS_ERR_INVALID; }
   SelectParams p{};
   p.mode = kLists; p.keys = lists; p.counts = counts; p.n_slices = lay.n_slices; p.spread = lay.spread; p.cap = lay.cap;
@@ -331,6 +355,7 @@ int launch_merge_lists(const uint64_t* lists, const int* counts, const float* pu
   p.serial_prefix = env_on("TS_SELECT_V1") ? 1 : 0;
   p.L = lay.n_slices; p.B = B; p.k_in = k; p.group = lay.n_slices; p.k_out = k;
   p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids; p.id_base = id_base;
+  if (push) p.push = *push;
   int rc = launch_select(p, 1, st);
   if (rc) return rc;
   if (launches) ++*launches;
@@ -371,14 +396,14 @@ int launch_exchange_wait_sum(const void* slots, long long slot_bytes, const unsi
 
 int launch_merge_pairs_wait(const float* scores, const int64_t* ids, long long stride_scores, long long stride_ids, int L, int B,
                             int k, const unsigned int* wait_flags, unsigned int wait_seq, float* out_scores, int64_t* out_ids,
-                            cudaStream_t st) {
+                            cudaStream_t st, int wait_flag_stride) {
   if (k <= 0 || k > TS_MAX_K || B <= 0 || L <= 0 || L > kSelThreads) { set_error("merge: bad L/B/k"); return TS_ERR_INVALID; }
   if ((long long)L * k > 65536) { set_error("merge: n_lists*k too large (%d*%d)", L, k); return TS_ERR_UNSUPPORTED; }
   SelectParams p{};
   p.mode = kPairs; p.scores = scores; p.ids = ids; p.L = L; p.B = B; p.k_in = k; p.group = L; p.k_out = k;
   p.pair_stride = stride_scores; p.pair_stride_ids = stride_ids;
   p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids;
-  p.wait_flags = wait_flags; p.wait_seq = wait_seq;
+  p.wait_flags = wait_flags; p.wait_seq = wait_seq; p.wait_flag_stride = wait_flag_stride;
   return launch_select(p, 1, st);
 }
 

@@ -95,14 +95,28 @@ int launch_s1_stream(const ScanArgs& a, cudaStream_t st, int* launches);
 int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, int* launches);
 
 // ---- top-k selection / merge ----------------------------------------------
+// Fused exchange (multi-GPU, peer memory): the select kernel's final pass also stores query b's [k] scores and ids
+// into slot `rank` of EVERY rank's receive buffer (16/8-byte stores over NVLink; the own buffer is one of them) and
+// then publishes flag[parity][rank][b] = seq there with a system-scope release.  Layout of a receive buffer
+// (ts_exchange_buffer_bytes): [parity][rank] slots of slot_bytes = scores [B_max*k_max] f32 | ids [B_max*k_max] i64,
+// then flags [parity][rank][B_max] u32.
+struct PushTarget {
+  const long long* peer_bases;   // device array [n_ranks]: base address of every rank's buffer as seen from this GPU
+  int n_ranks;
+  long long scores_off;          // byte offset of this rank's score slot (parity applied) inside a buffer
+  long long ids_off;             // ... of its id slot
+  long long flags_off;           // ... of flags[parity][rank][0]
+  unsigned int seq;              // sequence number of this step (never 0)
+};
 // keys [L][B][k] -> final (scores, ids) [B][k]; tmp0/tmp1 each hold
 // ceil(L/2)*B*k keys (only used when L*k exceeds one selection pass).
 int launch_merge_keys(const uint64_t* keys, int L, int B, int k, int64_t id_base, uint64_t* tmp0, uint64_t* tmp1,
-                      float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches);
+                      float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches, const PushTarget* push = nullptr);
 size_t merge_tmp_keys(int L, int B, int k);
 // unsorted per-(CTA, query) candidate lists of the umma scan -> final (scores, ids) [B][k]
 int launch_merge_lists(const uint64_t* lists, const int* counts, const float* pub, const UmmaLayout& lay, int B, int k,
-                       int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches);
+                       int64_t id_base, float* out_scores, int64_t* out_ids, cudaStream_t st, int* launches,
+                       const PushTarget* push = nullptr);
 // strides = elements between consecutive lists (floats for scores, int64s for ids)
 int launch_merge_pairs(const float* scores, const int64_t* ids, long long stride_scores, long long stride_ids, int L,
                        int B, int k, float* out_scores, int64_t* out_ids, cudaStream_t st);
@@ -111,9 +125,11 @@ int launch_exchange_push(const void* blob, long long nbytes, const long long* pe
                          long long flag_off, unsigned int seq, cudaStream_t st);
 int launch_exchange_wait_sum(const void* slots, long long slot_bytes, const unsigned int* flags, int n_ranks, unsigned int seq,
                              long long n, float* out, cudaStream_t st);
+// wait_flag_stride = 0: one flag per list (whole [B,k] blob published at once); > 0: flag of (list l, query b) at
+// wait_flags[l * stride + b] (the fused exchange publishes per query)
 int launch_merge_pairs_wait(const float* scores, const int64_t* ids, long long stride_scores, long long stride_ids, int L, int B,
                             int k, const unsigned int* wait_flags, unsigned int wait_seq, float* out_scores, int64_t* out_ids,
-                            cudaStream_t st);
+                            cudaStream_t st, int wait_flag_stride = 0);
 int launch_rank_desc(const float* scores, const int32_t* n_cand, int B, int C, int top_k, float* out_scores,
                      int32_t* out_pos, cudaStream_t st);
 

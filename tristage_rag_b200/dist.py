@@ -34,6 +34,11 @@ import torch
 import torch.distributed as dist
 
 
+# flipped to True once the fused peer-memory exchange has been validated on hardware (tools/dist_check.py on 2 and
+# 8 GPUs); until then the NCCL all-gather + merge kernel is the default data plane and TS_P2P=1 opts in
+P2P_DEFAULT = False
+
+
 def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous balanced partition: the first ``n_total % world`` ranks get one extra row."""
     base, rem = divmod(int(n_total), int(world))
@@ -188,10 +193,13 @@ class ShardedIndex:
             self._packed = False
         self._bufs = {}
         self.merge_fn = merge_fn
-        # TS_P2P=1: replace all-gather + merge by the peer-memory exchange (ts_exchange_*); opt-in
-        self._p2p = bool(self._packed and self.world > 1 and os.environ.get("TS_P2P", "0") not in ("", "0"))
+        # peer-memory exchange fused into the select kernel (ts_exchange, include/tristage.h) instead of all-gather +
+        # merge: TS_P2P=1 / 0 forces it on / off; by default it is used when the local index is a plain ts_index on
+        # a CUDA device (every rank decides together, see _agree_on_setup, and falls back to NCCL otherwise)
+        env = os.environ.get("TS_P2P", "")
+        fused_ok = self._packed and self.world > 1 and hasattr(local_index, "_h") and not hasattr(local_index, "ivf")
+        self._p2p = bool(fused_ok and (env not in ("", "0") or (env == "" and P2P_DEFAULT)))
         self._p2p_state = None
-        self._step = 0
 
     def search(self, q: torch.Tensor, k: int, **kw) -> Tuple[torch.Tensor, torch.Tensor]:
         """q replicated on every rank -> identical merged (scores, ids) on every rank."""
@@ -235,52 +243,53 @@ class ShardedIndex:
         return cls(local, man["n_total"], group=group, merge_fn=merge_fn)
 
     def _p2p_setup(self, B: int, k: int, device: torch.device):
-        """Symmetric receive buffer of this rank, mapped into every rank of the group (torch's symmetric
-        memory does the handle exchange): 2 parities x world slots + 2 x world flags (include/tristage.h)."""
+        """Symmetric receive buffer of this rank, mapped into every rank of the group (torch's symmetric memory does
+        the handle exchange), wrapped in a ``ts_exchange`` (include/tristage.h): capacity for batches up to
+        max(B, 1024) x max(k, 128)."""
         import torch.distributed._symmetric_memory as symm
 
-        from ._lib import packed_layout
+        from ._lib import Exchange
 
-        ids_off, nbytes = packed_layout(B, k)
-        slot = (nbytes + 15) // 16 * 16
-        flags_off = 2 * self.world * slot
-        total = (flags_off + 2 * self.world * 4 + 15) // 16 * 16
+        B_max, k_max = max(int(B), 1024), max(int(k), 128)
+        total = Exchange.buffer_bytes(self.world, B_max, k_max)
         buf = symm.empty(total, dtype=torch.uint8, device=device)
         buf.zero_()
         hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
-        bases = torch.tensor([int(x) for x in hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        bases = [int(x) for x in hdl.buffer_ptrs]
         torch.cuda.current_stream(device).synchronize()
         hdl.barrier()                                   # every buffer is zeroed before anybody pushes into it
-        return {"key": (B, k), "buf": buf, "hdl": hdl, "bases": bases, "slot": slot, "ids_off": ids_off,
-                "nbytes": nbytes, "flags_off": flags_off,
-                "mine": torch.zeros(slot, dtype=torch.uint8, device=device)}
+        return {"cap": (B_max, k_max), "buf": buf, "hdl": hdl,
+                "x": Exchange(device.index, self.rank, self.world, bases, B_max, k_max)}
+
+    def _p2p_state_for(self, B: int, k: int, device: torch.device):
+        st = self._p2p_state
+        if st is None or B > st["cap"][0] or k > st["cap"][1]:
+            st = self._p2p_state = _agree_on_setup(lambda: self._p2p_setup(B, k, device), device, self.group)
+        return st
 
     def _search_p2p(self, q, k, **kw):
-        """Local search -> push the packed result into every rank's buffer over NVLink -> wait + merge.
-        Two kernels instead of an NCCL all-gather and a merge; no collective call in the steady state."""
-        import ctypes as C
+        """scan -> select kernel pushes the [k] rows of every query into every rank's buffer over NVLink -> wait+merge
+        kernel.  Four launches in one C call, no collective-library call in the steady state."""
+        return self._p2p_state_for(q.shape[0], k, q.device)["x"].search(self.local, q, k, **kw)
 
-        from . import _lib
+    def search_host(self, q, k: int, out=None, **kw):
+        """numpy / pinned host buffers in and out, ONE C call per step on the peer-memory data plane (H2D, step, D2H,
+        synchronise); falls back to search() + copies when the exchange is not available."""
+        import numpy as np
 
-        B = q.shape[0]
-        st = self._p2p_state
-        if st is None or st["key"] != (B, k):
-            st = self._p2p_state = _agree_on_setup(lambda: self._p2p_setup(B, k, q.device), q.device, self.group)
-            self._step = 0
-        dev = q.device.index
-        self.local.search_packed(q, k, st["mine"], **kw)
-        parity, seq = self._step & 1, (self._step % 0x7FFFFFFF) + 1
-        self._step += 1
-        stream = _lib._stream_ptr(dev)
-        _lib.check(_lib.lib().ts_exchange_push(dev, C.c_void_p(st["mine"].data_ptr()), st["nbytes"],
-                                               C.c_void_p(st["bases"].data_ptr()), self.world, self.rank, st["slot"],
-                                               st["flags_off"], parity, seq, stream))
-        out_s = torch.empty((B, k), dtype=torch.float32, device=q.device)
-        out_i = torch.empty((B, k), dtype=torch.int64, device=q.device)
-        _lib.check(_lib.lib().ts_exchange_wait_merge(dev, C.c_void_p(st["buf"].data_ptr()), self.world, B, k, st["slot"],
-                                                     st["ids_off"], st["flags_off"], parity, seq,
-                                                     C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()), stream))
-        return out_s, out_i
+        if self._p2p and self.world > 1:
+            try:
+                st = self._p2p_state_for(len(q), k, torch.device("cuda", self.local.device))
+                return st["x"].search_host(self.local, q, k, out=out, **kw)
+            except PeerExchangeUnavailable:
+                self._p2p = False
+        dev = torch.device("cuda", self.local.device)
+        s, i = self.search(torch.from_numpy(np.ascontiguousarray(q, np.float32)).to(dev), k, **kw)
+        if out is not None:
+            out[0][...] = s.cpu().numpy()
+            out[1][...] = i.cpu().numpy()
+            return out
+        return s.cpu().numpy(), i.cpu().numpy()
 
     def _search_packed(self, q, k, **kw):
         """GPU fast path: scores + ids in one buffer -> ONE all-gather -> one merge kernel."""
