@@ -25,8 +25,9 @@
 // Work is split by flat candidate number, [c*T/G, (c+1)*T/G) for CTA c of G.
 // Roofline: HBM, algorithmic bytes per candidate = pad8(Ld) * dim * 2.
 //
-// Roles (192 threads): warp 0 producer, warp 1 one MMA thread (tcgen05.mma M128 x N(used) x K16, two
-// 256-column TMEM accumulators), warps 2-5 epilogue (tcgen05.ld, column maxima, slot atomics, finalize).
+// Roles (320 threads): warp 0 producer, warp 1 one MMA thread (tcgen05.mma M128 x N(used) x K16, two
+// 256-column TMEM accumulators), warps 2-9 epilogue (two per TMEM lane quarter: tcgen05.ld, column maxima,
+// slot atomics, finalize).
 #include <stdlib.h>
 
 #include "ts_common.cuh"
@@ -41,7 +42,8 @@ namespace {
 
 using namespace ts::ptx;
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                        // two per TMEM lane quarter: each takes half of the quarter's columns
+constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kTileM = 128, kChunkK = 64;
 constexpr int kAChunkBytes = kTileM * kChunkK * 2;   // 16 KB: one 64-wide K chunk of the query tile (SWIZZLE_128B)
 constexpr int kMaxStages = 6;
@@ -128,9 +130,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   for (int i = threadIdx.x; i < (kSlots * p.slot_stride) / 4; i += kThreads) reinterpret_cast<uint32_t*>(slots)[i] = 0u;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); mbar_init(&afull_bar[a], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); mbar_init(&afull_bar[a], 1); }
     for (int g = 0; g < kBatches; ++g) mbar_init(&gfree_bar[g], 1);
-    for (int s = 0; s < kMetaSlots; ++s) { mbar_init(&mfull_bar[s], 1); mbar_init(&mempty_bar[s], 4); }
+    for (int s = 0; s < kMetaSlots; ++s) { mbar_init(&mfull_bar[s], 1); mbar_init(&mempty_bar[s], kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -392,21 +394,24 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     // -------------------------------------------------- epilogue ----------
-    // lq <= 32: the query tokens sit in ALL four lane quarters, warp (quarter q) drains columns [64q, 64q+64).
-    // lq > 32: tokens span the quarters, every warp walks all columns of its 32 tokens.  A thread's maximum
-    // over a doc's columns goes into the doc's slot with atomicMax on an order-preserving integer.
+    // Two warps per TMEM lane quarter (a warp may only read lanes 32 * (warp % 4) ..): `half` picks the warp's
+    // share of the quarter's columns.  lq <= 32: the query tokens sit in ALL four lane quarters, the warps of
+    // quarter q drain columns [64q, 64q+64), 32 each.  lq > 32: tokens span the quarters, the two warps of a
+    // quarter walk one half of the tile's columns each for its 32 tokens.  A thread's maximum over a doc's
+    // columns goes into the doc's slot with atomicMax on an order-preserving integer.
     unsigned long long tr_meta = 0, tr_tfull = 0, tr_drain = 0, tr_fin = 0;
     const int quarter = warp & 3;
-    const int ew = warp - 2;
+    const int ew = warp - 2;                              // 0 .. kEpiWarps-1
+    const int half = ew >> 2;
     int acc = 0; uint32_t acc_phase = 0;
     int fin_done = 0;                                     // docs finalised so far (all four warps agree)
     const bool colbert = p.mode != TS_S2_MAXSIM;
 
     // finalise docs [fin_done, fin_done + n): one doc per lane, by the warp whose turn it is
     auto finalize = [&](int n) {
-      named_bar_sync(1, 128);                             // every warp's atomics for these docs are done
+      named_bar_sync(1, kEpiWarps * 32);                  // every warp's atomics for these docs are done
       const int batch = fin_done / kBatch;
-      if ((batch & 3) == ew) {
+      if ((batch % kEpiWarps) == ew) {
         if (lane < n) {
           const int slot = (fin_done + lane) % kSlots;
           uint32_t* sp = reinterpret_cast<uint32_t*>(slots + slot * p.slot_stride);
@@ -469,8 +474,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (warp_active) {
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccCols);
         unsigned char* my_tok = slots + (rep4 ? lane : quarter * 32 + lane) * 4;
-        const int b_lo = rep4 ? quarter * 64 : 0;
-        const int b_hi = rep4 ? min(used, b_lo + 64) : used;
+        const int half_cols = (1 << p.tile_shift) >> 1;
+        const int b_lo = rep4 ? quarter * 64 + half * 32 : half * half_cols;
+        const int b_hi = rep4 ? min(used, b_lo + 32) : min(used, b_lo + half_cols);
         for (int c_lo = b_lo; c_lo < b_hi; c_lo += 64) {
           const int c_hi = min(b_hi, c_lo + 64);
           // segment holding column c_lo, and the 8-column units of this block that start a new segment
