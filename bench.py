@@ -429,10 +429,11 @@ def side_stage2(dev, pk, rank, world, dist_on, parity=True):
     rec = {"cand_per_s": r3(Bq * C * steps / (ms / 1e3)), "ms": r3(ms / steps), "kernel_ms": r3(kms),
            "gbs_per_gpu": r3(gb), "frac": r3(gb / pk["hbm_gbs"]), "exchange_ms": r3(max(0.0, (ms - ms_local) / steps)),
            "cand_max_over_mean": r3(float(own.max()) / max(1.0, float(own.mean())))}
+    scores_t = fn() if parity else None                 # every rank: the exchange is a collective step
     if parity and rank == 0 and kept is not None:
         from oracle import c_oracle
 
-        scores = fn().cpu().numpy()
+        scores = scores_t.cpu().numpy()
         tok0, ln0 = kept
         off0 = np.concatenate([[0], np.cumsum(ln0.astype(np.int64))])
         tok0 = tok0.float().cpu().numpy()
@@ -450,6 +451,10 @@ def side_stage2(dev, pk, rank, world, dist_on, parity=True):
             ok &= bool(np.allclose(scores[b][js], ref, rtol=1e-3, atol=2e-4))
             n_chk += len(js)
         rec.update(oracle_ok=ok, oracle_pairs=n_chk, max_abs_err=r3(worst))
+    if dist_on:
+        import torch.distributed as dist
+
+        dist.barrier()          # rank 0 checked alone: re-align before the next exchange step (bounded waits on the peer plane)
     del st, sst
     return rec
 
@@ -618,6 +623,8 @@ def main():
         par["ok"] = bool(par.get("planted_ok")) and bool(par.get("oracle_ok", True)) and "error" not in par
         line["parity"] = par
         roof["parity_ok"] = par["ok"]
+        if dist_on:
+            dist.barrier()      # rank 0 checked alone for seconds: re-align before the next exchange step
 
     # ---- side measurements: the other batch sizes, Stage 2, the C5 chain ------------
     if not args.no_extra:

@@ -269,6 +269,37 @@ def test_tensor_scan_variants_agree_bit_for_bit(sim, monkeypatch):
     assert (I == two[1]).all() and (D == two[0]).all()
 
 
+@pytest.mark.parametrize("sms,B,k,order", [(12, 48, 10, "random"), (16, 5, 16, "random"), (12, 128, 12, "ascending"), (40, 33, 7, "constant")])
+def test_kth_of_slices_bound_never_drops_a_result(sim, monkeypatch, sms, B, k, order):
+    """kth_rule (s1_umma.cu): with one published best per slice and n_slices >= k the shared bound is the k-th
+    largest of the slices' bests (CTA q sorts them for query q) instead of their minimum.  The result must be the
+    oracle's and bit-equal to the scan without the rule, in the two-launch and the single-launch (TS_FUSE) scan,
+    for random rows, ascending scores (every new row beats the bound) and all-equal scores (ties at the bound)."""
+    monkeypatch.setenv("HOSTSIM_SM_COUNT", str(sms))
+    N, d = 9000, 64
+    if order == "random":
+        X, Q = make(N, d, B, seed=sms + B, planted=6)
+    else:
+        rng = np.random.default_rng(4)
+        u = flat_ip.normalize_rows(rng.standard_normal((1, d)).astype(np.float32))[0].astype(np.float32)
+        v = (np.linspace(0.05, 1.0, N) if order == "ascending" else np.full(N, 0.5)).astype(np.float32)
+        X = (v[:, None] * u[None, :]).astype(np.float32)
+        Q = np.concatenate([u[None, :], flat_ip.normalize_rows(rng.standard_normal((B - 1, d)).astype(np.float32))]).astype(np.float32)
+    idx = _lib.Index(d, "bf16", "ip", 0)
+    idx.add(X)
+    rD, rI, sc = oracle_search(X, Q, k, "bf16")
+    monkeypatch.setenv("TS_DBG_NOKTH", "1")
+    D0, I0 = idx.search_host(Q, k, path="umma")
+    monkeypatch.delenv("TS_DBG_NOKTH")
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("TS_FUSE", fuse)
+        D, I = idx.search_host(Q, k, path="umma")
+        assert not flat_ip.check_topk(D, I, sc, rD, rI, rel=REL), (fuse, order)
+        assert (I == I0).all() and (D == D0).all(), (fuse, order)
+        if order == "constant":
+            assert I[0].tolist() == list(range(k))
+
+
 @pytest.mark.parametrize("N,d,B,k,dtype", [(3000, 64, 200, 10, "bf16"), (5000, 128, 300, 100, "bf16"), (600, 100, 129, 7, "fp16"),
                                            (6000, 64, 1024, 100, "bf16"), (4000, 256, 256, 500, "bf16"), (5, 72, 130, 50, "bf16")])
 def test_cta_pair_scan_equals_the_single_cta_scan(sim, monkeypatch, N, d, B, k, dtype):

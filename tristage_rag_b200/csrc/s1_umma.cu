@@ -88,9 +88,32 @@ struct UmmaParams {
   int* counts;     // [grid][rows_per_cta] entries per list (out)
   float* pub;      // [n_slices][bpad] per-slice j-th best score per query
   float* tau_g;    // [bpad] min over slices of pub, refreshed by slice 0
+  float* tau_k;    // [bpad] k-th largest of the slices' best scores (kth_rule), refreshed by CTA q for query q
+  int kth_rule;    // 1: jrank == 1 and n_slices >= k -- the slices' bests are n_slices distinct rows
   const float* inv_norm;
   unsigned long long* stats;  // debug: [0] appends [1] prunes [2] slow-path chunks (null = off)
 };
+
+// kth_rule.  With one published value per slice (jrank == 1) and at least k slices, the published bests are
+// n_slices DISTINCT rows of the corpus: the k-th largest of them is a lower bound of the global k-th best --
+// far tighter than their minimum (after one 256-row tile per slice: ~2.65 sigma instead of ~1.8 sigma for
+// k = 100 of 148 slices, i.e. ~1 instead of ~9 survivors per query and tile while the scan warms up).
+// One warp sorts the <= 256 values of ONE query; CTA q does it for query q (whole warp must call).
+__device__ __forceinline__ void kth_of_slices(const UmmaParams& p, int q, int lane) {
+  uint64_t v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = j * 32 + lane;
+    v[j] = (c < p.n_slices) ? ((uint64_t)f2ord(__ldcg(p.pub + (size_t)c * p.bpad + q)) << 32) : 0ull;
+  }
+  warp_sort_desc<8>(v, lane);
+  const int e = p.k - 1;                       // element e of the descending order lives in v[e >> 5] of lane e & 31
+  uint64_t mine = 0ull;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mine = ((e >> 5) == j) ? v[j] : mine;
+  const uint64_t kth = __shfl_sync(0xffffffffu, mine, e & 31);
+  if (lane == 0 && kth != 0ull) p.tau_k[q] = ord2f((uint32_t)(kth >> 32));
+}
 
 // per-thread state of one query (one TMEM lane of one accumulator)
 struct QState {
@@ -208,7 +231,7 @@ __device__ __forceinline__ void init_state(const UmmaParams& p, QState& s, int a
 __device__ __forceinline__ void start_state(const UmmaParams& p, QState& s, int slice, bool prepass) {
   if (!s.active) return;
   if (prepass) {
-    if (slice == 0) p.tau_g[s.q] = -INFINITY;   // reset before the scan kernel reads it
+    if (slice == 0) { p.tau_g[s.q] = -INFINITY; p.tau_k[s.q] = -INFINITY; }   // reset before the scan kernel reads them
   } else {
     // never publish below what the pre-pass already published for this slot
     s.pub_last = __ldcg(p.pub + (size_t)slice * p.bpad + s.q);
@@ -229,6 +252,7 @@ __device__ __forceinline__ void share_state(const UmmaParams& p, QState& s, int 
   } else {
     m = __ldcg(p.tau_g + s.q);
   }
+  if (p.kth_rule) m = fmaxf(m, __ldcg(p.tau_k + s.q));
   if (!p.dbg_notopk) s.tau = fmaxf(s.tau, nextafterf(m, -INFINITY));
 }
 
@@ -403,6 +427,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (J > 0 && !fused) {
       start_state(p, s0, slice, prepass);
       start_state(p, s1, slice, prepass);
+      if (p.kth_rule && !prepass && warp == 2)
+        for (int q = (int)blockIdx.x; q < p.B; q += (int)gridDim.x) kth_of_slices(p, q, lane);
     }
 
     const bool wact0 = __any_sync(0xffffffffu, s0.active);
@@ -421,9 +447,11 @@ __global__ void __launch_bounds__(kThreads, 1)
           drain_acc(p, s0, lane_addr + (uint32_t)(acc * kTileN), n0, ncols, wact0, true, J, CAP, lane);
           if (s0.active) {
             p.pub[(size_t)slice * p.bpad + s0.q] = s0.tjJ;
-            if (slice == 0) p.tau_g[s0.q] = -INFINITY;   // never let a stale bound of an earlier call be read
+            if (slice == 0) { p.tau_g[s0.q] = -INFINITY; p.tau_k[s0.q] = -INFINITY; }   // never let a stale bound of an earlier call be read
           }
           grid_barrier_epilogue(p.grid_bar, gen0, warp, lane);
+          if (p.kth_rule && warp == 2)
+            for (int q = (int)blockIdx.x; q < p.B; q += (int)gridDim.x) kth_of_slices(p, q, lane);
           // pass 2 re-reads the same accumulator with the shared bound in place; the J-best
           // registers restart from scratch so no row is counted twice
           s0.tjJ = -INFINITY;
@@ -452,6 +480,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (!prepass && J > 0) {
         share_state(p, s0, slice, iter);
         share_state(p, s1, slice, iter);
+        if (p.kth_rule && warp == 2 && (iter & 3) == 3)          // refresh the tighter bound every fourth tile
+          for (int q = (int)blockIdx.x; q < p.B; q += (int)gridDim.x) kth_of_slices(p, q, lane);
       }
     }
     finish_state(p, s0, 0, slice, prepass, J, rows_per_cta, lane_row, true, (int)blockIdx.x);
@@ -680,12 +710,14 @@ int s1_umma_plan(const ScanArgs& a, UmmaLayout* lay) {
   lay->bpad = pl.n_mt * kTileM;
   lay->lists_keys = (size_t)pl.grid * lay->rows_per_cta * lay->cap;
   lay->counts_n = (size_t)pl.grid * lay->rows_per_cta;
-  lay->pub_n = (size_t)(pl.n_slices + 1) * lay->bpad;   // + one row for tau_g
+  lay->pub_n = (size_t)(pl.n_slices + 2) * lay->bpad;   // + one row for tau_g, one for tau_k
   const int j = (a.k + pl.n_slices - 1) / pl.n_slices;
   lay->jrank = (j <= 8 && !env_on("TS_DBG_NOSHARE")) ? j : 0;
   // One cooperative launch (pre-pass + grid barrier + scan) instead of two launches: bit-equal to the
   // two-launch sequence on a B200 and x1.02-1.03 on 1.25 M-row shards (profiles/README.md); TS_FUSE=0 for A/B.
   lay->fused = (lay->jrank > 0 && !pl.dual && !pl.pair && env_flag("TS_FUSE", kDefaultFuse)) ? 1 : 0;
+  lay->kth_rule = (lay->jrank == 1 && lay->n_slices >= a.k && lay->n_slices <= 256 && lay->n_mt == 1 && !lay->dual && !lay->pair &&
+                   !env_on("TS_DBG_NOKTH")) ? 1 : 0;
   return TS_OK;
 }
 
@@ -705,6 +737,8 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
   p.dbg_notopk = env_on("TS_DBG_NOTOPK") ? 1 : 0;
   p.jrank = lay.jrank; p.bpad = lay.bpad; p.dual = lay.dual;
   p.lists = a.lists; p.counts = a.counts; p.pub = a.pub; p.tau_g = a.pub + (size_t)lay.n_slices * lay.bpad;
+  p.tau_k = p.tau_g + lay.bpad;
+  p.kth_rule = lay.kth_rule;
   p.inv_norm = a.inv_norm;
   static unsigned long long* d_stats = nullptr;
   if (env_on("TS_DBG_STATS")) {

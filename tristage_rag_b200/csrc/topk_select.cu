@@ -45,6 +45,7 @@ struct SelectParams {
   long long pair_stride;  // kPairs: elements between consecutive lists (scores: floats, ids: int64s)
   long long pair_stride_ids;
   const float* pub;       // kLists: final per-slice J-th best scores [n_slices][bpad] (null = no filter)
+  const float* tau_k;     // kLists: k-th largest of the slices' bests (s1_umma.cu kth_rule), a tighter valid bound; or null
   int bpad;
   int serial_prefix;      // kLists: 1 = first version of the count prefix / filter loop (TS_SELECT_V1)
   // kPairs after a peer-memory exchange: the lists are written by the other GPUs; flag l holds the sequence
@@ -58,7 +59,8 @@ struct SelectParams {
 
 // system-scope flag accesses for the peer-memory exchange (NVLink): the producer's data stores are made
 // visible by __threadfence_system() + st.release.sys, the consumer pairs them with ld.acquire.sys
-constexpr long long kExchangeTimeoutCycles = 8000000000ll;   // ~4 s: a missing peer traps instead of hanging the GPU
+constexpr long long kExchangeTimeoutCycles = 40000000000ll;  // ~20 s: a missing peer traps instead of hanging the GPU; ranks of an
+                                                              // SPMD job may reach a step seconds apart (host-side work in between)
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 #ifdef TS_CUDASIM
   return *reinterpret_cast<const volatile unsigned int*>(p);
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     __syncthreads();
     m = s_min[0];
     for (int w = 1; w < kSelThreads / 32; ++w) m = fminf(m, s_min[w]);
+    if (p.tau_k) m = fmaxf(m, __ldcg(p.tau_k + b));
     const uint64_t thr = (uint64_t)f2ord(m) << 32;      // smallest key with score m
     if (p.serial_prefix) {
       for (int i = threadIdx.x; i < total; i += blockDim.x) {
@@ -352,6 +355,7 @@ int launch_merge_lists(const uint64_t* lists, const int* counts, const float* pu
   p.mode = kLists; p.keys = lists; p.counts = counts; p.n_slices = lay.n_slices; p.spread = lay.spread; p.cap = lay.cap;
   p.dual = lay.dual; p.rows_per_cta = lay.rows_per_cta;
   p.pub = (lay.jrank > 0) ? pub : nullptr; p.bpad = lay.bpad;
+  p.tau_k = (lay.jrank > 0 && lay.kth_rule) ? pub + (size_t)(lay.n_slices + 1) * lay.bpad : nullptr;
   p.serial_prefix = env_on("TS_SELECT_V1") ? 1 : 0;
   p.L = lay.n_slices; p.B = B; p.k_in = k; p.group = lay.n_slices; p.k_out = k;
   p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids; p.id_base = id_base;
