@@ -99,20 +99,28 @@ struct UmmaParams {
 // far tighter than their minimum (after one 256-row tile per slice: ~2.65 sigma instead of ~1.8 sigma for
 // k = 100 of 148 slices, i.e. ~1 instead of ~9 survivors per query and tile while the scan warms up).
 // One warp sorts the <= 256 values of ONE query; CTA q does it for query q (whole warp must call).
-__device__ __forceinline__ void kth_of_slices(const UmmaParams& p, int q, int lane) {
-  uint64_t v[8];
+// The k-th largest is found by bisection on the order-preserving integer image of the scores (32 rounds of
+// "how many values are >= candidate", 8 compares per lane + one warp reduction each) in a ROLLED loop: a fully
+// unrolled warp sort here (~5 000 straight-line instructions executed once per call) cost ~55 us per call in
+// instruction-cache misses on a B200 and doubled the scan time of the CTAs that ran it.
+__device__ __noinline__ void kth_of_slices(const float* pub, float* tau_k, int n_slices, int bpad, int k, int q, int lane) {
+  uint32_t v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = j * 32 + lane;
-    v[j] = (c < p.n_slices) ? ((uint64_t)f2ord(__ldcg(p.pub + (size_t)c * p.bpad + q)) << 32) : 0ull;
+    v[j] = (c < n_slices) ? f2ord(__ldcg(pub + (size_t)c * bpad + q)) : 0u;    // 0 sorts below every score
   }
-  warp_sort_desc<8>(v, lane);
-  const int e = p.k - 1;                       // element e of the descending order lives in v[e >> 5] of lane e & 31
-  uint64_t mine = 0ull;
+  uint32_t key = 0u;                           // largest x with |{v >= x}| >= k, built from the top bit down
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = key | (1u << bit);
+    int n = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) mine = ((e >> 5) == j) ? v[j] : mine;
-  const uint64_t kth = __shfl_sync(0xffffffffu, mine, e & 31);
-  if (lane == 0 && kth != 0ull) p.tau_k[q] = ord2f((uint32_t)(kth >> 32));
+    for (int j = 0; j < 8; ++j) n += (v[j] >= cand) ? 1 : 0;
+    n = warp_sum_int(n);
+    if (n >= k) key = cand;
+  }
+  if (lane == 0 && key != 0u) tau_k[q] = ord2f(key);
 }
 
 // per-thread state of one query (one TMEM lane of one accumulator)
@@ -428,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       start_state(p, s0, slice, prepass);
       start_state(p, s1, slice, prepass);
       if (p.kth_rule && !prepass && warp == 2)
-        for (int q = (int)blockIdx.x; q < p.B; q += (int)gridDim.x) kth_of_slices(p, q, lane);
+        for (int q = (int)blockIdx.x; q < p.B; q += (int)gridDim.x) kth_of_slices(p.pub, p.tau_k, p.n_slices, p.bpad, p.k, q, lane);
     }
 
     const bool wact0 = __any_sync(0xffffffffu, s0.active);
@@ -451,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           grid_barrier_epilogue(p.grid_bar, gen0, warp, lane);
           if (p.kth_rule && warp == 2)
-            for (int q = (int)blockIdx.x; q < p.B; q += (int)gridDim.x) kth_of_slices(p, q, lane);
+            for (int q = (int)blockIdx.x; q < p.B; q += (int)gridDim.x) kth_of_slices(p.pub, p.tau_k, p.n_slices, p.bpad, p.k, q, lane);
           // pass 2 re-reads the same accumulator with the shared bound in place; the J-best
           // registers restart from scratch so no row is counted twice
           s0.tjJ = -INFINITY;
@@ -481,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         share_state(p, s0, slice, iter);
         share_state(p, s1, slice, iter);
         if (p.kth_rule && warp == 2 && (iter & 3) == 3)          // refresh the tighter bound every fourth tile
-          for (int q = (int)blockIdx.x; q < p.B; q += (int)gridDim.x) kth_of_slices(p, q, lane);
+          for (int q = (int)blockIdx.x; q < p.B; q += (int)gridDim.x) kth_of_slices(p.pub, p.tau_k, p.n_slices, p.bpad, p.k, q, lane);
       }
     }
     finish_state(p, s0, 0, slice, prepass, J, rows_per_cta, lane_row, true, (int)blockIdx.x);

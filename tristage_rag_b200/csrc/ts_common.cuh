@@ -214,6 +214,15 @@ __host__ __device__ __forceinline__ size_t tok_elem(int layout, long long row, i
   return (size_t)(row >> 3) * 8 * dim + (size_t)(c >> 3) * 64 + (size_t)(row & 7) * 8 + (c & 7);
 }
 
+__device__ __forceinline__ int warp_sum_int(int v) {
+#if defined(TS_CUDASIM)
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+#else
+  return __reduce_add_sync(0xffffffffu, v);      // redux.sync: one instruction
+#endif
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
