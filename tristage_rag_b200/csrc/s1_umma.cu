@@ -60,6 +60,7 @@ namespace {
 using namespace ts::ptx;
 
 constexpr int kThreads = 192;
+constexpr int kThreadsScan = 224;   // single-CTA scan: + one "bound" warp that keeps the kth_rule bound fresh off the epilogue's path
 constexpr int kTileM = 128, kTileN = 256, kChunkK = 64;   // kChunkK: 16-bit elements per K chunk (one 128-B swizzle row)
 constexpr int kChunkBytes = kChunkK * 2;
 constexpr int kABytes = kTileM * kChunkBytes;  // 16 KB
@@ -312,7 +313,7 @@ __device__ __forceinline__ void grid_barrier_epilogue(unsigned int* bar, unsigne
 }
 
 template <int OP>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsScan, 1)
     s1_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ8,
                    const __grid_constant__ CUtensorMap tmX, const UmmaParams p) {
   constexpr int CK = (OP == kOpTF32) ? kChunkBytes / 4 : kChunkK;   // elements per K chunk
@@ -329,6 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* tfull_bar = bars + 2 * kMaxStages;      // [2] MMA -> epilogue (per accumulator)
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2; // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  int* scan_done = reinterpret_cast<int*>(tmem_slot + 1);      // epilogue -> bound warp: this CTA's scan is over
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mg = blockIdx.x / p.n_slices, slice = blockIdx.x % p.n_slices;   // mg: query tile (or pair of tiles)
@@ -340,6 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     fence_mbar_init();
+    *scan_done = 0;
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, kTmemCols);
@@ -350,7 +353,24 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 6) {
+    // ------------------------------------------------ bound warp (kth_rule) ----
+    // CTA q keeps tau_k[q] -- the k-th largest of the slices' published bests -- fresh while its epilogue
+    // warps scan: the bisection (~2 us) runs beside them instead of delaying one of them
+    if (p.kth_rule && p.mode != 0 && (int)blockIdx.x < p.B) {
+      volatile int* done = scan_done;
+      if (p.mode == 2) {
+        // the first-tile bests are complete once the grid barrier of this launch has opened
+        const unsigned int gen0 = *reinterpret_cast<volatile unsigned int*>(p.grid_bar + 1);
+        while (*reinterpret_cast<volatile unsigned int*>(p.grid_bar + 1) == gen0 && !*done) { TS_SPIN_YIELD(); ts_nanosleep(500); }
+      }
+      while (!*done) {
+        for (int q = (int)blockIdx.x; q < p.B; q += (int)gridDim.x) kth_of_slices(p.pub, p.tau_k, p.n_slices, p.bpad, p.k, q, lane);
+        TS_SPIN_YIELD();
+        ts_nanosleep(4000);
+      }
+    }
+  } else if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------ TMA producer ------
       prefetch_tmap(&tmQ); prefetch_tmap(&tmQ8); prefetch_tmap(&tmX);
@@ -435,8 +455,6 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (J > 0 && !fused) {
       start_state(p, s0, slice, prepass);
       start_state(p, s1, slice, prepass);
-      if (p.kth_rule && !prepass && warp == 2)
-        for (int q = (int)blockIdx.x; q < p.B; q += (int)gridDim.x) kth_of_slices(p.pub, p.tau_k, p.n_slices, p.bpad, p.k, q, lane);
     }
 
     const bool wact0 = __any_sync(0xffffffffu, s0.active);
@@ -458,8 +476,6 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (slice == 0) { p.tau_g[s0.q] = -INFINITY; p.tau_k[s0.q] = -INFINITY; }   // never let a stale bound of an earlier call be read
           }
           grid_barrier_epilogue(p.grid_bar, gen0, warp, lane);
-          if (p.kth_rule && warp == 2)
-            for (int q = (int)blockIdx.x; q < p.B; q += (int)gridDim.x) kth_of_slices(p.pub, p.tau_k, p.n_slices, p.bpad, p.k, q, lane);
           // pass 2 re-reads the same accumulator with the shared bound in place; the J-best
           // registers restart from scratch so no row is counted twice
           s0.tjJ = -INFINITY;
@@ -488,12 +504,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (!prepass && J > 0) {
         share_state(p, s0, slice, iter);
         share_state(p, s1, slice, iter);
-        if (p.kth_rule && warp == 2 && (iter & 3) == 3)          // refresh the tighter bound every fourth tile
-          for (int q = (int)blockIdx.x; q < p.B; q += (int)gridDim.x) kth_of_slices(p.pub, p.tau_k, p.n_slices, p.bpad, p.k, q, lane);
       }
     }
     finish_state(p, s0, 0, slice, prepass, J, rows_per_cta, lane_row, true, (int)blockIdx.x);
     finish_state(p, s1, 1, slice, prepass, J, rows_per_cta, lane_row, dual, (int)blockIdx.x);
+    if (warp == 2 && lane == 0) *reinterpret_cast<volatile int*>(scan_done) = 1;
   }
 
   tc_fence_before();
@@ -784,21 +799,21 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
     p.mode = 2;
     p.grid_bar = a.grid_bar;
 #ifdef TS_CUDASIM
-    cudasim::launch_cooperative(lay.grid, kThreads, kSmemBytes, [&]() { kern(tmQ, tmQ8, tmX, p); });
+    cudasim::launch_cooperative(lay.grid, kThreadsScan, kSmemBytes, [&]() { kern(tmQ, tmQ8, tmX, p); });
 #else
     void* args[] = {(void*)&tmQ, (void*)&tmQ8, (void*)&tmX, (void*)&p};
-    TS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(lay.grid), dim3(kThreads), args, kSmemBytes, st));
+    TS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(lay.grid), dim3(kThreadsScan), args, kSmemBytes, st));
 #endif
     if (launches) ++*launches;
   } else {
     if (p.jrank > 0) {
       p.mode = 0;   // threshold pre-pass over the first tile of every slice
-      TS_LAUNCH(kern, lay.grid, kThreads, kSmemBytes, st, tmQ, tmQ8, tmX, p);
+      TS_LAUNCH(kern, lay.grid, kThreadsScan, kSmemBytes, st, tmQ, tmQ8, tmX, p);
       TS_CUDA_OK(cudaGetLastError());
       if (launches) ++*launches;
     }
     p.mode = 1;
-    TS_LAUNCH(kern, lay.grid, kThreads, kSmemBytes, st, tmQ, tmQ8, tmX, p);
+    TS_LAUNCH(kern, lay.grid, kThreadsScan, kSmemBytes, st, tmQ, tmQ8, tmX, p);
     TS_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
   }

@@ -9,8 +9,10 @@
   cudasim::launch((grid), (block), (size_t)(smem), [&]() { kern(__VA_ARGS__); })
 #define TS_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(cudasim::dyn_smem())
 #define TS_SPIN_YIELD() cudasim::yield_spin()
+#define ts_nanosleep(ns) ((void)0)
 #else
 #define TS_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define TS_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #define TS_SPIN_YIELD() ((void)0)   /* a spinning thread of the emulator lets the others run */
+#define ts_nanosleep(ns) __nanosleep(ns)
 #endif
