@@ -271,10 +271,10 @@ def test_tensor_scan_variants_agree_bit_for_bit(sim, monkeypatch):
 
 @pytest.mark.parametrize("sms,B,k,order", [(12, 48, 10, "random"), (16, 5, 16, "random"), (12, 128, 12, "ascending"), (40, 33, 7, "constant")])
 def test_kth_of_slices_bound_never_drops_a_result(sim, monkeypatch, sms, B, k, order):
-    """kth_rule (s1_umma.cu): with one published best per slice and n_slices >= k the shared bound is the k-th
-    largest of the slices' bests (CTA q sorts them for query q) instead of their minimum.  The result must be the
-    oracle's and bit-equal to the scan without the rule, in the two-launch and the single-launch (TS_FUSE) scan,
-    for random rows, ascending scores (every new row beats the bound) and all-equal scores (ties at the bound)."""
+    """kth_rule (topk_select.cu): with one published best per slice and n_slices >= k the select kernel filters the
+    candidate lists with the k-th largest of the slices' bests instead of their minimum.  The result must be the
+    oracle's and bit-equal to the result without the rule, after the two-launch and the single-launch (TS_FUSE)
+    scan, for random rows, ascending scores and all-equal scores (ties exactly at the bound)."""
     monkeypatch.setenv("HOSTSIM_SM_COUNT", str(sms))
     N, d = 9000, 64
     if order == "random":

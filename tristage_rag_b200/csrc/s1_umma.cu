@@ -60,7 +60,6 @@ namespace {
 using namespace ts::ptx;
 
 constexpr int kThreads = 192;
-constexpr int kThreadsScan = 224;   // single-CTA scan: + one "bound" warp that keeps the kth_rule bound fresh off the epilogue's path
 constexpr int kTileM = 128, kTileN = 256, kChunkK = 64;   // kChunkK: 16-bit elements per K chunk (one 128-B swizzle row)
 constexpr int kChunkBytes = kChunkK * 2;
 constexpr int kABytes = kTileM * kChunkBytes;  // 16 KB
@@ -89,40 +88,9 @@ struct UmmaParams {
   int* counts;     // [grid][rows_per_cta] entries per list (out)
   float* pub;      // [n_slices][bpad] per-slice j-th best score per query
   float* tau_g;    // [bpad] min over slices of pub, refreshed by slice 0
-  float* tau_k;    // [bpad] k-th largest of the slices' best scores (kth_rule), refreshed by CTA q for query q
-  int kth_rule;    // 1: jrank == 1 and n_slices >= k -- the slices' bests are n_slices distinct rows
   const float* inv_norm;
   unsigned long long* stats;  // debug: [0] appends [1] prunes [2] slow-path chunks (null = off)
 };
-
-// kth_rule.  With one published value per slice (jrank == 1) and at least k slices, the published bests are
-// n_slices DISTINCT rows of the corpus: the k-th largest of them is a lower bound of the global k-th best --
-// far tighter than their minimum (after one 256-row tile per slice: ~2.65 sigma instead of ~1.8 sigma for
-// k = 100 of 148 slices, i.e. ~1 instead of ~9 survivors per query and tile while the scan warms up).
-// One warp sorts the <= 256 values of ONE query; CTA q does it for query q (whole warp must call).
-// The k-th largest is found by bisection on the order-preserving integer image of the scores (32 rounds of
-// "how many values are >= candidate", 8 compares per lane + one warp reduction each) in a ROLLED loop: a fully
-// unrolled warp sort here (~5 000 straight-line instructions executed once per call) cost ~55 us per call in
-// instruction-cache misses on a B200 and doubled the scan time of the CTAs that ran it.
-__device__ __noinline__ void kth_of_slices(const float* pub, float* tau_k, int n_slices, int bpad, int k, int q, int lane) {
-  uint32_t v[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = j * 32 + lane;
-    v[j] = (c < n_slices) ? f2ord(__ldcg(pub + (size_t)c * bpad + q)) : 0u;    // 0 sorts below every score
-  }
-  uint32_t key = 0u;                           // largest x with |{v >= x}| >= k, built from the top bit down
-#pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t cand = key | (1u << bit);
-    int n = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) n += (v[j] >= cand) ? 1 : 0;
-    n = warp_sum_int(n);
-    if (n >= k) key = cand;
-  }
-  if (lane == 0 && key != 0u) tau_k[q] = ord2f(key);
-}
 
 // per-thread state of one query (one TMEM lane of one accumulator)
 struct QState {
@@ -240,7 +208,7 @@ __device__ __forceinline__ void init_state(const UmmaParams& p, QState& s, int a
 __device__ __forceinline__ void start_state(const UmmaParams& p, QState& s, int slice, bool prepass) {
   if (!s.active) return;
   if (prepass) {
-    if (slice == 0) { p.tau_g[s.q] = -INFINITY; p.tau_k[s.q] = -INFINITY; }   // reset before the scan kernel reads them
+    if (slice == 0) p.tau_g[s.q] = -INFINITY;   // reset before the scan kernel reads it
   } else {
     // never publish below what the pre-pass already published for this slot
     s.pub_last = __ldcg(p.pub + (size_t)slice * p.bpad + s.q);
@@ -261,7 +229,6 @@ __device__ __forceinline__ void share_state(const UmmaParams& p, QState& s, int 
   } else {
     m = __ldcg(p.tau_g + s.q);
   }
-  if (p.kth_rule) m = fmaxf(m, __ldcg(p.tau_k + s.q));
   if (!p.dbg_notopk) s.tau = fmaxf(s.tau, nextafterf(m, -INFINITY));
 }
 
@@ -313,7 +280,7 @@ __device__ __forceinline__ void grid_barrier_epilogue(unsigned int* bar, unsigne
 }
 
 template <int OP>
-__global__ void __launch_bounds__(kThreadsScan, 1)
+__global__ void __launch_bounds__(kThreads, 1)
     s1_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ8,
                    const __grid_constant__ CUtensorMap tmX, const UmmaParams p) {
   constexpr int CK = (OP == kOpTF32) ? kChunkBytes / 4 : kChunkK;   // elements per K chunk
@@ -330,7 +297,6 @@ __global__ void __launch_bounds__(kThreadsScan, 1)
   uint64_t* tfull_bar = bars + 2 * kMaxStages;      // [2] MMA -> epilogue (per accumulator)
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2; // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-  int* scan_done = reinterpret_cast<int*>(tmem_slot + 1);      // epilogue -> bound warp: this CTA's scan is over
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mg = blockIdx.x / p.n_slices, slice = blockIdx.x % p.n_slices;   // mg: query tile (or pair of tiles)
@@ -342,7 +308,6 @@ __global__ void __launch_bounds__(kThreadsScan, 1)
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     fence_mbar_init();
-    *scan_done = 0;
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, kTmemCols);
@@ -353,24 +318,7 @@ __global__ void __launch_bounds__(kThreadsScan, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 6) {
-    // ------------------------------------------------ bound warp (kth_rule) ----
-    // CTA q keeps tau_k[q] -- the k-th largest of the slices' published bests -- fresh while its epilogue
-    // warps scan: the bisection (~2 us) runs beside them instead of delaying one of them
-    if (p.kth_rule && p.mode != 0 && (int)blockIdx.x < p.B) {
-      volatile int* done = scan_done;
-      if (p.mode == 2) {
-        // the first-tile bests are complete once the grid barrier of this launch has opened
-        const unsigned int gen0 = *reinterpret_cast<volatile unsigned int*>(p.grid_bar + 1);
-        while (*reinterpret_cast<volatile unsigned int*>(p.grid_bar + 1) == gen0 && !*done) { TS_SPIN_YIELD(); ts_nanosleep(500); }
-      }
-      while (!*done) {
-        for (int q = (int)blockIdx.x; q < p.B; q += (int)gridDim.x) kth_of_slices(p.pub, p.tau_k, p.n_slices, p.bpad, p.k, q, lane);
-        TS_SPIN_YIELD();
-        ts_nanosleep(4000);
-      }
-    }
-  } else if (warp == 0) {
+  if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------ TMA producer ------
       prefetch_tmap(&tmQ); prefetch_tmap(&tmQ8); prefetch_tmap(&tmX);
@@ -473,7 +421,7 @@ __global__ void __launch_bounds__(kThreadsScan, 1)
           drain_acc(p, s0, lane_addr + (uint32_t)(acc * kTileN), n0, ncols, wact0, true, J, CAP, lane);
           if (s0.active) {
             p.pub[(size_t)slice * p.bpad + s0.q] = s0.tjJ;
-            if (slice == 0) { p.tau_g[s0.q] = -INFINITY; p.tau_k[s0.q] = -INFINITY; }   // never let a stale bound of an earlier call be read
+            if (slice == 0) p.tau_g[s0.q] = -INFINITY;   // never let a stale bound of an earlier call be read
           }
           grid_barrier_epilogue(p.grid_bar, gen0, warp, lane);
           // pass 2 re-reads the same accumulator with the shared bound in place; the J-best
@@ -508,7 +456,6 @@ __global__ void __launch_bounds__(kThreadsScan, 1)
     }
     finish_state(p, s0, 0, slice, prepass, J, rows_per_cta, lane_row, true, (int)blockIdx.x);
     finish_state(p, s1, 1, slice, prepass, J, rows_per_cta, lane_row, dual, (int)blockIdx.x);
-    if (warp == 2 && lane == 0) *reinterpret_cast<volatile int*>(scan_done) = 1;
   }
 
   tc_fence_before();
@@ -733,14 +680,13 @@ int s1_umma_plan(const ScanArgs& a, UmmaLayout* lay) {
   lay->bpad = pl.n_mt * kTileM;
   lay->lists_keys = (size_t)pl.grid * lay->rows_per_cta * lay->cap;
   lay->counts_n = (size_t)pl.grid * lay->rows_per_cta;
-  lay->pub_n = (size_t)(pl.n_slices + 2) * lay->bpad;   // + one row for tau_g, one for tau_k
+  lay->pub_n = (size_t)(pl.n_slices + 1) * lay->bpad;   // + one row for tau_g
   const int j = (a.k + pl.n_slices - 1) / pl.n_slices;
   lay->jrank = (j <= 8 && !env_on("TS_DBG_NOSHARE")) ? j : 0;
   // One cooperative launch (pre-pass + grid barrier + scan) instead of two launches: bit-equal to the
   // two-launch sequence on a B200 and x1.02-1.03 on 1.25 M-row shards (profiles/README.md); TS_FUSE=0 for A/B.
   lay->fused = (lay->jrank > 0 && !pl.dual && !pl.pair && env_flag("TS_FUSE", kDefaultFuse)) ? 1 : 0;
-  lay->kth_rule = (lay->jrank == 1 && lay->n_slices >= a.k && lay->n_slices <= 256 && lay->n_mt == 1 && !lay->dual && !lay->pair &&
-                   !env_on("TS_DBG_NOKTH")) ? 1 : 0;
+  lay->kth_rule = (lay->jrank == 1 && lay->n_slices >= a.k && lay->n_slices <= 256 && !env_on("TS_DBG_NOKTH")) ? 1 : 0;
   return TS_OK;
 }
 
@@ -760,8 +706,6 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
   p.dbg_notopk = env_on("TS_DBG_NOTOPK") ? 1 : 0;
   p.jrank = lay.jrank; p.bpad = lay.bpad; p.dual = lay.dual;
   p.lists = a.lists; p.counts = a.counts; p.pub = a.pub; p.tau_g = a.pub + (size_t)lay.n_slices * lay.bpad;
-  p.tau_k = p.tau_g + lay.bpad;
-  p.kth_rule = lay.kth_rule;
   p.inv_norm = a.inv_norm;
   static unsigned long long* d_stats = nullptr;
   if (env_on("TS_DBG_STATS")) {
@@ -799,21 +743,21 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
     p.mode = 2;
     p.grid_bar = a.grid_bar;
 #ifdef TS_CUDASIM
-    cudasim::launch_cooperative(lay.grid, kThreadsScan, kSmemBytes, [&]() { kern(tmQ, tmQ8, tmX, p); });
+    cudasim::launch_cooperative(lay.grid, kThreads, kSmemBytes, [&]() { kern(tmQ, tmQ8, tmX, p); });
 #else
     void* args[] = {(void*)&tmQ, (void*)&tmQ8, (void*)&tmX, (void*)&p};
-    TS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(lay.grid), dim3(kThreadsScan), args, kSmemBytes, st));
+    TS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(lay.grid), dim3(kThreads), args, kSmemBytes, st));
 #endif
     if (launches) ++*launches;
   } else {
     if (p.jrank > 0) {
       p.mode = 0;   // threshold pre-pass over the first tile of every slice
-      TS_LAUNCH(kern, lay.grid, kThreadsScan, kSmemBytes, st, tmQ, tmQ8, tmX, p);
+      TS_LAUNCH(kern, lay.grid, kThreads, kSmemBytes, st, tmQ, tmQ8, tmX, p);
       TS_CUDA_OK(cudaGetLastError());
       if (launches) ++*launches;
     }
     p.mode = 1;
-    TS_LAUNCH(kern, lay.grid, kThreadsScan, kSmemBytes, st, tmQ, tmQ8, tmX, p);
+    TS_LAUNCH(kern, lay.grid, kThreads, kSmemBytes, st, tmQ, tmQ8, tmX, p);
     TS_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
   }

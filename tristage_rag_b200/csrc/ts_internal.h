@@ -86,7 +86,8 @@ struct ScanArgs {
 // where the umma scan leaves its candidates (consumed by launch_merge_lists)
 struct UmmaLayout {
   int n_slices, n_mt, grid, cap, spread, bpad, jrank, dual, rows_per_cta, fused, pair;
-  int kth_rule;   // the scan also keeps tau_k[bpad] behind tau_g (k-th largest of the slices' bests): pub + (n_slices + 1) * bpad
+  int kth_rule;   // jrank == 1 and n_slices >= k: the slices' published bests are n_slices distinct rows, so the select kernel may
+                  // filter with their k-th largest instead of their minimum
   size_t lists_keys, counts_n, pub_n;
 };
 // number of partial lists L a scan will emit / scratch it needs
