@@ -90,7 +90,18 @@ struct UmmaParams {
   float* tau_g;    // [bpad] min over slices of pub, refreshed by slice 0
   const float* inv_norm;
   unsigned long long* stats;  // debug: [0] appends [1] prunes [2] slow-path chunks (null = off)
+  unsigned long long* trace;  // debug (TS_DBG_TRACE): [grid][kTraceSlots] globaltimer stamps of epilogue warp 2 (null = off)
 };
+constexpr int kTraceSlots = 64;   // [0] entry, [1] pass-1 done, [2] grid barrier passed, [3] exit, [4] tiles, [8 + i] accumulator i ready
+__device__ __forceinline__ void trace_stamp(const UmmaParams& p, int slot) {
+#ifndef TS_CUDASIM
+  if (p.trace && slot < kTraceSlots) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[(size_t)blockIdx.x * kTraceSlots + slot] = t;
+  }
+#endif
+}
 
 // per-thread state of one query (one TMEM lane of one accumulator)
 struct QState {
@@ -407,6 +418,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     const bool wact0 = __any_sync(0xffffffffu, s0.active);
     const bool wact1 = __any_sync(0xffffffffu, s1.active);
+    const bool tracer = (p.trace != nullptr) && warp == 2 && lane == 0;
+    if (tracer) trace_stamp(p, 0);
     int iter = 0;
     for (int t = slice; t < t_end; t += p.n_slices, ++iter) {
       const int64_t n0 = (int64_t)t * kTileN;
@@ -416,6 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int acc = iter & 1;
         mbar_wait(&tfull_bar[acc], (uint32_t)((iter >> 1) & 1), 4);
         tc_fence_after();
+        if (tracer) trace_stamp(p, 8 + iter);
         if (fused && iter == 0) {
           // first tile, pass 1: only the thread's J best scores -> publish -> wait for every slice
           drain_acc(p, s0, lane_addr + (uint32_t)(acc * kTileN), n0, ncols, wact0, true, J, CAP, lane);
@@ -423,7 +437,9 @@ __global__ void __launch_bounds__(kThreads, 1)
             p.pub[(size_t)slice * p.bpad + s0.q] = s0.tjJ;
             if (slice == 0) p.tau_g[s0.q] = -INFINITY;   // never let a stale bound of an earlier call be read
           }
+          if (tracer) trace_stamp(p, 1);
           grid_barrier_epilogue(p.grid_bar, gen0, warp, lane);
+          if (tracer) trace_stamp(p, 2);
           // pass 2 re-reads the same accumulator with the shared bound in place; the J-best
           // registers restart from scratch so no row is counted twice
           s0.tjJ = -INFINITY;
@@ -456,6 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     finish_state(p, s0, 0, slice, prepass, J, rows_per_cta, lane_row, true, (int)blockIdx.x);
     finish_state(p, s1, 1, slice, prepass, J, rows_per_cta, lane_row, dual, (int)blockIdx.x);
+    if (tracer) { trace_stamp(p, 3); p.trace[(size_t)blockIdx.x * kTraceSlots + 4] = (unsigned long long)iter; }
   }
 
   tc_fence_before();
@@ -713,6 +730,12 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
     cudaMemsetAsync(d_stats, 0, 32, st);
     p.stats = d_stats;
   }
+  static unsigned long long* d_trace = nullptr;
+  if (env_on("TS_DBG_TRACE") && !lay.pair) {
+    if (!d_trace) cudaMalloc((void**)&d_trace, (size_t)1024 * kTraceSlots * 8);
+    cudaMemsetAsync(d_trace, 0, (size_t)1024 * kTraceSlots * 8, st);
+    p.trace = d_trace;
+  }
   const bool bf16 = a.dtype == TS_BF16;
   if (lay.pair) {
     CUtensorMap tmXh;
@@ -760,6 +783,26 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
     TS_LAUNCH(kern, lay.grid, kThreads, kSmemBytes, st, tmQ, tmQ8, tmX, p);
     TS_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
+  }
+  if (p.trace) {
+    // one JSON line per launch on stderr: per-CTA stamps relative to the earliest entry (ns)
+    const size_t n = (size_t)lay.grid * kTraceSlots;
+    unsigned long long* h = (unsigned long long*)malloc(n * 8);
+    cudaMemcpyAsync(h, d_trace, n * 8, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    unsigned long long t0 = ~0ull;
+    for (int c = 0; c < lay.grid; ++c) if (h[(size_t)c * kTraceSlots] && h[(size_t)c * kTraceSlots] < t0) t0 = h[(size_t)c * kTraceSlots];
+    fprintf(stderr, "[ts trace] {\"B\": %d, \"grid\": %d, \"ctas\": [", a.B, lay.grid);
+    for (int c = 0; c < lay.grid; ++c) {
+      const unsigned long long* r = h + (size_t)c * kTraceSlots;
+      const int tiles = (int)r[4];
+      fprintf(stderr, "%s{\"entry\": %lld, \"pass1\": %lld, \"bar\": %lld, \"exit\": %lld, \"acc\": [", c ? ", " : "", (long long)(r[0] - t0),
+              r[1] ? (long long)(r[1] - t0) : -1ll, r[2] ? (long long)(r[2] - t0) : -1ll, (long long)(r[3] - t0));
+      for (int i = 0; i < tiles && 8 + i < kTraceSlots; ++i) fprintf(stderr, "%s%lld", i ? ", " : "", (long long)(r[8 + i] - t0));
+      fprintf(stderr, "]}");
+    }
+    fprintf(stderr, "]}\n");
+    free(h);
   }
   if (p.stats) {
     unsigned long long h[4];
