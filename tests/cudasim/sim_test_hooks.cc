@@ -7,7 +7,7 @@ extern "C" int cudasim_merge_lists(const uint64_t* lists, const int* counts, con
                                    float* out_scores, int64_t* out_ids) {
   ts::UmmaLayout lay{};
   lay.n_slices = n_slices; lay.n_mt = n_mt; lay.grid = n_mt * n_slices; lay.cap = cap; lay.spread = spread;
-  lay.bpad = bpad; lay.jrank = jrank; lay.dual = 0; lay.rows_per_cta = 128; lay.fused = 0;
+  lay.bpad = bpad; lay.jrank = jrank; lay.rows_per_cta = 128; lay.fused = 0;
   int launches = 0;
   return ts::launch_merge_lists(lists, counts, pub, lay, B, k, id_base, out_scores, out_ids, nullptr, &launches);
 }

@@ -231,7 +231,7 @@ def test_tensor_scan_adversarial_score_orders(sim, order, k):
 
 def test_tensor_scan_variants_agree_bit_for_bit(sim, monkeypatch):
     """tests/test_gpu_zzz_fullsize.py::test_scan_variants_agree_bit_for_bit on the emulator: without
-    threshold sharing, with two query tiles per CTA (TS_DUAL), without the small-batch spread, and
+    threshold sharing, without the small-batch spread, and
     with the first select kernel -- identical ids and scores."""
     N, d, B, k = 20000, 128, 48, 100
     X, Q = make(N, d, B, seed=77, planted=20)
@@ -242,7 +242,7 @@ def test_tensor_scan_variants_agree_bit_for_bit(sim, monkeypatch):
     assert not flat_ip.check_topk(base[0], base[1], sc, rD, rI, rel=REL)
     Q2 = make(10, d, 300, seed=78)[1]
     base2 = idx.search_host(Q2, k, path="umma")
-    for var in ("TS_DBG_NOSHARE", "TS_DUAL", "TS_DBG_NOSPREAD", "TS_SELECT_V1"):
+    for var in ("TS_DBG_NOSHARE", "TS_DBG_NOSPREAD", "TS_SELECT_V1"):
         monkeypatch.setenv(var, "1")
         D, I = idx.search_host(Q, k, path="umma")
         D2, I2 = idx.search_host(Q2, k, path="umma")
@@ -897,7 +897,7 @@ def test_few_sms_many_tiles_per_cta_wrap_every_ring(sim, monkeypatch, sms, async
         D, I = idx.search_host(Q, k, path="umma")
         rD, rI, sc = oracle_search(X, Q, k, "bf16")
         assert not flat_ip.check_topk(D, I, sc, rD, rI, rel=REL)
-        for var in ("TS_FUSE", "TS_PAIR", "TS_DUAL", "TS_DBG_NOSHARE"):
+        for var in ("TS_FUSE", "TS_PAIR", "TS_DBG_NOSHARE"):
             monkeypatch.setenv(var, "1")
             D2, I2 = idx.search_host(Q, k, path="umma")
             monkeypatch.delenv(var)

@@ -274,7 +274,7 @@ def test_scan_variants_agree_bit_for_bit(cuda_device, monkeypatch):
     base2 = idx.search_host(Q2, k, path="umma")
     # defaults: one cooperative launch (TS_FUSE) and CTA pairs for B >= 129 (TS_PAIR); the alternatives -- two
     # launches, single-CTA tiles, no threshold sharing, two query tiles per CTA -- must give the same bits
-    variants = [("TS_DBG_NOSHARE", "1"), ("TS_FUSE", "0"), ("TS_PAIR", "0"), ("TS_DUAL", "1")]
+    variants = [("TS_DBG_NOSHARE", "1"), ("TS_FUSE", "0"), ("TS_PAIR", "0")]
     for var, val in variants:
         monkeypatch.setenv(var, val)
         D, I = idx.search_host(Q, k, path="umma")

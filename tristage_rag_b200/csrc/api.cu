@@ -260,7 +260,7 @@ static int index_search_impl(ts_index* h, const void* q_dev, int q_dtype, int B,
     if (rc) return rc;
     rc = launch_convert_rows((const char*)q_dev + (size_t)b0 * h->dim * dtype_size(q_dtype), q_dtype, h->dim, h->qbuf,
                              h->dtype, h->ld, Bc, h->dim, (flags & TS_FLAG_NORMALIZE_Q) ? kNormStage1 : kNormNone,
-                             nullptr, st);
+                             nullptr, st, h->grid_bar);
     if (rc) return rc;
     ++h->launches;
     ScanArgs a{};

@@ -18,8 +18,12 @@ namespace {
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256) convert_rows_kernel(const TS* __restrict__ src, int64_t src_ld,
                                                            TD* __restrict__ dst, int64_t dst_ld, int64_t n, int dim,
-                                                           int norm_mode, float* __restrict__ inv_norm_out) {
+                                                           int norm_mode, float* __restrict__ inv_norm_out,
+                                                           unsigned int* __restrict__ zero_word) {
   const int lane = threadIdx.x & 31;
+  // query prep of a search: reset the arrival counter of the scan's in-kernel grid barrier (s1_umma.cu) -- the
+  // kernel boundary orders this store before the scan, so the barrier needs no reset protocol of its own
+  if (zero_word && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0u;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
     const TS* s = src + row * src_ld;
@@ -51,13 +55,13 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const TS* __restrict_
 
 template <typename TS, typename TD>
 int launch_t(const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t n, int dim, int norm_mode,
-             float* inv, cudaStream_t st) {
+             float* inv, cudaStream_t st, unsigned int* zero_word) {
   if (n == 0) return TS_OK;
   const int warps_per_block = 8;
   int64_t blocks = (n + warps_per_block - 1) / warps_per_block;
   if (blocks > 148 * 16) blocks = 148 * 16;
   auto kern = convert_rows_kernel<TS, TD>;
-  TS_LAUNCH(kern, (unsigned)blocks, 256, 0, st, (const TS*)src, src_ld, (TD*)dst, dst_ld, n, dim, norm_mode, inv);
+  TS_LAUNCH(kern, (unsigned)blocks, 256, 0, st, (const TS*)src, src_ld, (TD*)dst, dst_ld, n, dim, norm_mode, inv, zero_word);
   TS_CUDA_OK(cudaGetLastError());
   return TS_OK;
 }
@@ -65,10 +69,10 @@ int launch_t(const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t
 }  // namespace
 
 int launch_convert_rows(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld,
-                        int64_t n, int dim, int norm_mode, float* inv, cudaStream_t st) {
+                        int64_t n, int dim, int norm_mode, float* inv, cudaStream_t st, unsigned int* zero_word) {
 #define TS_CASE(SD, ST_, DD, DT_)                                                                 \
   if (src_dtype == SD && dst_dtype == DD)                                                         \
-    return launch_t<ST_, DT_>(src, src_ld, dst, dst_ld, n, dim, norm_mode, inv, st);
+    return launch_t<ST_, DT_>(src, src_ld, dst, dst_ld, n, dim, norm_mode, inv, st, zero_word);
   TS_CASE(TS_F32, float, TS_F32, float)
   TS_CASE(TS_F32, float, TS_BF16, __nv_bfloat16)
   TS_CASE(TS_F32, float, TS_F16, __half)

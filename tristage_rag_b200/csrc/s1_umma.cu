@@ -66,7 +66,7 @@ constexpr int kABytes = kTileM * kChunkBytes;  // 16 KB
 constexpr int kBBytes = kTileN * kChunkBytes;  // 32 KB
 // operand kinds of the single-CTA kernel (the values are the UMMA A/B format codes)
 constexpr int kOpF16 = 0, kOpBF16 = 1, kOpTF32 = 2;
-constexpr int kRingBytes = 192 * 1024;         // 4 x (A + B) or 3 x (A0 + A1 + B)
+constexpr int kRingBytes = 192 * 1024;         // 4 x (A + B); the CTA-pair kernel: 6 x (A + B/2)
 constexpr int kBarBytes = 256;
 constexpr int kSmemBytes = kRingBytes + kBarBytes + 1024;  // + alignment slack
 constexpr int kTmemCols = 512;
@@ -77,11 +77,10 @@ struct UmmaParams {
   int nK, B, k;
   int n_slices, n_tiles;
   int spread, n_qgroups, cap;
-  int dual;        // 1: the CTA owns TWO query tiles (2*mp, 2*mp+1) that share every corpus chunk
   int dbg_notopk;
   int mode;        // 0 = threshold pre-pass (first tile of every slice, publishes pub), 1 = scan,
                    // 2 = both in one cooperative launch (grid barrier after the first tile)
-  unsigned int* grid_bar;  // [0] arrival counter, [1] generation (mode 2)
+  unsigned int* grid_bar;  // arrival counter of the grid barrier (mode 2), zero at launch
   int jrank;       // j = ceil(k / n_slices) if <= 8, else 0 (threshold sharing off)
   int bpad;        // row pitch of pub
   uint64_t* lists; // [grid][rows_per_cta][cap] candidate keys
@@ -103,10 +102,11 @@ __device__ __forceinline__ void trace_stamp(const UmmaParams& p, int slot) {
 #endif
 }
 
-// per-thread state of one query (one TMEM lane of one accumulator)
+// per-thread state of one query (one TMEM lane of one accumulator).  Scalars only: an array member indexed by the
+// run-time J put the whole struct into local memory (208-byte stack frame, LDL/STL on every access of the epilogue).
 struct QState {
   float tau, tjJ, pub_last;
-  float tj[8];       // best 8 scores appended so far, descending
+  float t0, t1, t2, t3, t4, t5, t6, t7;   // best 8 scores appended so far, descending (J > 1 only)
   int cnt, q;
   int n_app, n_prune, n_slow;   // debug counters
   bool active;
@@ -114,29 +114,37 @@ struct QState {
 };
 
 __device__ __forceinline__ float min_over_slices(const UmmaParams& p, int q) {
+  // 32 independent L2 loads in flight per round: ~5 rounds for 148 slices (the first version issued 8 per round,
+  // 19 dependent rounds = ~7 us -- longer than the slack the fused start-up has, see the TS_DBG_TRACE timeline)
   float m = INFINITY;
   int c = 0;
-  for (; c + 8 <= p.n_slices; c += 8) {
-    float v[8];
+  for (; c + 32 <= p.n_slices; c += 32) {
+    float v[32];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldcg(p.pub + (size_t)(c + u) * p.bpad + q);
+    for (int u = 0; u < 32; ++u) v[u] = __ldcg(p.pub + (size_t)(c + u) * p.bpad + q);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) m = fminf(m, v[u]);
+    for (int u = 0; u < 32; ++u) m = fminf(m, v[u]);
+  }
+  for (; c + 4 <= p.n_slices; c += 4) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldcg(p.pub + (size_t)(c + u) * p.bpad + q);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) m = fminf(m, v[u]);
   }
   for (; c < p.n_slices; ++c) m = fminf(m, __ldcg(p.pub + (size_t)c * p.bpad + q));
   return m;
 }
 
+__device__ __forceinline__ void topj_reset(QState& s) {
+  s.tjJ = -INFINITY;
+  s.t0 = s.t1 = s.t2 = s.t3 = s.t4 = s.t5 = s.t6 = s.t7 = -INFINITY;
+}
 __device__ __forceinline__ void topj_insert(QState& s, float v, int J) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float hi = fmaxf(s.tj[i], v);
-    v = fminf(s.tj[i], v);
-    s.tj[i] = hi;
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i == J - 1) s.tjJ = s.tj[i];
+#define TS_INS(t) { const float hi = fmaxf(t, v); v = fminf(t, v); t = hi; }
+  TS_INS(s.t0) TS_INS(s.t1) TS_INS(s.t2) TS_INS(s.t3) TS_INS(s.t4) TS_INS(s.t5) TS_INS(s.t6) TS_INS(s.t7)
+#undef TS_INS
+  s.tjJ = J == 1 ? s.t0 : J == 2 ? s.t1 : J == 3 ? s.t2 : J == 4 ? s.t3 : J == 5 ? s.t4 : J == 6 ? s.t5 : J == 7 ? s.t6 : s.t7;
 }
 
 // one accumulator (this warp's 32 lanes x ncols columns) -> candidates of this thread's query
@@ -148,40 +156,59 @@ __device__ __forceinline__ void drain_acc(const UmmaParams& p, QState& s, uint32
     tmem_ld_32x32b_x32(t_addr + (uint32_t)c0, r);
     tmem_ld_wait();
     if (s.active) {
-      const bool whole = (c0 + 32 <= ncols);
       if (p.inv_norm) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           r[j] = __float_as_uint(__uint_as_float(r[j]) * __ldg(p.inv_norm + n0 + ((c0 + j < ncols) ? c0 + j : 0)));
       }
-      // fast path: one max over the 32 scores, compared once
-      float m = -INFINITY;
+      if (c0 + 32 > ncols) {        // last, partial chunk of the corpus: columns past the end never win
 #pragma unroll
-      for (int j = 0; j < 32; ++j) m = fmaxf(m, (whole || c0 + j < ncols) ? __uint_as_float(r[j]) : -INFINITY);
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j >= ncols) r[j] = __float_as_uint(-INFINITY);
+      }
+      // fast path: the maximum of the 32 scores, as a tree over eight groups of four (depth 5: this warp is alone
+      // on its scheduler, a 32-long dependent chain would cost ~130 cycles per chunk), compared once
+      float g[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        g[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
+                     fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+      const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
       const float thr = prepass ? s.tjJ : s.tau;
       if (m > thr) {
-        // slow path (a few percent of the chunks): bit mask of the survivors,
-        // then one short loop iteration per survivor.  The 32 scores are
-        // spilled to a local array here so the loop can index them.
+        // slow path (a few percent of the chunks per query, but most chunks of a warp while the bound warms up):
+        // only the groups whose maximum passes are looked at, their survivors are appended straight from the
+        // registers.  (The first version copied the 32 scores to local memory and walked a bit mask: ~1-2 us per
+        // chunk, 10 us per pass over the first tile -- TS_DBG_TRACE timeline, profiles/README.md.)
         ++s.n_slow;
-        uint32_t mask = 0;
-        float loc[32];
+        if (!prepass) {
+          int cnt = s.cnt;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = __uint_as_float(r[j]);
-          loc[j] = v;
-          mask |= (v > thr && (whole || c0 + j < ncols)) ? (1u << j) : 0u;
+          for (int i = 0; i < 8; ++i) {
+            if (g[i] > thr) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float v = __uint_as_float(r[4 * i + u]);
+                if (v > thr) s.lst[cnt++] = make_key(v, (uint32_t)(n0 + c0 + 4 * i + u));
+              }
+            }
+          }
+          s.n_app += cnt - s.cnt;
+          s.cnt = cnt;
         }
-        while (mask) {
-          const int j = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const float v = loc[j];
-          if (prepass) {
-            if (v > s.tjJ) topj_insert(s, v, J);
-          } else {
-            s.lst[s.cnt++] = make_key(v, (uint32_t)(n0 + c0 + j));
-            ++s.n_app;
-            if (J > 0 && v > s.tjJ) topj_insert(s, v, J);
+        if (J == 1) {
+          s.tjJ = fmaxf(s.tjJ, m);   // the slice's best score is the running maximum: no insertion
+        } else if (J > 1 && m > s.tjJ) {
+          // scores that enter the slice's own J best: ~J * ln(rows / J) times per scan
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (g[i] > s.tjJ) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float v = __uint_as_float(r[4 * i + u]);
+                if (v > s.tjJ) topj_insert(s, v, J);
+              }
+            }
           }
         }
       }
@@ -208,9 +235,7 @@ __device__ __forceinline__ void init_state(const UmmaParams& p, QState& s, int a
   s.lst = p.lists + ((size_t)cta_id * rows_per_cta + a * kTileM + lane_row) * CAP;
   s.cnt = 0;
   s.n_app = s.n_prune = s.n_slow = 0;
-  s.tjJ = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s.tj[i] = -INFINITY;
+  topj_reset(s);
   s.tau = p.dbg_notopk ? INFINITY : -INFINITY;
   s.pub_last = -INFINITY;
 }
@@ -261,31 +286,30 @@ __device__ __forceinline__ void finish_state(const UmmaParams& p, QState& s, int
 
 __device__ __forceinline__ void named_bar_sync128(int id) { named_bar_sync(id, 128); }
 
-// Grid-wide barrier for the epilogue threads of a cooperative launch (all CTAs
-// co-resident).  Self-resetting (arrival counter + generation word), so it
-// also works when the launch is replayed from a CUDA graph.  `gen0` must have
-// been read before this CTA arrives.  Bounded spin: a protocol bug traps.
-__device__ __forceinline__ void grid_barrier_epilogue(unsigned int* bar, unsigned int gen0, int warp, int lane) {
-  __threadfence();
-  named_bar_sync128(1);
+// Grid-wide barrier for the epilogue threads of a cooperative launch (all CTAs co-resident).  One arrival counter,
+// zeroed by the query-prep kernel that precedes every scan (convert_rows.cu), so there is no reset / generation
+// protocol: one release-add per CTA, then acquire-polls until the count reaches the grid size.  The first version
+// (__threadfence = fence.sc.gpu around an add + exchange + generation word) completed 4-13 us after the last
+// arrival while the TMA stream was saturating the memory system (TS_DBG_TRACE) -- longer than the one tile time
+// (11 us) the first accumulator can be held without stalling the pipeline.  Bounded spin: a protocol bug traps.
+__device__ __forceinline__ void grid_barrier_epilogue(unsigned int* bar, int warp, int lane) {
+  named_bar_sync128(1);        // the CTA's pub stores are ordered before lane 0's release (CTA-scope barrier + cumulativity)
   if (warp == 2 && lane == 0) {
-    __threadfence();
-    const unsigned int old = atomicAdd(bar, 1u);
-    if (old == gridDim.x - 1) {
-      atomicExch(bar, 0u);
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
-    } else {
-      const long long t0 = clock64();
-      while (*reinterpret_cast<volatile unsigned int*>(bar + 1) == gen0) {
-        TS_SPIN_YIELD();
-        if (clock64() - t0 > TS_WAIT_TIMEOUT_CYCLES) {
-          printf("[tristage] grid barrier timeout: block %d\n", (int)blockIdx.x);
-          __trap();
-        }
+#ifdef TS_CUDASIM
+    atomicAdd(bar, 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(bar) < gridDim.x) TS_SPIN_YIELD();
+#else
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    const long long t0 = clock64();
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+      if (seen < gridDim.x && clock64() - t0 > TS_WAIT_TIMEOUT_CYCLES) {
+        printf("[tristage] grid barrier timeout: block %d saw %u of %u\n", (int)blockIdx.x, seen, gridDim.x);
+        __trap();
       }
-    }
-    __threadfence();
+    } while (seen < gridDim.x);
+#endif
   }
   named_bar_sync128(1);
 }
@@ -296,10 +320,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                    const __grid_constant__ CUtensorMap tmX, const UmmaParams p) {
   constexpr int CK = (OP == kOpTF32) ? kChunkBytes / 4 : kChunkK;   // elements per K chunk
   const int CAP = p.cap;
-  const bool dual = p.dual != 0;
-  const int n_stages = dual ? 3 : 4;
-  const int stage_bytes = dual ? (2 * kABytes + kBBytes) : (kABytes + kBBytes);
-  const int b_off = dual ? 2 * kABytes : kABytes;     // B chunk offset inside a stage
+  constexpr int n_stages = kMaxStages;
+  constexpr int stage_bytes = kABytes + kBBytes;
+  constexpr int b_off = kABytes;                      // B chunk offset inside a stage
   TS_DYN_SMEM(unsigned char, smem_raw);
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes);
@@ -310,8 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mg = blockIdx.x / p.n_slices, slice = blockIdx.x % p.n_slices;   // mg: query tile (or pair of tiles)
-  const int mt0 = dual ? 2 * mg : mg;
+  const int mt0 = blockIdx.x / p.n_slices, slice = blockIdx.x % p.n_slices;   // mt0: query tile
   // the pre-pass looks at the first tile of the slice only
   const int t_end = (p.mode == 0) ? ((slice + 1 < p.n_tiles) ? slice + 1 : p.n_tiles) : p.n_tiles;
 
@@ -333,8 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       // ------------------------------------------------ TMA producer ------
       prefetch_tmap(&tmQ); prefetch_tmap(&tmQ8); prefetch_tmap(&tmX);
-      const bool has1 = dual && ((mt0 + 1) * kTileM < p.B);
-      const uint32_t tx = (p.spread ? (uint32_t)p.n_qgroups * 1024u : (uint32_t)kABytes * (has1 ? 2u : 1u)) + (uint32_t)kBBytes;
+      const uint32_t tx = (p.spread ? (uint32_t)p.n_qgroups * 1024u : (uint32_t)kABytes) + (uint32_t)kBBytes;
       const uint64_t x_policy = (gridDim.x > (unsigned)p.n_slices) ? kEvictNormal : kEvictFirst;
       int stage = 0; uint32_t phase = 0;
       for (int t = slice; t < t_end; t += p.n_slices) {
@@ -350,7 +371,6 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           } else {
             tma_load_2d(sA, &tmQ, &full_bar[stage], kc * CK, mt0 * kTileM, kEvictLast);
-            if (has1) tma_load_2d(sA + kABytes, &tmQ, &full_bar[stage], kc * CK, (mt0 + 1) * kTileM, kEvictLast);
           }
           tma_load_2d(sB, &tmX, &full_bar[stage], kc * CK, t * kTileN, x_policy);
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
@@ -368,9 +388,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       int stage = 0; uint32_t phase = 0;
       int iter = 0;
       for (int t = slice; t < t_end; t += p.n_slices, ++iter) {
-        // single: accumulators alternate per tile.  dual: both are written every tile.
-        const int acc = dual ? 0 : (iter & 1);
-        const uint32_t par = dual ? (uint32_t)(iter & 1) : (uint32_t)((iter >> 1) & 1);
+        const int acc = iter & 1;                       // the two accumulators alternate per tile
+        const uint32_t par = (uint32_t)((iter >> 1) & 1);
         mbar_wait(&tempty_bar[acc], par ^ 1u, 2);
         tc_fence_after();
         for (int kc = 0; kc < p.nK; ++kc) {
@@ -383,41 +402,25 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int ks = 0; ks < kSteps; ++ks)
             mma(tmem_base + (uint32_t)(acc * kTileN), adesc + ks * kDescKStep, bdesc + ks * kDescKStep, idesc,
                 (kc | ks) ? 1u : 0u);
-          if (dual) {
-            if (kc == 0) { mbar_wait(&tempty_bar[1], par ^ 1u, 5); tc_fence_after(); }
-            const uint64_t adesc1 = make_desc_kmajor_sw128(a_addr + kABytes);
-#pragma unroll
-            for (int ks = 0; ks < kSteps; ++ks)
-              mma(tmem_base + (uint32_t)kTileN, adesc1 + ks * kDescKStep, bdesc + ks * kDescKStep, idesc,
-                  (kc | ks) ? 1u : 0u);
-          }
           umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[acc]);      // accumulator(s) complete
-        if (dual) umma_commit(&tfull_bar[1]);
+        umma_commit(&tfull_bar[acc]);      // accumulator complete
       }
     }
   } else {
     // -------------------------------------------------- epilogue ----------
     const int quarter = warp & 3;
     const int lane_row = quarter * 32 + lane;
-    const int rows_per_cta = dual ? 2 * kTileM : kTileM;
+    constexpr int rows_per_cta = kTileM;
     const bool prepass = (p.mode == 0);
-    const bool fused = (p.mode == 2);          // pre-pass + scan in one cooperative launch (never with dual)
+    const bool fused = (p.mode == 2);          // pre-pass + scan in one cooperative launch 
     const int J = p.jrank;
-    unsigned int gen0 = 0;
-    if (fused) gen0 = *reinterpret_cast<volatile unsigned int*>(p.grid_bar + 1);
-    QState s0, s1;
+    QState s0;
     init_state(p, s0, 0, mt0, quarter, lane, lane_row, rows_per_cta, CAP, true, (int)blockIdx.x);
-    init_state(p, s1, 1, mt0, quarter, lane, lane_row, rows_per_cta, CAP, dual, (int)blockIdx.x);
-    if (J > 0 && !fused) {
-      start_state(p, s0, slice, prepass);
-      start_state(p, s1, slice, prepass);
-    }
+    if (J > 0 && !fused) start_state(p, s0, slice, prepass);
 
     const bool wact0 = __any_sync(0xffffffffu, s0.active);
-    const bool wact1 = __any_sync(0xffffffffu, s1.active);
     const bool tracer = (p.trace != nullptr) && warp == 2 && lane == 0;
     if (tracer) trace_stamp(p, 0);
     int iter = 0;
@@ -425,53 +428,32 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int64_t n0 = (int64_t)t * kTileN;
       const int ncols = (int)((p.N - n0) < (int64_t)kTileN ? (p.N - n0) : (int64_t)kTileN);
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      if (!dual) {
-        const int acc = iter & 1;
-        mbar_wait(&tfull_bar[acc], (uint32_t)((iter >> 1) & 1), 4);
-        tc_fence_after();
-        if (tracer) trace_stamp(p, 8 + iter);
-        if (fused && iter == 0) {
-          // first tile, pass 1: only the thread's J best scores -> publish -> wait for every slice
-          drain_acc(p, s0, lane_addr + (uint32_t)(acc * kTileN), n0, ncols, wact0, true, J, CAP, lane);
-          if (s0.active) {
-            p.pub[(size_t)slice * p.bpad + s0.q] = s0.tjJ;
-            if (slice == 0) p.tau_g[s0.q] = -INFINITY;   // never let a stale bound of an earlier call be read
-          }
-          if (tracer) trace_stamp(p, 1);
-          grid_barrier_epilogue(p.grid_bar, gen0, warp, lane);
-          if (tracer) trace_stamp(p, 2);
-          // pass 2 re-reads the same accumulator with the shared bound in place; the J-best
-          // registers restart from scratch so no row is counted twice
-          s0.tjJ = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) s0.tj[i] = -INFINITY;
-          start_state(p, s0, slice, false);
+      const int acc = iter & 1;
+      mbar_wait(&tfull_bar[acc], (uint32_t)((iter >> 1) & 1), 4);
+      tc_fence_after();
+      if (tracer) trace_stamp(p, 8 + iter);
+      if (fused && iter == 0) {
+        // first tile, pass 1: only the thread's J best scores -> publish -> wait for every slice
+        drain_acc(p, s0, lane_addr + (uint32_t)(acc * kTileN), n0, ncols, wact0, true, J, CAP, lane);
+        if (s0.active) {
+          p.pub[(size_t)slice * p.bpad + s0.q] = s0.tjJ;
+          if (slice == 0) p.tau_g[s0.q] = -INFINITY;   // never let a stale bound of an earlier call be read
         }
-        drain_acc(p, s0, lane_addr + (uint32_t)(acc * kTileN), n0, ncols, wact0, prepass, J, CAP, lane);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      } else {
-        mbar_wait(&tfull_bar[0], (uint32_t)(iter & 1), 4);
-        tc_fence_after();
-        drain_acc(p, s0, lane_addr, n0, ncols, wact0, prepass, J, CAP, lane);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[0]);
-        mbar_wait(&tfull_bar[1], (uint32_t)(iter & 1), 6);
-        tc_fence_after();
-        drain_acc(p, s1, lane_addr + (uint32_t)kTileN, n0, ncols, wact1, prepass, J, CAP, lane);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[1]);
+        if (tracer) trace_stamp(p, 1);
+        grid_barrier_epilogue(p.grid_bar, warp, lane);
+        if (tracer) trace_stamp(p, 2);
+        // pass 2 re-reads the same accumulator with the shared bound in place; the J-best
+        // registers restart from scratch so no row is counted twice
+        topj_reset(s0);
+        start_state(p, s0, slice, false);
       }
-      if (!prepass && J > 0) {
-        share_state(p, s0, slice, iter);
-        share_state(p, s1, slice, iter);
-      }
+      drain_acc(p, s0, lane_addr + (uint32_t)(acc * kTileN), n0, ncols, wact0, prepass, J, CAP, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (!prepass && J > 0) share_state(p, s0, slice, iter);
     }
     finish_state(p, s0, 0, slice, prepass, J, rows_per_cta, lane_row, true, (int)blockIdx.x);
-    finish_state(p, s1, 1, slice, prepass, J, rows_per_cta, lane_row, dual, (int)blockIdx.x);
     if (tracer) { trace_stamp(p, 3); p.trace[(size_t)blockIdx.x * kTraceSlots + 4] = (unsigned long long)iter; }
   }
 
@@ -660,24 +642,22 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, in
 }
 
 namespace {
-struct UmmaPlan { int n_mt, n_mg, dual, n_slices, n_tiles, grid, pair; };
+struct UmmaPlan { int n_mt, n_slices, n_tiles, grid, pair; };
 UmmaPlan umma_plan(const ScanArgs& a) {
   UmmaPlan pl;
   pl.n_mt = (a.B + kTileM - 1) / kTileM;
-  // Two query tiles per CTA sharing each corpus chunk halve the L2->SM traffic, but the two
-  // accumulators then cannot be double buffered against the epilogue; measured on B200 the
-  // single-tile layout is faster (19.2 vs 21.5 ms at B=1024, 10M x 1024), so it is opt-in.
-  pl.dual = (pl.n_mt >= 2 && env_on("TS_DUAL")) ? 1 : 0;
+  // (A single-CTA variant with two query tiles per CTA -- TS_DUAL -- halved the L2->SM traffic too, but its two
+  // accumulators could not be double buffered against the epilogue: 21.5 vs 19.2 ms at B = 1024, 10 M x 1024.  The
+  // CTA-pair kernel below is the design that keeps the double buffering; the variant was removed in round 2.)
   // CTA pairs (cta_group::2): two query tiles per cluster; an odd tile count is padded with an idle tile
-  pl.pair = (pl.n_mt >= 2 && !pl.dual && a.sm_count >= 2 && a.dtype != TS_F32 && env_flag("TS_PAIR", kDefaultPair)) ? 1 : 0;
+  pl.pair = (pl.n_mt >= 2 && a.sm_count >= 2 && a.dtype != TS_F32 && env_flag("TS_PAIR", kDefaultPair)) ? 1 : 0;
   if (pl.pair) pl.n_mt = (pl.n_mt + 1) & ~1;
-  pl.n_mg = pl.dual ? (pl.n_mt + 1) / 2 : pl.n_mt;
   pl.n_tiles = (int)((a.n + kTileN - 1) / kTileN);
-  int s = a.sm_count / pl.n_mg;
+  int s = a.sm_count / pl.n_mt;
   if (s < 1) s = 1;
   if (s > pl.n_tiles) s = pl.n_tiles;
   pl.n_slices = s;
-  pl.grid = pl.n_mg * pl.n_slices;
+  pl.grid = pl.n_mt * pl.n_slices;
   return pl;
 }
 }  // namespace
@@ -688,8 +668,7 @@ int s1_umma_plan(const ScanArgs& a, UmmaLayout* lay) {
   const UmmaPlan pl = umma_plan(a);
   lay->n_slices = pl.n_slices;
   lay->n_mt = pl.n_mt;
-  lay->dual = pl.dual;
-  lay->rows_per_cta = pl.dual ? 2 * kTileM : kTileM;
+  lay->rows_per_cta = kTileM;
   lay->grid = pl.grid;
   lay->cap = cap_for_k(a.k);
   lay->pair = pl.pair;
@@ -702,7 +681,7 @@ int s1_umma_plan(const ScanArgs& a, UmmaLayout* lay) {
   lay->jrank = (j <= 8 && !env_on("TS_DBG_NOSHARE")) ? j : 0;
   // One cooperative launch (pre-pass + grid barrier + scan) instead of two launches: bit-equal to the
   // two-launch sequence on a B200 and x1.02-1.03 on 1.25 M-row shards (profiles/README.md); TS_FUSE=0 for A/B.
-  lay->fused = (lay->jrank > 0 && !pl.dual && !pl.pair && env_flag("TS_FUSE", kDefaultFuse)) ? 1 : 0;
+  lay->fused = (lay->jrank > 0 && !pl.pair && env_flag("TS_FUSE", kDefaultFuse)) ? 1 : 0;
   lay->kth_rule = (lay->jrank == 1 && lay->n_slices >= a.k && lay->n_slices <= 256 && !env_on("TS_DBG_NOKTH")) ? 1 : 0;
   return TS_OK;
 }
@@ -721,7 +700,7 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
   p.n_qgroups = (a.B + 7) / 8;
   p.cap = lay.cap;
   p.dbg_notopk = env_on("TS_DBG_NOTOPK") ? 1 : 0;
-  p.jrank = lay.jrank; p.bpad = lay.bpad; p.dual = lay.dual;
+  p.jrank = lay.jrank; p.bpad = lay.bpad;
   p.lists = a.lists; p.counts = a.counts; p.pub = a.pub; p.tau_g = a.pub + (size_t)lay.n_slices * lay.bpad;
   p.inv_norm = a.inv_norm;
   static unsigned long long* d_stats = nullptr;
@@ -808,8 +787,8 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
     unsigned long long h[4];
     cudaMemcpyAsync(h, d_stats, 32, cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
-    fprintf(stderr, "[ts stats] B=%d k=%d grid=%d slices=%d dual=%d J=%d: appends=%llu (%.1f/list) prunes=%llu slow_chunks=%llu\n", a.B, a.k, lay.grid,
-            lay.n_slices, lay.dual, lay.jrank, h[0], (double)h[0] / ((double)lay.n_slices * a.B), h[1], h[2]);
+    fprintf(stderr, "[ts stats] B=%d k=%d grid=%d slices=%d pair=%d J=%d: appends=%llu (%.1f/list) prunes=%llu slow_chunks=%llu\n", a.B, a.k, lay.grid,
+            lay.n_slices, lay.pair, lay.jrank, h[0], (double)h[0] / ((double)lay.n_slices * a.B), h[1], h[2]);
   }
   return TS_OK;
 }

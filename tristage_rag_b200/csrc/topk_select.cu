@@ -41,7 +41,7 @@ struct SelectParams {
   int64_t id_base;
   // kLists: unsorted candidate lists of the umma scan, lists[(cta*128 + row)*cap .. +counts[cta*128+row])
   const int* counts;
-  int n_slices, spread, cap, dual, rows_per_cta;
+  int n_slices, spread, cap, rows_per_cta;
   long long pair_stride;  // kPairs: elements between consecutive lists (scores: floats, ids: int64s)
   long long pair_stride_ids;
   const float* pub;       // kLists: final per-slice J-th best scores [n_slices][bpad] (null = no filter)
@@ -146,8 +146,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     const int mt = b >> 7, qi = b & 127;
     int row = qi;
     if (p.spread) { const int grp = qi >> 3; row = ((grp & 3) * 32) + ((grp >> 2) * 8) + (qi & 7); }
-    const int mg = p.dual ? (mt >> 1) : mt;                 // CTA group owning this query tile
-    list_row0 = (size_t)mg * p.n_slices * p.rows_per_cta + (p.dual ? (mt & 1) * 128 : 0) + row;
+    list_row0 = (size_t)mt * p.n_slices * p.rows_per_cta + row;   // CTAs (mt, 0..n_slices) own this query tile
     if (p.serial_prefix) {
       // first version (TS_SELECT_V1=1, kept for A/B timing): thread 0 walks the counts -- n_slices
       // dependent global loads, ~20 us of the ~30 us this kernel took at B <= 32
@@ -382,7 +381,7 @@ int launch_merge_lists(const uint64_t* lists, const int* counts, const float* pu
   if (k <= 0 || k > TS_MAX_K || B <= 0 || lay.n_slices > kMaxLists) { set_error("merge_lists: bad arguments"); return TS_ERR_INVALID; }
   SelectParams p{};
   p.mode = kLists; p.keys = lists; p.counts = counts; p.n_slices = lay.n_slices; p.spread = lay.spread; p.cap = lay.cap;
-  p.dual = lay.dual; p.rows_per_cta = lay.rows_per_cta;
+  p.rows_per_cta = lay.rows_per_cta;
   p.pub = (lay.jrank > 0) ? pub : nullptr; p.bpad = lay.bpad;
   p.kth_rule = (lay.jrank == 1 && lay.kth_rule) ? 1 : 0;
   p.serial_prefix = env_on("TS_SELECT_V1") ? 1 : 0;

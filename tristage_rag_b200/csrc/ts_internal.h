@@ -20,7 +20,7 @@ const char* get_error();
     }                                                                                      \
   } while (0)
 
-// experiment switches (TS_DBG_*, TS_DUAL, TS_SELECT_V1): on when set to anything but "" or "0"
+// experiment switches (TS_DBG_*, TS_SELECT_V1): on when set to anything but "" or "0"
 inline bool env_on(const char* name) {
   const char* e = getenv(name);
   return e && e[0] && !(e[0] == '0' && !e[1]);
@@ -64,7 +64,8 @@ enum NormMode { kNormNone = 0, kNormStage1 = 1 /* x/(|x|+1e-8) */, kNormStage2 =
 // is given, in which case values are stored un-normalised and 1/(|x|+eps) is
 // written to inv_norm_out[n] (METRIC_COSINE).
 int launch_convert_rows(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld,
-                        int64_t n, int dim, int norm_mode, float* inv_norm_out, cudaStream_t st);
+                        int64_t n, int dim, int norm_mode, float* inv_norm_out, cudaStream_t st,
+                        unsigned int* zero_word = nullptr);   // zero_word: set to 0 by the kernel (grid-barrier counter of the scan)
 
 // ---- Stage-1 scans -> partial keys [L][B][k] ------------------------------
 struct ScanArgs {
@@ -80,12 +81,12 @@ struct ScanArgs {
   size_t partial_keys;    // capacity in keys
   int* counts;            // umma path out: entries per candidate list
   float* pub;             // umma path scratch: published per-slice thresholds
-  unsigned int* grid_bar; // umma path: {arrival counter, generation} of the in-kernel grid barrier
+  unsigned int* grid_bar; // umma path: arrival counter of the in-kernel grid barrier, zeroed by the query-prep kernel of the same call
   int sm_count;
 };
 // where the umma scan leaves its candidates (consumed by launch_merge_lists)
 struct UmmaLayout {
-  int n_slices, n_mt, grid, cap, spread, bpad, jrank, dual, rows_per_cta, fused, pair;
+  int n_slices, n_mt, grid, cap, spread, bpad, jrank, rows_per_cta, fused, pair;
   int kth_rule;   // jrank == 1 and n_slices >= k: the slices' published bests are n_slices distinct rows, so the select kernel may
                   // filter with their k-th largest instead of their minimum
   size_t lists_keys, counts_n, pub_n;
