@@ -40,7 +40,7 @@ namespace ts {
 
 int launch_convert_rows(const void* src, int sdt, int64_t src_ld, void* dst, int ddt, int64_t dst_ld, int64_t n, int dim,
                         int norm_mode, float* inv_norm_out, cudaStream_t, unsigned int* zero_word) {
-  if (zero_word) *zero_word = 0u;
+  if (zero_word) for (int i = 0; i < 16; ++i) zero_word[i] = 0u;
   for (int64_t r = 0; r < n; ++r) {
     float denom = 1.f; bool scale = false;
     if (norm_mode != kNormNone) {

@@ -135,8 +135,10 @@ int ts_index_create(ts_index** out, int device, int dim, int storage_dtype, int 
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
     h->coop = coop;
-    if (coop && cudaMalloc((void**)&h->grid_bar, 8) == cudaSuccess) cudaMemset(h->grid_bar, 0, 8);
-    else h->grid_bar = nullptr;
+    // [0] arrival counter of the fused scan's grid barrier, [1 + mt] next-tile counter of query tile mt: all 16 words
+    // are zeroed by the query-prep kernel of every search
+    if (cudaMalloc((void**)&h->grid_bar, 64) == cudaSuccess) cudaMemset(h->grid_bar, 0, 64);
+    else { cudaGetLastError(); h->grid_bar = nullptr; }
   }
   if (reserve_rows > 0) {
     h->cap = 0;
@@ -296,15 +298,22 @@ static int index_search_impl(ts_index* h, const void* q_dev, int q_dtype, int B,
       if ((rc = ensure_bytes(&h->counts, &h->counts_b, lay.counts_n * sizeof(int)))) return rc;
       if ((rc = ensure_bytes(&h->pub, &h->pub_b, lay.pub_n * sizeof(float)))) return rc;
       a.lists = (uint64_t*)h->lists; a.lists_keys = lay.lists_keys;
-      a.counts = (int*)h->counts; a.pub = (float*)h->pub; a.grid_bar = h->grid_bar;
+      a.counts = (int*)h->counts; a.pub = (float*)h->pub; a.grid_bar = h->grid_bar; a.coop = h->coop;
       h->timer->begin(st);
       rc = launch_s1_umma(a, lay, st, &launches);
       h->timer->end(st);
       if (rc) return rc;
+      lay.dbg_stamp = (h->grid_bar && env_on("TS_DBG_TRACE")) ? reinterpret_cast<unsigned long long*>(h->grid_bar + 14) : nullptr;
       rc = launch_merge_lists((const uint64_t*)h->lists, (const int*)h->counts, (const float*)h->pub, lay, Bc, k, h->id_base,
                               out_scores ? out_scores + (size_t)b0 * k : nullptr, out_ids ? out_ids + (size_t)b0 * k : nullptr, st,
                               &launches, push);
       if (rc) return rc;
+      if (lay.dbg_stamp) {      // TS_DBG_TRACE: absolute globaltimer of the select kernel's start (the scan printed its own t0)
+        unsigned long long t = 0;
+        cudaStreamSynchronize(st);
+        cudaMemcpy(&t, lay.dbg_stamp, 8, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[ts trace select] %llu\n", t);
+      }
     }
     h->launches += launches;
   }

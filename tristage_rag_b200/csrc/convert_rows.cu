@@ -21,9 +21,9 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const TS* __restrict_
                                                            int norm_mode, float* __restrict__ inv_norm_out,
                                                            unsigned int* __restrict__ zero_word) {
   const int lane = threadIdx.x & 31;
-  // query prep of a search: reset the arrival counter of the scan's in-kernel grid barrier (s1_umma.cu) -- the
-  // kernel boundary orders this store before the scan, so the barrier needs no reset protocol of its own
-  if (zero_word && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0u;
+  // query prep of a search: reset the 16 scheduling words of the scan (grid-barrier arrivals, next-tile counters:
+  // s1_umma.cu) -- the kernel boundary orders these stores before the scan, so neither needs a reset protocol
+  if (zero_word && blockIdx.x == 0 && threadIdx.x < 16) zero_word[threadIdx.x] = 0u;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
     const TS* s = src + row * src_ld;
@@ -51,6 +51,18 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const TS* __restrict_
       d[c] = Elem<TD>::from_f32(v);
     }
   }
+#ifndef TS_CUDASIM
+  // time line of a search step (TS_DBG_TRACE prints it): when block 0 of the query prep ends -- words 12-13 of the
+  // scheduling area, which the scan never touches
+  if (zero_word && blockIdx.x == 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      *reinterpret_cast<unsigned long long*>(zero_word + 12) = t;
+    }
+  }
+#endif
 }
 
 template <typename TS, typename TD>

@@ -71,6 +71,14 @@ constexpr int kBarBytes = 256;
 constexpr int kSmemBytes = kRingBytes + kBarBytes + 1024;  // + alignment slack
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 4;
+// Dynamic tile schedule of the scan: a CTA's first tile is `slice` (the fused pre-pass needs one tile per CTA), every
+// further tile comes from an atomic counter, so an SM that streams a few percent slower than the others (the
+// TS_DBG_TRACE timeline shows +-3.5 % per-SM tile times: 87 us between the median and the last CTA of a 10 M-row
+// scan) takes fewer tiles instead of finishing late.  The producer thread draws the tile and hands its number to the
+// MMA and epilogue warps through an 8-slot shared-memory ring; it can be at most ~4 tiles ahead of the epilogue
+// (4 ring stages + 2 accumulators), so 8 slots never wrap onto an unread entry.
+constexpr int kSchedSlots = 8;
+static_assert((16 + kSchedSlots) * 8 + kSchedSlots * 4 <= kBarBytes, "barrier area too small");
 
 struct UmmaParams {
   int64_t N;
@@ -81,6 +89,7 @@ struct UmmaParams {
   int mode;        // 0 = threshold pre-pass (first tile of every slice, publishes pub), 1 = scan,
                    // 2 = both in one cooperative launch (grid barrier after the first tile)
   unsigned int* grid_bar;  // arrival counter of the grid barrier (mode 2), zero at launch
+  unsigned int* tile_ctr;  // scan modes: next-tile counters [n_mt], zero at launch (null = static round-robin tiles)
   int jrank;       // j = ceil(k / n_slices) if <= 8, else 0 (threshold sharing off)
   int bpad;        // row pitch of pub
   uint64_t* lists; // [grid][rows_per_cta][cap] candidate keys
@@ -331,6 +340,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* tfull_bar = bars + 2 * kMaxStages;      // [2] MMA -> epilogue (per accumulator)
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2; // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint64_t* sched_bar = bars + 16;                  // [kSchedSlots] producer -> MMA / epilogue: tile number of iteration i is in sched[i % 8]
+  volatile int* sched = reinterpret_cast<volatile int*>(bars + 16 + kSchedSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt0 = blockIdx.x / p.n_slices, slice = blockIdx.x % p.n_slices;   // mt0: query tile
@@ -340,6 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int i = 0; i < kSchedSlots; ++i) mbar_init(&sched_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -350,6 +362,16 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool dynamic = (p.mode != 0) && (p.tile_ctr != nullptr);
+  // tile of iteration `iter` as the MMA / epilogue warps learn it (-1 = no more tiles)
+  auto tile_of = [&](int iter) -> int {
+    if (dynamic) {
+      mbar_wait(&sched_bar[iter & (kSchedSlots - 1)], (uint32_t)((iter / kSchedSlots) & 1), 7);
+      return sched[iter & (kSchedSlots - 1)];
+    }
+    const int t = slice + iter * p.n_slices;
+    return t < t_end ? t : -1;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -358,7 +380,17 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t tx = (p.spread ? (uint32_t)p.n_qgroups * 1024u : (uint32_t)kABytes) + (uint32_t)kBBytes;
       const uint64_t x_policy = (gridDim.x > (unsigned)p.n_slices) ? kEvictNormal : kEvictFirst;
       int stage = 0; uint32_t phase = 0;
-      for (int t = slice; t < t_end; t += p.n_slices) {
+      for (int iter = 0;; ++iter) {
+        int t = slice + iter * p.n_slices;
+        if (dynamic) {
+          if (iter > 0) t = p.n_slices + (int)atomicAdd(p.tile_ctr + mt0, 1u);
+          if (t >= t_end) t = -1;
+          sched[iter & (kSchedSlots - 1)] = t;
+          mbar_arrive(&sched_bar[iter & (kSchedSlots - 1)]);     // release: the tile number is visible to whoever completes the wait
+        } else if (t >= t_end) {
+          t = -1;
+        }
+        if (t < 0) break;
         for (int kc = 0; kc < p.nK; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
           unsigned char* sA = smem + stage * stage_bytes;
@@ -386,8 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if constexpr (OP == kOpTF32) umma_tf32_ss(d, ad, bd, id, accumulate); else umma_f16_ss(d, ad, bd, id, accumulate);
       };
       int stage = 0; uint32_t phase = 0;
-      int iter = 0;
-      for (int t = slice; t < t_end; t += p.n_slices, ++iter) {
+      for (int iter = 0; tile_of(iter) >= 0; ++iter) {
         const int acc = iter & 1;                       // the two accumulators alternate per tile
         const uint32_t par = (uint32_t)((iter >> 1) & 1);
         mbar_wait(&tempty_bar[acc], par ^ 1u, 2);
@@ -424,7 +455,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     const bool tracer = (p.trace != nullptr) && warp == 2 && lane == 0;
     if (tracer) trace_stamp(p, 0);
     int iter = 0;
-    for (int t = slice; t < t_end; t += p.n_slices, ++iter) {
+    for (;; ++iter) {
+      const int t = tile_of(iter);
+      if (t < 0) break;
       const int64_t n0 = (int64_t)t * kTileN;
       const int ncols = (int)((p.N - n0) < (int64_t)kTileN ? (p.N - n0) : (int64_t)kTileN);
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -703,6 +736,7 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
   p.jrank = lay.jrank; p.bpad = lay.bpad;
   p.lists = a.lists; p.counts = a.counts; p.pub = a.pub; p.tau_g = a.pub + (size_t)lay.n_slices * lay.bpad;
   p.inv_norm = a.inv_norm;
+  p.tile_ctr = (a.grid_bar && !env_on("TS_DBG_STATIC")) ? a.grid_bar + 1 : nullptr;   // TS_DBG_STATIC=1: round-robin tiles (A/B)
   static unsigned long long* d_stats = nullptr;
   if (env_on("TS_DBG_STATS")) {
     if (!d_stats) cudaMalloc((void**)&d_stats, 32);
@@ -740,15 +774,22 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
   }
   auto kern = bf16 ? s1_umma_kernel<kOpBF16> : (a.dtype == TS_F16 ? s1_umma_kernel<kOpF16> : s1_umma_kernel<kOpTF32>);
   TS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  if (p.jrank > 0 && lay.fused && a.grid_bar) {
+  if (p.jrank > 0 && lay.fused && a.grid_bar && a.coop) {
     // one cooperative launch (all CTAs co-resident): first tile -> publish -> grid barrier -> scan
     p.mode = 2;
     p.grid_bar = a.grid_bar;
 #ifdef TS_CUDASIM
     cudasim::launch_cooperative(lay.grid, kThreads, kSmemBytes, [&]() { kern(tmQ, tmQ8, tmX, p); });
 #else
-    void* args[] = {(void*)&tmQ, (void*)&tmQ8, (void*)&tmX, (void*)&p};
-    TS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(lay.grid), dim3(kThreads), args, kSmemBytes, st));
+    if (env_on("TS_DBG_NOCOOP")) {
+      // measurement only: a plain launch of the same grid (one CTA per SM is co-resident on an idle GPU, but nothing
+      // guarantees it) -- shows what the cooperative launch itself costs
+      TS_LAUNCH(kern, lay.grid, kThreads, kSmemBytes, st, tmQ, tmQ8, tmX, p);
+      TS_CUDA_OK(cudaGetLastError());
+    } else {
+      void* args[] = {(void*)&tmQ, (void*)&tmQ8, (void*)&tmX, (void*)&p};
+      TS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(lay.grid), dim3(kThreads), args, kSmemBytes, st));
+    }
 #endif
     if (launches) ++*launches;
   } else {
@@ -771,7 +812,12 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
     cudaStreamSynchronize(st);
     unsigned long long t0 = ~0ull;
     for (int c = 0; c < lay.grid; ++c) if (h[(size_t)c * kTraceSlots] && h[(size_t)c * kTraceSlots] < t0) t0 = h[(size_t)c * kTraceSlots];
-    fprintf(stderr, "[ts trace] {\"B\": %d, \"grid\": %d, \"ctas\": [", a.B, lay.grid);
+    // scheduling words 12-13: end of this step's query prep; 14-15: start of the PREVIOUS step's select kernel (the
+    // convert kernel zeroes the area, so read them before / keep them in host statics)
+    unsigned long long sw[2] = {0, 0};
+    if (a.grid_bar) cudaMemcpy(sw, a.grid_bar + 12, 8, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[ts trace] {\"B\": %d, \"grid\": %d, \"t0\": %llu, \"prep_exit\": %lld, \"ctas\": [", a.B, lay.grid, t0,
+            sw[0] ? (long long)(sw[0] - t0) : 0ll);
     for (int c = 0; c < lay.grid; ++c) {
       const unsigned long long* r = h + (size_t)c * kTraceSlots;
       const int tiles = (int)r[4];

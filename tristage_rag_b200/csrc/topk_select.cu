@@ -56,6 +56,7 @@ struct SelectParams {
   int wait_flag_stride;   // 0: flag l covers the whole list; > 0: flag of (list l, query b) at l * stride + b
   // final pass of a local search in a multi-GPU step: push the rows into every rank's receive buffer (PushTarget)
   PushTarget push;
+  unsigned long long* dbg_entry;   // TS_DBG_TRACE: CTA 0 stamps its start here (null = off)
 };
 
 // system-scope flag accesses for the peer-memory exchange (NVLink): the producer's data stores are made
@@ -124,6 +125,13 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   __shared__ int s_wsum[kSelThreads / 32];
   __shared__ int s_cnt;
   const int b = blockIdx.x, g = blockIdx.y;
+#ifndef TS_CUDASIM
+  if (p.dbg_entry && b == 0 && g == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *p.dbg_entry = t;
+  }
+#endif
   if (p.wait_flags) {
     // one thread per list spins (system-scope acquire) until its producer GPU has published this step
     if ((int)threadIdx.x < p.L) {
@@ -385,6 +393,7 @@ int launch_merge_lists(const uint64_t* lists, const int* counts, const float* pu
   p.pub = (lay.jrank > 0) ? pub : nullptr; p.bpad = lay.bpad;
   p.kth_rule = (lay.jrank == 1 && lay.kth_rule) ? 1 : 0;
   p.serial_prefix = env_on("TS_SELECT_V1") ? 1 : 0;
+  p.dbg_entry = lay.dbg_stamp;
   p.L = lay.n_slices; p.B = B; p.k_in = k; p.group = lay.n_slices; p.k_out = k;
   p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids; p.id_base = id_base;
   if (push) p.push = *push;

@@ -58,7 +58,7 @@ struct ts_index {
   void* tmp1; size_t tmp1_b;
   void* counts; size_t counts_b;
   void* pub; size_t pub_b;
-  unsigned int* grid_bar;            // arrival counter of the fused scan's grid barrier (zeroed by every query-prep launch)
+  unsigned int* grid_bar;            // 16 words zeroed by every query-prep launch: grid-barrier arrivals + next-tile counters of the scan
   int coop;                          // device supports cooperative launch
   void* stage; size_t stage_b;       // staging for host inputs (add / search_host)
   void* hout; size_t hout_b;         // device result buffers for search_host

@@ -81,7 +81,9 @@ struct ScanArgs {
   size_t partial_keys;    // capacity in keys
   int* counts;            // umma path out: entries per candidate list
   float* pub;             // umma path scratch: published per-slice thresholds
-  unsigned int* grid_bar; // umma path: arrival counter of the in-kernel grid barrier, zeroed by the query-prep kernel of the same call
+  unsigned int* grid_bar; // umma path: 16 words zeroed by the query-prep kernel of the same call -- [0] arrival counter of the
+                          // in-kernel grid barrier, [1 + mt] next-tile counter of query tile mt (dynamic tile schedule)
+  int coop;               // the device supports cooperative launches (needed for the fused pre-pass)
   int sm_count;
 };
 // where the umma scan leaves its candidates (consumed by launch_merge_lists)
@@ -90,6 +92,7 @@ struct UmmaLayout {
   int kth_rule;   // jrank == 1 and n_slices >= k: the slices' published bests are n_slices distinct rows, so the select kernel may
                   // filter with their k-th largest instead of their minimum
   size_t lists_keys, counts_n, pub_n;
+  unsigned long long* dbg_stamp;   // TS_DBG_TRACE: where the select kernel stamps its start (words 14-15 of the scheduling area)
 };
 // number of partial lists L a scan will emit / scratch it needs
 int s1_stream_plan(const ScanArgs& a, int* L, size_t* lists_keys);
