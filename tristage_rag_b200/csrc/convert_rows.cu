@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const TS* __restrict_
     bool scale = false;
     if (norm_mode != kNormNone) {
       float ss = 0.f;
+#pragma unroll 8
       for (int c = lane; c < dim; c += 32) {
         const float v = Elem<TS>::to_f32(s[c]);
         ss = fmaf(v, v, ss);
@@ -45,7 +46,8 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const TS* __restrict_
         scale = true;
       }
     }
-    for (int c = lane; c < (int)dst_ld; c += 32) {
+#pragma unroll 8
+    for (int c = lane; c < (int)dst_ld; c += 32) {     // eight independent loads in flight (the query prep of a search is latency-bound)
       float v = (c < dim) ? Elem<TS>::to_f32(s[c]) : 0.f;
       if (scale) v = __fdiv_rn(v, denom);
       d[c] = Elem<TD>::from_f32(v);

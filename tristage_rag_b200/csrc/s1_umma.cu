@@ -91,6 +91,7 @@ struct UmmaParams {
   unsigned int* grid_bar;  // arrival counter of the grid barrier (mode 2), zero at launch
   unsigned int* tile_ctr;  // scan modes: next-tile counters [n_mt], zero at launch (null = static round-robin tiles)
   int jrank;       // j = ceil(k / n_slices) if <= 8, else 0 (threshold sharing off)
+  int kth_rule;    // jrank == 1 and k <= n_slices <= 256: the slices' bests are n_slices distinct rows, their k-th largest is a bound
   int bpad;        // row pitch of pub
   uint64_t* lists; // [grid][rows_per_cta][cap] candidate keys
   int* counts;     // [grid][rows_per_cta] entries per list (out)
@@ -100,7 +101,8 @@ struct UmmaParams {
   unsigned long long* stats;  // debug: [0] appends [1] prunes [2] slow-path chunks (null = off)
   unsigned long long* trace;  // debug (TS_DBG_TRACE): [grid][kTraceSlots] globaltimer stamps of epilogue warp 2 (null = off)
 };
-constexpr int kTraceSlots = 64;   // [0] entry, [1] pass-1 done, [2] grid barrier passed, [3] exit, [4] tiles, [8 + i] accumulator i ready
+constexpr int kTraceSlots = 64;   // [0] entry, [1] pass-1 done, [2] grid barrier passed, [3] exit, [4] tiles, [5] first bound in hand,
+                                  // [6] first tile drained, [8 + i] accumulator i ready
 __device__ __forceinline__ void trace_stamp(const UmmaParams& p, int slot) {
 #ifndef TS_CUDASIM
   if (p.trace && slot < kTraceSlots) {
@@ -268,7 +270,7 @@ __device__ __forceinline__ void share_state(const UmmaParams& p, QState& s, int 
   if (!s.active) return;
   if (s.tjJ > s.pub_last) { p.pub[(size_t)slice * p.bpad + s.q] = s.tjJ; s.pub_last = s.tjJ; }
   float m;
-  if (slice == 0 && (iter & 1)) {          // designated refresher of the shared bound
+  if (!p.kth_rule && slice == 0 && (iter & 1)) {   // designated refresher of the shared bound (kth_rule: see kth_refresh)
     m = min_over_slices(p, s.q);
     p.tau_g[s.q] = m;
   } else {
@@ -302,25 +304,89 @@ __device__ __forceinline__ void named_bar_sync128(int id) { named_bar_sync(id, 1
 // arrival while the TMA stream was saturating the memory system (TS_DBG_TRACE) -- longer than the one tile time
 // (11 us) the first accumulator can be held without stalling the pipeline.  Bounded spin: a protocol bug traps.
 __device__ __forceinline__ void grid_barrier_epilogue(unsigned int* bar, int warp, int lane) {
-  named_bar_sync128(1);        // the CTA's pub stores are ordered before lane 0's release (CTA-scope barrier + cumulativity)
-  if (warp == 2 && lane == 0) {
+  named_bar_sync128(1);        // the CTA's pub stores are ordered before the release below (CTA-scope barrier + cumulativity)
+  if (warp == 2) {
+    // the whole warp polls (one request per load: same address), so it stays converged up to the barrier below
 #ifdef TS_CUDASIM
-    atomicAdd(bar, 1u);
+    if (lane == 0) atomicAdd(bar, 1u);
+    __syncwarp();
     while (*reinterpret_cast<volatile unsigned int*>(bar) < gridDim.x) TS_SPIN_YIELD();
 #else
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    __syncwarp();
     const long long t0 = clock64();
     unsigned int seen;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
       if (seen < gridDim.x && clock64() - t0 > TS_WAIT_TIMEOUT_CYCLES) {
-        printf("[tristage] grid barrier timeout: block %d saw %u of %u\n", (int)blockIdx.x, seen, gridDim.x);
+        if (lane == 0) printf("[tristage] grid barrier timeout: block %d saw %u of %u\n", (int)blockIdx.x, seen, gridDim.x);
         __trap();
       }
-    } while (seen < gridDim.x);
+    } while (__any_sync(0xffffffffu, seen < gridDim.x));
 #endif
   }
   named_bar_sync128(1);
+}
+
+// k-th largest of the n_slices (<= 256) published per-slice bests of query q, by one warp: 8 values per lane,
+// bisection over their order-preserving integer image (32 rounds of "how many are >= candidate").  The slices are
+// disjoint row sets, so k rows score >= this value: a valid bound, and a far tighter one than the minimum of the
+// bests (0.4 % of the rows pass it instead of 2 % right after the first tile of a 148-slice scan at k = 100).
+__device__ __forceinline__ float warp_kth_of_slices(const UmmaParams& p, int q, int lane) {
+  uint32_t v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = j * 32 + lane;
+    v[j] = (c < p.n_slices) ? f2ord(__ldcg(p.pub + (size_t)c * p.bpad + q)) : 0u;
+  }
+  uint32_t key = 0u;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = key | (1u << bit);
+    int n = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) n += (v[j] >= cand) ? 1 : 0;
+#ifdef TS_CUDASIM
+    n = warp_sum_int(n);
+#else
+    n = __reduce_add_sync(0xffffffffu, n);   // redux.sync: one instruction instead of five shuffle + add steps per round
+#endif
+    if (n >= p.k) key = cand;
+  }
+  return fmaxf(ord2f(key), -3.0e38f);    // finite: -inf is the "not published yet" value of tau_g
+}
+
+// fused start-up with the k-th-of-slices rule: CTA q (q < B) owns the first bound of query q -- its warp 2 computes
+// it right after the grid barrier and publishes it in tau_g[q]; every thread then waits for the bound of its own
+// query (all CTAs are co-resident, and every owner publishes before it waits, so the waits cannot form a cycle).
+__device__ __forceinline__ void kth_start(const UmmaParams& p, QState& s, float published, int warp, int lane) {
+  if (warp == 2 && (int)blockIdx.x < p.B) {
+    const float kth = warp_kth_of_slices(p, (int)blockIdx.x, lane);
+    if (lane == 0) {
+#ifdef TS_CUDASIM
+      *reinterpret_cast<volatile float*>(p.tau_g + blockIdx.x) = kth;
+#else
+      asm volatile("st.release.gpu.global.f32 [%0], %1;" ::"l"(p.tau_g + blockIdx.x), "f"(kth) : "memory");
+#endif
+    }
+  }
+  if (!s.active) return;
+  s.pub_last = published;
+  float m;
+#ifdef TS_CUDASIM
+  while ((m = *reinterpret_cast<volatile float*>(p.tau_g + s.q)) == -INFINITY) TS_SPIN_YIELD();
+#else
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.f32 %0, [%1];" : "=f"(m) : "l"(p.tau_g + s.q) : "memory");
+    if (m != -INFINITY) break;
+    if (clock64() - t0 > TS_WAIT_TIMEOUT_CYCLES) {
+      printf("[tristage] first-bound wait timeout: block %d query %d\n", (int)blockIdx.x, s.q);
+      __trap();
+    }
+  }
+#endif
+  if (!p.dbg_notopk) s.tau = nextafterf(m, -INFINITY);   // keep rows that tie with the bound
 }
 
 template <int OP>
@@ -343,6 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* sched_bar = bars + 16;                  // [kSchedSlots] producer -> MMA / epilogue: tile number of iteration i is in sched[i % 8]
   volatile int* sched = reinterpret_cast<volatile int*>(bars + 16 + kSchedSlots);
 
+  grid_dep_launch();   // the select kernel (launched with programmatic stream serialization) may become resident now; it waits for this grid's completion
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt0 = blockIdx.x / p.n_slices, slice = blockIdx.x % p.n_slices;   // mt0: query tile
   // the pre-pass looks at the first tile of the slice only
@@ -452,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (J > 0 && !fused) start_state(p, s0, slice, prepass);
 
     const bool wact0 = __any_sync(0xffffffffu, s0.active);
-    const bool tracer = (p.trace != nullptr) && warp == 2 && lane == 0;
+    const bool tracer = (p.trace != nullptr) && warp == 4 && lane == 0;   // warp 4 = TMEM lane quarter 0: holds query 0 for every B
     if (tracer) trace_stamp(p, 0);
     int iter = 0;
     for (;; ++iter) {
@@ -468,8 +535,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (fused && iter == 0) {
         // first tile, pass 1: only the thread's J best scores -> publish -> wait for every slice
         drain_acc(p, s0, lane_addr + (uint32_t)(acc * kTileN), n0, ncols, wact0, true, J, CAP, lane);
+        const float published = s0.tjJ;
         if (s0.active) {
-          p.pub[(size_t)slice * p.bpad + s0.q] = s0.tjJ;
+          p.pub[(size_t)slice * p.bpad + s0.q] = published;
           if (slice == 0) p.tau_g[s0.q] = -INFINITY;   // never let a stale bound of an earlier call be read
         }
         if (tracer) trace_stamp(p, 1);
@@ -478,13 +546,24 @@ __global__ void __launch_bounds__(kThreads, 1)
         // pass 2 re-reads the same accumulator with the shared bound in place; the J-best
         // registers restart from scratch so no row is counted twice
         topj_reset(s0);
-        start_state(p, s0, slice, false);
+        if (p.kth_rule) kth_start(p, s0, published, warp, lane);
+        else start_state(p, s0, slice, false);
+        if (tracer) trace_stamp(p, 5);
       }
       drain_acc(p, s0, lane_addr + (uint32_t)(acc * kTileN), n0, ncols, wact0, prepass, J, CAP, lane);
+      if (tracer && iter == 0) trace_stamp(p, 6);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (!prepass && J > 0) share_state(p, s0, slice, iter);
+      if (!prepass && J > 0) {
+        // k-th-of-slices rule: CTA q keeps the bound of query q fresh (every other tile, one warp, ~1.5 us), so the
+        // refresh work is spread over B CTAs instead of slice 0 recomputing B minima
+        if (p.kth_rule && (iter & 1) && warp == 2 && (int)blockIdx.x < p.B) {
+          const float kth = warp_kth_of_slices(p, (int)blockIdx.x, lane);
+          if (lane == 0) p.tau_g[blockIdx.x] = kth;
+        }
+        share_state(p, s0, slice, iter);
+      }
     }
     finish_state(p, s0, 0, slice, prepass, J, rows_per_cta, lane_row, true, (int)blockIdx.x);
     if (tracer) { trace_stamp(p, 3); p.trace[(size_t)blockIdx.x * kTraceSlots + 4] = (unsigned long long)iter; }
@@ -531,6 +610,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* tempty_bar = bars + 2 * kPairStages + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 4);
 
+  grid_dep_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = (int)(blockIdx.x >> 1) / p.n_slices, slice = (int)(blockIdx.x >> 1) % p.n_slices;
@@ -733,7 +813,9 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
   p.n_qgroups = (a.B + 7) / 8;
   p.cap = lay.cap;
   p.dbg_notopk = env_on("TS_DBG_NOTOPK") ? 1 : 0;
-  p.jrank = lay.jrank; p.bpad = lay.bpad;
+  p.jrank = lay.jrank; p.bpad = lay.bpad; 
+  // in the scan every query needs an owner CTA (blockIdx.x == q) for its bound: grid >= B (the select kernel's use of the rule has no such need)
+  p.kth_rule = (lay.kth_rule && lay.grid >= a.B && !lay.pair && !env_on("TS_DBG_NOKTHSTART")) ? 1 : 0;
   p.lists = a.lists; p.counts = a.counts; p.pub = a.pub; p.tau_g = a.pub + (size_t)lay.n_slices * lay.bpad;
   p.inv_norm = a.inv_norm;
   p.tile_ctr = (a.grid_bar && !env_on("TS_DBG_STATIC")) ? a.grid_bar + 1 : nullptr;   // TS_DBG_STATIC=1: round-robin tiles (A/B)
@@ -821,8 +903,9 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
     for (int c = 0; c < lay.grid; ++c) {
       const unsigned long long* r = h + (size_t)c * kTraceSlots;
       const int tiles = (int)r[4];
-      fprintf(stderr, "%s{\"entry\": %lld, \"pass1\": %lld, \"bar\": %lld, \"exit\": %lld, \"acc\": [", c ? ", " : "", (long long)(r[0] - t0),
-              r[1] ? (long long)(r[1] - t0) : -1ll, r[2] ? (long long)(r[2] - t0) : -1ll, (long long)(r[3] - t0));
+      fprintf(stderr, "%s{\"entry\": %lld, \"pass1\": %lld, \"bar\": %lld, \"bound\": %lld, \"tile0\": %lld, \"exit\": %lld, \"acc\": [", c ? ", " : "",
+              (long long)(r[0] - t0), r[1] ? (long long)(r[1] - t0) : -1ll, r[2] ? (long long)(r[2] - t0) : -1ll,
+              r[5] ? (long long)(r[5] - t0) : -1ll, r[6] ? (long long)(r[6] - t0) : -1ll, (long long)(r[3] - t0));
       for (int i = 0; i < tiles && 8 + i < kTraceSlots; ++i) fprintf(stderr, "%s%lld", i ? ", " : "", (long long)(r[8 + i] - t0));
       fprintf(stderr, "]}");
     }

@@ -22,6 +22,8 @@ namespace {
 
 constexpr int kSelThreads = 512;
 constexpr int kSelCap = 4096;  // keys of shared memory per CTA (32 KB)
+constexpr int kSelCapLists = 2048;  // kLists after the umma scan: 16 KB, so a select CTA fits on an SM beside a scan CTA (198 KB) and
+                                    // programmatic dependent launch can make it resident before the scan ends
 
 enum SelMode { kKeys = 0, kPairs = 1, kRank = 2, kLists = 3 };
 constexpr int kMaxLists = 256;
@@ -57,6 +59,7 @@ struct SelectParams {
   // final pass of a local search in a multi-GPU step: push the rows into every rank's receive buffer (PushTarget)
   PushTarget push;
   unsigned long long* dbg_entry;   // TS_DBG_TRACE: CTA 0 stamps its start here (null = off)
+  int sel_cap;                     // keys of dynamic shared memory this launch has (kSelCap or kSelCapLists)
 };
 
 // system-scope flag accesses for the peer-memory exchange (NVLink): the producer's data stores are made
@@ -125,6 +128,12 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   __shared__ int s_wsum[kSelThreads / 32];
   __shared__ int s_cnt;
   const int b = blockIdx.x, g = blockIdx.y;
+  // programmatic dependent launch: let the next kernel of the stream become resident now; our own inputs come from
+  // the predecessor (scan / all-gather) -- except in the wait-merge of the peer exchange, whose inputs are guarded
+  // by the peers' flags: it starts merging while this GPU's select kernel is still pushing and only orders itself
+  // behind it at the very end (stream order stays transitive)
+  grid_dep_launch();
+  if (!p.wait_flags) grid_dep_wait();
 #ifndef TS_CUDASIM
   if (p.dbg_entry && b == 0 && g == 0 && threadIdx.x == 0) {
     unsigned long long t;
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
         const uint64_t key = load(i);
         if (key >= thr && key != 0ull) {
           const int pos = atomicAdd(&s_cnt, 1);
-          if (pos < kSelCap) sbuf[pos] = key;
+          if (pos < p.sel_cap) sbuf[pos] = key;
         }
       }
     } else {
@@ -274,14 +283,14 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
         for (int u = 0; u < 4; ++u) {
           if (key[u] >= thr && key[u] != 0ull) {
             const int pos = atomicAdd(&s_cnt, 1);
-            if (pos < kSelCap) sbuf[pos] = key[u];
+            if (pos < p.sel_cap) sbuf[pos] = key[u];
           }
         }
       }
     }
     __syncthreads();
     const int kept = s_cnt;
-    if (kept <= kSelCap) {
+    if (kept <= p.sel_cap) {
       const int n = next_pow2(max(max(kept, p.k_out), 2));
       for (int i = kept + threadIdx.x; i < n; i += blockDim.x) sbuf[i] = 0ull;
       __syncthreads();
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     }
     __syncthreads();
   }
-  if (!done) block_select_topk(sbuf, kSelCap, p.k_out, total, load);
+  if (!done) block_select_topk(sbuf, p.sel_cap, p.k_out, total, load);
   // sbuf[0..k_out) sorted descending, zero padded
   for (int r = threadIdx.x; r < p.k_out; r += blockDim.x) {
     const uint64_t key = sbuf[r];
@@ -334,11 +343,14 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
       st_release_sys(reinterpret_cast<unsigned int*>(base + p.push.flags_off) + b, p.push.seq);
     }
   }
+  if (p.wait_flags) grid_dep_wait();
 }
 
-int launch_select(const SelectParams& p, int n_groups, cudaStream_t st) {
+int launch_select(SelectParams p, int n_groups, cudaStream_t st, bool pdl = false) {
   dim3 grid(p.B, n_groups);
-  TS_LAUNCH(select_kernel, grid, kSelThreads, kSelCap * sizeof(uint64_t), st, p);
+  if (p.sel_cap == 0) p.sel_cap = kSelCap;
+  if (pdl && env_flag("TS_PDL", kDefaultPdl)) TS_LAUNCH_PDL(select_kernel, grid, kSelThreads, p.sel_cap * sizeof(uint64_t), st, p);
+  else TS_LAUNCH(select_kernel, grid, kSelThreads, p.sel_cap * sizeof(uint64_t), st, p);
   TS_CUDA_OK(cudaGetLastError());
   return TS_OK;
 }
@@ -397,7 +409,8 @@ int launch_merge_lists(const uint64_t* lists, const int* counts, const float* pu
   p.L = lay.n_slices; p.B = B; p.k_in = k; p.group = lay.n_slices; p.k_out = k;
   p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids; p.id_base = id_base;
   if (push) p.push = *push;
-  int rc = launch_select(p, 1, st);
+  p.sel_cap = (k <= 128) ? kSelCapLists : kSelCap;   // k = 500 (J = 4 bound): a few thousand keys pass the filter, keep the 32 KB buffer
+  int rc = launch_select(p, 1, st, /*pdl=*/true);     // the scan executes griddepcontrol.launch_dependents at its start
   if (rc) return rc;
   if (launches) ++*launches;
   return TS_OK;
@@ -445,7 +458,7 @@ int launch_merge_pairs_wait(const float* scores, const int64_t* ids, long long s
   p.pair_stride = stride_scores; p.pair_stride_ids = stride_ids;
   p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids;
   p.wait_flags = wait_flags; p.wait_seq = wait_seq; p.wait_flag_stride = wait_flag_stride;
-  return launch_select(p, 1, st);
+  return launch_select(p, 1, st, /*pdl=*/true);      // overlaps this GPU's select + push kernel
 }
 
 int launch_rank_desc(const float* scores, const int32_t* n_cand, int B, int C, int top_k, float* out_scores,

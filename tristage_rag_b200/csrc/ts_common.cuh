@@ -214,6 +214,18 @@ __host__ __device__ __forceinline__ size_t tok_elem(int layout, long long row, i
   return (size_t)(row >> 3) * 8 * dim + (size_t)(c >> 3) * 64 + (size_t)(row & 7) * 8 + (c & 7);
 }
 
+// programmatic dependent launch (see TS_LAUNCH_PDL): no-ops when the kernel was launched the ordinary way
+__device__ __forceinline__ void grid_dep_wait() {
+#ifndef TS_CUDASIM
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void grid_dep_launch() {
+#ifndef TS_CUDASIM
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 __device__ __forceinline__ int warp_sum_int(int v) {
 #if defined(TS_CUDASIM)
   for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -68,8 +68,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
 }
 
 // named barrier over a subset of the CTA (the epilogue warps)
+// (barrier.sync, not bar.sync = barrier.sync.aligned: the aligned form is undefined when the lanes of a warp reach
+// it at different times, and nothing makes the compiler reconverge a warp in front of an inline-asm barrier -- the
+// TS_DBG_TRACE timeline showed three of the four epilogue warps leaving the fused scan's grid barrier while lane 0
+// of the fourth was still polling.)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+  asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ------------------------------------------------------------------ TMA ----
