@@ -611,6 +611,14 @@ def main():
                 "d2h_bytes_per_step": B * k * 12, "ms_per_step": r3(e2e_ms / args.steps)},
         "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
     }
+    if world > 1:
+        # which data plane carried the [B, k] lists (the driver's NCCL evidence covers the communicator only: with the
+        # peer-memory exchange NCCL does the barriers, the max-over-ranks reduction and the set-up agreement, no data)
+        line["comm"] = {"stage1_exchange": roof["exchange"], "nranks": world,
+                        "nccl_used_for": ("barriers + timing all-reduce + set-up agreement" if p2p
+                                          else "all-gather of the packed [B, k] lists + barriers + timing all-reduce"),
+                        "stage2_exchange": "nccl all-reduce(SUM) of the [B, C] scores" if os.environ.get("TS_P2P", "0") in ("", "0")
+                                           else "peer-memory push + wait-sum"}
     _PENDING["line"] = line
 
     # ---- parity of the timed workload -------------------------------------------

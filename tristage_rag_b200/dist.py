@@ -34,9 +34,10 @@ import torch
 import torch.distributed as dist
 
 
-# flipped to True once the fused peer-memory exchange has been validated on hardware (tools/dist_check.py on 2 and
-# 8 GPUs); until then the NCCL all-gather + merge kernel is the default data plane and TS_P2P=1 opts in
-P2P_DEFAULT = False
+# The fused peer-memory exchange is the default Stage-1 data plane on CUDA (validated on 2 and 8 B200s: tools/dist_check.py
+# and the parity check of bench.py, profiles/README.md); TS_P2P=0 selects the NCCL all-gather + merge kernel, and every
+# rank falls back to it together when symmetric memory cannot be set up (_agree_on_setup).
+P2P_DEFAULT = True
 
 
 def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
@@ -198,7 +199,7 @@ class ShardedIndex:
         # a CUDA device (every rank decides together, see _agree_on_setup, and falls back to NCCL otherwise)
         env = os.environ.get("TS_P2P", "")
         fused_ok = self._packed and self.world > 1 and hasattr(local_index, "_h") and not hasattr(local_index, "ivf")
-        self._p2p = bool(fused_ok and (env not in ("", "0") or (env == "" and P2P_DEFAULT)))
+        self._p2p = bool(fused_ok and torch.cuda.is_available() and (env not in ("", "0") or (env == "" and P2P_DEFAULT)))
         self._p2p_state = None
 
     def search(self, q: torch.Tensor, k: int, **kw) -> Tuple[torch.Tensor, torch.Tensor]:
