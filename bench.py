@@ -617,8 +617,8 @@ def main():
         line["comm"] = {"stage1_exchange": roof["exchange"], "nranks": world,
                         "nccl_used_for": ("barriers + timing all-reduce + set-up agreement" if p2p
                                           else "all-gather of the packed [B, k] lists + barriers + timing all-reduce"),
-                        "stage2_exchange": "nccl all-reduce(SUM) of the [B, C] scores" if os.environ.get("TS_P2P", "0") in ("", "0")
-                                           else "peer-memory push + wait-sum"}
+                        "stage2_exchange": ("nccl all-reduce(SUM) of the [B, C] scores" if os.environ.get("TS_P2P", "") == "0"
+                                            else "scatter fused into the scoring kernel (owners store into every rank's matrix) + wait-take")}
     _PENDING["line"] = line
 
     # ---- parity of the timed workload -------------------------------------------

@@ -198,6 +198,24 @@ int ts_index_search_sharded_host(ts_index* h, ts_exchange* x, const void* q_host
 int ts_exchange_wait_sum(int device, const void* local_base_dev, int n_ranks, int64_t n_floats, int64_t slot_bytes,
                          int64_t flags_offset, int parity, uint32_t seq, float* out_dev, void* stream);
 
+/* Stage 2 with the exchange FUSED into the scoring kernel (replaces ts_maxsim + all-reduce(SUM); the loop it stands
+ * for is stage2_rescorer.py:268-291 run on every shard): every candidate has exactly one owner, so the owner's kernel
+ * stores each finalised score at its flat position b*C + j of the [B, C] fp32 matrix at matrix_offset inside EVERY
+ * rank's receive buffer (peer_bases_dev[n_ranks]: the buffers as seen from this GPU, NVLink stores) -- nothing is left
+ * to reduce.  The last CTA of the grid then publishes seq (never 0) in u32 flag `rank` at flags_offset of every
+ * buffer (system-scope release).  Needs the tile-layout tensor kernel (bf16/fp16 store, dim % 16 == 0, dim <= 256,
+ * lq_stride <= 128), else TS_ERR_UNSUPPORTED -- decide for the whole group before the first call.
+ * ts_exchange_wait_take is the consumer: it waits (system-scope acquire, bounded) until the n_ranks flags at
+ * flags_dev show seq, copies the n_floats of matrix_dev to out_dev and leaves ZEROS behind: positions nobody owns
+ * read 0.0 like ts_maxsim's output, and the matrix is clean when it is used again.  Use two (matrix, flags) pairs
+ * alternately (step parity): a rank can be at most one step ahead of its slowest peer.                            */
+int ts_maxsim_scatter(ts_tokstore* h, const void* q_tok_dev, int q_dtype, const int32_t* q_len_dev, int B,
+                      int lq_stride, const int64_t* cand_dev, const int32_t* n_cand_dev, int C, int mode,
+                      unsigned flags, const int64_t* peer_bases_dev, int n_ranks, int rank,
+                      int64_t matrix_offset, int64_t flags_offset, uint32_t seq, void* stream);
+int ts_exchange_wait_take(int device, void* matrix_dev, const void* flags_dev, int n_ranks, uint32_t seq,
+                          int64_t n_floats, float* out_dev, void* stream);
+
 /* faiss.write_index / read_index  (stage1_retriever.py:436,463): one shard
  * file per handle (layout: see "shard files" below).  save synchronises the
  * device; load verifies the file's checksums.                                */

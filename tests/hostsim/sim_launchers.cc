@@ -123,5 +123,7 @@ int launch_exchange_push(const void*, long long, const long long*, int, long lon
 int launch_exchange_wait_sum(const void*, long long, const unsigned int*, int, unsigned int, long long, float*, cudaStream_t) { return not_simulated("exchange_wait_sum"); }
 int launch_merge_pairs_wait(const float*, const int64_t*, long long, long long, int, int, int, const unsigned int*, unsigned int, float*, int64_t*, cudaStream_t, int) { return not_simulated("merge_pairs_wait"); }
 int launch_maxsim(const MaxSimArgs&, cudaStream_t, int*) { return not_simulated("maxsim"); }
+bool maxsim_flow_takes(const MaxSimArgs&) { return false; }
+int launch_exchange_wait_take(void*, const unsigned int*, int, unsigned int, long long, float*, cudaStream_t) { return not_simulated("exchange_wait_take"); }
 
 }  // namespace ts

@@ -987,3 +987,47 @@ def test_peer_memory_sum_of_stage2_scores(sim):
             out = np.empty((B, Cn), np.float32)
             _lib.check(sim.ts_exchange_wait_sum(0, p(bufs[r]), G, n, slot, flags_off, parity, seq, p(out), None))
             assert np.array_equal(out, ref), (step, r)
+
+
+def test_stage2_scatter_fused_into_the_scoring_kernel(sim):
+    """ts_maxsim_scatter + ts_exchange_wait_take with three in-process ranks: every rank's flow kernel stores the scores
+    of the candidates it owns into ALL ranks' matrices and its last CTA publishes the step; the consumer takes the
+    matrix and leaves zeros.  Result == the single-store kernel on the whole corpus (un-owned / invalid ids and
+    positions beyond n_cand read 0.0), over several steps so both parities are reused."""
+    G, B, Cn, dim, Lq = 3, 5, 41, 32, 8
+    n = B * Cn
+    slot = (n * 4 + 15) // 16 * 16
+    flags_off = 2 * slot
+    bufs = [np.zeros(flags_off + 2 * G * 4 + 16, np.uint8) for _ in range(G)]
+    bases = np.array([b.ctypes.data for b in bufs], np.int64)
+    rng = np.random.default_rng(5)
+    lens = rng.integers(2, 70, size=90)
+    tok = rng.standard_normal((int(lens.sum()), dim)).astype(np.float32)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    stores = []
+    for r in range(G):
+        lo, hi = r * 30, (r + 1) * 30
+        st = _lib.TokStore(dim, "bf16", 0)
+        assert st.layout == 1
+        st.add(tok[off[lo]:off[hi]], lens[lo:hi], normalize=True)
+        st.set_id_base(lo)
+        stores.append(st)
+    whole = _lib.TokStore(dim, "bf16", 0)
+    whole.add(tok, lens, normalize=True)
+    for step in range(4):
+        q = rng.standard_normal((B, Lq, dim)).astype(np.float32)
+        cand = rng.integers(-2, 95, size=(B, Cn)).astype(np.int64)         # a few ids nobody owns
+        n_cand = rng.integers(Cn // 2, Cn + 1, size=B).astype(np.int32)
+        parity, seq = step & 1, step + 1
+        mat_off, f_off = parity * slot, flags_off + parity * G * 4
+        for r in range(G):
+            _lib.check(sim.ts_maxsim_scatter(stores[r]._h, p(q), _lib.TS_F32, None, B, Lq, p(cand), p(n_cand), Cn, 0,
+                                             _lib.TS_FLAG_NORMALIZE_Q, p(bases), G, r, mat_off, f_off, seq, None))
+        ref = whole.maxsim_host(q, cand, n_cand=n_cand)
+        for r in range(G):
+            out = np.empty((B, Cn), np.float32)
+            mat = bufs[r][mat_off:].ctypes.data
+            flg = bufs[r][f_off:].ctypes.data
+            _lib.check(sim.ts_exchange_wait_take(0, C.c_void_p(mat), C.c_void_p(flg), G, seq, n, p(out), None))
+            assert np.array_equal(out, ref), (step, r, np.abs(out - ref).max())
+            assert not bufs[r][mat_off:mat_off + n * 4].any()              # left clean for step + 2

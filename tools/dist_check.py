@@ -89,6 +89,23 @@ def main():
     ref = np.array([[maxsim.maxsim_score(nr(q[b]), nr(tok[off[c]:off[c + 1]]), normalize=False) for c in cand[b]]
                     for b in range(4)])
     assert np.allclose(got, ref, rtol=1e-3, atol=2e-4), float(np.abs(got - ref).max())
+    # the scatter fused into the scoring kernel (default on CUDA) and the all-reduce of the shards' outputs give the same
+    # matrix, bit for bit, over several steps (both parities of the receive buffer, ids nobody owns, ragged n_cand)
+    qd = torch.from_numpy(q).to(dev)
+    for step in range(5):
+        cand2 = torch.from_numpy(rng.integers(-3, ndocs + 5, size=(4, 200)).astype(np.int64)).to(dev)
+        ncd = torch.from_numpy(rng.integers(50, 201, size=4).astype(np.int32)).to(dev)
+        a1 = sst.maxsim(qd, cand2, n_cand=ncd)
+        os.environ["TS_S2_SCATTER"] = "0"
+        saved = os.environ.pop("TS_P2P", None)
+        os.environ["TS_P2P"] = "0"
+        a2 = sst.maxsim(qd, cand2, n_cand=ncd)
+        del os.environ["TS_S2_SCATTER"], os.environ["TS_P2P"]
+        if saved is not None:
+            os.environ["TS_P2P"] = saved
+        torch.cuda.synchronize()
+        assert torch.equal(a1, a2), (rank, step, float((a1 - a2).abs().max()))
+    stage2_plane = "scatter fused into the scoring kernel" if sst._scatter_ok(qd) else "all-reduce / push + sum"
     # load balance of candidate ownership
     own = np.bincount(np.searchsorted([shard_range(ndocs, r, world)[1] for r in range(world)], cand.ravel(), side="right"),
                       minlength=world)
@@ -119,7 +136,7 @@ def main():
     dist.barrier()
     if rank == 0:
         mode = "peer-memory exchange (fused select+push, wait+merge)" if sh._p2p else "nccl all-gather + merge kernel"
-        print(f"dist_check ok: world={world} merge via {mode}; stage2 candidates per rank max/mean = {own.max() / own.mean():.3f}",
+        print(f"dist_check ok: world={world} merge via {mode}; stage2 via {stage2_plane}; stage2 candidates per rank max/mean = {own.max() / own.mean():.3f}",
               flush=True)
     sys.stdout.flush()
     os._exit(0)          # no NCCL teardown (it can block for minutes after the work is done)

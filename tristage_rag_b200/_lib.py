@@ -71,6 +71,8 @@ SYMBOLS = {
     "ts_exchange_push": (_i, [_i, _vp, _i64, _vp, _i, _i, _i64, _i64, _i, _u, _vp]),
     "ts_exchange_wait_merge": (_i, [_i, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _u, _vp, _vp, _vp]),
     "ts_exchange_wait_sum": (_i, [_i, _vp, _i, _i64, _i64, _i64, _i, _u, _vp, _vp]),
+    "ts_maxsim_scatter": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _u, _vp, _i, _i, _i64, _i64, _u, _vp]),
+    "ts_exchange_wait_take": (_i, [_i, _vp, _vp, _i, _u, _i64, _vp, _vp]),
     "ts_index_save": (_i, [_vp, C.c_char_p]),
     "ts_index_load": (_i, [C.POINTER(_vp), _i, C.c_char_p]),
     "ts_index_append_file": (_i, [_vp, C.c_char_p, _i64, _i64, _vp]),
@@ -855,6 +857,22 @@ class TokStore:
                               TS_FLAG_NORMALIZE_Q if normalize_q else 0, C.c_void_p(out.data_ptr()),
                               _stream_ptr(self.device)))
         return out
+
+    @_locked
+    def maxsim_scatter(self, q_tok, cand, peer_bases_dev, n_ranks: int, rank: int, matrix_offset: int, flags_offset: int,
+                       seq: int, q_len=None, n_cand=None, mode: int = TS_S2_MAXSIM, normalize_q: bool = True) -> None:
+        """ts_maxsim_scatter: score the candidates this shard owns and store every score into all ranks' [B, C]
+        matrices (peer_bases_dev: int64 cuda tensor [n_ranks] of the receive buffers' addresses); async."""
+        assert q_tok.is_cuda and q_tok.dim() == 3 and q_tok.shape[2] == self.dim
+        q_tok, cand = q_tok.contiguous(), cand.contiguous()
+        B, Lq, _ = q_tok.shape
+        check(lib().ts_maxsim_scatter(self._h, C.c_void_p(q_tok.data_ptr()), _code_of_torch(q_tok.dtype),
+                                      C.c_void_p(q_len.data_ptr()) if q_len is not None else None, B, Lq,
+                                      C.c_void_p(cand.data_ptr()),
+                                      C.c_void_p(n_cand.data_ptr()) if n_cand is not None else None, cand.shape[1], int(mode),
+                                      TS_FLAG_NORMALIZE_Q if normalize_q else 0, C.c_void_p(peer_bases_dev.data_ptr()),
+                                      int(n_ranks), int(rank), int(matrix_offset), int(flags_offset), int(seq),
+                                      _stream_ptr(self.device)))
 
     @_locked
     def maxsim_host(self, q_tok, cand, q_len=None, n_cand=None, mode: int = TS_S2_MAXSIM,

@@ -508,6 +508,13 @@ int ts_exchange_wait_sum(int device, const void* local_base_dev, int n_ranks, in
   return launch_exchange_wait_sum(slots, slot_bytes, flags, n_ranks, seq, n_floats, out_dev, (cudaStream_t)stream);
 }
 
+int ts_exchange_wait_take(int device, void* matrix_dev, const void* flags_dev, int n_ranks, uint32_t seq, int64_t n_floats,
+                          float* out_dev, void* stream) {
+  if (!matrix_dev || !flags_dev || !out_dev || n_ranks < 1 || n_floats <= 0 || seq == 0) { set_error("ts_exchange_wait_take: invalid argument"); return TS_ERR_INVALID; }
+  TS_CUDA_OK(cudaSetDevice(device));
+  return launch_exchange_wait_take(matrix_dev, (const unsigned int*)flags_dev, n_ranks, seq, n_floats, out_dev, (cudaStream_t)stream);
+}
+
 int ts_index_get_rows(const ts_index* h, int64_t start, int64_t n, float* out_host) {
   if (!h || start < 0 || n < 0 || start + n > h->n || (n > 0 && !out_host)) { set_error("ts_index_get_rows: bad range"); return TS_ERR_INVALID; }
   if (n == 0) return TS_OK;
@@ -551,7 +558,7 @@ int ts_tokstore_create(ts_tokstore** out, int device, int dim, int storage_dtype
 int ts_tokstore_destroy(ts_tokstore* h) {
   if (!h) return TS_OK;
   cudaSetDevice(h->device);
-  void* ptrs[] = {h->tok, h->doc_off, h->doc_len, h->qbuf, h->stage, h->meta, h->hbuf};
+  void* ptrs[] = {h->tok, h->doc_off, h->doc_len, h->qbuf, h->stage, h->meta, h->hbuf, h->done_ctr, h->scratch_out};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->timer) { h->timer->destroy(); delete h->timer; }
   delete h;
@@ -660,8 +667,48 @@ int ts_tokstore_reset(ts_tokstore* h) { if (!h) return TS_ERR_INVALID; h->ndocs 
 int ts_tokstore_set_id_base(ts_tokstore* h, int64_t b) { if (!h) return TS_ERR_INVALID; h->id_base = b; return TS_OK; }
 int64_t ts_tokstore_launch_count(const ts_tokstore* h) { return h ? h->launches : -1; }
 
+}  // extern "C"
+
+namespace ts {
+struct ScatterTarget { const long long* bases; int n_ranks, rank; long long off, flags_off; unsigned int seq; };
+static int maxsim_impl(ts_tokstore* h, const void* q_tok, int q_dtype, const int32_t* q_len, int B, int lq_stride,
+                       const int64_t* cand, const int32_t* n_cand, int C, int mode, unsigned flags, float* out, void* stream,
+                       const ScatterTarget* sc);
+}
+
+extern "C" {
+
 int ts_maxsim(ts_tokstore* h, const void* q_tok, int q_dtype, const int32_t* q_len, int B, int lq_stride,
               const int64_t* cand, const int32_t* n_cand, int C, int mode, unsigned flags, float* out, void* stream) {
+  if (!out) { set_error("ts_maxsim: invalid argument"); return TS_ERR_INVALID; }
+  return ts::maxsim_impl(h, q_tok, q_dtype, q_len, B, lq_stride, cand, n_cand, C, mode, flags, out, stream, nullptr);
+}
+
+int ts_maxsim_scatter(ts_tokstore* h, const void* q_tok, int q_dtype, const int32_t* q_len, int B, int lq_stride,
+                      const int64_t* cand, const int32_t* n_cand, int C, int mode, unsigned flags,
+                      const int64_t* peer_bases_dev, int n_ranks, int rank, int64_t matrix_offset, int64_t flags_offset,
+                      uint32_t seq, void* stream) {
+  if (!h || !peer_bases_dev || n_ranks < 1 || n_ranks > 256 || rank < 0 || rank >= n_ranks || (matrix_offset & 3) || (flags_offset & 3) || seq == 0) {
+    set_error("ts_maxsim_scatter: invalid argument");
+    return TS_ERR_INVALID;
+  }
+  TS_CUDA_OK(cudaSetDevice(h->device));
+  if (!h->done_ctr) {
+    if (cudaMalloc((void**)&h->done_ctr, 16) != cudaSuccess) { cudaGetLastError(); set_error("ts_maxsim_scatter: cudaMalloc failed"); return TS_ERR_NOMEM; }
+    TS_CUDA_OK(cudaMemset(h->done_ctr, 0, 16));
+  }
+  int rc = ensure_bytes(&h->scratch_out, &h->scratch_out_b, (size_t)B * C * sizeof(float));
+  if (rc) return rc;
+  ts::ScatterTarget sc{(const long long*)peer_bases_dev, n_ranks, rank, matrix_offset, flags_offset, seq};
+  return ts::maxsim_impl(h, q_tok, q_dtype, q_len, B, lq_stride, cand, n_cand, C, mode, flags, (float*)h->scratch_out, stream, &sc);
+}
+
+}  // extern "C"
+
+namespace ts {
+static int maxsim_impl(ts_tokstore* h, const void* q_tok, int q_dtype, const int32_t* q_len, int B, int lq_stride,
+                       const int64_t* cand, const int32_t* n_cand, int C, int mode, unsigned flags, float* out, void* stream,
+                       const ScatterTarget* sc) {
   if (!h || !q_tok || !cand || !out || B <= 0 || C <= 0 || lq_stride <= 0) { set_error("ts_maxsim: invalid argument"); return TS_ERR_INVALID; }
   if ((mode & 0xff) != TS_S2_MAXSIM && (mode & 0xff) != TS_S2_COLBERT) { set_error("ts_maxsim: bad mode %d", mode); return TS_ERR_INVALID; }
   if (q_dtype != TS_F32 && q_dtype != h->dtype) { set_error("ts_maxsim: query dtype must be f32 or the storage dtype"); return TS_ERR_INVALID; }
@@ -682,6 +729,13 @@ int ts_maxsim(ts_tokstore* h, const void* q_tok, int q_dtype, const int32_t* q_l
   a.ntok_rows = h->nrows; a.dim = h->dim; a.dtype = h->dtype; a.q = h->qbuf; a.q_len = q_len; a.B = B;
   a.lq_stride = lq_stride; a.cand = cand; a.n_cand = n_cand; a.C = C; a.mode = mode; a.out = out;
   a.sm_count = h->info.sm_count;
+  if (sc) {
+    // the scatter lives in the flow kernel's finalize step: other kernels (row-major shards, fp32, Lq > 128) are
+    // refused and the caller exchanges the matrix the ordinary way
+    if (!maxsim_flow_takes(a) || (mode & 0x100)) { set_error("ts_maxsim_scatter: needs the tile-layout tensor kernel"); return TS_ERR_UNSUPPORTED; }
+    a.scatter_bases = sc->bases; a.scatter_n = sc->n_ranks; a.scatter_rank = sc->rank; a.scatter_off = sc->off;
+    a.scatter_flags_off = sc->flags_off; a.scatter_seq = sc->seq; a.scatter_done = h->done_ctr;
+  }
   int launches = 0;
   h->timer->begin(st);
   rc = launch_maxsim(a, st, &launches);
@@ -689,6 +743,9 @@ int ts_maxsim(ts_tokstore* h, const void* q_tok, int q_dtype, const int32_t* q_l
   h->launches += launches;
   return rc;
 }
+}  // namespace ts
+
+extern "C" {
 
 int ts_maxsim_host(ts_tokstore* h, const void* q_tok, int q_dtype, const int32_t* q_len, int B, int lq_stride,
                    const int64_t* cand, const int32_t* n_cand, int C, int mode, unsigned flags, float* out,

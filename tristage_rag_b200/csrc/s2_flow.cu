@@ -85,6 +85,12 @@ struct FlowParams {
   int lq_cap;                  // 32 or 128
   float* out;
   unsigned long long* trace;   // [grid][kTraceSlots] cycle counters (TRACE instantiation only)
+  // multi-GPU scatter (MaxSimArgs::scatter_*): 0 ranks = off
+  const long long* sc_bases;
+  int sc_n, sc_rank;
+  long long sc_off, sc_flags_off;
+  unsigned int sc_seq;
+  unsigned int* sc_done;
 };
 
 __host__ __device__ constexpr int flow_fixed_bytes(int slot_stride) {
@@ -98,6 +104,7 @@ template <bool BF16, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
     maxsim_flow_kernel(const __grid_constant__ CUtensorMap tmQ8, const __grid_constant__ CUtensorMap tmQ32,
                        const __grid_constant__ CUtensorMap tmQ128, const FlowParams p) {
+  grid_dep_launch();   // the consumer of a multi-GPU scatter (exchange_wait_take_kernel) may become resident and poll the peers' flags
   TS_DYN_SMEM(unsigned char, smem_raw);
   // offset arithmetic on the __shared__ array keeps the address space known to the compiler (LDS/STS)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -435,6 +442,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             res = sacc / z;
           }
           p.out[doc_out[slot]] = res;
+          // multi-GPU: the owner of a candidate stores its score straight into every rank's score matrix over NVLink
+          // (consecutive lanes hold consecutive candidates: one 128-byte store per peer and batch).  Every entry has
+          // exactly one owner, so there is nothing to reduce -- this replaces the all-reduce(SUM) of the shards' outputs.
+          for (int d = 0; d < p.sc_n; ++d)
+            reinterpret_cast<float*>(reinterpret_cast<char*>(p.sc_bases[d]) + p.sc_off)[doc_out[slot]] = res;
           uint4 zero; zero.x = zero.y = zero.z = zero.w = 0u;
           for (int i = 0; i < p.lq_cap; i += 4) *reinterpret_cast<uint4*>(sp + i) = zero;
         }
@@ -526,9 +538,28 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   }
 
+  if (p.sc_n) __threadfence_system();     // this thread's peer stores are ordered before the CTA's arrival below
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if (p.sc_n && threadIdx.x == 0) {
+    // last CTA of the grid publishes the step in every rank's buffer: all CTAs' stores happen-before its release
+    // (fence + arrival by each CTA, acquire-side fence here: cumulativity carries them across)
+    __threadfence();
+    const unsigned int old = atomicAdd(p.sc_done, 1u);
+    if (old == gridDim.x - 1) {
+      *p.sc_done = 0u;                    // the next launch on this handle is stream-ordered behind this kernel
+      __threadfence_system();
+      for (int d = 0; d < p.sc_n; ++d) {
+        unsigned int* f = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(p.sc_bases[d]) + p.sc_flags_off) + p.sc_rank;
+#ifdef TS_CUDASIM
+        *reinterpret_cast<volatile unsigned int*>(f) = p.sc_seq;
+#else
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(p.sc_seq) : "memory");
+#endif
+      }
+    }
+  }
   if constexpr (TRACE) {
     if (threadIdx.x == 0) p.trace[(size_t)blockIdx.x * kTraceSlots + 14] = (unsigned long long)(clock64() - t_start);
   }
@@ -558,6 +589,8 @@ int launch_maxsim_flow(const MaxSimArgs& a, cudaStream_t st, int* launches) {
   p.q_len = a.q_len; p.B = a.B; p.lq_stride = a.lq_stride; p.nK = (a.dim + kChunkK - 1) / kChunkK; p.dim = a.dim;
   p.cand = a.cand; p.n_cand = a.n_cand; p.C = a.C; p.mode = a.mode & 0xff;
   p.out = a.out;
+  p.sc_bases = a.scatter_bases; p.sc_n = a.scatter_bases ? a.scatter_n : 0; p.sc_rank = a.scatter_rank;
+  p.sc_off = a.scatter_off; p.sc_flags_off = a.scatter_flags_off; p.sc_seq = a.scatter_seq; p.sc_done = a.scatter_done;
   p.lq_cap = a.lq_stride <= 32 ? 32 : 128;
   p.slot_stride = p.lq_cap * 4 + 16;        // + 16: consecutive slots start in different 16-byte bank groups
   // shared memory: query tile(s) + ring + slots within the 227 KB opt-in limit

@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(EPI2 ? kThreadsEpi2 : kThreads, 1)
 int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches) {
   if (a.B <= 0 || a.C <= 0) { set_error("maxsim: empty batch"); return TS_ERR_INVALID; }
   TS_CUDA_OK(cudaMemsetAsync(a.out, 0, (size_t)a.B * a.C * sizeof(float), st));
-  if (a.ndocs == 0) return TS_OK;
+  if (a.ndocs == 0 && !a.scatter_bases) return TS_OK;   // (a scatter call still has to publish its step: the flow kernel runs over no work)
   // tensor kernels: the flow kernel reads tile-layout shards, the first kernel row-major ones; everything
   // else (fp32, odd dims, Lq > 128, the test switch) takes the CUDA-core kernel, which reads either layout
   bool tensor_ok = (a.dtype == TS_BF16 || a.dtype == TS_F16) && (a.dim % 8 == 0) && a.lq_stride >= 1 &&

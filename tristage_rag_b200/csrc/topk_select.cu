@@ -121,6 +121,34 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Consumer of the Stage-2 scatter (ts_maxsim_scatter): wait until all n_ranks owners have published the step, then move
+// this rank's score matrix out of the receive buffer and leave zeros behind -- entries nobody owns (ids outside every
+// shard, positions beyond n_cand) read 0.0 like the local kernel's output, and the buffer is clean when its parity
+// comes round again two steps later (no rank can be writing it before this rank's next push, see the parity argument
+// in include/tristage.h).
+__global__ void __launch_bounds__(256)
+    exchange_wait_take_kernel(float* __restrict__ matrix, const unsigned int* __restrict__ flags, int n_ranks, unsigned int seq,
+                              long long n, float* __restrict__ out) {
+  grid_dep_launch();
+  if ((int)threadIdx.x < n_ranks) {
+    const unsigned int* f = flags + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) != seq) {
+      TS_SPIN_YIELD();
+      if (clock64() - t0 > kExchangeTimeoutCycles) {
+        printf("[tristage] exchange timeout: rank %d never published Stage-2 step %u\n", (int)threadIdx.x, seq);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    out[i] = __ldcg(matrix + i);
+    matrix[i] = 0.f;
+  }
+  grid_dep_wait();     // launched with programmatic stream serialization behind the scatter kernel: stay ordered behind it
+}
+
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
   TS_DYN_SMEM(uint64_t, sbuf);
   __shared__ int pre[kMaxLists + 1];
@@ -444,6 +472,17 @@ int launch_exchange_wait_sum(const void* slots, long long slot_bytes, const unsi
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   TS_LAUNCH(exchange_wait_sum_kernel, (unsigned)blocks, 256, 0, st, (const char*)slots, slot_bytes, flags, n_ranks, seq, n, out);
+  TS_CUDA_OK(cudaGetLastError());
+  return TS_OK;
+}
+
+int launch_exchange_wait_take(void* matrix, const unsigned int* flags, int n_ranks, unsigned int seq, long long n, float* out,
+                              cudaStream_t st) {
+  if (!matrix || !flags || !out || n_ranks < 1 || n_ranks > 256 || n <= 0) { set_error("exchange_wait_take: bad arguments"); return TS_ERR_INVALID; }
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (env_flag("TS_PDL", kDefaultPdl)) TS_LAUNCH_PDL(exchange_wait_take_kernel, (unsigned)blocks, 256, 0, st, (float*)matrix, flags, n_ranks, seq, n, out);
+  else TS_LAUNCH(exchange_wait_take_kernel, (unsigned)blocks, 256, 0, st, (float*)matrix, flags, n_ranks, seq, n, out);
   TS_CUDA_OK(cudaGetLastError());
   return TS_OK;
 }

@@ -80,6 +80,8 @@ struct ts_tokstore {
   void* stage; size_t stage_b;
   void* meta; size_t meta_b;         // per-add src offsets scratch / host-variant buffers
   void* hbuf; size_t hbuf_b;
+  unsigned int* done_ctr;           // last-CTA election of the multi-GPU scatter (ts_maxsim_scatter), zero between launches
+  void* scratch_out; size_t scratch_out_b;   // local [B][C] matrix of a scatter call (the result lives in the receive buffers)
   ts::ScanTimer* timer;
 };
 

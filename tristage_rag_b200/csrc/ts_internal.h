@@ -130,6 +130,8 @@ int launch_merge_pairs(const float* scores, const int64_t* ids, long long stride
 // peer-memory exchange (multi-GPU merge without a collective library call)
 int launch_exchange_push(const void* blob, long long nbytes, const long long* peer_bases_dev, int n_ranks, long long slot_off,
                          long long flag_off, unsigned int seq, cudaStream_t st);
+int launch_exchange_wait_take(void* matrix, const unsigned int* flags, int n_ranks, unsigned int seq, long long n, float* out,
+                              cudaStream_t st);
 int launch_exchange_wait_sum(const void* slots, long long slot_bytes, const unsigned int* flags, int n_ranks, unsigned int seq,
                              long long n, float* out, cudaStream_t st);
 // wait_flag_stride = 0: one flag per list (whole [B,k] blob published at once); > 0: flag of (list l, query b) at
@@ -175,6 +177,14 @@ struct MaxSimArgs {
   int C, mode;
   float* out;              // [B][C]
   int sm_count;
+  // multi-GPU scatter (flow kernel only; all null / 0 otherwise): every finalised score is ALSO stored at its flat
+  // position of the [B][C] matrix at scatter_off inside every rank's receive buffer, and the last CTA publishes
+  // `seq` in flag `rank` of every buffer (system-scope release) -- see ts_maxsim_scatter in include/tristage.h
+  const long long* scatter_bases;   // device array [scatter_n] of the buffers' base addresses as seen from this GPU
+  int scatter_n, scatter_rank;
+  long long scatter_off, scatter_flags_off;
+  unsigned int scatter_seq;
+  unsigned int* scatter_done;       // device counter (zero between launches) for the last-CTA election
 };
 int launch_maxsim(const MaxSimArgs& a, cudaStream_t st, int* launches);
 // s2_flow.cu: resident query tile, docs split across full tiles (dim <= 256); launch_maxsim dispatches to it

@@ -396,7 +396,67 @@ class ShardedTokStore:
                                                    st["flags_off"], parity, seq, C.c_void_p(res.data_ptr()), stream))
         return res
 
+    # ---- Stage 2 with the exchange fused into the scoring kernel (ts_maxsim_scatter) ---------------------------
+    def _scatter_ok(self, q_tok: torch.Tensor) -> bool:
+        """The same answer on every rank (it depends on shapes, the store's layout and the environment only)."""
+        if self.world < 2 or not q_tok.is_cuda or getattr(self, "_p2p_off", False):
+            return False
+        env = os.environ.get("TS_P2P", "")
+        if env == "0" or (env == "" and not P2P_DEFAULT):
+            return False
+        loc = self.local
+        return (hasattr(loc, "maxsim_scatter") and getattr(loc, "layout", 0) == 1 and q_tok.dim() == 3
+                and q_tok.shape[1] <= 128 and os.environ.get("TS_S2_SCATTER", "1") != "0")
+
+    def _scatter_setup(self, n_floats: int, device: torch.device):
+        """Symmetric receive buffer: two [B*C] fp32 matrices (step parity) + 2 x world u32 flags, zeroed."""
+        import torch.distributed._symmetric_memory as symm
+
+        slot = (n_floats * 4 + 15) // 16 * 16
+        flags_off = 2 * slot
+        total = (flags_off + 2 * self.world * 4 + 15) // 16 * 16
+        buf = symm.empty(total, dtype=torch.uint8, device=device)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+        bases = torch.tensor([int(x) for x in hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        torch.cuda.current_stream(device).synchronize()
+        hdl.barrier()
+        return {"key": n_floats, "buf": buf, "hdl": hdl, "bases": bases, "slot": slot, "flags_off": flags_off}
+
+    def _maxsim_scatter(self, q_tok: torch.Tensor, cand: torch.Tensor, **kw) -> torch.Tensor:
+        """Every rank's kernel stores the scores of the candidates it owns into ALL ranks' matrices over NVLink and the
+        last CTA publishes the step; the consumer kernel waits for the world's flags and takes the matrix.  Two
+        launches of ours per step (+ the query prep), no collective call, nothing to reduce."""
+        import ctypes as C
+
+        from . import _lib
+
+        B, Cn = cand.shape
+        n = B * Cn
+        st = getattr(self, "_sc_state", None)
+        if st is None or st["key"] != n:
+            st = self._sc_state = _agree_on_setup(lambda: self._scatter_setup(n, q_tok.device), q_tok.device, self.group)
+            self._sc_step = 0
+        parity, seq = self._sc_step & 1, (self._sc_step % 0x7FFFFFFF) + 1
+        self._sc_step += 1
+        mat_off, flags_off = parity * st["slot"], st["flags_off"] + parity * self.world * 4
+        self.local.maxsim_scatter(q_tok, cand, st["bases"], self.world, self.rank, mat_off, flags_off, seq, **kw)
+        res = torch.empty((B, Cn), dtype=torch.float32, device=q_tok.device)
+        base = st["buf"].data_ptr()
+        dev = q_tok.device.index
+        _lib.check(_lib.lib().ts_exchange_wait_take(dev, C.c_void_p(base + mat_off), C.c_void_p(base + flags_off), self.world, seq,
+                                                    n, C.c_void_p(res.data_ptr()), _lib._stream_ptr(dev)))
+        return res
+
     def maxsim(self, q_tok: torch.Tensor, cand: torch.Tensor, **kw) -> torch.Tensor:
+        if self._scatter_ok(q_tok):
+            try:
+                return self._maxsim_scatter(q_tok, cand, **kw)
+            except PeerExchangeUnavailable as e:      # decided by all ranks together
+                import logging
+
+                logging.getLogger(__name__).warning(f"peer-memory exchange unavailable ({e}); using all-reduce")
+                self._p2p_off = True
         out = self.local.maxsim(q_tok, cand, **kw)        # 0.0 for ids this shard does not own
         if self.world > 1:
             if out.is_cuda and os.environ.get("TS_P2P", "0") not in ("", "0") and not getattr(self, "_p2p_off", False):
