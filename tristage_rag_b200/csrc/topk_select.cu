@@ -438,7 +438,9 @@ int launch_merge_lists(const uint64_t* lists, const int* counts, const float* pu
   p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids; p.id_base = id_base;
   if (push) p.push = *push;
   p.sel_cap = (k <= 128) ? kSelCapLists : kSelCap;   // k = 500 (J = 4 bound): a few thousand keys pass the filter, keep the 32 KB buffer
-  int rc = launch_select(p, 1, st, /*pdl=*/true);     // the scan executes griddepcontrol.launch_dependents at its start
+  // programmatic dependent launch only with the small buffer: a 32 KB select CTA cannot sit beside a scan CTA, and at
+  // k = 500 the pre-launched kernel measured +55 us on whatever follows it in the stream (graph replay, D2H of the host call)
+  int rc = launch_select(p, 1, st, /*pdl=*/p.sel_cap == kSelCapLists);   // the scan executes griddepcontrol.launch_dependents at its start
   if (rc) return rc;
   if (launches) ++*launches;
   return TS_OK;
