@@ -47,6 +47,13 @@ def main():
         # the host-buffer call (one C call per step on the peer-memory plane) returns the same
         hD, hI = sh.search_host(Q, k)
         assert (hI == i.cpu().numpy()).all() and (hD == s.cpu().numpy()).all(), (rank, B, "host call")
+        # one kernel for the whole exchange (default when B <= SM count) and the two-kernel form agree bit for bit
+        if sh._p2p:
+            os.environ["TS_XFUSE"] = "0"
+            s2, i2 = sh.search(torch.from_numpy(Q).to(dev), k)
+            del os.environ["TS_XFUSE"]
+            torch.cuda.synchronize()
+            assert torch.equal(i2, i) and torch.equal(s2, s), (rank, B, "two-kernel exchange")
     # approximate mode: the same centroids on every rank, lists over the local rows -> the merged result is what
     # one GPU holding all rows returns for the same probes (oracle/ivf.py on the full data)
     from oracle import ivf as oivf

@@ -371,6 +371,51 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
       st_release_sys(reinterpret_cast<unsigned int*>(base + p.push.flags_off) + b, p.push.seq);
     }
   }
+  if (p.final_pass && p.push.peer_bases && p.push.merge_scores) {
+    // ---- fused wait + merge: the exchange of a multi-GPU step in ONE kernel.  This CTA has pushed query b's row to
+    // every rank; now it waits for the G rows of query b that the other ranks' CTAs b push into THIS rank's buffer
+    // (every rank pushes before it waits, and the launcher only fuses when all B CTAs are co-resident: no cycle), and
+    // merges G * k -> k exactly like the separate wait-merge kernel (key = score, then position across lists).
+    const int G = p.push.n_ranks, k = p.k_out;
+    if ((int)threadIdx.x < G) {
+      const unsigned int* f = p.push.merge_flags + (size_t)threadIdx.x * p.push.merge_flag_stride + b;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(f) != p.push.seq) {
+        TS_SPIN_YIELD();
+        if (clock64() - t0 > kExchangeTimeoutCycles) {
+          printf("[tristage] exchange timeout: rank %d never pushed query %d of step %u\n", (int)threadIdx.x, b, p.push.seq);
+          __trap();
+        }
+      }
+    }
+    __syncthreads();                 // flags seen by the pollers, and every thread is done reading sbuf[0..k)
+    const int total_m = G * k;
+    const int n = next_pow2(max(total_m, 2));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      uint64_t key = 0ull;
+      if (i < total_m) {
+        const int l = i / k, r = i % k;
+        const size_t at = (size_t)b * k + r;
+        const int64_t id = __ldcg(p.push.merge_ids + (size_t)l * p.push.merge_stride_i + at);
+        if (id >= 0) key = make_key(__ldcg(p.push.merge_scores + (size_t)l * p.push.merge_stride_f + at), (uint32_t)i);
+      }
+      sbuf[i] = key;
+    }
+    __syncthreads();
+    block_sort_desc(sbuf, n);
+    for (int r = threadIdx.x; r < k; r += blockDim.x) {
+      const uint64_t key = sbuf[r];
+      float sc = kLowestF32;
+      int64_t id = -1;
+      if (key != 0ull) {
+        sc = key_score(key);
+        const uint32_t idx = key_idx(key);
+        id = __ldcg(p.push.merge_ids + (size_t)(idx / k) * p.push.merge_stride_i + (size_t)b * k + (idx % k));
+      }
+      p.push.merge_out_scores[(size_t)b * k + r] = sc;
+      p.push.merge_out_ids[(size_t)b * k + r] = id;
+    }
+  }
   if (p.wait_flags) grid_dep_wait();
 }
 

@@ -114,6 +114,15 @@ struct PushTarget {
   long long ids_off;             // ... of its id slot
   long long flags_off;           // ... of flags[parity][rank][0]
   unsigned int seq;              // sequence number of this step (never 0)
+  // fused wait + merge (null merge_scores = off): after pushing query b's row the same CTA waits for the G rows of
+  // query b in THIS rank's buffer and merges them -- the whole exchange is one kernel (see select_kernel)
+  const float* merge_scores;     // this rank's buffer: score slot of rank 0, this parity
+  const int64_t* merge_ids;      // ... id slot of rank 0
+  long long merge_stride_f, merge_stride_i;   // floats / int64s between consecutive ranks' slots
+  const unsigned int* merge_flags;            // flags[parity][0][0] of this rank's buffer; flag (l, b) at l * merge_flag_stride + b
+  int merge_flag_stride;
+  float* merge_out_scores;       // [B][k] merged result
+  int64_t* merge_out_ids;
 };
 // keys [L][B][k] -> final (scores, ids) [B][k]; tmp0/tmp1 each hold
 // ceil(L/2)*B*k keys (only used when L*k exceeds one selection pass).
