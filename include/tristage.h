@@ -185,8 +185,12 @@ int ts_index_search_push(ts_index* h, ts_exchange* x, const void* q_dev, int q_d
                          int path, void* stream);
 /* wait for all ranks' rows of this step and merge them: identical [B, k] result on every rank                    */
 int ts_exchange_merge(ts_exchange* x, int B, int k, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
-/* both, back to back; the _host variant takes pinned or pageable HOST buffers (H2D, step, D2H, synchronise) --
- * the sharded counterpart of ts_index_search_host                                                               */
+/* the whole step in one call.  When every CTA of the select kernel is co-resident (B <= SM count) and the n_ranks * k
+ * keys of a query fit its buffer (k <= 128, n_ranks * k <= 2048) the exchange is ONE kernel: CTA b pushes query b's row,
+ * then waits for the peers' rows of query b and merges them (every rank pushes before it waits: no cycle); otherwise
+ * ts_index_search_push + ts_exchange_merge back to back.  Same results either way (TS_XFUSE=0 forces two kernels).
+ * The _host variant takes pinned or pageable HOST buffers (H2D, step, D2H, synchronise) -- the sharded counterpart
+ * of ts_index_search_host                                                                                        */
 int ts_index_search_sharded(ts_index* h, ts_exchange* x, const void* q_dev, int q_dtype, int B, int k, unsigned flags,
                             int path, float* out_scores_dev, int64_t* out_ids_dev, void* stream);
 int ts_index_search_sharded_host(ts_index* h, ts_exchange* x, const void* q_host, int q_dtype, int B, int k,
