@@ -38,7 +38,7 @@ PLANT_QUERIES, PLANT_ROWS = 2, 100
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="tristage", choices=["tristage", "reference"])
     ap.add_argument("--batch", type=int, default=32)
