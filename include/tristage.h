@@ -220,6 +220,13 @@ int ts_maxsim_scatter(ts_tokstore* h, const void* q_tok_dev, int q_dtype, const 
 int ts_exchange_wait_take(int device, void* matrix_dev, const void* flags_dev, int n_ranks, uint32_t seq,
                           int64_t n_floats, float* out_dev, void* stream);
 
+/* Measurement aid: with TS_DBG_TIMELINE=1 in the environment the kernels of a tensor-path search stamp the GPU's
+ * globaltimer (ns) into 16 slots of the handle; this call synchronises the device and copies the slots of the LAST step:
+ * [0] query prep starts, [1] ends, [2] first scan CTA enters its epilogue, [3] last scan CTA leaves, [4] select kernel
+ * (CTA 0) starts, [5] local rows sorted, [6] pushed to every rank + published, [7] the peers' rows of query 0 are in,
+ * [8] merged result written (0 = not reached in this configuration).                                                 */
+int ts_index_debug_timeline(ts_index* h, uint64_t* out16);
+
 /* faiss.write_index / read_index  (stage1_retriever.py:436,463): one shard
  * file per handle (layout: see "shard files" below).  save synchronises the
  * device; load verifies the file's checksums.                                */

@@ -39,7 +39,7 @@ void store(void* p, int dt, size_t i, float v) {
 namespace ts {
 
 int launch_convert_rows(const void* src, int sdt, int64_t src_ld, void* dst, int ddt, int64_t dst_ld, int64_t n, int dim,
-                        int norm_mode, float* inv_norm_out, cudaStream_t, unsigned int* zero_word) {
+                        int norm_mode, float* inv_norm_out, cudaStream_t, unsigned int* zero_word, unsigned long long*) {
   if (zero_word) for (int i = 0; i < 16; ++i) zero_word[i] = 0u;
   for (int64_t r = 0; r < n; ++r) {
     float denom = 1.f; bool scale = false;

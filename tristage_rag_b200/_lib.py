@@ -73,6 +73,7 @@ SYMBOLS = {
     "ts_exchange_wait_sum": (_i, [_i, _vp, _i, _i64, _i64, _i64, _i, _u, _vp, _vp]),
     "ts_maxsim_scatter": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _u, _vp, _i, _i, _i64, _i64, _u, _vp]),
     "ts_exchange_wait_take": (_i, [_i, _vp, _vp, _i, _u, _i64, _vp, _vp]),
+    "ts_index_debug_timeline": (_i, [_vp, _vp]),
     "ts_index_save": (_i, [_vp, C.c_char_p]),
     "ts_index_load": (_i, [C.POINTER(_vp), _i, C.c_char_p]),
     "ts_index_append_file": (_i, [_vp, C.c_char_p, _i64, _i64, _vp]),
@@ -255,6 +256,14 @@ class Index:
         ms, n = C.c_float(), C.c_int()
         check(lib().ts_index_scan_time(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
+
+    def debug_timeline(self):
+        """TS_DBG_TIMELINE=1: the 16 globaltimer slots (ns) of the last search step (ts_index_debug_timeline)."""
+        import numpy as np
+
+        out = np.zeros(16, np.uint64)
+        check(lib().ts_index_debug_timeline(self._h, C.c_void_p(out.ctypes.data)))
+        return out
 
     @_locked
     def reset(self) -> None:

@@ -137,7 +137,8 @@ int ts_index_create(ts_index** out, int device, int dim, int storage_dtype, int 
     h->coop = coop;
     // [0] arrival counter of the fused scan's grid barrier, [1 + mt] next-tile counter of query tile mt: all 16 words
     // are zeroed by the query-prep kernel of every search
-    if (cudaMalloc((void**)&h->grid_bar, 64) == cudaSuccess) cudaMemset(h->grid_bar, 0, 64);
+    // (+ 192 bytes behind them: the TS_DBG_TIMELINE slots, ts_index_debug_timeline)
+    if (cudaMalloc((void**)&h->grid_bar, 256) == cudaSuccess) cudaMemset(h->grid_bar, 0, 256);
     else { cudaGetLastError(); h->grid_bar = nullptr; }
   }
   if (reserve_rows > 0) {
@@ -256,13 +257,14 @@ static int index_search_impl(ts_index* h, const void* q_dev, int q_dtype, int B,
 
   const int esz = dtype_size(h->dtype);
   const int chunkB = 1024;
+  unsigned long long* tl = (h->grid_bar && env_on("TS_DBG_TIMELINE")) ? reinterpret_cast<unsigned long long*>(h->grid_bar + 16) : nullptr;
   for (int b0 = 0; b0 < B; b0 += chunkB) {
     const int Bc = (B - b0) < chunkB ? (B - b0) : chunkB;
     int rc = ensure_bytes(&h->qbuf, &h->qbuf_b, (size_t)chunkB * h->ld * esz);
     if (rc) return rc;
     rc = launch_convert_rows((const char*)q_dev + (size_t)b0 * h->dim * dtype_size(q_dtype), q_dtype, h->dim, h->qbuf,
                              h->dtype, h->ld, Bc, h->dim, (flags & TS_FLAG_NORMALIZE_Q) ? kNormStage1 : kNormNone,
-                             nullptr, st, h->grid_bar);
+                             nullptr, st, h->grid_bar, tl);
     if (rc) return rc;
     ++h->launches;
     ScanArgs a{};
@@ -298,22 +300,16 @@ static int index_search_impl(ts_index* h, const void* q_dev, int q_dtype, int B,
       if ((rc = ensure_bytes(&h->counts, &h->counts_b, lay.counts_n * sizeof(int)))) return rc;
       if ((rc = ensure_bytes(&h->pub, &h->pub_b, lay.pub_n * sizeof(float)))) return rc;
       a.lists = (uint64_t*)h->lists; a.lists_keys = lay.lists_keys;
-      a.counts = (int*)h->counts; a.pub = (float*)h->pub; a.grid_bar = h->grid_bar; a.coop = h->coop;
+      a.counts = (int*)h->counts; a.pub = (float*)h->pub; a.grid_bar = h->grid_bar; a.coop = h->coop; a.tl = tl;
       h->timer->begin(st);
       rc = launch_s1_umma(a, lay, st, &launches);
       h->timer->end(st);
       if (rc) return rc;
-      lay.dbg_stamp = (h->grid_bar && env_on("TS_DBG_TRACE")) ? reinterpret_cast<unsigned long long*>(h->grid_bar + 14) : nullptr;
+      lay.tl = tl;
       rc = launch_merge_lists((const uint64_t*)h->lists, (const int*)h->counts, (const float*)h->pub, lay, Bc, k, h->id_base,
                               out_scores ? out_scores + (size_t)b0 * k : nullptr, out_ids ? out_ids + (size_t)b0 * k : nullptr, st,
                               &launches, push);
       if (rc) return rc;
-      if (lay.dbg_stamp) {      // TS_DBG_TRACE: absolute globaltimer of the select kernel's start (the scan printed its own t0)
-        unsigned long long t = 0;
-        cudaStreamSynchronize(st);
-        cudaMemcpy(&t, lay.dbg_stamp, 8, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[ts trace select] %llu\n", t);
-      }
     }
     h->launches += launches;
   }
@@ -538,6 +534,14 @@ int ts_exchange_wait_take(int device, void* matrix_dev, const void* flags_dev, i
   if (!matrix_dev || !flags_dev || !out_dev || n_ranks < 1 || n_floats <= 0 || seq == 0) { set_error("ts_exchange_wait_take: invalid argument"); return TS_ERR_INVALID; }
   TS_CUDA_OK(cudaSetDevice(device));
   return launch_exchange_wait_take(matrix_dev, (const unsigned int*)flags_dev, n_ranks, seq, n_floats, out_dev, (cudaStream_t)stream);
+}
+
+int ts_index_debug_timeline(ts_index* h, uint64_t* out16) {
+  if (!h || !out16 || !h->grid_bar) { set_error("ts_index_debug_timeline: invalid argument"); return TS_ERR_INVALID; }
+  TS_CUDA_OK(cudaSetDevice(h->device));
+  TS_CUDA_OK(cudaDeviceSynchronize());
+  TS_CUDA_OK(cudaMemcpy(out16, h->grid_bar + 16, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return TS_OK;
 }
 
 int ts_index_get_rows(const ts_index* h, int64_t start, int64_t n, float* out_host) {

@@ -19,8 +19,12 @@ template <typename TS, typename TD>
 __global__ void __launch_bounds__(256) convert_rows_kernel(const TS* __restrict__ src, int64_t src_ld,
                                                            TD* __restrict__ dst, int64_t dst_ld, int64_t n, int dim,
                                                            int norm_mode, float* __restrict__ inv_norm_out,
-                                                           unsigned int* __restrict__ zero_word) {
+                                                           unsigned int* __restrict__ zero_word,
+                                                           unsigned long long* __restrict__ tl) {
   const int lane = threadIdx.x & 31;
+  // TS_DBG_TIMELINE: GPU time line of one search step (ts_index_debug_timeline): this kernel's start, and the reset of
+  // the scan's first-entry / last-exit slots
+  if (tl && blockIdx.x == 0 && threadIdx.x == 0) { tl[0] = ts_globaltimer(); tl[2] = ~0ull; tl[3] = 0ull; }
   // query prep of a search: reset the 16 scheduling words of the scan (grid-barrier arrivals, next-tile counters:
   // s1_umma.cu) -- the kernel boundary orders these stores before the scan, so neither needs a reset protocol
   if (zero_word && blockIdx.x == 0 && threadIdx.x < 16) zero_word[threadIdx.x] = 0u;
@@ -53,29 +57,21 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const TS* __restrict_
       d[c] = Elem<TD>::from_f32(v);
     }
   }
-#ifndef TS_CUDASIM
-  // time line of a search step (TS_DBG_TRACE prints it): when block 0 of the query prep ends -- words 12-13 of the
-  // scheduling area, which the scan never touches
-  if (zero_word && blockIdx.x == 0) {
+  if (tl && blockIdx.x == 0) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      *reinterpret_cast<unsigned long long*>(zero_word + 12) = t;
-    }
+    if (threadIdx.x == 0) tl[1] = ts_globaltimer();
   }
-#endif
 }
 
 template <typename TS, typename TD>
 int launch_t(const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t n, int dim, int norm_mode,
-             float* inv, cudaStream_t st, unsigned int* zero_word) {
+             float* inv, cudaStream_t st, unsigned int* zero_word, unsigned long long* tl) {
   if (n == 0) return TS_OK;
   const int warps_per_block = 8;
   int64_t blocks = (n + warps_per_block - 1) / warps_per_block;
   if (blocks > 148 * 16) blocks = 148 * 16;
   auto kern = convert_rows_kernel<TS, TD>;
-  TS_LAUNCH(kern, (unsigned)blocks, 256, 0, st, (const TS*)src, src_ld, (TD*)dst, dst_ld, n, dim, norm_mode, inv, zero_word);
+  TS_LAUNCH(kern, (unsigned)blocks, 256, 0, st, (const TS*)src, src_ld, (TD*)dst, dst_ld, n, dim, norm_mode, inv, zero_word, tl);
   TS_CUDA_OK(cudaGetLastError());
   return TS_OK;
 }
@@ -83,10 +79,11 @@ int launch_t(const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t
 }  // namespace
 
 int launch_convert_rows(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld,
-                        int64_t n, int dim, int norm_mode, float* inv, cudaStream_t st, unsigned int* zero_word) {
+                        int64_t n, int dim, int norm_mode, float* inv, cudaStream_t st, unsigned int* zero_word,
+                        unsigned long long* tl) {
 #define TS_CASE(SD, ST_, DD, DT_)                                                                 \
   if (src_dtype == SD && dst_dtype == DD)                                                         \
-    return launch_t<ST_, DT_>(src, src_ld, dst, dst_ld, n, dim, norm_mode, inv, st, zero_word);
+    return launch_t<ST_, DT_>(src, src_ld, dst, dst_ld, n, dim, norm_mode, inv, st, zero_word, tl);
   TS_CASE(TS_F32, float, TS_F32, float)
   TS_CASE(TS_F32, float, TS_BF16, __nv_bfloat16)
   TS_CASE(TS_F32, float, TS_F16, __half)

@@ -100,6 +100,7 @@ struct UmmaParams {
   const float* inv_norm;
   unsigned long long* stats;  // debug: [0] appends [1] prunes [2] slow-path chunks (null = off)
   unsigned long long* trace;  // debug (TS_DBG_TRACE): [grid][kTraceSlots] globaltimer stamps of epilogue warp 2 (null = off)
+  unsigned long long* tl;     // debug (TS_DBG_TIMELINE): step time line, [2] = min over CTAs of the entry, [3] = max of the exit
 };
 constexpr int kTraceSlots = 64;   // [0] entry, [1] pass-1 done, [2] grid barrier passed, [3] exit, [4] tiles, [5] first bound in hand,
                                   // [6] first tile drained, [8 + i] accumulator i ready
@@ -528,6 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const bool wact0 = __any_sync(0xffffffffu, s0.active);
     const bool tracer = (p.trace != nullptr) && warp == 4 && lane == 0;   // warp 4 = TMEM lane quarter 0: holds query 0 for every B
     if (tracer) trace_stamp(p, 0);
+    if (p.tl && warp == 4 && lane == 0) atomicMin(p.tl + 2, ts_globaltimer());
     int iter = 0;
     for (;; ++iter) {
       const int t = tile_of(iter);
@@ -574,6 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     finish_state(p, s0, 0, slice, prepass, J, rows_per_cta, lane_row, true, (int)blockIdx.x);
     if (tracer) { trace_stamp(p, 3); p.trace[(size_t)blockIdx.x * kTraceSlots + 4] = (unsigned long long)iter; }
+    if (p.tl && warp == 4 && lane == 0 && p.mode != 0) atomicMax(p.tl + 3, ts_globaltimer());
   }
 
   tc_fence_before();
@@ -824,7 +827,7 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
   // in the scan every query needs an owner CTA (blockIdx.x == q) for its bound: grid >= B (the select kernel's use of the rule has no such need)
   p.kth_rule = (lay.kth_rule && lay.grid >= a.B && !lay.pair && !env_on("TS_DBG_NOKTHSTART")) ? 1 : 0;
   p.lists = a.lists; p.counts = a.counts; p.pub = a.pub; p.tau_g = a.pub + (size_t)lay.n_slices * lay.bpad;
-  p.inv_norm = a.inv_norm;
+  p.inv_norm = a.inv_norm; p.tl = a.tl;
   p.tile_ctr = (a.grid_bar && !env_on("TS_DBG_STATIC")) ? a.grid_bar + 1 : nullptr;   // TS_DBG_STATIC=1: round-robin tiles (A/B)
   static unsigned long long* d_stats = nullptr;
   if (env_on("TS_DBG_STATS")) {
@@ -901,12 +904,7 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
     cudaStreamSynchronize(st);
     unsigned long long t0 = ~0ull;
     for (int c = 0; c < lay.grid; ++c) if (h[(size_t)c * kTraceSlots] && h[(size_t)c * kTraceSlots] < t0) t0 = h[(size_t)c * kTraceSlots];
-    // scheduling words 12-13: end of this step's query prep; 14-15: start of the PREVIOUS step's select kernel (the
-    // convert kernel zeroes the area, so read them before / keep them in host statics)
-    unsigned long long sw[2] = {0, 0};
-    if (a.grid_bar) cudaMemcpy(sw, a.grid_bar + 12, 8, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[ts trace] {\"B\": %d, \"grid\": %d, \"t0\": %llu, \"prep_exit\": %lld, \"ctas\": [", a.B, lay.grid, t0,
-            sw[0] ? (long long)(sw[0] - t0) : 0ll);
+    fprintf(stderr, "[ts trace] {\"B\": %d, \"grid\": %d, \"t0\": %llu, \"ctas\": [", a.B, lay.grid, t0);
     for (int c = 0; c < lay.grid; ++c) {
       const unsigned long long* r = h + (size_t)c * kTraceSlots;
       const int tiles = (int)r[4];

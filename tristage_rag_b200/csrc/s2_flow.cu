@@ -538,14 +538,14 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   }
 
-  if (p.sc_n) __threadfence_system();     // this thread's peer stores are ordered before the CTA's arrival below
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
   if (p.sc_n && threadIdx.x == 0) {
-    // last CTA of the grid publishes the step in every rank's buffer: all CTAs' stores happen-before its release
-    // (fence + arrival by each CTA, acquire-side fence here: cumulativity carries them across)
-    __threadfence();
+    // last CTA of the grid publishes the step in every rank's buffer: the CTA barrier above orders every thread's peer
+    // stores before this thread's system-scope fence, each CTA's arrival is ordered behind its fence, and the last
+    // CTA's release is cumulative over all of it (the construction a cooperative-groups grid sync relies on)
+    __threadfence_system();
     const unsigned int old = atomicAdd(p.sc_done, 1u);
     if (old == gridDim.x - 1) {
       *p.sc_done = 0u;                    // the next launch on this handle is stream-ordered behind this kernel

@@ -58,7 +58,7 @@ struct SelectParams {
   int wait_flag_stride;   // 0: flag l covers the whole list; > 0: flag of (list l, query b) at l * stride + b
   // final pass of a local search in a multi-GPU step: push the rows into every rank's receive buffer (PushTarget)
   PushTarget push;
-  unsigned long long* dbg_entry;   // TS_DBG_TRACE: CTA 0 stamps its start here (null = off)
+  unsigned long long* tl;          // TS_DBG_TIMELINE: CTA 0 stamps [4] entry, [5] local rows sorted, [6] pushed + published, [7] peers' rows in, [8] exit
   int sel_cap;                     // keys of dynamic shared memory this launch has (kSelCap or kSelCapLists)
 };
 
@@ -162,13 +162,8 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   // behind it at the very end (stream order stays transitive)
   grid_dep_launch();
   if (!p.wait_flags) grid_dep_wait();
-#ifndef TS_CUDASIM
-  if (p.dbg_entry && b == 0 && g == 0 && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    *p.dbg_entry = t;
-  }
-#endif
+  const bool tl_on = p.tl && b == 0 && g == 0 && threadIdx.x == 0;
+  if (tl_on && !p.wait_flags) p.tl[4] = ts_globaltimer();
   if (p.wait_flags) {
     // one thread per list spins (system-scope acquire) until its producer GPU has published this step
     if ((int)threadIdx.x < p.L) {
@@ -281,7 +276,11 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
           int n = 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) n += (v[j] >= cand) ? 1 : 0;
+#ifdef TS_CUDASIM
           n = warp_sum_int(n);
+#else
+          n = __reduce_add_sync(0xffffffffu, n);     // redux.sync: one instruction per round instead of five shuffle + add steps
+#endif
           if (n >= p.k_out) key = cand;
         }
         if (threadIdx.x == 0) s_min[0] = key ? fmaxf(m, ord2f(key)) : m;
@@ -329,6 +328,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   }
   if (!done) block_select_topk(sbuf, p.sel_cap, p.k_out, total, load);
   // sbuf[0..k_out) sorted descending, zero padded
+  if (tl_on) p.tl[p.wait_flags ? 7 : 5] = ts_globaltimer();      // (wait-merge kernel: its peers' rows were in before the sort)
   for (int r = threadIdx.x; r < p.k_out; r += blockDim.x) {
     const uint64_t key = sbuf[r];
     if (!p.final_pass) {
@@ -363,13 +363,15 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     }
   }
   if (p.final_pass && p.push.peer_bases) {
-    // publish: this query's row is complete in every rank's buffer
-    __threadfence_system();
+    // publish: this query's row is complete in every rank's buffer.  The CTA barrier orders every thread's peer stores
+    // before the flag threads' release, and a release is cumulative over what happens-before it (the construction a
+    // cooperative-groups grid sync relies on): no system-scope fence per storing thread (it cost ~5 us per step here).
     __syncthreads();
     if ((int)threadIdx.x < p.push.n_ranks) {
       char* base = reinterpret_cast<char*>(p.push.peer_bases[threadIdx.x]);
       st_release_sys(reinterpret_cast<unsigned int*>(base + p.push.flags_off) + b, p.push.seq);
     }
+    if (tl_on) p.tl[6] = ts_globaltimer();
   }
   if (p.final_pass && p.push.peer_bases && p.push.merge_scores) {
     // ---- fused wait + merge: the exchange of a multi-GPU step in ONE kernel.  This CTA has pushed query b's row to
@@ -389,6 +391,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
       }
     }
     __syncthreads();                 // flags seen by the pollers, and every thread is done reading sbuf[0..k)
+    if (tl_on) p.tl[7] = ts_globaltimer();
     const int total_m = G * k;
     const int n = next_pow2(max(total_m, 2));
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -416,6 +419,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
       p.push.merge_out_ids[(size_t)b * k + r] = id;
     }
   }
+  if (p.tl && b == 0 && g == 0) { __syncthreads(); if (threadIdx.x == 0) p.tl[8] = ts_globaltimer(); }
   if (p.wait_flags) grid_dep_wait();
 }
 
@@ -478,7 +482,7 @@ int launch_merge_lists(const uint64_t* lists, const int* counts, const float* pu
   p.pub = (lay.jrank > 0) ? pub : nullptr; p.bpad = lay.bpad;
   p.kth_rule = (lay.jrank == 1 && lay.kth_rule) ? 1 : 0;
   p.serial_prefix = env_on("TS_SELECT_V1") ? 1 : 0;
-  p.dbg_entry = lay.dbg_stamp;
+  p.tl = lay.tl;
   p.L = lay.n_slices; p.B = B; p.k_in = k; p.group = lay.n_slices; p.k_out = k;
   p.final_pass = 1; p.out_scores = out_scores; p.out_ids = out_ids; p.id_base = id_base;
   if (push) p.push = *push;

@@ -214,6 +214,15 @@ __host__ __device__ __forceinline__ size_t tok_elem(int layout, long long row, i
   return (size_t)(row >> 3) * 8 * dim + (size_t)(c >> 3) * 64 + (size_t)(row & 7) * 8 + (c & 7);
 }
 
+__device__ __forceinline__ unsigned long long ts_globaltimer() {
+#ifdef TS_CUDASIM
+  return 0ull;
+#else
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+#endif
+}
 // programmatic dependent launch (see TS_LAUNCH_PDL): no-ops when the kernel was launched the ordinary way
 __device__ __forceinline__ void grid_dep_wait() {
 #ifndef TS_CUDASIM

@@ -69,7 +69,8 @@ enum NormMode { kNormNone = 0, kNormStage1 = 1 /* x/(|x|+1e-8) */, kNormStage2 =
 // written to inv_norm_out[n] (METRIC_COSINE).
 int launch_convert_rows(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld,
                         int64_t n, int dim, int norm_mode, float* inv_norm_out, cudaStream_t st,
-                        unsigned int* zero_word = nullptr);   // zero_word: set to 0 by the kernel (grid-barrier counter of the scan)
+                        unsigned int* zero_word = nullptr,    // 16 scheduling words of the scan, zeroed by the kernel
+                        unsigned long long* tl = nullptr);    // TS_DBG_TIMELINE slots (see ts_index_debug_timeline)
 
 // ---- Stage-1 scans -> partial keys [L][B][k] ------------------------------
 struct ScanArgs {
@@ -88,6 +89,7 @@ struct ScanArgs {
   unsigned int* grid_bar; // umma path: 16 words zeroed by the query-prep kernel of the same call -- [0] arrival counter of the
                           // in-kernel grid barrier, [1 + mt] next-tile counter of query tile mt (dynamic tile schedule)
   int coop;               // the device supports cooperative launches (needed for the fused pre-pass)
+  unsigned long long* tl; // TS_DBG_TIMELINE: time-line slots of the step (null = off): [2] first CTA entry, [3] last CTA exit
   int sm_count;
 };
 // where the umma scan leaves its candidates (consumed by launch_merge_lists)
@@ -96,7 +98,7 @@ struct UmmaLayout {
   int kth_rule;   // jrank == 1 and n_slices >= k: the slices' published bests are n_slices distinct rows, so the select kernel may
                   // filter with their k-th largest instead of their minimum
   size_t lists_keys, counts_n, pub_n;
-  unsigned long long* dbg_stamp;   // TS_DBG_TRACE: where the select kernel stamps its start (words 14-15 of the scheduling area)
+  unsigned long long* tl;          // TS_DBG_TIMELINE: the step's time-line slots (null = off)
 };
 // number of partial lists L a scan will emit / scratch it needs
 int s1_stream_plan(const ScanArgs& a, int* L, size_t* lists_keys);
