@@ -419,7 +419,7 @@ def scan_output_contract(Sc, n_slices, k, cap, rng, extra_frac=0.5):
                 pub[c, b] = s[J - 1] if len(s) >= J else -np.inf
         bound = pub[:, b].min() if jrank else -np.inf
         mt, qi = b >> 7, b & 127
-        row = ((qi >> 3) & 3) * 32 + ((qi >> 3) >> 2) * 8 + (qi & 7) if spread else qi
+        row = 64 + qi if spread else qi
         for c in range(n_slices):
             rows = members[c]
             must = rows[Sc[b, rows] >= bound]

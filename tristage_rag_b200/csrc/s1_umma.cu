@@ -45,9 +45,12 @@
 //   round's GPU budget was spent: taken only when asked for (path = TS_PATH_UMMA on an fp32
 //   index, or TS_TF32=1), the default for fp32 storage stays the CUDA-core scan.
 //
-// Small batches (B <= 64): the queries are spread over the four TMEM lane
-//   quarters in groups of 8 rows (8-row TMA boxes), so all four epilogue warps
-//   share the work instead of one.
+// Small batches (B <= 64): the query tile is ONE right-sized TMA box (8 / 16 / 32 / 64 rows) placed at rows 64.. of the A
+//   tile, i.e. the queries sit in TMEM lane quarters 2 and 3 -- epilogue warps 2 and 3, the two that do not share a warp
+//   scheduler with the TMA producer (warp 0) or the MMA issuer (warp 1).  The first layout spread the queries over all four
+//   quarters in 8-row boxes: every extra small box per K chunk cost ~27 ns of the producer / TMA path (B = 1 3.01 ms,
+//   B = 32 (4 boxes) 3.28 ms, B = 64 (8 boxes) 3.82 ms on 10 M x 1024), and one 128-row box with >= 96 out-of-bounds rows
+//   cost more still (4.5 ms).
 #include <stdlib.h>
 
 #include "ts_common.cuh"
@@ -84,7 +87,7 @@ struct UmmaParams {
   int64_t N;
   int nK, B, k;
   int n_slices, n_tiles;
-  int spread, n_qgroups, cap;
+  int spread, q_box_rows, cap;   // spread: B <= 64, the queries are rows 64.. of the A tile (one q_box_rows-row TMA box)
   int dbg_notopk;
   int mode;        // 0 = threshold pre-pass (first tile of every slice, publishes pub), 1 = scan,
                    // 2 = both in one cooperative launch (grid barrier after the first tile)
@@ -248,9 +251,9 @@ __device__ __forceinline__ void drain_acc(const UmmaParams& p, QState& s, uint32
 
 __device__ __forceinline__ void init_state(const UmmaParams& p, QState& s, int a, int mt0, int quarter, int lane,
                                            int lane_row, int rows_per_cta, int CAP, bool present, int cta_id) {
-  const int qi = p.spread ? ((((lane >> 3) * 4 + quarter) * 8) + (lane & 7)) : lane_row;
+  const int qi = p.spread ? lane_row - 64 : lane_row;      // small batches live in lane quarters 2 and 3
   s.q = (mt0 + a) * kTileM + qi;
-  s.active = present && s.q < p.B;
+  s.active = present && qi >= 0 && s.q < p.B;
   s.lst = p.lists + ((size_t)cta_id * rows_per_cta + a * kTileM + lane_row) * CAP;
   s.cnt = 0;
   s.n_app = s.n_prune = s.n_slow = 0;
@@ -452,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       // ------------------------------------------------ TMA producer ------
       prefetch_tmap(&tmQ); prefetch_tmap(&tmQ8); prefetch_tmap(&tmX);
-      const uint32_t tx = (p.spread ? (uint32_t)p.n_qgroups * 1024u : (uint32_t)kABytes) + (uint32_t)kBBytes;
+      const uint32_t tx = (p.spread ? (uint32_t)p.q_box_rows * 128u : (uint32_t)kABytes) + (uint32_t)kBBytes;
       const uint64_t x_policy = (gridDim.x > (unsigned)p.n_slices) ? kEvictNormal : kEvictFirst;
       int stage = 0; uint32_t phase = 0;
       for (int iter = 0;; ++iter) {
@@ -472,10 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           unsigned char* sB = sA + b_off;
           mbar_arrive_expect_tx(&full_bar[stage], tx);
           if (p.spread) {
-            for (int g = 0; g < p.n_qgroups; ++g) {
-              const int row = ((g & 3) * 32) + ((g >> 2) * 8);
-              tma_load_2d(sA + row * 128, &tmQ8, &full_bar[stage], kc * CK, g * 8, kEvictLast);
-            }
+            tma_load_2d(sA + 64 * 128, &tmQ8, &full_bar[stage], kc * CK, 0, kEvictLast);   // tmQ8: the q_box_rows-row box
           } else {
             tma_load_2d(sA, &tmQ, &full_bar[stage], kc * CK, mt0 * kTileM, kEvictLast);
           }
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (J > 0 && !fused) start_state(p, s0, slice, prepass);
 
     const bool wact0 = __any_sync(0xffffffffu, s0.active);
-    const bool tracer = (p.trace != nullptr) && warp == 4 && lane == 0;   // warp 4 = TMEM lane quarter 0: holds query 0 for every B
+    const bool tracer = (p.trace != nullptr) && warp == (p.spread ? 2 : 4) && lane == 0;   // the warp that holds query 0 (lane 64 for small batches, else lane 0)
     if (tracer) trace_stamp(p, 0);
     if (p.tl && warp == 4 && lane == 0) atomicMin(p.tl + 2, ts_globaltimer());
     int iter = 0;
@@ -813,14 +813,15 @@ int launch_s1_umma(const ScanArgs& a, const UmmaLayout& lay, cudaStream_t st, in
   int rc;
   CUtensorMap tmQ, tmQ8, tmX;
   if ((rc = make_tmap_2d(&tmQ, a.q, a.dtype, a.B, a.dim, a.ld, kTileM))) return rc;
-  if ((rc = make_tmap_2d(&tmQ8, a.q, a.dtype, a.B, a.dim, a.ld, 8))) return rc;
+  const int q_box_rows = a.B <= 8 ? 8 : a.B <= 16 ? 16 : a.B <= 32 ? 32 : 64;
+  if ((rc = make_tmap_2d(&tmQ8, a.q, a.dtype, a.B, a.dim, a.ld, q_box_rows))) return rc;
   if ((rc = make_tmap_2d(&tmX, a.rows, a.dtype, a.n, a.dim, a.ld, kTileN))) return rc;
   UmmaParams p{};
   const int chunk_elems = kChunkBytes / dtype_size(a.dtype);
   p.N = a.n; p.nK = (a.dim + chunk_elems - 1) / chunk_elems; p.B = a.B; p.k = a.k;
   p.n_slices = lay.n_slices; p.n_tiles = (int)((a.n + kTileN - 1) / kTileN);
   p.spread = lay.spread;
-  p.n_qgroups = (a.B + 7) / 8;
+  p.q_box_rows = q_box_rows;
   p.cap = lay.cap;
   p.dbg_notopk = env_on("TS_DBG_NOTOPK") ? 1 : 0;
   p.jrank = lay.jrank; p.bpad = lay.bpad; 

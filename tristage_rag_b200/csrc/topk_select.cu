@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   if (p.mode == kLists) {
     const int mt = b >> 7, qi = b & 127;
     int row = qi;
-    if (p.spread) { const int grp = qi >> 3; row = ((grp & 3) * 32) + ((grp >> 2) * 8) + (qi & 7); }
+    if (p.spread) row = 64 + qi;       // small batches (B <= 64): the scan keeps query qi in TMEM lane 64 + qi
     list_row0 = (size_t)mt * p.n_slices * p.rows_per_cta + row;   // CTAs (mt, 0..n_slices) own this query tile
     if (p.serial_prefix) {
       // first version (TS_SELECT_V1=1, kept for A/B timing): thread 0 walks the counts -- n_slices
