@@ -10,40 +10,38 @@
 // tensor pipe beyond (2*B*N*ld flop).
 //
 // Decomposition
-//   grid = n_mt * n_slices CTAs, one per SM.  CTA (mt, slice) owns query tile
-//   mt (128 queries = the M rows of the MMA = TMEM lanes) and corpus tiles
-//   slice, slice+n_slices, ... (256 rows = the N columns of the MMA).
-//   Per tile and 64-element K chunk, TMA (SWIZZLE_128B) brings A = 128x64 of Q
-//   and B = 256x64 of X into a 4-stage shared-memory ring; one thread issues
-//   four tcgen05.mma (M128 N256 K16, bf16/fp16 in, fp32 accumulate in TMEM).
-//   Two 256-column TMEM accumulators are double buffered against the epilogue.
+//   grid = n_mt * n_slices CTAs, one per SM.  CTA (mt, slice) owns query tile mt (128 queries = the M rows of the MMA
+//   = TMEM lanes) and corpus tiles of 256 rows (= the N columns of the MMA): its first tile is `slice`, every further
+//   tile comes from an atomic counter (dynamic tile schedule, kSchedSlots below).  Per tile and 64-element K chunk, TMA
+//   (SWIZZLE_128B) brings A = 128x64 of Q and B = 256x64 of X into a 4-stage shared-memory ring; one thread issues four
+//   tcgen05.mma (M128 N256 K16, bf16/fp16 in, fp32 accumulate in TMEM).  Two 256-column TMEM accumulators are double
+//   buffered against the epilogue.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = MMA
-//   issuer (one lane), warps 2-5 = epilogue; epilogue warp w reads TMEM lane
-//   quarter (w % 4) with tcgen05.ld 32x32b.x32, so thread t owns ONE query and
-//   walks its 256 scores of the tile.
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warps 2-5 = epilogue;
+//   epilogue warp w reads TMEM lane quarter (w % 4) with tcgen05.ld 32x32b.x32, so thread t owns ONE query and walks
+//   its 256 scores of the tile.
 //
 // Fused exact top-k (the [B, N] score matrix never exists):
-//   * fast path: per 32-column chunk a thread takes the max of its 32 scores and compares it
-//     ONCE with its threshold tau; 96-99 % of the chunks end here.
-//   * slow path: survivors are appended to the thread's candidate list in global memory (L2
-//     resident).  Within 32 entries of CAP the whole warp bitonic-sorts the list in registers
-//     (warp_prune_list), keeps the best k and raises tau (never needed on the benchmark
-//     configurations; exercised by adversarial score orders).
-//   * shared threshold: each slice c publishes pub[c][q] = the J-th best score it has seen for
-//     query q, J = ceil(k / n_slices) (8 registers per thread).  n_slices * J >= k rows score
-//     >= min_c pub[c][q], so the global k-th best is >= that minimum and every thread may drop
-//     anything below it.  A one-tile pre-pass launch (mode 0) seeds pub; during the scan
-//     (mode 1) slice 0 recomputes the minimum every other tile into tau_g, everybody else reads
-//     tau_g.  Mode 2 (opt-in, TS_FUSE) does both in one cooperative launch with a grid barrier.
-//   * the lists leave the kernel UNSORTED with their counts; topk_select.cu filters them with
-//     the final bound, compacts and sorts a few hundred survivors per query.
+//   * fast path: per 32-column chunk a thread takes the max of its 32 scores (a tree over eight groups of four) and
+//     compares it ONCE with its bound tau; 96-99 % of a query's chunks end here.
+//   * slow path: the groups whose maximum passes are visited, their survivors are appended straight from registers to
+//     the thread's candidate list in global memory (L2 resident).  Within 32 entries of CAP the whole warp
+//     bitonic-sorts the list in registers (warp_prune_list), keeps the best k and raises tau (never needed on the
+//     benchmark configurations; exercised by adversarial score orders).
+//   * shared bound: each slice c publishes pub[c][q] = the J-th best score it has seen for query q,
+//     J = ceil(k / n_slices).  n_slices * J >= k rows score >= min_c pub[c][q], so every thread may drop anything
+//     below that minimum.  With J = 1 and n_slices >= k the slices' bests are n_slices DISTINCT rows and their k-th
+//     largest is a (much tighter) bound too: CTA q keeps it fresh for query q in tau_g[q] (kth_start / the refresh in
+//     the main loop); otherwise slice 0 refreshes the minimum every other tile.
+//   * one cooperative launch per search (mode 2, TS_FUSE, default): first tile -> pass 1 (per-slice best only) ->
+//     publish -> grid barrier -> first bound -> pass 2 re-drains the same accumulator -> scan.  Modes 0 / 1 are the
+//     two-launch form (pre-pass over every slice's first tile, then the scan).
+//   * the lists leave the kernel UNSORTED with their counts; topk_select.cu filters them with the final bound, compacts
+//     and sorts a few hundred survivors per query.
 //
-// fp32 storage (the reference's own dtype) runs the same kernel with kind::tf32: the TMA map
-//   converts fp32 -> tf32 (round to nearest) on the way into shared memory, a K chunk is 32
-//   elements (the same 128-byte swizzle row), one MMA covers 8 of them.  Written after the
-//   round's GPU budget was spent: taken only when asked for (path = TS_PATH_UMMA on an fp32
-//   index, or TS_TF32=1), the default for fp32 storage stays the CUDA-core scan.
+// fp32 storage (the reference's own dtype) runs the same kernel with kind::tf32: the TMA map converts fp32 -> tf32
+//   (round to nearest) on the way into shared memory, a K chunk is 32 elements (the same 128-byte swizzle row), one MMA
+//   covers 8 of them.  Default for B > 4 (TS_TF32); the CUDA-core scan keeps exact fp32 products for B <= 4.
 //
 // Small batches (B <= 64): the query tile is ONE right-sized TMA box (8 / 16 / 32 / 64 rows) placed at rows 64.. of the A
 //   tile, i.e. the queries sit in TMEM lane quarters 2 and 3 -- epilogue warps 2 and 3, the two that do not share a warp
@@ -585,8 +583,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 // ---------------------------------------------------------------------------
-// CTA-pair variant (opt-in TS_PAIR=1, B >= 129; written without a GPU -- the instruction forms are
-// CUTLASS's and assemble for sm_100a, the protocol is checked on the emulator, hardware pending).
+// CTA-pair variant (TS_PAIR, default for B >= 129; bit-equal to the single-CTA scan on hardware, x1.12 at B = 256,
+// x1.03-1.09 at B = 1024 -- profiles/README.md).
 //
 // Why: for B >= 256 the scan is bound by L2->SM throughput (each CTA pulls 16 KB of Q and 32 KB of X
 // per K chunk: ~12.5 TB/s chip-wide at the measured rate, the LTS cap).  A cluster of two CTAs on one

@@ -37,10 +37,9 @@ constexpr bool kDefaultFuse = true;    // TS_FUSE : threshold pre-pass + scan in
 constexpr bool kDefaultS2V2 = false;   // TS_S2_V2: second Stage-2 epilogue
 constexpr bool kDefaultS2Flow = true;   // TS_S2_FLOW: Stage-2 tensor kernel with the resident query tile (s2_flow.cu); 0 = first kernel
 constexpr bool kDefaultS2Epi2 = false; // TS_S2_EPI2: two Stage-2 epilogue warpgroups (320 threads), one per accumulator
-constexpr bool kDefaultPdl = false;    // TS_PDL  : select / wait-merge / wait-take kernels use programmatic dependent launch.  Off: every clean
-                                       // measurement (no events between the kernels) showed the pre-launched kernel neutral or SLOWER --
-                                       // CUDA-graph replay of the 1-GPU step +8 us at B = 32, +54 us at k = 500; the 8-GPU step 0.468 ms
-                                       // against 0.448 ms with an event record (which defeats the pre-launch) between scan and select
+constexpr bool kDefaultPdl = false;    // TS_PDL  : select / wait-merge / wait-take kernels use programmatic dependent launch.  Off: a clean,
+                                       // interleaved A/B (no events between the kernels) shows the pre-launched kernel neutral or slower:
+                                       // +4 us per 440 us step at B = 32, +4-8 us under CUDA-graph replay, +14 us on the k = 500 host call
 constexpr bool kDefaultPair = true;    // TS_PAIR : cta_group::2 CTA pairs for B >= 129
 constexpr bool kDefaultTf32 = true;    // TS_TF32 : fp32 storage takes the tensor path (kind::tf32) for B > 4 under TS_PATH_AUTO
 inline bool env_flag(const char* name, bool dflt) {
