@@ -779,8 +779,10 @@ def test_flow_maxsim_splits_docs_across_tiles_and_keeps_the_query_resident(sim, 
 
 
 # ------------------------------------------- multi-GPU exchange over peer memory ---
-def test_peer_memory_exchange_equals_gather_and_merge(sim):
-    """ts_exchange_push / ts_exchange_wait_merge with G ranks living in one process (every rank's receive
+@pytest.mark.parametrize("N", [1500, 90])
+def test_peer_memory_exchange_equals_gather_and_merge(sim, N):
+    """(N = 90: 30 rows per shard < k, so every list ends in a -1 tail and the merged result is padded too.)
+    ts_exchange_push / ts_exchange_wait_merge with G ranks living in one process (every rank's receive
     buffer is plain host memory here, so "peer" pointers are ordinary pointers): after all ranks pushed step
     s, every rank's wait+merge returns what ts_topk_merge_packed returns over the gathered lists; steps
     alternate the two parities and the sequence numbers."""
@@ -790,10 +792,10 @@ def test_peer_memory_exchange_equals_gather_and_merge(sim):
     flags_off = 2 * G * slot
     bufs = [np.zeros(flags_off + 2 * G * 4 + 16, np.uint8) for _ in range(G)]
     bases = np.array([b.ctypes.data for b in bufs], np.int64)
-    N, d = 1500, 32
+    d = 32
     X, _ = make(N, d, 1, seed=4)
-    X[700] = X[3]
-    X[1400] = X[3]                                             # exact ties across shards: ids must ascend
+    X[N // 2] = X[3]
+    X[N - 7] = X[3]                                            # exact ties across shards: ids must ascend
     shards = []
     for r in range(G):
         lo, hi = r * N // G, (r + 1) * N // G

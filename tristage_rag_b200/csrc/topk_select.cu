@@ -149,6 +149,55 @@ __global__ void __launch_bounds__(256)
   grid_dep_wait();     // launched with programmatic stream serialization behind the scatter kernel: stay ordered behind it
 }
 
+// Merge of the exchange: G lists of k (score, id) pairs for query b, each SORTED the way the select kernel writes
+// them (key = score, then position, strictly descending; id < 0 marks the unused tail).  A key's final rank is its
+// position in its own list plus, for every other list, the number of greater keys there (binary search in shared
+// memory): two block barriers instead of the ~55 of a 1024-key bitonic sort (12 -> ~3 us for 8 x 100 on the step
+// time line).  Keys are unique (the position is part of the key), so the ranks are a permutation and the result is
+// the one the sort gives.  G * k <= 4 * blockDim keys.
+__device__ __forceinline__ void rank_merge_sorted(const float* __restrict__ scores, const int64_t* __restrict__ ids,
+                                                  long long stride_f, long long stride_i, int G, int k, int b, uint64_t* sbuf,
+                                                  float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  const int total = G * k;
+  uint64_t my_key[4];
+  int64_t my_id[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = (int)threadIdx.x + u * (int)blockDim.x;
+    my_key[u] = 0ull; my_id[u] = -1;
+    if (i < total) {
+      const int l = i / k, r = i - l * k;
+      const size_t at = (size_t)b * k + r;
+      my_id[u] = __ldcg(ids + (size_t)l * stride_i + at);
+      if (my_id[u] >= 0) my_key[u] = make_key(__ldcg(scores + (size_t)l * stride_f + at), (uint32_t)i);
+      sbuf[i] = my_key[u];
+    }
+  }
+  for (int r = threadIdx.x; r < k; r += blockDim.x) {      // fewer than k valid rows in all lists together: the tail stays padded
+    out_scores[(size_t)b * k + r] = kLowestF32;
+    out_ids[(size_t)b * k + r] = -1;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = (int)threadIdx.x + u * (int)blockDim.x;
+    if (i >= total || my_key[u] == 0ull) continue;
+    const int l = i / k;
+    int rank = i - l * k;
+    for (int l2 = 0; l2 < G; ++l2) {
+      if (l2 == l) continue;
+      const uint64_t* lst = sbuf + l2 * k;
+      int lo = 0, hi = k;                                   // keys greater than mine in list l2 (its invalid tail is 0: never greater)
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (lst[mid] > my_key[u]) lo = mid + 1; else hi = mid; }
+      rank += lo;
+    }
+    if (rank < k) {
+      out_scores[(size_t)b * k + rank] = key_score(my_key[u]);
+      out_ids[(size_t)b * k + rank] = my_id[u];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
   TS_DYN_SMEM(uint64_t, sbuf);
   __shared__ int pre[kMaxLists + 1];
@@ -178,6 +227,15 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
       }
     }
     __syncthreads();
+    if (p.mode == kPairs && p.final_pass && gridDim.y == 1 && p.k_in == p.k_out && p.out_scores &&
+        p.L * p.k_in <= p.sel_cap && p.L * p.k_in <= 4 * (int)blockDim.x) {
+      // the wait-merge kernel of the two-kernel exchange: the lists are the peers' select outputs, i.e. sorted
+      if (tl_on) p.tl[7] = ts_globaltimer();
+      rank_merge_sorted(p.scores, p.ids, p.pair_stride, p.pair_stride_ids, p.L, p.k_in, b, sbuf, p.out_scores, p.out_ids);
+      if (p.tl && b == 0) { __syncthreads(); if (threadIdx.x == 0) p.tl[8] = ts_globaltimer(); }
+      grid_dep_wait();
+      return;
+    }
   }
   int total;
   const int l0 = g * p.group;
@@ -392,32 +450,8 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     }
     __syncthreads();                 // flags seen by the pollers, and every thread is done reading sbuf[0..k)
     if (tl_on) p.tl[7] = ts_globaltimer();
-    const int total_m = G * k;
-    const int n = next_pow2(max(total_m, 2));
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      uint64_t key = 0ull;
-      if (i < total_m) {
-        const int l = i / k, r = i % k;
-        const size_t at = (size_t)b * k + r;
-        const int64_t id = __ldcg(p.push.merge_ids + (size_t)l * p.push.merge_stride_i + at);
-        if (id >= 0) key = make_key(__ldcg(p.push.merge_scores + (size_t)l * p.push.merge_stride_f + at), (uint32_t)i);
-      }
-      sbuf[i] = key;
-    }
-    __syncthreads();
-    block_sort_desc(sbuf, n);
-    for (int r = threadIdx.x; r < k; r += blockDim.x) {
-      const uint64_t key = sbuf[r];
-      float sc = kLowestF32;
-      int64_t id = -1;
-      if (key != 0ull) {
-        sc = key_score(key);
-        const uint32_t idx = key_idx(key);
-        id = __ldcg(p.push.merge_ids + (size_t)(idx / k) * p.push.merge_stride_i + (size_t)b * k + (idx % k));
-      }
-      p.push.merge_out_scores[(size_t)b * k + r] = sc;
-      p.push.merge_out_ids[(size_t)b * k + r] = id;
-    }
+    rank_merge_sorted(p.push.merge_scores, p.push.merge_ids, p.push.merge_stride_f, p.push.merge_stride_i, G, k, b, sbuf,
+                      p.push.merge_out_scores, p.push.merge_out_ids);
   }
   if (p.tl && b == 0 && g == 0) { __syncthreads(); if (threadIdx.x == 0) p.tl[8] = ts_globaltimer(); }
   if (p.wait_flags) grid_dep_wait();
