@@ -140,10 +140,37 @@ def main():
         s2, i2 = one.search(qd, k)
         torch.cuda.synchronize()
         assert torch.equal(i2, i0) and torch.equal(s2, s0)
+    # the drop-in classes striped over the group (Stage1Config.sharded / Stage2Config.sharded): every rank makes the calls the
+    # reference's orchestrator makes and gets what the un-sharded classes return (fake encoders: no weights on the box)
+    from oracle import fakes
+    from tristage_rag_b200 import ColBERTScorer, Stage1Config, Stage1Retriever, Stage2Config
+
+    docs = [f"document number {i} talks about topic {i % 7} and item {i * 3 % 11} in some detail {i}" for i in range(40)]
+    queries = ["topic 3 item 5", "document number 12 in detail", "item 9"]
+    with tempfile.TemporaryDirectory() as tmp:
+        kw = dict(device="cpu", cache_dir=os.path.join(tmp, "m"), index_dir=os.path.join(tmp, "i"), top_k_candidates=12,
+                  enable_bm25=False, storage_dtype="fp32", gpu_index=local)
+        one = Stage1Retriever(Stage1Config(**kw), model=fakes.FakeSentenceEncoder(64))
+        many = Stage1Retriever(Stage1Config(sharded=True, **kw), model=fakes.FakeSentenceEncoder(64))
+        for part in (docs[:1], docs[1:9], docs[9:]):
+            one.add_documents(list(part))
+            many.add_documents(list(part))
+        tok = fakes.FakeTokenizer()
+        s_one = ColBERTScorer(Stage2Config(device="cpu", top_k_candidates=6, gpu_index=local), tokenizer=tok, model=fakes.FakeTokenModel(tok, 32))
+        s_many = ColBERTScorer(Stage2Config(device="cpu", top_k_candidates=6, gpu_index=local, sharded=True), tokenizer=tok,
+                               model=fakes.FakeTokenModel(tok, 32))
+        for qq in queries:
+            a, b2 = one.search(qq), many.search(qq)
+            assert [x["doc_id"] for x in a] == [x["doc_id"] for x in b2] and len(b2) == 12, (rank, qq)
+            assert np.allclose([x["score"] for x in a], [x["score"] for x in b2], rtol=1e-5)
+            ra, rb = s_one.rescore_candidates(qq, a), s_many.rescore_candidates(qq, b2)
+            assert [x["doc_id"] for x in ra] == [x["doc_id"] for x in rb] and len(rb) == 6, (rank, qq)
+            assert np.allclose([x["stage2_score"] for x in ra], [x["stage2_score"] for x in rb], rtol=1e-3, atol=2e-4)
+        assert many.faiss_index.local.ntotal < len(docs) and s_many._store.ndocs < s_one._store.ndocs
     dist.barrier()
     if rank == 0:
         mode = "peer-memory exchange (fused select+push, wait+merge)" if sh._p2p else "nccl all-gather + merge kernel"
-        print(f"dist_check ok: world={world} merge via {mode}; stage2 via {stage2_plane}; stage2 candidates per rank max/mean = {own.max() / own.mean():.3f}",
+        print(f"dist_check ok: world={world} merge via {mode}; stage2 via {stage2_plane}; sharded drop-in classes ok; stage2 candidates per rank max/mean = {own.max() / own.mean():.3f}",
               flush=True)
     sys.stdout.flush()
     os._exit(0)          # no NCCL teardown (it can block for minutes after the work is done)
