@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE ONLY -- scheduler of the SIMT emulator (see cudasim.h).
 #include "cudasim.h"
+#include <unistd.h>
 
 #include <algorithm>
 #include <unordered_map>
@@ -384,7 +385,7 @@ static void setup_block(Block& B, int n, dim3 grid, dim3 block, unsigned bx, uns
 // CUDASIM_ASYNC the visiting order is reshuffled every round and some runnable threads sit a round out)
 static void run_blocks(Block** blocks, int nb) {
   unsigned long long last_progress = ~0ull;
-  int idle_rounds = 0;
+  int idle_rounds = 0, external_idle = 0;
   bool skipped_any = false;      // a runnable thread sat the previous round out: that round proves nothing
   std::vector<std::pair<int, int>> order;
   for (;;) {
@@ -401,7 +402,18 @@ static void run_blocks(Block** blocks, int nb) {
     idle_rounds = (progress == last_progress && pending == 0 && !skipped_any) ? idle_rounds + 1 : 0;
     skipped_any = false;
     g_blk = blocks[0];
-    if (idle_rounds > 3) die("deadlock: no simulated thread can make progress");
+    if (idle_rounds > 3) {
+      // CUDASIM_EXTERNAL_WAITS=1: the kernel may be spinning on memory another PROCESS writes (the multi-rank tests of
+      // the peer-memory exchange map the receive buffers into several emulator processes): wait instead of giving up,
+      // but not for ever
+      static const bool external = getenv("CUDASIM_EXTERNAL_WAITS") && getenv("CUDASIM_EXTERNAL_WAITS")[0] == '1';
+      if (!external || ++external_idle > 400000) die(external ? "timeout: a peer process never wrote what a simulated thread waits for"
+                                                              : "deadlock: no simulated thread can make progress");
+      usleep(50);
+      idle_rounds = 0;
+    } else if (progress != last_progress) {
+      external_idle = 0;
+    }
     last_progress = progress;
     order.clear();
     for (int i = 0; i < nb; ++i)

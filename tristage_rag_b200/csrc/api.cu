@@ -391,11 +391,16 @@ int ts_exchange_merge(ts_exchange* x, int B, int k, float* out_scores_dev, int64
 int ts_index_search_sharded(ts_index* h, ts_exchange* x, const void* q_dev, int q_dtype, int B, int k, unsigned flags, int path,
                             float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
   if (!h || !x || !out_scores_dev || !out_ids_dev || B < 1 || B > x->B_max || k < 1 || k > x->k_max) { set_error("ts_index_search_sharded: B / k outside the exchange's capacity"); return TS_ERR_INVALID; }
-#ifndef TS_CUDASIM
   // One kernel for the whole exchange (select + push + wait + merge) when every CTA of it is co-resident (one per
   // query, B <= SM count) and the G * k keys of a query fit the select kernel's small buffer; TS_XFUSE=0: two kernels.
-  // (The emulator runs its in-process "ranks" one after the other: a kernel that waits for its peers cannot run there.)
-  if (B <= h->info.sm_count && k <= 128 && (long long)x->n_ranks * k <= 2048 && env_flag("TS_XFUSE", true)) {
+  // (The emulator runs in-process "ranks" one after the other -- a kernel that waits for its peers cannot run there --
+  // so its build fuses only when the ranks are separate emulator PROCESSES sharing the buffers: TS_SIM_XFUSE=1.)
+#ifdef TS_CUDASIM
+  const bool may_fuse = env_on("TS_SIM_XFUSE");
+#else
+  const bool may_fuse = true;
+#endif
+  if (may_fuse && B <= h->info.sm_count && k <= 128 && (long long)x->n_ranks * k <= 2048 && env_flag("TS_XFUSE", true)) {
     if (x->device != h->device) { set_error("ts_index_search_sharded: index and exchange live on different devices"); return TS_ERR_INVALID; }
     const int parity = (int)(x->step & 1);
     PushTarget pt{};
@@ -414,7 +419,6 @@ int ts_index_search_sharded(ts_index* h, ts_exchange* x, const void* q_dev, int 
     ++x->step;
     return ts::index_search_impl(h, q_dev, q_dtype, B, k, flags, path, nullptr, nullptr, stream, &pt);
   }
-#endif
   int rc = ts_index_search_push(h, x, q_dev, q_dtype, B, k, flags, path, stream);
   if (rc) return rc;
   return ts_exchange_merge(x, B, k, out_scores_dev, out_ids_dev, stream);
