@@ -37,7 +37,7 @@ def machine(rng, max_sms=148):
 
 
 def stage1_case(rng):
-    variant = str(rng.choice(["", "", "TS_PAIR", "TS_DBG_NOSHARE", "TS_SELECT_V1", "TS_FUSE"]))
+    variant = str(rng.choice(["", "", "TS_PAIR", "TS_DBG_NOSHARE", "TS_SELECT_V1", "TS_FUSE", "TS_DBG_STATIC", "TS_DBG_NOKTHSTART", "TS_DBG_NOSPREAD"]))
     hw = machine(rng, 16 if variant == "TS_FUSE" else 148)      # a cooperative grid keeps every CTA alive at once
     dtype = rng.choice(["bf16", "fp16", "fp32"], p=[0.6, 0.25, 0.15])
     N = int(rng.choice([1, 3, 50, 255, 256, 257, 1000, 4000, 12000]))
